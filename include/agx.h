@@ -1,0 +1,301 @@
+/*
+ * agx.h -- C ABI of libagx.so: the B200 (sm_100a) kernels of the ArtGraph hetero-GNN + fusion-head
+ * hot path.  No torch / C++ types cross this boundary: plain pointers, sizes and POD descriptor
+ * structs.  Pointers are DEVICE pointers unless the parameter name starts with `h_`.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative agx_status otherwise; agx_last_error()
+ *     returns a thread-local message.  No C++ exception leaves the library.
+ *   - every function only ENQUEUES work on `stream` (a cudaStream_t passed as void*); nothing
+ *     synchronises, allocates or frees.  Workspaces are caller-owned (size query functions).
+ *     Descriptor tables (h_*) are read on the host during the call and are passed to the kernels
+ *     by value, so a call can be captured into a CUDA graph.
+ *   - the library is re-entrant and keeps no state besides the thread-local error string.
+ *   - features are row-major float32 (`AGX_F32`) or bfloat16 (`AGX_BF16`, aggregation only);
+ *     accumulation is always float32.  Indices are int32 inside the library; the reference's
+ *     int64 `edge_index` tensors are consumed by agx_csr_build only.
+ *
+ * The reference has no native interface of its own (it is pure Python on PyG / torch); each entry
+ * point cites the reference call site (path relative to the reference repo root) whose arithmetic
+ * it replaces.  INTEGRATION.md shows the ctypes binding.
+ */
+#ifndef AGX_H_
+#define AGX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGX_VERSION 100          /* 0.1.0 */
+
+typedef enum {
+    AGX_OK = 0,
+    AGX_ERR_INVALID = -1,        /* bad argument (message says which) */
+    AGX_ERR_CUDA = -2,           /* a CUDA runtime call or launch failed */
+    AGX_ERR_WORKSPACE = -3,      /* caller workspace too small */
+    AGX_ERR_UNSUPPORTED = -4
+} agx_status;
+
+enum { AGX_F32 = 0, AGX_BF16 = 1 };
+enum { AGX_SUM = 0, AGX_MEAN = 1 };
+
+int agx_version(void);
+const char* agx_last_error(void);
+/* fills a comma separated list of the __global__ kernels compiled into the library */
+int agx_kernel_inventory(char* h_buf, size_t h_buf_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  CSR / CSC construction (stable counting sort of the edge lists)
+ *   replaces: the implicit neighbour ordering of PyG `MessagePassing.propagate` on a dense
+ *   `edge_index` (gather + torch_scatter.scatter in edge order), called from
+ *   src/models/models_graph.py:30,38; edge_index layout of src/data/artgraph.py:106-112.
+ * ------------------------------------------------------------------------------------------ */
+#define AGX_MAX_CSR_RELS 40
+
+typedef struct {
+    const int64_t* keys;      /* [n_edges] row key per edge (dst for CSR, src for CSC)          */
+    const int64_t* vals;      /* [n_edges] column value per edge (src for CSR, dst for CSC)     */
+    int64_t n_edges;
+    int64_t n_rows;           /* keys must lie in [0, n_rows)                                    */
+    int64_t n_cols;           /* vals must lie in [0, n_cols)                                    */
+} agx_edge_list_t;
+
+/* Workspace bytes for agx_csr_build over relations with the given totals. */
+size_t agx_csr_workspace_bytes(int64_t total_edges, int64_t total_rows);
+
+/* Sorts all `n_rels` edge lists in ONE stable LSD radix sort over the composite key
+ * (relation, key).  Outputs, relation r at offsets rows_before(r)+r / edges_before(r):
+ *   rowptr [sum(n_rows_r + 1)] int32   local edge positions, rowptr_r[n_rows_r] == n_edges_r
+ *   col    [sum(n_edges_r)]    int32   vals in sorted order
+ *   eid    [sum(n_edges_r)]    int32   original edge id (the permutation); nullable
+ *   cnt    [sum(n_rows_r)]     float   max(degree, 1) (the clamp of scatter-mean); nullable
+ *   err    [1]                 int32   set to 1 if any key/val is out of range (never cleared)
+ * Bit-exact with a stable sort by key: within a row, neighbours keep edge-list order. */
+int agx_csr_build(const agx_edge_list_t* h_rels, int n_rels, int32_t* rowptr, int32_t* col,
+                  int32_t* eid, float* cnt, int32_t* err, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/* a-2: `T.ToUndirected()` for a non-bipartite store (src/train_gnn_embeddings.py:117-120):
+ * coalesce(cat([row,col]), cat([col,row])): unique pairs ascending in row*n+col.
+ * out_row/out_col [2*n_edges] int64; out_count[1] int64 = number of unique pairs. */
+size_t agx_coalesce_workspace_bytes(int64_t n_edges);
+int agx_coalesce_undirected(const int64_t* row, const int64_t* col, int64_t n_edges, int64_t n_nodes,
+                            int64_t* out_row, int64_t* out_col, int64_t* out_count,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2/K3  neighbour aggregation (gather + segmented reduce), forward and transpose
+ *   replaces: `x_src.index_select(0, ei[0])` + `torch_scatter.scatter(.., reduce)` inside
+ *   SAGEConv/GraphConv.propagate (call sites src/models/models_graph.py:30,38) and, run over the
+ *   CSC with neighbour scales, their autograd transposes (`index_add_`, gather of grad_out).
+ * ------------------------------------------------------------------------------------------ */
+#define AGX_MAX_REL_PER_GROUP 8
+#define AGX_MAX_GROUPS 24
+#define AGX_MAX_CHUNK_SEGS 24
+#define AGX_CHUNK_EDGES 128
+
+typedef struct {
+    const int32_t* rowptr;    /* [n_rows+1]                                                      */
+    const int32_t* col;       /* [n_edges]                                                       */
+    const void* x;            /* source rows [*, F], leading dimension ldx (elements)            */
+    int64_t ldx;
+    const float* row_cnt;     /* nullable: divide the row sum by row_cnt[row]   (scatter-mean)   */
+    const float* nbr_scale;   /* nullable: multiply neighbour j's row by 1/nbr_scale[j]
+                                 (transpose of scatter-mean)                                      */
+} agx_rel_t;
+
+/* One output row = sum over up to 8 relations of that relation's (scaled) neighbour sum:
+ * the per-destination-type `torch.add` chain of to_hetero (a-3) fused into the gather. */
+typedef struct {
+    void* out;                /* [n_rows, F], leading dimension ldo                              */
+    int64_t ldo;
+    int32_t n_rows;
+    int32_t n_rel;
+    int32_t accumulate;       /* 1: out += result                                                 */
+    int32_t relu_dmask;       /* reserved                                                         */
+    agx_rel_t rel[AGX_MAX_REL_PER_GROUP];
+} agx_row_group_t;
+
+/* warp (or sub-warp) per destination row; deterministic edge-order accumulation */
+int agx_aggregate_rows(const agx_row_group_t* h_groups, int n_groups, int F, int dtype,
+                       void* stream);
+
+typedef struct {
+    agx_rel_t rel;
+    void* out;                /* [n_rows, F]; rows of degree 0 are written as 0                  */
+    int64_t ldo;
+    int32_t n_rows;
+    int32_t n_edges;
+    float* frag;              /* [agx_chunk_frag_floats(n_edges, F)] scratch                     */
+} agx_chunk_seg_t;
+
+size_t agx_chunk_frag_floats(int64_t n_edges, int F);
+/* edge-balanced variant for relations with long rows (few destination rows, many edges):
+ * one warp per 128 consecutive CSR edges, row fragments combined in fixed chunk order */
+int agx_aggregate_chunks(const agx_chunk_seg_t* h_segs, int n_segs, int F, int dtype,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4  dense transforms (lin_l / lin_r / head Linear), float32 with float32 accumulation
+ *   replaces: F.linear inside PyG Linear (SAGEConv.lin_l/lin_r, GraphConv.lin_rel/lin_root) and
+ *   nn.Linear of src/models/models_kg.py:148-150,174-180,225-231,254,272, plus their autograd
+ *   backward GEMMs.
+ *   C[M,N] (+)= sum_s opA_s[M,K_s] * opB_s[K_s,N] (+ bias[N]) ; element (i,k) of opA_s is
+ *   A[i*a_rs + k*a_cs], element (k,j) of opB_s is B[k*b_rs + j*b_cs].
+ * ------------------------------------------------------------------------------------------ */
+#define AGX_MAX_GEMM_PROBLEMS 24
+#define AGX_MAX_GEMM_SEGS 64
+
+typedef struct {
+    const float* A; int64_t a_rs, a_cs;
+    const float* B; int64_t b_rs, b_cs;
+    const float* A_mask;      /* nullable: opA is multiplied elementwise by A_mask (same strides);
+                                 the Dropout in front of the head Linear, never materialised     */
+    const float* B_mask;      /* nullable: same for opB                                          */
+    int32_t K;
+    int32_t pad_;
+} agx_gemm_seg_t;
+
+typedef struct {
+    float* C; int64_t ldc;
+    const float* bias;        /* nullable, [N]                                                    */
+    const float* row_scale;   /* nullable, [M]: C row i is divided by row_scale[i] in the epilogue */
+    int32_t M, N;
+    int32_t accumulate;       /* 1: C += result                                                   */
+    int32_t seg_begin, seg_count;  /* into the segment table                                      */
+    int32_t split_k;          /* >1: reduction of the single segment is split into this many
+                                 slabs through `partial`, combined in slab order               */
+    float* partial;           /* [split_k, M, N] when split_k > 1                                 */
+    const int32_t* skip_flag; /* nullable: if *skip_flag != 0 the problem is skipped on device    */
+} agx_gemm_problem_t;
+
+int agx_gemm_grouped(const agx_gemm_problem_t* h_problems, int n_problems,
+                     const agx_gemm_seg_t* h_segs, int n_segs, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * small batched elementwise / reduction kernels of the GNN step
+ * ------------------------------------------------------------------------------------------ */
+#define AGX_MAX_TENSORS 48
+
+/* out = sum of up to 8 equally-sized float arrays (sum of lin_r weights / lin_l biases that share
+ * a destination type; exact restatement of adding the per-relation outputs, a-3) */
+typedef struct { float* out; const float* in[8]; int32_t n_in; int64_t numel; } agx_sum_desc_t;
+int agx_sum_arrays(const agx_sum_desc_t* h_descs, int n, void* stream);
+
+/* a-7  BatchNorm1d per node type (src/models/models_graph.py:19,32-33), batched over types, with
+ * the following activation + dropout (:34-37) fused into the normalising pass.
+ * Training statistics: two passes (mean, then centred second moment), per-slab float32 partials
+ * combined in float64 (the reference's CPU kernel accumulates in double). */
+typedef struct {
+    const float* x; float* y;            /* [n_rows, F] contiguous                               */
+    float* y_act;                         /* nullable: relu(y) * dmask                            */
+    const float* dmask;                   /* nullable: [n_rows, F] multiplicative dropout mask    */
+    const float* weight; const float* bias;   /* [F] affine                                       */
+    float* running_mean; float* running_var;  /* [F]; updated in training mode, read in eval mode */
+    float* save_mean; float* save_invstd;     /* [F] saved for backward                           */
+    int32_t n_rows;
+    int32_t pad_;
+} agx_bn_desc_t;
+size_t agx_bn_workspace_floats(int64_t total_rows, int n_descs, int F);
+int agx_bn_forward(const agx_bn_desc_t* h_descs, int n, int F, int training, float momentum,
+                   float eps, float* workspace, size_t workspace_floats, void* stream);
+
+typedef struct {
+    const float* x;                       /* BN input saved from forward                          */
+    const float* y;                       /* BN output (relu mask); required if dy_act            */
+    const float* dy;                      /* grad wrt y (nullable -> 0)                           */
+    const float* dy_act;                  /* grad wrt y_act (nullable -> 0)                       */
+    const float* dmask;                   /* nullable                                             */
+    const float* weight;
+    const float* save_mean; const float* save_invstd;
+    float* dx;                            /* nullable                                             */
+    float* dweight; float* dbias;         /* nullable; accumulated (+=)                           */
+    int32_t n_rows;
+    int32_t pad_;
+} agx_bn_bwd_desc_t;
+int agx_bn_backward(const agx_bn_bwd_desc_t* h_descs, int n, int F, int training, float* workspace,
+                    size_t workspace_floats, void* stream);
+
+/* column sums: out[F] (+)= sum_rows x[rows, F] (bias gradients) */
+typedef struct { const float* x; int64_t ldx; float* out; int32_t n_rows; int32_t F; int32_t accumulate; int32_t pad_; } agx_colsum_desc_t;
+size_t agx_colsum_workspace_floats(int64_t total_rows, int n_descs, int max_F);
+int agx_colsum(const agx_colsum_desc_t* h_descs, int n, float* workspace, size_t workspace_floats,
+               void* stream);
+
+/* a-8  log_softmax(dim=1) + nll_loss (src/models/models_graph.py:39,
+ * src/train_gnn_embeddings.py:29-30) and, with class weights, CrossEntropyLoss of the heads
+ * (src/train_new_multimodal_multitask.py:48-55,79-81).  logp (nullable) receives the
+ * log-probabilities.  With labels: row_ws[2*n_rows] scratch, loss_sum[2] = (sum w_y*nll, sum w_y)
+ * reduced in row order in float64.  Labels outside [0,C) (ignore_index) get weight 0. */
+int agx_log_softmax_nll(const float* logits, int64_t ld, int32_t n_rows, int32_t C,
+                        const int64_t* labels, const float* class_w, float* logp, int64_t ldp,
+                        float* loss_sum, float* row_ws, void* stream);
+/* F.nll_loss on given log-probabilities (src/train_gnn_embeddings.py:29-30, the reference's call
+ * shape): loss_sum[2] as above; backward writes the full dlogp [n_rows, C]
+ * (-coef*gscale*w_y/loss_sum[1] at the label, 0 elsewhere). */
+int agx_nll_forward(const float* logp, int64_t ld, int32_t n_rows, int32_t C, const int64_t* labels,
+                    const float* class_w, float* loss_sum, float* row_ws, void* stream);
+int agx_nll_backward(int32_t n_rows, int32_t C, const int64_t* labels, const float* class_w,
+                     const float* loss_sum, const float* gscale, float coef, float* dlogp,
+                     int64_t ld, void* stream);
+/* loss[0] (+)= coef * loss_sum[0] / loss_sum[1]   (mean reduction) */
+int agx_loss_finish(const float* loss_sum, float coef, float* loss, int accumulate, void* stream);
+/* dlogits = coef * gscale[0] * w_y * (softmax - onehot) / loss_sum[1]
+ *           (+ dlogp - softmax * rowsum(dlogp) when an upstream gradient on logp is given) */
+int agx_log_softmax_nll_bwd(const float* logp, int64_t ldp, int32_t n_rows, int32_t C,
+                            const int64_t* labels, const float* class_w, const float* loss_sum,
+                            const float* gscale, float coef, const float* dlogp, int64_t lddp,
+                            float* dlogits, int64_t ld, void* stream);
+
+/* a-9  torch.optim.Adam step over a flat parameter arena (src/train_gnn_embeddings.py:144,
+ * src/train_projector.py:34): exp_avg.lerp_, exp_avg_sq.mul_().addcmul_(), bias corrections from
+ * the device step counter (so a captured CUDA graph advances). */
+int agx_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                  int64_t numel, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  const int32_t* step /* device scalar, 1-based */, void* stream);
+
+/* F.dropout / nn.Dropout mask (src/models/models_graph.py:37, src/models/models_kg.py:148,175):
+ * mask[i] = (u_i >= p) / (1 - p), u_i from Philox4x32-10 keyed by seed[0], counter seed[1] + i/4.
+ * seed is a DEVICE pointer to two uint64 so that graph replays draw fresh masks. */
+int agx_dropout_mask(float* mask, int64_t numel, float p, const uint64_t* seed, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K5/K6  fusion / projector heads
+ *   cat -> Dropout -> Linear of src/models/models_kg.py:237-243 (and :158-162, :208-215) is a
+ *   two-segment agx_gemm_grouped problem (feat and emb against column slices of W, A_mask = the
+ *   dropout mask): the concatenation is never materialised.  The losses:
+ *   CrossEntropyLoss = agx_log_softmax_nll above; SmoothL1Loss (src/train_projector.py:33,52) here.
+ * ------------------------------------------------------------------------------------------ */
+/* SmoothL1 (beta = 1, mean): loss[0] = mean(huber(out - target)); dout = clamp(diff,-1,1)/numel */
+size_t agx_smooth_l1_workspace_floats(void);
+int agx_smooth_l1(const float* out, const float* target, int64_t numel, float* loss,
+                  float* dout /*nullable*/, float* workspace, void* stream);
+
+/* misc elementwise */
+int agx_fill_f32(float* p, int64_t numel, float v, void* stream);
+int agx_scale_mask(const float* x, const float* mask, float* y, int64_t numel, void* stream);
+/* rows gather: out[i,:] = table[idx[i],:]  (a-11 head input selection, src/data/data_kg.py:169-178)*/
+int agx_gather_rows(const float* table, int64_t ld, const int64_t* idx, int64_t n, int32_t F,
+                    float* out, int64_t ldo, void* stream);
+/* identity detection for one-hot inputs (src/data/artgraph.py:93-95): flag[0] = 1 iff x == eye(n);
+ * scratch[1] int32 */
+int agx_is_identity(const float* x, int64_t ld, int32_t n, int32_t* flag, int32_t* scratch,
+                    void* stream);
+/* out[j, i] = in[i, j] ; in [rows, cols]; skipped on device when only_if_flag && *only_if_flag==0 */
+int agx_transpose(const float* in, int64_t ld_in, int32_t rows, int32_t cols, float* out,
+                  int64_t ld_out, const int32_t* only_if_flag, void* stream);
+
+/* halo exchange support (config 5): pack rows listed in idx into a contiguous send buffer, and
+ * scatter-add received gradient rows back (deterministic: idx is unique per call) */
+int agx_pack_rows(const float* x, int64_t ld, const int32_t* idx, int32_t n, int32_t F, float* out,
+                  void* stream);
+int agx_unpack_rows_add(float* x, int64_t ld, const int32_t* idx, int32_t n, int32_t F,
+                        const float* in, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGX_H_ */

@@ -1,0 +1,46 @@
+// Library-level entry points: version, thread-local error string, kernel inventory.
+#include <stdarg.h>
+#include <string.h>
+
+#include "agx_common.cuh"
+
+namespace agx {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return AGX_ERR_CUDA;
+}
+
+}  // namespace agx
+
+extern "C" int agx_version(void) { return AGX_VERSION; }
+
+extern "C" const char* agx_last_error(void) { return agx::g_err; }
+
+extern "C" int agx_kernel_inventory(char* h_buf, size_t h_buf_bytes) {
+    static const char* names =
+        "csr_make_keys,radix_hist,radix_scatter,scan_reduce,scan_spine,scan_apply,csr_finalize,"
+        "csr_rowptr,coalesce_prepare,coalesce_flag,coalesce_compact,"
+        "agg_rows,agg_chunks,agg_chunks_fixup,"
+        "gemm_f32,gemm_splitk_reduce,"
+        "sum_arrays,bn_stats,bn_apply,bn_bwd_reduce,bn_bwd_apply,colsum,"
+        "log_softmax_nll,log_softmax_nll_bwd,adam_step,head_forward,ce_forward,ce_finish,"
+        "smooth_l1,fill_f32,scale_mask,gather_rows,is_identity,transpose,pack_rows,"
+        "unpack_rows_add";
+    if (!h_buf || h_buf_bytes == 0) {
+        agx::set_error("agx_kernel_inventory: null buffer");
+        return AGX_ERR_INVALID;
+    }
+    strncpy(h_buf, names, h_buf_bytes - 1);
+    h_buf[h_buf_bytes - 1] = 0;
+    return AGX_OK;
+}

@@ -1,0 +1,927 @@
+// Batched small kernels of the hetero-GNN training step and the heads: per-node-type BatchNorm1d
+// (training statistics in two passes with float64 combination, so they match the reference's
+// double-accumulating CPU kernel), ReLU + dropout mask, log_softmax + nll, Adam, SmoothL1, and
+// utility copies.  All reductions are two-stage (per-CTA partials -> one combining CTA) in a fixed
+// order: no float atomics, results are reproducible.
+#include "agx_common.cuh"
+
+namespace agx {
+
+// ------------------------------------------------------------------------------------------------
+// sum of up to 8 arrays
+// ------------------------------------------------------------------------------------------------
+struct SumParams {
+    agx_sum_desc_t d[AGX_MAX_TENSORS];
+    int64_t start[AGX_MAX_TENSORS + 1];
+    int32_t n;
+};
+
+__global__ void __launch_bounds__(256) sum_arrays(const __grid_constant__ SumParams P) {
+    const int64_t total = P.start[P.n];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int di = 0;
+        while (i >= P.start[di + 1]) ++di;
+        const agx_sum_desc_t& D = P.d[di];
+        const int64_t e = i - P.start[di];
+        float v = D.in[0][e];
+        for (int k = 1; k < D.n_in; ++k) v += D.in[k][e];
+        D.out[e] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm1d over [n_rows, F] per descriptor.  Slabs of kBnSlab rows per CTA.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBnSlab = 128;
+constexpr int kBnThreads = 256;
+
+struct BnParams {
+    agx_bn_desc_t d[AGX_MAX_GROUPS];
+    int32_t slab_start[AGX_MAX_GROUPS + 1];
+    int32_t n;
+    int32_t F;
+    float* ws;            // [2][total_slabs][F] partials
+    int32_t training;
+    float momentum, eps;
+};
+
+// pass: 0 -> sum x ; 1 -> sum (x - mean)^2
+__global__ void __launch_bounds__(kBnThreads) bn_stats(const __grid_constant__ BnParams P, int pass) {
+    int di = 0;
+    while ((int)blockIdx.x >= P.slab_start[di + 1]) ++di;
+    const agx_bn_desc_t& D = P.d[di];
+    const int slab = blockIdx.x - P.slab_start[di];
+    const int r0 = slab * kBnSlab, r1 = min(D.n_rows, r0 + kBnSlab);
+    const int F = P.F;
+    float* part = P.ws + (size_t)blockIdx.x * F;
+    // thread t owns column (t % F) for F <= 256 lanes-of-columns; row groups stride over t / F
+    __shared__ float red[kBnThreads];
+    for (int c0 = 0; c0 < F; c0 += kBnThreads) {
+        const int cols = min(kBnThreads, F - c0);
+        const int groups = kBnThreads / cols > 0 ? kBnThreads / cols : 1;   // row groups
+        const int c = threadIdx.x % cols, g = threadIdx.x / cols;
+        float s = 0.f;
+        if (g < groups) {
+            const float m = pass ? D.save_mean[c0 + c] : 0.f;
+            for (int r = r0 + g; r < r1; r += groups) {
+                const float v = D.x[(int64_t)r * F + c0 + c] - m;
+                s += pass ? v * v : v;
+            }
+        }
+        red[threadIdx.x] = s;
+        __syncthreads();
+        if (threadIdx.x < cols) {
+            float t = 0.f;
+            for (int gg = 0; gg < groups; ++gg) t += red[gg * cols + threadIdx.x];
+            part[c0 + threadIdx.x] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// one CTA per descriptor; thread per column, float64 combination of slab partials
+__global__ void __launch_bounds__(256) bn_finalize(const __grid_constant__ BnParams P, int pass) {
+    const agx_bn_desc_t& D = P.d[blockIdx.x];
+    const int s0 = P.slab_start[blockIdx.x], s1 = P.slab_start[blockIdx.x + 1];
+    const int F = P.F;
+    for (int c = threadIdx.x; c < F; c += blockDim.x) {
+        if (!P.training) {
+            if (pass == 0) {
+                D.save_mean[c] = D.running_mean[c];
+                D.save_invstd[c] = (float)(1.0 / sqrt((double)D.running_var[c] + (double)P.eps));
+            }
+            continue;
+        }
+        double acc = 0.0;
+        for (int s = s0; s < s1; ++s) acc += (double)P.ws[(size_t)s * F + c];
+        const double n = (double)D.n_rows;
+        if (pass == 0) {
+            D.save_mean[c] = (float)(acc / n);
+        } else {
+            const double var = acc / n;
+            D.save_invstd[c] = (float)(1.0 / sqrt(var + (double)P.eps));
+            if (D.running_mean) {
+                const double unbiased = D.n_rows > 1 ? acc / (n - 1.0) : var;
+                D.running_mean[c] = (float)((1.0 - P.momentum) * D.running_mean[c] +
+                                            P.momentum * (double)D.save_mean[c]);
+                D.running_var[c] = (float)((1.0 - P.momentum) * D.running_var[c] +
+                                           P.momentum * unbiased);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_apply(const __grid_constant__ BnParams P) {
+    int di = 0;
+    while ((int)blockIdx.x >= P.slab_start[di + 1]) ++di;
+    const agx_bn_desc_t& D = P.d[di];
+    const int slab = blockIdx.x - P.slab_start[di];
+    const int F = P.F;
+    const int64_t e0 = (int64_t)slab * kBnSlab * F;
+    const int64_t e1 = min((int64_t)D.n_rows * F, e0 + (int64_t)kBnSlab * F);
+    for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        const int c = (int)(e % F);
+        const float xh = (D.x[e] - D.save_mean[c]) * D.save_invstd[c];
+        const float y = xh * D.weight[c] + D.bias[c];
+        D.y[e] = y;
+        if (D.y_act) {
+            float a = y > 0.f ? y : 0.f;
+            if (D.dmask) a *= D.dmask[e];
+            D.y_act[e] = a;
+        }
+    }
+}
+
+struct BnBwdParams {
+    agx_bn_bwd_desc_t d[AGX_MAX_GROUPS];
+    int32_t slab_start[AGX_MAX_GROUPS + 1];
+    int32_t n;
+    int32_t F;
+    float* ws;            // [total_slabs][2F] partials: sum dy, sum dy*xhat ; then [n][2F] totals
+    float* totals;
+    int32_t training;
+};
+
+__device__ __forceinline__ float bn_dy_total(const agx_bn_bwd_desc_t& D, int64_t e) {
+    float g = D.dy ? D.dy[e] : 0.f;
+    if (D.dy_act) {
+        float a = D.dy_act[e];
+        if (D.dmask) a *= D.dmask[e];
+        if (!(D.y[e] > 0.f)) a = 0.f;
+        g += a;
+    }
+    return g;
+}
+
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce(const __grid_constant__ BnBwdParams P) {
+    int di = 0;
+    while ((int)blockIdx.x >= P.slab_start[di + 1]) ++di;
+    const agx_bn_bwd_desc_t& D = P.d[di];
+    const int slab = blockIdx.x - P.slab_start[di];
+    const int r0 = slab * kBnSlab, r1 = min(D.n_rows, r0 + kBnSlab);
+    const int F = P.F;
+    float* part = P.ws + (size_t)blockIdx.x * 2 * F;
+    __shared__ float red0[kBnThreads], red1[kBnThreads];
+    for (int c0 = 0; c0 < F; c0 += kBnThreads) {
+        const int cols = min(kBnThreads, F - c0);
+        const int groups = kBnThreads / cols > 0 ? kBnThreads / cols : 1;
+        const int c = threadIdx.x % cols, g = threadIdx.x / cols;
+        float s0 = 0.f, s1 = 0.f;
+        if (g < groups) {
+            const float m = D.save_mean[c0 + c], is = D.save_invstd[c0 + c];
+            for (int r = r0 + g; r < r1; r += groups) {
+                const int64_t e = (int64_t)r * F + c0 + c;
+                const float gy = bn_dy_total(D, e);
+                s0 += gy;
+                s1 += gy * (D.x[e] - m) * is;
+            }
+        }
+        red0[threadIdx.x] = s0;
+        red1[threadIdx.x] = s1;
+        __syncthreads();
+        if (threadIdx.x < cols) {
+            float t0 = 0.f, t1 = 0.f;
+            for (int gg = 0; gg < groups; ++gg) {
+                t0 += red0[gg * cols + threadIdx.x];
+                t1 += red1[gg * cols + threadIdx.x];
+            }
+            part[c0 + threadIdx.x] = t0;
+            part[F + c0 + threadIdx.x] = t1;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_finalize(const __grid_constant__ BnBwdParams P) {
+    const agx_bn_bwd_desc_t& D = P.d[blockIdx.x];
+    const int s0 = P.slab_start[blockIdx.x], s1 = P.slab_start[blockIdx.x + 1];
+    const int F = P.F;
+    for (int c = threadIdx.x; c < F; c += blockDim.x) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int s = s0; s < s1; ++s) {
+            a0 += (double)P.ws[(size_t)s * 2 * F + c];
+            a1 += (double)P.ws[(size_t)s * 2 * F + F + c];
+        }
+        P.totals[(size_t)blockIdx.x * 2 * F + c] = (float)a0;
+        P.totals[(size_t)blockIdx.x * 2 * F + F + c] = (float)a1;
+        if (D.dbias) D.dbias[c] += (float)a0;
+        if (D.dweight) D.dweight[c] += (float)a1;
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply(const __grid_constant__ BnBwdParams P) {
+    int di = 0;
+    while ((int)blockIdx.x >= P.slab_start[di + 1]) ++di;
+    const agx_bn_bwd_desc_t& D = P.d[di];
+    if (!D.dx) return;
+    const int slab = blockIdx.x - P.slab_start[di];
+    const int F = P.F;
+    const float* tot = P.totals + (size_t)di * 2 * F;
+    const float inv_n = 1.0f / (float)D.n_rows;
+    const int64_t e0 = (int64_t)slab * kBnSlab * F;
+    const int64_t e1 = min((int64_t)D.n_rows * F, e0 + (int64_t)kBnSlab * F);
+    for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        const int c = (int)(e % F);
+        const float gy = bn_dy_total(D, e);
+        const float is = D.save_invstd[c];
+        float dx;
+        if (P.training) {
+            const float xh = (D.x[e] - D.save_mean[c]) * is;
+            dx = D.weight[c] * is * (gy - tot[c] * inv_n - xh * tot[F + c] * inv_n);
+        } else {
+            dx = D.weight[c] * is * gy;
+        }
+        D.dx[e] = dx;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums (bias gradients): partial per 256-row slab, then ordered combine
+// ------------------------------------------------------------------------------------------------
+struct ColsumParams {
+    agx_colsum_desc_t d[AGX_MAX_TENSORS];
+    int32_t slab_start[AGX_MAX_TENSORS + 1];
+    int32_t part_start[AGX_MAX_TENSORS + 1];     // float offset of the descriptor's partials
+    int32_t n;
+    float* ws;
+};
+
+constexpr int kColsumSlab = 512;
+
+__global__ void __launch_bounds__(256) colsum_partial(const __grid_constant__ ColsumParams P) {
+    int di = 0;
+    while ((int)blockIdx.x >= P.slab_start[di + 1]) ++di;
+    const agx_colsum_desc_t& D = P.d[di];
+    const int slab = blockIdx.x - P.slab_start[di];
+    const int r0 = slab * kColsumSlab, r1 = min(D.n_rows, r0 + kColsumSlab);
+    const int F = D.F;
+    float* part = P.ws + P.part_start[di] + (size_t)slab * F;
+    __shared__ float red[256];
+    for (int c0 = 0; c0 < F; c0 += 256) {
+        const int cols = min(256, F - c0);
+        const int groups = 256 / cols > 0 ? 256 / cols : 1;
+        const int c = threadIdx.x % cols, g = threadIdx.x / cols;
+        float s = 0.f;
+        if (g < groups)
+            for (int r = r0 + g; r < r1; r += groups) s += D.x[(int64_t)r * D.ldx + c0 + c];
+        red[threadIdx.x] = s;
+        __syncthreads();
+        if (threadIdx.x < cols) {
+            float t = 0.f;
+            for (int gg = 0; gg < groups; ++gg) t += red[gg * cols + threadIdx.x];
+            part[c0 + threadIdx.x] = t;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) colsum_final(const __grid_constant__ ColsumParams P) {
+    const agx_colsum_desc_t& D = P.d[blockIdx.x];
+    const int slabs = P.slab_start[blockIdx.x + 1] - P.slab_start[blockIdx.x];
+    const float* part = P.ws + P.part_start[blockIdx.x];
+    for (int c = threadIdx.x; c < D.F; c += blockDim.x) {
+        double a = 0.0;
+        for (int s = 0; s < slabs; ++s) a += (double)part[(size_t)s * D.F + c];
+        D.out[c] = D.accumulate ? D.out[c] + (float)a : (float)a;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// log_softmax + (weighted) nll ; warp per row
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+log_softmax_nll(const float* __restrict__ logits, int64_t ld, int n_rows, int C,
+                const int64_t* __restrict__ labels, const float* __restrict__ class_w,
+                float* __restrict__ logp, int64_t ldp, float* __restrict__ row_ws) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const float* x = logits + (int64_t)row * ld;
+    float mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, x[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += expf(x[c] - mx);
+    s = warp_sum(s);
+    const float lse = mx + logf(s);
+    if (logp)
+        for (int c = lane; c < C; c += 32) logp[(int64_t)row * ldp + c] = x[c] - lse;
+    if (labels && lane == 0) {
+        const int64_t y = labels[row];
+        const bool ok = y >= 0 && y < C;                 // ignore_index (-100) / invalid -> weight 0
+        const float w = ok ? (class_w ? class_w[y] : 1.0f) : 0.f;
+        row_ws[2 * (int64_t)row] = ok ? -(x[y] - lse) * w : 0.f;
+        row_ws[2 * (int64_t)row + 1] = w;
+    }
+}
+
+// ordered float64 reduction of interleaved pairs: out[0] = sum in[2i], out[1] = sum in[2i+1]
+__global__ void __launch_bounds__(1024)
+reduce_pairs(const float* __restrict__ in, int64_t n, float* __restrict__ out, int accumulate) {
+    __shared__ double s0[1024], s1[1024];
+    double a0 = 0.0, a1 = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) {
+        a0 += (double)in[2 * i];
+        a1 += (double)in[2 * i + 1];
+    }
+    s0[threadIdx.x] = a0;
+    s1[threadIdx.x] = a1;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            s0[threadIdx.x] += s0[threadIdx.x + o];
+            s1[threadIdx.x] += s1[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[0] = (accumulate ? out[0] : 0.f) + (float)s0[0];
+        out[1] = (accumulate ? out[1] : 0.f) + (float)s1[0];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+log_softmax_nll_bwd(const float* __restrict__ logp, int64_t ldp, int n_rows, int C,
+                    const int64_t* __restrict__ labels, const float* __restrict__ class_w,
+                    const float* __restrict__ loss_sum, const float* __restrict__ gscale,
+                    float coef, const float* __restrict__ dlogp, int64_t lddp,
+                    float* __restrict__ dlogits, int64_t ld) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const float* lp = logp + (int64_t)row * ldp;
+    float g = 0.f;
+    int64_t y = -1;
+    if (labels) {
+        y = labels[row];
+        const bool ok = y >= 0 && y < C;
+        const float w = ok ? (class_w ? class_w[y] : 1.0f) : 0.f;
+        g = w * coef * (gscale ? gscale[0] : 1.0f) / loss_sum[1];
+        if (!ok) y = -1;
+    }
+    // optional upstream gradient on log-probabilities: d/dx = dlogp - softmax * sum(dlogp)
+    float sd = 0.f;
+    if (dlogp) {
+        for (int c = lane; c < C; c += 32) sd += dlogp[(int64_t)row * lddp + c];
+        sd = warp_sum(sd);
+    }
+    for (int c = lane; c < C; c += 32) {
+        const float p = expf(lp[c]);
+        float d = g * (p - (c == y ? 1.0f : 0.f));
+        if (dlogp) d += dlogp[(int64_t)row * lddp + c] - p * sd;
+        dlogits[(int64_t)row * ld + c] = d;
+    }
+}
+
+// nll on given log-probabilities (F.nll_loss): thread per row
+__global__ void __launch_bounds__(256)
+nll_forward(const float* __restrict__ logp, int64_t ld, int n_rows, int C,
+            const int64_t* __restrict__ labels, const float* __restrict__ class_w,
+            float* __restrict__ row_ws) {
+    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += gridDim.x * blockDim.x) {
+        const int64_t y = labels[row];
+        const bool ok = y >= 0 && y < C;
+        const float w = ok ? (class_w ? class_w[y] : 1.0f) : 0.f;
+        row_ws[2 * (int64_t)row] = ok ? -logp[(int64_t)row * ld + y] * w : 0.f;
+        row_ws[2 * (int64_t)row + 1] = w;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+nll_backward(int n_rows, int C, const int64_t* __restrict__ labels, const float* __restrict__ class_w,
+             const float* __restrict__ loss_sum, const float* __restrict__ gscale, float coef,
+             float* __restrict__ dlogp, int64_t ld) {
+    const int64_t total = (int64_t)n_rows * C;
+    const float gs = coef * (gscale ? gscale[0] : 1.0f) / loss_sum[1];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(i / C), c = (int)(i % C);
+        const int64_t y = labels[row];
+        float v = 0.f;
+        if (y == c) v = -gs * (class_w ? class_w[y] : 1.0f);
+        dlogp[(int64_t)row * ld + c] = v;
+    }
+}
+
+__global__ void finish_loss(const float* __restrict__ loss_sum, float coef, float* __restrict__ loss,
+                            int accumulate) {
+    const float v = coef * loss_sum[0] / loss_sum[1];
+    loss[0] = accumulate ? loss[0] + v : v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam single-tensor arithmetic, amsgrad=False, maximize=False)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adam_step(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+          float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float wd,
+          const int32_t* __restrict__ step) {
+    const int t = *step;
+    const double bc1 = 1.0 - pow((double)b1, (double)t);
+    const double bc2 = 1.0 - pow((double)b2, (double)t);
+    const float step_size = (float)((double)lr / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float grad = g[i];
+        if (wd != 0.f) grad += wd * p[i];
+        const float mi = m[i] + (grad - m[i]) * (1.0f - b1);           // lerp_
+        const float vi = v[i] * b2 + (1.0f - b2) * grad * grad;        // mul_ + addcmul_
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = p[i] - step_size * (mi / denom);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dropout mask: Philox4x32-10, 4 uniforms per counter
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+dropout_mask(float* __restrict__ mask, int64_t n, float p, const uint64_t* __restrict__ seed) {
+    const uint64_t key = seed[0], base = seed[1];
+    const float keep = 1.0f / (1.0f - p);
+    const int64_t n4 = (n + 3) / 4;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n4;
+         q += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t ctr = base + (uint64_t)q;
+        uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
+        philox4x32_10(c, (uint32_t)key, (uint32_t)(key >> 32));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t e = q * 4 + i;
+            if (e < n) {
+                const float u = (float)(c[i] >> 8) * (1.0f / 16777216.0f);   // [0, 1)
+                mask[e] = u >= p ? keep : 0.f;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SmoothL1 (beta = 1), mean
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+smooth_l1_partial(const float* __restrict__ out, const float* __restrict__ target, int64_t n,
+                  float* __restrict__ dout, float* __restrict__ part) {
+    __shared__ float red[256];
+    float s = 0.f;
+    const float inv_n = 1.0f / (float)n;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const float d = out[i] - target[i];
+        const float a = fabsf(d);
+        s += a < 1.0f ? 0.5f * d * d : a - 0.5f;
+        if (dout) dout[i] = (a < 1.0f ? d : (d > 0.f ? 1.0f : -1.0f)) * inv_n;
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+
+__global__ void __launch_bounds__(256)
+smooth_l1_final(const float* __restrict__ part, int nparts, int64_t n, float* __restrict__ loss) {
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += 256) s += (double)part[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) loss[0] = (float)(red[0] / (double)n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// misc
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fill_f32(float* p, int64_t n, float v) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+__global__ void __launch_bounds__(256)
+scale_mask(const float* __restrict__ x, const float* __restrict__ mask, float* __restrict__ y, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = x[i] * mask[i];
+}
+
+__global__ void __launch_bounds__(256)
+gather_rows(const float* __restrict__ table, int64_t ld, const int64_t* __restrict__ idx, int64_t n,
+            int F, float* __restrict__ out, int64_t ldo) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t r = blockIdx.x * 8 + (threadIdx.x >> 5); r < n; r += (int64_t)gridDim.x * 8) {
+        const float* s = table + idx[r] * ld;
+        for (int c = lane; c < F; c += 32) out[r * ldo + c] = s[c];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+pack_rows(const float* __restrict__ x, int64_t ld, const int32_t* __restrict__ idx, int n, int F,
+          float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t r = blockIdx.x * 8 + (threadIdx.x >> 5); r < n; r += (int64_t)gridDim.x * 8) {
+        const float* s = x + (int64_t)idx[r] * ld;
+        for (int c = lane; c < F; c += 32) out[r * F + c] = s[c];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+unpack_rows_add(float* __restrict__ x, int64_t ld, const int32_t* __restrict__ idx, int n, int F,
+                const float* __restrict__ in) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t r = blockIdx.x * 8 + (threadIdx.x >> 5); r < n; r += (int64_t)gridDim.x * 8) {
+        float* d = x + (int64_t)idx[r] * ld;
+        for (int c = lane; c < F; c += 32) d[c] += in[r * F + c];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+is_identity(const float* __restrict__ x, int64_t ld, int n, int32_t* __restrict__ not_identity) {
+    const int64_t total = (int64_t)n * n;
+    bool bad = false;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / n), c = (int)(i % n);
+        const float v = x[(int64_t)r * ld + c];
+        if (v != (r == c ? 1.0f : 0.f)) bad = true;
+    }
+    if (bad) *not_identity = 1;
+}
+
+__global__ void __launch_bounds__(256)
+flag_invert(const int32_t* __restrict__ not_identity, int32_t* __restrict__ flag) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *flag = *not_identity ? 0 : 1;
+}
+
+__global__ void __launch_bounds__(256)
+transpose(const float* __restrict__ in, int64_t ld_in, int rows, int cols, float* __restrict__ out,
+          int64_t ld_out, const int32_t* __restrict__ only_if_flag) {
+    if (only_if_flag && *only_if_flag == 0) return;
+    __shared__ float tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {
+        const int r = by + j, c = bx + tx;
+        tile[j][tx] = (r < rows && c < cols) ? in[(int64_t)r * ld_in + c] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int c = bx + j, r = by + tx;          // out[c][r]
+        if (c < cols && r < rows) out[(int64_t)c * ld_out + r] = tile[tx][j];
+    }
+}
+
+static inline int grid_for(int64_t n, int per_block) {
+    const int64_t b = ceil_div(n, per_block);
+    const int64_t cap = (int64_t)kNumSMs * 16;
+    return (int)(b < 1 ? 1 : (b < cap ? b : cap));
+}
+
+}  // namespace agx
+
+using namespace agx;
+
+extern "C" int agx_sum_arrays(const agx_sum_desc_t* h_descs, int n, void* stream) {
+    AGX_CHECK_ARG(h_descs && n >= 1 && n <= AGX_MAX_TENSORS, "agx_sum_arrays: n=%d", n);
+    SumParams P;
+    P.n = n;
+    P.start[0] = 0;
+    for (int i = 0; i < n; ++i) {
+        const agx_sum_desc_t& D = h_descs[i];
+        AGX_CHECK_ARG(D.n_in >= 1 && D.n_in <= 8 && D.numel >= 0 && (D.numel == 0 || D.out),
+                      "agx_sum_arrays: desc %d invalid", i);
+        for (int k = 0; k < D.n_in; ++k)
+            AGX_CHECK_ARG(D.numel == 0 || D.in[k], "agx_sum_arrays: desc %d input %d null", i, k);
+        P.d[i] = D;
+        P.start[i + 1] = P.start[i] + D.numel;
+    }
+    if (P.start[n] == 0) return AGX_OK;
+    sum_arrays<<<grid_for(P.start[n], 256), 256, 0, (cudaStream_t)stream>>>(P);
+    AGX_LAUNCH_CHECK("sum_arrays");
+    return AGX_OK;
+}
+
+extern "C" size_t agx_bn_workspace_floats(int64_t total_rows, int n_descs, int F) {
+    const int64_t slabs = ceil_div(total_rows, kBnSlab) + n_descs;
+    return (size_t)(slabs * 2 * F) + (size_t)n_descs * 2 * F;
+}
+
+extern "C" int agx_bn_forward(const agx_bn_desc_t* h_descs, int n, int F, int training,
+                              float momentum, float eps, float* workspace, size_t workspace_floats,
+                              void* stream) {
+    AGX_CHECK_ARG(h_descs && n >= 1 && n <= AGX_MAX_GROUPS, "agx_bn_forward: n=%d", n);
+    AGX_CHECK_ARG(F >= 1, "agx_bn_forward: F=%d", F);
+    BnParams P;
+    P.n = n;
+    P.F = F;
+    P.ws = workspace;
+    P.training = training;
+    P.momentum = momentum;
+    P.eps = eps;
+    P.slab_start[0] = 0;
+    int64_t rows = 0;
+    for (int i = 0; i < n; ++i) {
+        const agx_bn_desc_t& D = h_descs[i];
+        AGX_CHECK_ARG(D.n_rows >= 0 && D.x && D.y && D.weight && D.bias && D.save_mean &&
+                          D.save_invstd,
+                      "agx_bn_forward: desc %d has null pointers", i);
+        AGX_CHECK_ARG(training || (D.running_mean && D.running_var),
+                      "agx_bn_forward: desc %d: eval mode needs running stats", i);
+        AGX_CHECK_ARG(!training || D.n_rows > 1,
+                      "agx_bn_forward: desc %d: Expected more than 1 value per channel when "
+                      "training, got input size [%d, %d]", i, D.n_rows, F);
+        P.d[i] = D;
+        P.slab_start[i + 1] = P.slab_start[i] + (int32_t)ceil_div(D.n_rows, kBnSlab);
+        rows += D.n_rows;
+    }
+    if (training && workspace_floats < agx_bn_workspace_floats(rows, n, F)) {
+        set_error("agx_bn_forward: workspace too small");
+        return AGX_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int slabs = P.slab_start[n];
+    if (training && slabs > 0) {
+        bn_stats<<<slabs, kBnThreads, 0, st>>>(P, 0);
+        AGX_LAUNCH_CHECK("bn_stats");
+        bn_finalize<<<n, 256, 0, st>>>(P, 0);
+        AGX_LAUNCH_CHECK("bn_finalize");
+        bn_stats<<<slabs, kBnThreads, 0, st>>>(P, 1);
+        AGX_LAUNCH_CHECK("bn_stats");
+        bn_finalize<<<n, 256, 0, st>>>(P, 1);
+        AGX_LAUNCH_CHECK("bn_finalize");
+    } else {
+        bn_finalize<<<n, 256, 0, st>>>(P, 0);
+        AGX_LAUNCH_CHECK("bn_finalize");
+    }
+    if (slabs > 0) {
+        bn_apply<<<slabs, 256, 0, st>>>(P);
+        AGX_LAUNCH_CHECK("bn_apply");
+    }
+    return AGX_OK;
+}
+
+extern "C" int agx_bn_backward(const agx_bn_bwd_desc_t* h_descs, int n, int F, int training,
+                               float* workspace, size_t workspace_floats, void* stream) {
+    AGX_CHECK_ARG(h_descs && n >= 1 && n <= AGX_MAX_GROUPS, "agx_bn_backward: n=%d", n);
+    BnBwdParams P;
+    P.n = n;
+    P.F = F;
+    P.training = training;
+    P.slab_start[0] = 0;
+    int64_t rows = 0;
+    for (int i = 0; i < n; ++i) {
+        const agx_bn_bwd_desc_t& D = h_descs[i];
+        AGX_CHECK_ARG(D.n_rows >= 0 && D.x && D.weight && D.save_mean && D.save_invstd,
+                      "agx_bn_backward: desc %d has null pointers", i);
+        AGX_CHECK_ARG(!D.dy_act || D.y, "agx_bn_backward: desc %d: dy_act needs y", i);
+        P.d[i] = D;
+        P.slab_start[i + 1] = P.slab_start[i] + (int32_t)ceil_div(D.n_rows, kBnSlab);
+        rows += D.n_rows;
+    }
+    if (workspace_floats < agx_bn_workspace_floats(rows, n, F)) {
+        set_error("agx_bn_backward: workspace too small");
+        return AGX_ERR_WORKSPACE;
+    }
+    const int slabs = P.slab_start[n];
+    P.ws = workspace;
+    P.totals = workspace + (size_t)slabs * 2 * F;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (slabs == 0) return AGX_OK;
+    bn_bwd_reduce<<<slabs, kBnThreads, 0, st>>>(P);
+    AGX_LAUNCH_CHECK("bn_bwd_reduce");
+    bn_bwd_finalize<<<n, 256, 0, st>>>(P);
+    AGX_LAUNCH_CHECK("bn_bwd_finalize");
+    bn_bwd_apply<<<slabs, 256, 0, st>>>(P);
+    AGX_LAUNCH_CHECK("bn_bwd_apply");
+    return AGX_OK;
+}
+
+extern "C" size_t agx_colsum_workspace_floats(int64_t total_rows, int n_descs, int max_F) {
+    return (size_t)(ceil_div(total_rows, kColsumSlab) + n_descs) * (size_t)max_F;
+}
+
+extern "C" int agx_colsum(const agx_colsum_desc_t* h_descs, int n, float* workspace,
+                          size_t workspace_floats, void* stream) {
+    AGX_CHECK_ARG(h_descs && n >= 1 && n <= AGX_MAX_TENSORS, "agx_colsum: n=%d", n);
+    ColsumParams P;
+    P.n = n;
+    P.ws = workspace;
+    P.slab_start[0] = 0;
+    P.part_start[0] = 0;
+    for (int i = 0; i < n; ++i) {
+        AGX_CHECK_ARG(h_descs[i].out && (h_descs[i].x || h_descs[i].n_rows == 0) && h_descs[i].F >= 1,
+                      "agx_colsum: desc %d invalid", i);
+        P.d[i] = h_descs[i];
+        const int slabs = (int)ceil_div(h_descs[i].n_rows, kColsumSlab);
+        P.slab_start[i + 1] = P.slab_start[i] + slabs;
+        P.part_start[i + 1] = P.part_start[i] + slabs * h_descs[i].F;
+    }
+    if ((size_t)P.part_start[n] > workspace_floats || (P.part_start[n] > 0 && !workspace)) {
+        set_error("agx_colsum: workspace too small (%d floats needed)", P.part_start[n]);
+        return AGX_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (P.slab_start[n] > 0) {
+        colsum_partial<<<P.slab_start[n], 256, 0, st>>>(P);
+        AGX_LAUNCH_CHECK("colsum_partial");
+    }
+    colsum_final<<<n, 256, 0, st>>>(P);
+    AGX_LAUNCH_CHECK("colsum_final");
+    return AGX_OK;
+}
+
+extern "C" int agx_log_softmax_nll(const float* logits, int64_t ld, int32_t n_rows, int32_t C,
+                                   const int64_t* labels, const float* class_w, float* logp,
+                                   int64_t ldp, float* loss_sum, float* row_ws, void* stream) {
+    AGX_CHECK_ARG(logits && n_rows >= 0 && C >= 1, "agx_log_softmax_nll: bad arguments");
+    AGX_CHECK_ARG(!labels || (loss_sum && row_ws),
+                  "agx_log_softmax_nll: labels need loss_sum and row_ws");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_rows > 0) {
+        log_softmax_nll<<<(unsigned)ceil_div(n_rows, 8), 256, 0, st>>>(logits, ld, n_rows, C, labels,
+                                                                       class_w, logp, ldp, row_ws);
+        AGX_LAUNCH_CHECK("log_softmax_nll");
+    }
+    if (labels) {
+        reduce_pairs<<<1, 1024, 0, st>>>(row_ws, n_rows, loss_sum, 0);
+        AGX_LAUNCH_CHECK("reduce_pairs");
+    }
+    return AGX_OK;
+}
+
+extern "C" int agx_nll_forward(const float* logp, int64_t ld, int32_t n_rows, int32_t C,
+                               const int64_t* labels, const float* class_w, float* loss_sum,
+                               float* row_ws, void* stream) {
+    AGX_CHECK_ARG(logp && labels && loss_sum && row_ws && n_rows >= 0 && C >= 1,
+                  "agx_nll_forward: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_rows > 0) {
+        nll_forward<<<grid_for(n_rows, 256), 256, 0, st>>>(logp, ld, n_rows, C, labels, class_w,
+                                                           row_ws);
+        AGX_LAUNCH_CHECK("nll_forward");
+    }
+    reduce_pairs<<<1, 1024, 0, st>>>(row_ws, n_rows, loss_sum, 0);
+    AGX_LAUNCH_CHECK("reduce_pairs");
+    return AGX_OK;
+}
+
+extern "C" int agx_nll_backward(int32_t n_rows, int32_t C, const int64_t* labels,
+                                const float* class_w, const float* loss_sum, const float* gscale,
+                                float coef, float* dlogp, int64_t ld, void* stream) {
+    AGX_CHECK_ARG(labels && loss_sum && dlogp && n_rows >= 0 && C >= 1,
+                  "agx_nll_backward: bad arguments");
+    if (n_rows == 0) return AGX_OK;
+    nll_backward<<<grid_for((int64_t)n_rows * C, 256), 256, 0, (cudaStream_t)stream>>>(
+        n_rows, C, labels, class_w, loss_sum, gscale, coef, dlogp, ld);
+    AGX_LAUNCH_CHECK("nll_backward");
+    return AGX_OK;
+}
+
+extern "C" int agx_loss_finish(const float* loss_sum, float coef, float* loss, int accumulate,
+                               void* stream) {
+    AGX_CHECK_ARG(loss_sum && loss, "agx_loss_finish: null pointer");
+    finish_loss<<<1, 1, 0, (cudaStream_t)stream>>>(loss_sum, coef, loss, accumulate);
+    AGX_LAUNCH_CHECK("finish_loss");
+    return AGX_OK;
+}
+
+extern "C" int agx_log_softmax_nll_bwd(const float* logp, int64_t ldp, int32_t n_rows, int32_t C,
+                                       const int64_t* labels, const float* class_w,
+                                       const float* loss_sum, const float* gscale, float coef,
+                                       const float* dlogp, int64_t lddp, float* dlogits, int64_t ld,
+                                       void* stream) {
+    AGX_CHECK_ARG(logp && dlogits && n_rows >= 0 && C >= 1, "agx_log_softmax_nll_bwd: bad arguments");
+    AGX_CHECK_ARG(!labels || loss_sum, "agx_log_softmax_nll_bwd: labels need loss_sum");
+    if (n_rows == 0) return AGX_OK;
+    log_softmax_nll_bwd<<<(unsigned)ceil_div(n_rows, 8), 256, 0, (cudaStream_t)stream>>>(
+        logp, ldp, n_rows, C, labels, class_w, loss_sum, gscale, coef, dlogp, lddp, dlogits, ld);
+    AGX_LAUNCH_CHECK("log_softmax_nll_bwd");
+    return AGX_OK;
+}
+
+extern "C" int agx_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                             int64_t numel, float lr, float beta1, float beta2, float eps,
+                             float weight_decay, const int32_t* step, void* stream) {
+    AGX_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && step && numel >= 0,
+                  "agx_adam_step: null pointer");
+    if (numel == 0) return AGX_OK;
+    adam_step<<<grid_for(numel, 256), 256, 0, (cudaStream_t)stream>>>(
+        param, grad, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps, weight_decay, step);
+    AGX_LAUNCH_CHECK("adam_step");
+    return AGX_OK;
+}
+
+extern "C" int agx_dropout_mask(float* mask, int64_t numel, float p, const uint64_t* seed,
+                                void* stream) {
+    AGX_CHECK_ARG((mask && seed) || numel == 0, "agx_dropout_mask: null pointer");
+    AGX_CHECK_ARG(p >= 0.f && p < 1.f, "agx_dropout_mask: p=%f out of [0,1)", (double)p);
+    if (numel <= 0) return AGX_OK;
+    dropout_mask<<<grid_for((numel + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(mask, numel, p,
+                                                                                  seed);
+    AGX_LAUNCH_CHECK("dropout_mask");
+    return AGX_OK;
+}
+
+extern "C" size_t agx_smooth_l1_workspace_floats(void) { return 1024; }
+
+extern "C" int agx_smooth_l1(const float* out, const float* target, int64_t numel, float* loss,
+                             float* dout, float* workspace, void* stream) {
+    AGX_CHECK_ARG(out && target && loss && workspace && numel > 0, "agx_smooth_l1: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    int grid = grid_for(numel, 256);
+    if (grid > 1024) grid = 1024;
+    smooth_l1_partial<<<grid, 256, 0, st>>>(out, target, numel, dout, workspace);
+    AGX_LAUNCH_CHECK("smooth_l1_partial");
+    smooth_l1_final<<<1, 256, 0, st>>>(workspace, grid, numel, loss);
+    AGX_LAUNCH_CHECK("smooth_l1_final");
+    return AGX_OK;
+}
+
+extern "C" int agx_fill_f32(float* p, int64_t numel, float v, void* stream) {
+    AGX_CHECK_ARG(p || numel == 0, "agx_fill_f32: null pointer");
+    if (numel <= 0) return AGX_OK;
+    fill_f32<<<grid_for(numel, 256), 256, 0, (cudaStream_t)stream>>>(p, numel, v);
+    AGX_LAUNCH_CHECK("fill_f32");
+    return AGX_OK;
+}
+
+extern "C" int agx_scale_mask(const float* x, const float* mask, float* y, int64_t numel,
+                              void* stream) {
+    AGX_CHECK_ARG((x && mask && y) || numel == 0, "agx_scale_mask: null pointer");
+    if (numel <= 0) return AGX_OK;
+    scale_mask<<<grid_for(numel, 256), 256, 0, (cudaStream_t)stream>>>(x, mask, y, numel);
+    AGX_LAUNCH_CHECK("scale_mask");
+    return AGX_OK;
+}
+
+extern "C" int agx_gather_rows(const float* table, int64_t ld, const int64_t* idx, int64_t n,
+                               int32_t F, float* out, int64_t ldo, void* stream) {
+    AGX_CHECK_ARG((table && idx && out) || n == 0, "agx_gather_rows: null pointer");
+    if (n <= 0) return AGX_OK;
+    gather_rows<<<grid_for(n, 8), 256, 0, (cudaStream_t)stream>>>(table, ld, idx, n, F, out, ldo);
+    AGX_LAUNCH_CHECK("gather_rows");
+    return AGX_OK;
+}
+
+extern "C" int agx_pack_rows(const float* x, int64_t ld, const int32_t* idx, int32_t n, int32_t F,
+                             float* out, void* stream) {
+    AGX_CHECK_ARG((x && idx && out) || n == 0, "agx_pack_rows: null pointer");
+    if (n <= 0) return AGX_OK;
+    pack_rows<<<grid_for(n, 8), 256, 0, (cudaStream_t)stream>>>(x, ld, idx, n, F, out);
+    AGX_LAUNCH_CHECK("pack_rows");
+    return AGX_OK;
+}
+
+extern "C" int agx_unpack_rows_add(float* x, int64_t ld, const int32_t* idx, int32_t n, int32_t F,
+                                   const float* in, void* stream) {
+    AGX_CHECK_ARG((x && idx && in) || n == 0, "agx_unpack_rows_add: null pointer");
+    if (n <= 0) return AGX_OK;
+    unpack_rows_add<<<grid_for(n, 8), 256, 0, (cudaStream_t)stream>>>(x, ld, idx, n, F, in);
+    AGX_LAUNCH_CHECK("unpack_rows_add");
+    return AGX_OK;
+}
+
+extern "C" int agx_is_identity(const float* x, int64_t ld, int32_t n, int32_t* flag,
+                               int32_t* scratch, void* stream) {
+    AGX_CHECK_ARG(x && flag && scratch && n >= 1, "agx_is_identity: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    AGX_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int32_t), st));
+    is_identity<<<grid_for((int64_t)n * n, 256), 256, 0, st>>>(x, ld, n, scratch);
+    AGX_LAUNCH_CHECK("is_identity");
+    flag_invert<<<1, 32, 0, st>>>(scratch, flag);
+    AGX_LAUNCH_CHECK("flag_invert");
+    return AGX_OK;
+}
+
+extern "C" int agx_transpose(const float* in, int64_t ld_in, int32_t rows, int32_t cols, float* out,
+                             int64_t ld_out, const int32_t* only_if_flag, void* stream) {
+    AGX_CHECK_ARG(in && out && rows >= 0 && cols >= 0, "agx_transpose: bad arguments");
+    if (rows == 0 || cols == 0) return AGX_OK;
+    dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
+    transpose<<<grid, 256, 0, (cudaStream_t)stream>>>(in, ld_in, rows, cols, out, ld_out,
+                                                      only_if_flag);
+    AGX_LAUNCH_CHECK("transpose");
+    return AGX_OK;
+}

@@ -1,0 +1,661 @@
+"""Autograd functions over the agx kernels: the fused heterogeneous conv layer, batched
+BatchNorm+ReLU+dropout, log_softmax / nll, the fusion-head linear and SmoothL1.
+
+Arithmetic restated from (paths under /root/reference):
+  SAGEConv / GraphConv inside to_hetero            src/models/models_graph.py:17,23,30,38,45
+  BatchNorm1d / activation / dropout / log_softmax src/models/models_graph.py:19,32-39
+  nll_loss                                         src/train_gnn_embeddings.py:29-30
+  cat -> Dropout -> Linear, CE, SmoothL1           src/models/models_kg.py:237-243,
+                                                   src/train_new_multimodal_multitask.py:79-81,
+                                                   src/train_projector.py:33,52
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from . import ops
+from ._lib import check, lib, ptr, stream_ptr
+from .graph import HeteroPlan, Relation
+
+# relative cost model for choosing transform-first vs aggregate-first per relation
+_FLOP_RATE = 40e12      # sustained fp32 FFMA flop/s of the grouped GEMM
+_BYTE_RATE = 5e12       # gather bandwidth
+
+
+@dataclass
+class RelSpec:
+    rel: Relation
+    mean: bool                    # SAGEConv: mean ; GraphConv: add
+    i_wl: int                     # indices into the flat parameter list
+    i_bl: int                     # -1: no bias
+    i_wr: int                     # -1: no root weight
+    transform_first: bool = False
+
+
+@dataclass
+class ConvSpec:
+    """Static description of one hetero conv layer (all relations) for _HeteroConvFn."""
+    node_types: List[str]         # types whose features are passed in, in tensor order
+    rels: List[RelSpec]
+    out_channels: int
+    dst_types: List[str] = field(default_factory=list)   # output order
+    identity: Dict[str, bool] = field(default_factory=dict)   # type -> x[type] is eye(N)
+    planned: bool = False
+
+    def plan_modes(self, feat_dims: Dict[str, int]):
+        O = self.out_channels
+        for rs in self.rels:
+            r = rs.rel
+            fs = feat_dims[r.src]
+            tf = 2.0 * r.n_src * fs * O / _FLOP_RATE + r.n_edges * O * 4.0 / _BYTE_RATE
+            af = r.n_edges * fs * 4.0 / _BYTE_RATE + 2.0 * r.n_dst * fs * O / _FLOP_RATE
+            rs.transform_first = tf < af
+        self.dst_types = []
+        for rs in self.rels:
+            if rs.rel.dst not in self.dst_types:
+                self.dst_types.append(rs.rel.dst)
+        self.planned = True
+
+
+def _t(w: torch.Tensor) -> torch.Tensor:
+    return w.t()
+
+
+class _HeteroConvFn(torch.autograd.Function):
+    """out[t] = sum_{r: dst(r)=t} ( lin_l_r(aggr_r(x[src(r)])) + lin_r_r(x[t]) )  for all t at once.
+
+    Per relation the cheaper of transform-first (Y = X W_l^T on the small source table, then one
+    fused multi-relation gather per destination row) and aggregate-first (gather at input width,
+    then the product as one segment of the destination type's GEMM) is used; both equal the
+    reference's aggregate-then-transform in exact arithmetic (fp32 drift ~1e-7).
+    """
+
+    @staticmethod
+    def forward(ctx, spec: ConvSpec, *tensors):
+        nt = len(spec.node_types)
+        xs = {t: tensors[i] for i, t in enumerate(spec.node_types)}
+        params = tensors[nt:]
+        for t, x in xs.items():
+            L.require_cuda(x, f'x[{t}]')
+            if x.dtype != torch.float32 or not x.is_contiguous():
+                raise TypeError(f'x[{t}] must be contiguous float32')
+        if not spec.planned:
+            spec.plan_modes({t: x.shape[1] for t, x in xs.items()})
+        O = spec.out_channels
+        dev = tensors[0].device
+        by_dst: Dict[str, List[RelSpec]] = {t: [] for t in spec.dst_types}
+        for rs in spec.rels:
+            by_dst[rs.rel.dst].append(rs)
+
+        # s0: per destination type, the sum of root weights and of biases
+        wroot: Dict[str, Optional[torch.Tensor]] = {}
+        bsum: Dict[str, Optional[torch.Tensor]] = {}
+        sums = []
+        for t, lst in by_dst.items():
+            roots = [params[rs.i_wr] for rs in lst if rs.i_wr >= 0]
+            bias = [params[rs.i_bl] for rs in lst if rs.i_bl >= 0]
+            for store, items in ((wroot, roots), (bsum, bias)):
+                if not items:
+                    store[t] = None
+                elif len(items) == 1:
+                    store[t] = items[0]
+                else:
+                    acc = torch.empty_like(items[0])
+                    # at most 8 inputs per descriptor: chain
+                    cur, rest = items[:8], items[8:]
+                    sums.append((acc, cur))
+                    while rest:
+                        sums.append((acc, [acc] + rest[:7]))
+                        rest = rest[7:]
+                    store[t] = acc
+        if sums:
+            for s in sums:          # chained sums must run in order
+                ops.sum_arrays([s])
+
+        # s1: transform-first products on the source tables
+        Y: Dict[int, torch.Tensor] = {}
+        gb = ops.GemmBatch()
+        for k, rs in enumerate(spec.rels):
+            if rs.transform_first:
+                r = rs.rel
+                y = torch.empty(r.n_src, O, dtype=torch.float32, device=dev)
+                Y[k] = y
+                if spec.identity.get(r.src, False):
+                    ops.transpose_into(y, params[rs.i_wl])       # X = I  =>  X W^T = W^T exactly
+                else:
+                    gb.add(y, [(xs[r.src], _t(params[rs.i_wl]))])
+        if gb.problems:
+            gb.run()
+
+        # s2: gathers
+        outs: Dict[str, torch.Tensor] = {}
+        has_tf: Dict[str, bool] = {}
+        G: Dict[int, torch.Tensor] = {}
+        rows_by_F: Dict[int, list] = {}
+        chunks_by_F: Dict[int, list] = {}
+        id_root: Dict[str, bool] = {}
+        for t, lst in by_dst.items():
+            outs[t] = torch.empty(lst[0].rel.n_dst, O, dtype=torch.float32, device=dev)
+            # root product against one-hot features: x[t] W^T = W^T, written first, rest accumulates
+            id_root[t] = bool(spec.identity.get(t, False)) and wroot[t] is not None
+            if id_root[t]:
+                ops.transpose_into(outs[t], wroot[t])
+            tf = [(k, rs) for k, rs in enumerate(spec.rels) if rs.rel.dst == t and rs.transform_first]
+            has_tf[t] = bool(tf) or id_root[t]
+            for base in range(0, len(tf), L.MAX_REL_PER_GROUP):
+                part = tf[base:base + L.MAX_REL_PER_GROUP]
+                # groups that accumulate onto the same output go to later launches ("waves")
+                rows_by_F.setdefault((base // L.MAX_REL_PER_GROUP, O), []).append(
+                    (outs[t], [ops.RelArg(rs.rel.csr, Y[k], mean_rows=rs.mean) for k, rs in part],
+                     base > 0 or id_root[t]))
+        for k, rs in enumerate(spec.rels):
+            if rs.transform_first:
+                continue
+            r = rs.rel
+            fs = xs[r.src].shape[1]
+            g = torch.empty(r.n_dst, fs, dtype=torch.float32, device=dev)
+            G[k] = g
+            arg = ops.RelArg(r.csr, xs[r.src], mean_rows=rs.mean)
+            if r.csr.avg_degree > ops.LONG_ROW_AVG_DEGREE:
+                chunks_by_F.setdefault(fs, []).append((g, arg))
+            else:
+                rows_by_F.setdefault((0, fs), []).append((g, [arg], False))
+        for (wave, F) in sorted(rows_by_F.keys()):
+            ops.aggregate_rows(rows_by_F[(wave, F)], F)
+        for F, segs in chunks_by_F.items():
+            ops.aggregate_chunks(segs, F)
+
+        # s3: one multi-segment GEMM per destination type
+        gb = ops.GemmBatch()
+        for t, lst in by_dst.items():
+            segs = []
+            for k, rs in enumerate(spec.rels):
+                if rs.rel.dst == t and not rs.transform_first:
+                    segs.append((G[k], _t(params[rs.i_wl])))
+            if wroot[t] is not None and not id_root[t]:
+                segs.append((xs[t], _t(wroot[t])))
+            if not segs and bsum[t] is not None:
+                # bias only (no dense segment left): rank-1 product ones[N,1] @ bias[1,O]
+                ones = ops.fill_(torch.empty(outs[t].shape[0], 1, dtype=torch.float32, device=dev), 1.0)
+                gb.add(outs[t], [(ones, bsum[t].view(1, -1))], accumulate=has_tf[t])
+            elif segs:
+                gb.add(outs[t], segs, bias=bsum[t], accumulate=has_tf[t])
+            elif not has_tf[t]:
+                ops.fill_(outs[t], 0.0)
+        if gb.problems:
+            gb.run()
+
+        ctx.spec = spec
+        ctx.nt = nt
+        ctx.g_keys = list(G.keys())
+        ctx.save_for_backward(*tensors, *[G[k] for k in ctx.g_keys],
+                              *[w for w in wroot.values() if w is not None])
+        ctx.wroot_types = [t for t, w in wroot.items() if w is not None]
+        return tuple(outs[t] for t in spec.dst_types)
+
+    @staticmethod
+    def backward(ctx, *douts):
+        spec: ConvSpec = ctx.spec
+        nt = ctx.nt
+        saved = ctx.saved_tensors
+        n_in = nt + _n_params(spec)
+        tensors = saved[:n_in]
+        xs = {t: tensors[i] for i, t in enumerate(spec.node_types)}
+        params = tensors[nt:]
+        G = {k: saved[n_in + i] for i, k in enumerate(ctx.g_keys)}
+        wroot = {t: saved[n_in + len(G) + i] for i, t in enumerate(ctx.wroot_types)}
+        O = spec.out_channels
+        dev = tensors[0].device
+        dout: Dict[str, Optional[torch.Tensor]] = {}
+        for t, g in zip(spec.dst_types, douts):
+            dout[t] = None if g is None else g.contiguous()
+        need_x = {t: ctx.needs_input_grad[1 + i] for i, t in enumerate(spec.node_types)}
+        grads: List[Optional[torch.Tensor]] = [None] * len(tensors)
+        pidx = lambda i: nt + i                                            # noqa: E731
+
+        live = [(k, rs) for k, rs in enumerate(spec.rels) if dout[rs.rel.dst] is not None]
+
+        # b1: bias gradients = column sums of dout, shared by the relations of a type
+        cs_items = []
+        dbias: Dict[str, torch.Tensor] = {}
+        for t in spec.dst_types:
+            if dout[t] is not None and any(rs.i_bl >= 0 for _, rs in live if rs.rel.dst == t):
+                dbias[t] = torch.empty(O, dtype=torch.float32, device=dev)
+                cs_items.append((dout[t], dbias[t], False))
+        ops.colsum(cs_items)
+        for k, rs in live:
+            if rs.i_bl >= 0:
+                grads[pidx(rs.i_bl)] = dbias[rs.rel.dst]
+
+        # b4a: transform-first relations: dY = A^T dout  (transpose gather over the CSC)
+        dY: Dict[int, torch.Tensor] = {}
+        rows, chunks = [], []
+        for k, rs in live:
+            if not rs.transform_first:
+                continue
+            r = rs.rel
+            dy = torch.empty(r.n_src, O, dtype=torch.float32, device=dev)
+            dY[k] = dy
+            arg = ops.RelArg(r.csc, dout[r.dst], mean_rows=False,
+                             nbr_scale=r.csr.cnt if rs.mean else None)
+            if r.csc.avg_degree > ops.LONG_ROW_AVG_DEGREE:
+                chunks.append((dy, arg))
+            else:
+                rows.append((dy, [arg], False))
+        ops.aggregate_rows(rows, O)
+        ops.aggregate_chunks(chunks, O)
+
+        # b2/b3: weight gradients and the aggregate-first input gradients dG = dout W_l
+        gb = ops.GemmBatch()
+        dwroot: Dict[str, torch.Tensor] = {}
+        for t in spec.dst_types:
+            if dout[t] is None or t not in wroot:
+                continue
+            x = xs[t]
+            dw = torch.empty(O, x.shape[1], dtype=torch.float32, device=dev)
+            dwroot[t] = dw
+            if spec.identity.get(t, False):
+                ops.transpose_into(dw, dout[t])                  # dout^T I
+            else:
+                gb.add(dw, [(_t(dout[t]), x)], split_k=ops.split_k_for(x.shape[0]))
+        dG: Dict[int, torch.Tensor] = {}
+        for k, rs in live:
+            r = rs.rel
+            x = xs[r.src]
+            dw = torch.empty(O, x.shape[1], dtype=torch.float32, device=dev)
+            grads[pidx(rs.i_wl)] = dw
+            if rs.transform_first and spec.identity.get(r.src, False):
+                ops.transpose_into(dw, dY[k])
+            elif rs.transform_first:
+                gb.add(dw, [(_t(dY[k]), x)], split_k=ops.split_k_for(r.n_src))
+            else:
+                gb.add(dw, [(_t(dout[r.dst]), G[k])], split_k=ops.split_k_for(r.n_dst))
+                if need_x[r.src]:
+                    dg = torch.empty(r.n_dst, x.shape[1], dtype=torch.float32, device=dev)
+                    dG[k] = dg
+                    gb.add(dg, [(dout[r.dst], params[rs.i_wl])])
+        if gb.problems:
+            gb.run()
+        for k, rs in live:
+            if rs.i_wr >= 0:
+                grads[pidx(rs.i_wr)] = dwroot[rs.rel.dst]
+
+        # b5: input gradients per source type
+        groups = {}
+        for t in spec.node_types:
+            if not need_x[t]:
+                continue
+            af = [(k, rs) for k, rs in live if rs.rel.src == t and not rs.transform_first]
+            tf = [(k, rs) for k, rs in live if rs.rel.src == t and rs.transform_first]
+            root = dout.get(t) is not None and t in wroot
+            if not (af or tf or root):
+                continue
+            dx = torch.empty_like(xs[t])
+            grads[spec.node_types.index(t)] = dx
+            for base in range(0, len(af), L.MAX_REL_PER_GROUP):
+                part = af[base:base + L.MAX_REL_PER_GROUP]
+                groups.setdefault((base // L.MAX_REL_PER_GROUP, xs[t].shape[1]), []).append(
+                    (dx, [ops.RelArg(rs.rel.csc, dG[k], nbr_scale=rs.rel.csr.cnt if rs.mean else None)
+                          for k, rs in part], base > 0))
+            segs = [(dY[k], params[rs.i_wl]) for k, rs in tf]
+            if root:
+                segs.append((dout[t], wroot[t]))
+            groups.setdefault(('gemm',), []).append((dx, segs, bool(af)))
+        gb = ops.GemmBatch()
+        for key in sorted(k for k in groups.keys() if k != ('gemm',)):
+            ops.aggregate_rows(groups[key], key[1])
+        for dx, segs, acc in groups.get(('gemm',), []):
+            if segs:
+                gb.add(dx, segs, accumulate=acc)
+        if gb.problems:
+            gb.run()
+        return (None, *grads)
+
+
+def _n_params(spec: ConvSpec) -> int:
+    n = 0
+    for rs in spec.rels:
+        n = max(n, rs.i_wl + 1, rs.i_bl + 1, rs.i_wr + 1)
+    return n
+
+
+def hetero_conv(spec: ConvSpec, x_list: Sequence[torch.Tensor], params: Sequence[torch.Tensor]):
+    return _HeteroConvFn.apply(spec, *x_list, *params)
+
+
+# ------------------------------------------------------------------------------------------------
+# BatchNorm1d (+ ReLU + dropout) batched over node types
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class BNSpec:
+    n: int                                   # number of node types
+    F: int
+    training: bool
+    momentum: float
+    eps: float
+    running: List[Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]]   # per type buffers
+    with_act: bool                           # also produce relu(y) * dmask
+    dmasks: Optional[List[Optional[torch.Tensor]]] = None
+
+
+class _BNActFn(torch.autograd.Function):
+    """y_t = BatchNorm1d_t(x_t) for every node type t in one batched launch sequence; optionally
+    also a_t = relu(y_t) * dmask_t (the input of conv_out, src/models/models_graph.py:34-38)."""
+
+    @staticmethod
+    def forward(ctx, spec: BNSpec, *tensors):
+        n, F = spec.n, spec.F
+        xs, ws, bs = tensors[:n], tensors[n:2 * n], tensors[2 * n:3 * n]
+        dev = xs[0].device
+        arr = (L.BnDesc * n)()
+        ys, acts, means, invstds = [], [], [], []
+        rows = 0
+        for i in range(n):
+            x = xs[i]
+            L.require_cuda(x, 'BatchNorm input')
+            if x.dtype != torch.float32 or not x.is_contiguous() or x.shape[1] != F:
+                raise TypeError('BatchNorm input must be contiguous float32 [N, F]')
+            y = torch.empty_like(x)
+            a = torch.empty_like(x) if spec.with_act else None
+            m = torch.empty(F, dtype=torch.float32, device=dev)
+            s = torch.empty(F, dtype=torch.float32, device=dev)
+            dm = spec.dmasks[i] if (spec.with_act and spec.dmasks is not None) else None
+            rm, rv = spec.running[i]
+            arr[i] = L.BnDesc(ptr(x), ptr(y), ptr(a), ptr(dm), ptr(ws[i]), ptr(bs[i]), ptr(rm),
+                              ptr(rv), ptr(m), ptr(s), x.shape[0], 0)
+            ys.append(y); acts.append(a); means.append(m); invstds.append(s)
+            rows += x.shape[0]
+        n_ws = lib().agx_bn_workspace_floats(rows, n, F)
+        wsb = torch.empty(n_ws, dtype=torch.float32, device=dev)
+        check(lib().agx_bn_forward(arr, n, F, int(spec.training), spec.momentum, spec.eps, ptr(wsb),
+                                   n_ws, stream_ptr()), 'agx_bn_forward')
+        ctx.spec = spec
+        ctx.save_for_backward(*xs, *ws, *ys, *means, *invstds)
+        if spec.with_act:
+            return (*ys, *acts)
+        return tuple(ys)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        spec: BNSpec = ctx.spec
+        n, F = spec.n, spec.F
+        sv = ctx.saved_tensors
+        xs, ws, ys, means, invstds = (sv[0:n], sv[n:2 * n], sv[2 * n:3 * n], sv[3 * n:4 * n],
+                                      sv[4 * n:5 * n])
+        dys = grads[:n]
+        dacts = grads[n:2 * n] if spec.with_act else [None] * n
+        dev = xs[0].device
+        idx = [i for i in range(n) if dys[i] is not None or dacts[i] is not None]
+        dxs: List[Optional[torch.Tensor]] = [None] * n
+        dws: List[Optional[torch.Tensor]] = [None] * n
+        dbs: List[Optional[torch.Tensor]] = [None] * n
+        if idx:
+            arr = (L.BnBwdDesc * len(idx))()
+            rows = 0
+            keep = []
+            for j, i in enumerate(idx):
+                dy = None if dys[i] is None else dys[i].contiguous()
+                da = None if dacts[i] is None else dacts[i].contiguous()
+                keep += [dy, da]
+                dxs[i] = torch.empty_like(xs[i]) if ctx.needs_input_grad[1 + i] else None
+                dws[i] = ops.zeros(F, dev)
+                dbs[i] = ops.zeros(F, dev)
+                dm = spec.dmasks[i] if (spec.with_act and spec.dmasks is not None) else None
+                arr[j] = L.BnBwdDesc(ptr(xs[i]), ptr(ys[i]), ptr(dy), ptr(da), ptr(dm), ptr(ws[i]),
+                                     ptr(means[i]), ptr(invstds[i]), ptr(dxs[i]), ptr(dws[i]),
+                                     ptr(dbs[i]), xs[i].shape[0], 0)
+                rows += xs[i].shape[0]
+            n_ws = lib().agx_bn_workspace_floats(rows, len(idx), F)
+            wsb = torch.empty(n_ws, dtype=torch.float32, device=dev)
+            check(lib().agx_bn_backward(arr, len(idx), F, int(spec.training), ptr(wsb), n_ws,
+                                        stream_ptr()), 'agx_bn_backward')
+        return (None, *dxs, *dws, *dbs)
+
+
+def batch_norm_act(spec: BNSpec, xs, weights, biases):
+    return _BNActFn.apply(spec, *xs, *weights, *biases)
+
+
+# ------------------------------------------------------------------------------------------------
+# log_softmax, nll, cross entropy
+# ------------------------------------------------------------------------------------------------
+class _LogSoftmaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        L.require_cuda(x, 'log_softmax input')
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        check(lib().agx_log_softmax_nll(ptr(x), x.stride(0), x.shape[0], x.shape[1], None, None,
+                                        ptr(out), out.stride(0), None, None, stream_ptr()),
+              'agx_log_softmax_nll')
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (logp,) = ctx.saved_tensors
+        g = g.contiguous()
+        dx = torch.empty_like(logp)
+        check(lib().agx_log_softmax_nll_bwd(ptr(logp), logp.stride(0), logp.shape[0], logp.shape[1],
+                                            None, None, None, None, 1.0, ptr(g), g.stride(0),
+                                            ptr(dx), dx.stride(0), stream_ptr()),
+              'agx_log_softmax_nll_bwd')
+        return dx
+
+
+def log_softmax(x: torch.Tensor, dim: int = 1) -> torch.Tensor:
+    if x.dim() != 2 or dim not in (1, -1):
+        raise NotImplementedError('log_softmax: only 2-D input, dim=1')
+    return _LogSoftmaxFn.apply(x)
+
+
+class _SoftmaxNLLFn(torch.autograd.Function):
+    """coef * weighted-mean nll(log_softmax(logits), labels); also returns log-probabilities."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, class_w, coef):
+        L.require_cuda(logits, 'logits')
+        logits = logits.contiguous()
+        n, c = logits.shape
+        dev = logits.device
+        labels = labels.to(device=dev, dtype=torch.int64).contiguous()
+        logp = torch.empty_like(logits)
+        loss_sum = torch.empty(2, dtype=torch.float32, device=dev)
+        row_ws = torch.empty(2 * max(n, 1), dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        check(lib().agx_log_softmax_nll(ptr(logits), logits.stride(0), n, c, ptr(labels),
+                                        ptr(class_w), ptr(logp), logp.stride(0), ptr(loss_sum),
+                                        ptr(row_ws), stream_ptr()), 'agx_log_softmax_nll')
+        check(lib().agx_loss_finish(ptr(loss_sum), coef, ptr(loss), 0, stream_ptr()),
+              'agx_loss_finish')
+        ctx.save_for_backward(logp, labels, loss_sum, class_w if class_w is not None else logp)
+        ctx.has_w = class_w is not None
+        ctx.coef = coef
+        ctx.mark_non_differentiable(logp)
+        return loss.reshape(()), logp
+
+    @staticmethod
+    def backward(ctx, gloss, _glogp):
+        logp, labels, loss_sum, cw = ctx.saved_tensors
+        gs = gloss.reshape(1).to(torch.float32).contiguous()
+        dx = torch.empty_like(logp)
+        check(lib().agx_log_softmax_nll_bwd(ptr(logp), logp.stride(0), logp.shape[0], logp.shape[1],
+                                            ptr(labels), ptr(cw) if ctx.has_w else None,
+                                            ptr(loss_sum), ptr(gs), ctx.coef, None, 0, ptr(dx),
+                                            dx.stride(0), stream_ptr()), 'agx_log_softmax_nll_bwd')
+        return dx, None, None, None
+
+
+def cross_entropy(logits, labels, weight: Optional[torch.Tensor] = None, coef: float = 1.0):
+    """``coef * F.cross_entropy(logits, labels, weight)`` (weighted mean), fused fwd/bwd."""
+    return _SoftmaxNLLFn.apply(logits, labels, weight, coef)[0]
+
+
+def softmax_nll(logits, labels, weight=None, coef: float = 1.0):
+    """Returns (loss, log_softmax(logits)) -- the GNN's output + loss in one pass."""
+    return _SoftmaxNLLFn.apply(logits, labels, weight, coef)
+
+
+class _NLLFromLogpFn(torch.autograd.Function):
+    """F.nll_loss on log-probabilities already computed by log_softmax (reference call shape:
+    src/train_gnn_embeddings.py:29-30)."""
+
+    @staticmethod
+    def forward(ctx, logp, labels):
+        L.require_cuda(logp, 'nll_loss input')
+        n, c = logp.shape
+        dev = logp.device
+        labels = labels.to(device=dev, dtype=torch.int64).contiguous()
+        lp = logp.contiguous()
+        loss_sum = torch.empty(2, dtype=torch.float32, device=dev)
+        row_ws = torch.empty(2 * max(n, 1), dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        check(lib().agx_nll_forward(ptr(lp), lp.stride(0), n, c, ptr(labels), None, ptr(loss_sum),
+                                    ptr(row_ws), stream_ptr()), 'agx_nll_forward')
+        check(lib().agx_loss_finish(ptr(loss_sum), 1.0, ptr(loss), 0, stream_ptr()),
+              'agx_loss_finish')
+        ctx.save_for_backward(labels, loss_sum)
+        ctx.shape = (n, c)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        labels, loss_sum = ctx.saved_tensors
+        n, c = ctx.shape
+        dlp = torch.empty(n, c, dtype=torch.float32, device=labels.device)
+        gs = g.reshape(1).to(torch.float32).contiguous()
+        check(lib().agx_nll_backward(n, c, ptr(labels), None, ptr(loss_sum), ptr(gs), 1.0, ptr(dlp),
+                                     c, stream_ptr()), 'agx_nll_backward')
+        return dlp, None
+
+
+def nll_loss(logp: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    return _NLLFromLogpFn.apply(logp, labels)
+
+
+# ------------------------------------------------------------------------------------------------
+# heads: concat-free (feat | emb) -> dropout -> Linear ; projector Linear ; SmoothL1
+# ------------------------------------------------------------------------------------------------
+class _FusedLinearFn(torch.autograd.Function):
+    """out = (cat(parts, dim=1) * cat(masks, dim=1)) @ W^T + b without materialising the
+    concatenation: every part is one K-segment of the GEMM against a column slice of W, its
+    dropout mask (same shape as the part, nullable) is applied while the tile is staged."""
+
+    @staticmethod
+    def forward(ctx, weight, bias, n_parts, *parts_and_masks):
+        parts = tuple(p.contiguous() for p in parts_and_masks[:n_parts])
+        masks = tuple(parts_and_masks[n_parts:])
+        dev = weight.device
+        B = parts[0].shape[0]
+        Cn = weight.shape[0]
+        out = torch.empty(B, Cn, dtype=torch.float32, device=dev)
+        segs = []
+        off = 0
+        for p, m in zip(parts, masks):
+            L.require_cuda(p, 'head input')
+            if p.dtype != torch.float32:
+                raise TypeError('head inputs must be float32')
+            k = p.shape[1]
+            if m is not None and (m.shape != p.shape or m.stride() != p.stride()):
+                raise ValueError('dropout mask must have the shape and strides of its input part')
+            segs.append((p, _t(weight[:, off:off + k]), m, None))
+            off += k
+        if off != weight.shape[1]:
+            raise ValueError(f'head inputs have {off} columns, weight expects {weight.shape[1]}')
+        gb = ops.GemmBatch()
+        gb.add(out, segs, bias=bias)
+        gb.run()
+        ctx.n_parts = n_parts
+        ctx.mask_present = [m is not None for m in masks]
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(weight, *parts, *[m for m in masks if m is not None])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        sv = ctx.saved_tensors
+        n = ctx.n_parts
+        weight, parts = sv[0], sv[1:1 + n]
+        it = iter(sv[1 + n:])
+        masks = [next(it) if present else None for present in ctx.mask_present]
+        g = g.contiguous()
+        dev = g.device
+        B, Cn = g.shape
+        dW = torch.empty_like(weight)
+        gb = ops.GemmBatch()
+        off = 0
+        dparts: List[Optional[torch.Tensor]] = []
+        sk = ops.split_k_for(B)
+        for i, (p, m) in enumerate(zip(parts, masks)):
+            k = p.shape[1]
+            gb.add(dW[:, off:off + k], [(_t(g), p, None, m)], split_k=sk)   # g^T @ (p * mask)
+            if ctx.needs_input_grad[3 + i]:
+                dp = torch.empty_like(p)
+                gb.add(dp, [(g, weight[:, off:off + k])])
+                dparts.append(dp)
+            else:
+                dparts.append(None)
+            off += k
+        gb.run()
+        outs = [None if d is None else (ops.scale_mask(d, m) if m is not None else d)
+                for d, m in zip(dparts, masks)]
+        db = None
+        if ctx.has_bias:
+            db = torch.empty(Cn, dtype=torch.float32, device=dev)
+            ops.colsum([(g, db, False)])
+        return (dW, db, None, *outs, *([None] * n))
+
+
+def fused_linear(parts: Sequence[torch.Tensor], weight, bias=None,
+                 dmasks: Optional[Sequence[Optional[torch.Tensor]]] = None):
+    if dmasks is None:
+        dmasks = [None] * len(parts)
+    return _FusedLinearFn.apply(weight, bias, len(parts), *parts, *dmasks)
+
+
+class _MaskFn(torch.autograd.Function):
+    """y = x * mask (dropout with a precomputed multiplicative mask)."""
+
+    @staticmethod
+    def forward(ctx, x, mask):
+        ctx.save_for_backward(mask)
+        return ops.scale_mask(x.contiguous(), mask)
+
+    @staticmethod
+    def backward(ctx, g):
+        (mask,) = ctx.saved_tensors
+        return ops.scale_mask(g.contiguous(), mask), None
+
+
+def dropout_apply(x, mask):
+    return _MaskFn.apply(x, mask)
+
+
+class _SmoothL1Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, out, target):
+        L.require_cuda(out, 'smooth_l1 input')
+        out = out.contiguous()
+        target = target.to(out.device).contiguous()
+        loss = torch.empty(1, dtype=torch.float32, device=out.device)
+        dout = torch.empty_like(out)
+        ws = torch.empty(lib().agx_smooth_l1_workspace_floats(), dtype=torch.float32,
+                         device=out.device)
+        check(lib().agx_smooth_l1(ptr(out), ptr(target), out.numel(), ptr(loss), ptr(dout), ptr(ws),
+                                  stream_ptr()), 'agx_smooth_l1')
+        ctx.save_for_backward(dout)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (dout,) = ctx.saved_tensors
+        return dout * g, None
+
+
+def smooth_l1_loss(out, target):
+    """``torch.nn.SmoothL1Loss()`` (beta=1, mean), src/train_projector.py:33,52."""
+    return _SmoothL1Fn.apply(out, target)

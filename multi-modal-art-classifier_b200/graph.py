@@ -1,0 +1,124 @@
+"""Per-graph index structures: CSR (by destination) and CSC (by source) of every relation, built
+by ONE batched K1 sort, plus ``ToUndirected``.
+
+Reference sites: ``T.ToUndirected()`` at /root/reference/src/train_gnn_embeddings.py:117-120
+(PyG 2.0.2 semantics) and the dense ``edge_index`` consumed by
+``MessagePassing.propagate`` (src/models/models_graph.py:30,38)."""
+from __future__ import annotations
+
+from collections import OrderedDict
+from dataclasses import dataclass
+from typing import Dict, Tuple
+
+import torch
+
+from . import ops
+from ._lib import AgxError
+
+EdgeType = Tuple[str, str, str]
+
+
+def key2str(key) -> str:
+    return '__'.join(key) if isinstance(key, tuple) else key
+
+
+@dataclass
+class Relation:
+    src: str
+    rel: str
+    dst: str
+    n_src: int
+    n_dst: int
+    n_edges: int
+    csr: ops.CSR      # rows = destination nodes, cols = source ids   (forward gather)
+    csc: ops.CSR      # rows = source nodes, cols = destination ids   (transpose gather)
+
+    @property
+    def key(self) -> EdgeType:
+        return (self.src, self.rel, self.dst)
+
+
+class HeteroPlan:
+    """All relations of one heterograph in device CSR + CSC form."""
+
+    def __init__(self, edge_index_dict, num_nodes: Dict[str, int]):
+        self.num_nodes = dict(num_nodes)
+        lists = []
+        keys = list(edge_index_dict.keys())
+        for (s, r, d) in keys:
+            ei = edge_index_dict[(s, r, d)]
+            if not ei.is_cuda:
+                raise AgxError('edge_index must be a CUDA tensor: this package has no CPU path')
+            if ei.dim() != 2 or ei.shape[0] != 2 or ei.dtype != torch.int64:
+                raise ValueError(f'edge_index of {(s, r, d)} must be int64 [2, E]')
+            lists.append((ei[1], ei[0], num_nodes[d], num_nodes[s]))     # CSR: key = dst
+        for (s, r, d) in keys:
+            ei = edge_index_dict[(s, r, d)]
+            lists.append((ei[0], ei[1], num_nodes[s], num_nodes[d]))     # CSC: key = src
+        built = ops.csr_build(lists)
+        R = len(keys)
+        self.rels: "OrderedDict[EdgeType, Relation]" = OrderedDict()
+        for i, (s, r, d) in enumerate(keys):
+            self.rels[(s, r, d)] = Relation(s, r, d, num_nodes[s], num_nodes[d],
+                                            built[i].n_edges, built[i], built[R + i])
+        self.n_edges = sum(r.n_edges for r in self.rels.values())
+
+    def __getitem__(self, key: EdgeType) -> Relation:
+        return self.rels[key]
+
+
+_PLAN_CACHE: "OrderedDict[tuple, HeteroPlan]" = OrderedDict()
+_PLAN_CACHE_MAX = 8
+
+
+def get_plan(edge_index_dict, num_nodes: Dict[str, int], cache: bool = True) -> HeteroPlan:
+    """Plans are cached on the identity + version of the edge_index tensors (a static graph is
+    sorted once, like the reference never re-sorts because it never sorts)."""
+    if not cache:
+        return HeteroPlan(edge_index_dict, num_nodes)
+    sig = tuple((k, v.data_ptr(), tuple(v.shape), v._version) for k, v in edge_index_dict.items())
+    sig = (sig, tuple(sorted(num_nodes.items())))
+    plan = _PLAN_CACHE.get(sig)
+    if plan is None:
+        plan = HeteroPlan(edge_index_dict, num_nodes)
+        plan._keepalive = list(edge_index_dict.values())   # pin the addresses the key refers to
+        _PLAN_CACHE[sig] = plan
+        while len(_PLAN_CACHE) > _PLAN_CACHE_MAX:
+            _PLAN_CACHE.popitem(last=False)
+    return plan
+
+
+def clear_plan_cache():
+    _PLAN_CACHE.clear()
+
+
+def to_undirected_dict(edge_index_dict, num_nodes: Dict[str, int]):
+    """a-2 ``ToUndirected`` on an edge_index dict.  Bipartite stores get ``(dst,'rev_'+rel,src)``
+    with rows swapped (edge order kept); a non-bipartite store is replaced by its coalesced
+    symmetrisation (K1 sort + unique on the GPU).  New stores follow all originals."""
+    out = OrderedDict()
+    rev = OrderedDict()
+    for (s, r, d), ei in edge_index_dict.items():
+        if s != d:
+            out[(s, r, d)] = ei
+            rev[(d, 'rev_' + r, s)] = torch.stack([ei[1], ei[0]], dim=0)
+        else:
+            was_cpu = not ei.is_cuda
+            e = ei.cuda() if was_cpu else ei
+            n = int(num_nodes[s])
+            res = ops.coalesce_undirected(e[0], e[1], n)
+            out[(s, r, d)] = res.cpu() if was_cpu else res
+    out.update(rev)
+    return out
+
+
+class ToUndirected:
+    """Drop-in for ``torch_geometric.transforms.ToUndirected`` on the HeteroGraph container."""
+
+    def __call__(self, data):
+        new = to_undirected_dict(data.edge_index_dict, data.num_nodes_dict)
+        for k in list(data.edge_types):
+            del data[k]
+        for k, v in new.items():
+            data[k].edge_index = v
+        return data

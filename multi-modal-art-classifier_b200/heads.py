@@ -1,0 +1,115 @@
+"""Fusion / projector heads: the arithmetic after the backbone of the reference's
+``NewMultiModalMultiTask[ViT]``, ``NewMultiModalSingleTask[Vit]`` and ``LabelProjector[Vit]``
+(/root/reference/src/models/models_kg.py:139-280), with the same attribute names and state-dict
+keys (``class_style.1.weight``, ``class_genre.1.bias``, ``classifier.1.*``, ``encoder.*``) so a
+checkpoint of the reference loads into them and they can replace the ``cat -> Sequential`` lines
+(:237-243) inside the reference classes.
+
+``cat(feat, emb) -> Dropout -> Linear`` never materialises the concatenation or the dropped-out
+copy: ``feat`` and ``emb`` are two K-segments of one agx GEMM against column slices of the weight,
+with the Philox dropout mask applied as the operand is staged into shared memory.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import functional as AF
+from . import ops
+
+
+class _HeadBase(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self._seed = None
+        self.dropout_masks: Optional[Dict[str, torch.Tensor]] = None    # test hook
+
+    def _masks(self, name: str, seq: nn.Sequential, parts):
+        """One mask per input part (same shape), or None when dropout is inactive."""
+        if self.dropout_masks is not None:
+            full = self.dropout_masks.get(name)
+            if full is None:
+                return None
+            out, off = [], 0
+            for p in parts:
+                out.append(full[:, off:off + p.shape[1]].contiguous())
+                off += p.shape[1]
+            return out
+        p_drop = seq[0].p
+        if not self.training or p_drop == 0.0:
+            return None
+        device = parts[0].device
+        if self._seed is None or self._seed.device != device:
+            s = torch.initial_seed() & 0x7fffffffffffffff
+            self._seed = torch.tensor([s, 0], dtype=torch.int64, device=device)
+        out = []
+        for p in parts:
+            out.append(ops.dropout_mask(tuple(p.shape), p_drop, self._seed))
+            self._seed[1] += (p.numel() + 3) // 4
+        return out
+
+    def _head(self, name: str, seq: nn.Sequential, feat, emb):
+        lin = seq[1]
+        parts = [feat.contiguous(), emb.contiguous()]
+        return AF.fused_linear(parts, lin.weight, lin.bias, self._masks(name, seq, parts))
+
+
+class NewMultiModalMultiTaskHead(_HeadBase):
+    """models_kg.py:164-193 (ResNet, feat_size=2048) / :217-243 (ViT, feat_size=768)."""
+
+    def __init__(self, emb_size: int, num_classes: Dict[str, int], dropout: float,
+                 feat_size: int = 768):
+        super().__init__()
+        self.class_style = nn.Sequential(nn.Dropout(dropout),
+                                         nn.Linear(feat_size + emb_size, num_classes['style']))
+        self.class_genre = nn.Sequential(nn.Dropout(dropout),
+                                         nn.Linear(feat_size + emb_size, num_classes['genre']))
+
+    def forward(self, visual_features, embedding_style, embedding_genre) -> List[torch.Tensor]:
+        out_style = self._head('style', self.class_style, visual_features, embedding_style)
+        out_genre = self._head('genre', self.class_genre, visual_features, embedding_genre)
+        return [out_style, out_genre]
+
+
+class NewMultiModalSingleTaskHead(_HeadBase):
+    """models_kg.py:139-162 / :195-215."""
+
+    def __init__(self, emb_size: int, num_class: int, dropout: float, feat_size: int = 768):
+        super().__init__()
+        self.classifier = nn.Sequential(nn.Dropout(dropout),
+                                        nn.Linear(feat_size + emb_size, num_class))
+
+    def forward(self, visual_features, embedding):
+        return self._head('classifier', self.classifier, visual_features, embedding)
+
+
+class LabelProjectorHead(nn.Module):
+    """models_kg.py:245-280: ``encoder = Linear(feat_size, emb_size)``."""
+
+    def __init__(self, emb_size: int, feat_size: int = 768):
+        super().__init__()
+        self.encoder = nn.Linear(feat_size, emb_size)
+
+    def forward(self, visual_features):
+        return AF.fused_linear([visual_features], self.encoder.weight, self.encoder.bias)
+
+
+def multitask_loss(out, style_labels, genre_labels, w_style=None, w_genre=None):
+    """``0.5*CE(out[0], y_style; w) + 0.5*CE(out[1], y_genre; w)``
+    (src/train_new_multimodal_multitask.py:48-55,79-81), fused softmax+nll per head."""
+    style_loss = AF.cross_entropy(out[0], style_labels, w_style, coef=0.5)
+    genre_loss = AF.cross_entropy(out[1], genre_labels, w_genre, coef=0.5)
+    return style_loss + genre_loss
+
+
+def projector_loss(out, embedding):
+    """``SmoothL1Loss()(out, embedding)`` (src/train_projector.py:33,52)."""
+    return AF.smooth_l1_loss(out, embedding)
+
+
+def select_embeddings(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """a-11 head input selection (src/data/data_kg.py:169-178): ``embedding[idx]`` /
+    ``embedding[label_id]`` as one device row gather."""
+    return ops.gather_rows(table.contiguous(), idx.to(table.device, torch.int64).contiguous())

@@ -1,0 +1,311 @@
+"""``to_hetero(module, metadata, aggr)``: turns a homogeneous GNN module into a heterogeneous one
+(/root/reference/src/models/models_graph.py:45; PyG 2.0.2 ``to_hetero_transformer`` semantics,
+SURVEY.md a-3) and executes it with fused agx launches:
+
+  * every MessagePassing call site becomes ONE fused hetero layer over all edge types
+    (``functional._HeteroConvFn``) instead of one conv call + ``torch.add`` chain per relation;
+  * ``BatchNorm1d -> ReLU -> F.dropout`` per node type becomes one batched launch sequence over all
+    node types; values nobody consumes (the reference's dead first-layer relu/dropout,
+    models_graph.py:34-37) are not computed;
+  * ``F.log_softmax(dim=1)`` per node type runs on the agx softmax kernel.
+
+Leaf modules are duplicated exactly like PyG does (``ModuleDict`` keyed ``src__rel__dst`` for
+MessagePassing modules, by node type for the others, ``reset_parameters()`` on each copy), so
+state-dict keys match the reference: ``convs.0.artist__field_rel__field.lin_l.weight``,
+``bns.0.artwork.running_mean``, ...
+"""
+from __future__ import annotations
+
+import copy
+import warnings
+from collections import OrderedDict
+from typing import Dict, List, Optional
+
+import torch
+import torch.fx as fx
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functional as AF
+from . import ops
+from .functional import BNSpec, ConvSpec, RelSpec
+from .graph import get_plan, key2str
+from .nn import Linear, MessagePassing
+
+
+class _Tracer(fx.Tracer):
+    def is_leaf_module(self, m, qualname):
+        return isinstance(m, (MessagePassing, Linear)) or super().is_leaf_module(m, qualname)
+
+
+def _is_dropout_fn(node: fx.Node) -> bool:
+    return node.op == 'call_function' and node.target in (F.dropout, torch.dropout)
+
+
+def _is_log_softmax(node: fx.Node) -> bool:
+    return (node.op == 'call_function' and node.target in (F.log_softmax, torch.log_softmax)) or \
+        (node.op == 'call_method' and node.target == 'log_softmax')
+
+
+_IDENTITY_CACHE: Dict[tuple, bool] = {}
+
+
+def _is_identity_input(x: torch.Tensor) -> bool:
+    """One-hot node features (``torch.eye(N)``, src/data/artgraph.py:93-95) are detected once per
+    tensor so that X @ W^T can be replaced by a transposed copy of W (exact)."""
+    if x.dim() != 2 or x.shape[0] != x.shape[1] or x.shape[0] < 2:
+        return False
+    key = (x.data_ptr(), x.shape[0], x._version)
+    hit = _IDENTITY_CACHE.get(key)
+    if hit is None:
+        hit = bool(ops.is_identity(x).item())
+        if len(_IDENTITY_CACHE) > 256:
+            _IDENTITY_CACHE.clear()
+        _IDENTITY_CACHE[key] = hit
+    return hit
+
+
+class HeteroModule(nn.Module):
+    def __init__(self, module: nn.Module, metadata, aggr: str = 'sum', detect_identity: bool = True):
+        super().__init__()
+        if aggr != 'sum':
+            raise NotImplementedError("to_hetero: only aggr='sum' (the reference's setting, "
+                                      "src/train_gnn_embeddings.py:130) is implemented")
+        self.node_types, self.edge_types = list(metadata[0]), [tuple(e) for e in metadata[1]]
+        self.detect_identity = detect_identity
+        graph = _Tracer().trace(module)
+        self._graph = graph
+        called = []
+        for n in graph.nodes:
+            if n.op == 'call_module' and n.target not in called:
+                called.append(n.target)
+        for target in called:
+            sub = module.get_submodule(target)
+            keys = ([key2str(et) for et in self.edge_types] if isinstance(sub, MessagePassing)
+                    else list(self.node_types))
+            md = nn.ModuleDict()
+            for k in keys:
+                md[k] = copy.deepcopy(sub)
+                if hasattr(md[k], 'reset_parameters'):
+                    md[k].reset_parameters()
+            parent_name, _, leaf = target.rpartition('.')
+            parent = module.get_submodule(parent_name) if parent_name else module
+            if isinstance(parent, (nn.ModuleList, nn.Sequential)):
+                parent[int(leaf)] = md
+            else:
+                setattr(parent, leaf, md)
+        for name, child in module.named_children():
+            self.add_module(name, child)
+        for name, p in module.named_parameters(recurse=False):
+            self.register_parameter(name, p)
+        # analysis results are keyed by node NAME so that copy.deepcopy(model) (the reference's
+        # save_embeddings, src/train_gnn_embeddings.py:84-85) stays consistent
+        self._placeholders = [n.name for n in graph.nodes if n.op == 'placeholder']
+        self._live = self._liveness()
+        self._fusion = self._plan_fusion()
+        self._conv_specs: Dict[tuple, ConvSpec] = {}
+        self._warned = set()
+        self.dropout_masks: Optional[Dict[str, torch.Tensor]] = None   # test hook (injected masks)
+        self._seed = None
+
+    # ---- static analysis ----------------------------------------------------------------------
+    def _liveness(self):
+        live = set()
+        out = [n for n in self._graph.nodes if n.op == 'output'][0]
+        stack = [out]
+        while stack:
+            n = stack.pop()
+            if n in live:
+                continue
+            live.add(n)
+            stack.extend(n.all_input_nodes)
+        return {n.name for n in live}
+
+    def _plan_fusion(self):
+        """BatchNorm1d call -> (ReLU module call -> (F.dropout call)) chains whose intermediate
+        values have no other live consumer are computed by the BN kernel's epilogue."""
+        fusion = {}
+        for n in self._graph.nodes:
+            if n.op != 'call_module' or n.name not in self._live:
+                continue
+            sub = next(iter(self.get_submodule(n.target).values()))
+            if not isinstance(sub, nn.BatchNorm1d):
+                continue
+            relu = [u for u in n.users if u.name in self._live and u.op == 'call_module' and
+                    isinstance(next(iter(self.get_submodule(u.target).values())), nn.ReLU)]
+            if len(relu) != 1:
+                continue
+            relu = relu[0]
+            live_users = [u for u in relu.users if u.name in self._live]
+            drop = None
+            if len(live_users) == 1 and _is_dropout_fn(live_users[0]):
+                d = live_users[0]
+                training = d.kwargs.get('training', d.args[2] if len(d.args) > 2 else True)
+                if training is True and d.args[0] is relu:
+                    p = d.kwargs.get('p', d.args[1] if len(d.args) > 1 else 0.5)
+                    drop = (d.name, float(p))
+            fusion[n.name] = (relu.name, drop)
+        return fusion
+
+    # ---- execution ----------------------------------------------------------------------------
+    def _seed_state(self, device):
+        if self._seed is None or self._seed.device != device:
+            s = torch.initial_seed() & 0x7fffffffffffffff
+            self._seed = torch.tensor([s, 0], dtype=torch.int64, device=device)
+        return self._seed
+
+    def _mask(self, shape, p, device, t):
+        if self.dropout_masks is not None:
+            return self.dropout_masks[t]
+        st = self._seed_state(device)
+        m = ops.dropout_mask(shape, p, st)
+        n4 = (m.numel() + 3) // 4
+        st[1] += n4                  # advance the Philox counter (device side: graph-capturable)
+        return m
+
+    def _conv(self, node, x_dict, ei_dict, plan, is_input):
+        convs = self.get_submodule(node.target)
+        key = (node.target, id(plan))
+        types = [t for t in self.node_types if t in x_dict]
+        dev = x_dict[types[0]].device
+        params: List[torch.Tensor] = []
+        rel_specs = []
+        for et in self.edge_types:
+            s, _, d = et
+            conv = convs[key2str(et)]
+            wl, bl, wr = conv.rel_params(x_dict[s].shape[1], x_dict[d].shape[1], dev)
+            i_wl = len(params)
+            params.append(wl)
+            i_bl = i_wr = -1
+            if bl is not None:
+                i_bl = len(params)
+                params.append(bl)
+            if wr is not None:
+                i_wr = len(params)
+                params.append(wr)
+            rel_specs.append((et, conv.aggr == 'mean', i_wl, i_bl, i_wr))
+        spec = self._conv_specs.get(key)
+        if spec is None:
+            spec = ConvSpec(node_types=types,
+                            rels=[RelSpec(plan[et], mean, a, b, c) for et, mean, a, b, c in rel_specs],
+                            out_channels=params[0].shape[0])
+            if len(self._conv_specs) > 64:
+                self._conv_specs.clear()
+            self._conv_specs[key] = spec
+        spec.identity = ({t: _is_identity_input(x_dict[t]) for t in types}
+                         if (is_input and self.detect_identity) else {})
+        outs = AF.hetero_conv(spec, [x_dict[t].contiguous() for t in types], params)
+        return OrderedDict(zip(spec.dst_types, outs))
+
+    def _bn(self, node, x_dict):
+        bns = self.get_submodule(node.target)
+        relu, drop = self._fusion.get(node.name, (None, None))
+        types = list(x_dict.keys())
+        first = bns[types[0]]
+        dmasks = None
+        if drop is not None:
+            p = drop[1]
+            if p > 0 or self.dropout_masks is not None:
+                dmasks = [self._mask(x_dict[t].shape, p, x_dict[t].device, t) for t in types]
+        for t in types:
+            bn = bns[t]
+            if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+        spec = BNSpec(n=len(types), F=first.num_features, training=first.training or
+                      not first.track_running_stats, momentum=first.momentum, eps=first.eps,
+                      running=[(bns[t].running_mean, bns[t].running_var) for t in types],
+                      with_act=relu is not None, dmasks=dmasks)
+        res = AF.batch_norm_act(spec, [x_dict[t].contiguous() for t in types],
+                                [bns[t].weight for t in types], [bns[t].bias for t in types])
+        n = len(types)
+        y = OrderedDict(zip(types, res[:n]))
+        act = OrderedDict(zip(types, res[n:])) if relu is not None else None
+        return y, act, relu, drop
+
+    def _generic_warn(self, what):
+        if what not in self._warned:
+            self._warned.add(what)
+            warnings.warn(f'mmac_b200.to_hetero: {what} runs through generic torch CUDA ops, not an '
+                          f'agx kernel', stacklevel=3)
+
+    def forward(self, x, edge_index):
+        x_dict, ei_dict = x, edge_index
+        num_nodes = {t: v.shape[0] for t, v in x_dict.items()}
+        ei_dict = OrderedDict((tuple(k), v) for k, v in ei_dict.items())
+        plan = get_plan(OrderedDict((et, ei_dict[et]) for et in self.edge_types), num_nodes)
+        env = {self._placeholders[0]: x_dict, self._placeholders[1]: ei_dict}
+        provided = {}
+
+        def load(a, key=None):
+            def f(n):
+                v = env[n.name]
+                return v[key] if (key is not None and isinstance(v, dict)) else v
+            return fx.node.map_arg(a, f)
+
+        def dict_keys(args, kwargs):
+            found = []
+            fx.node.map_arg((args, kwargs), lambda n: found.append(env[n.name]))
+            for v in found:
+                if isinstance(v, dict):
+                    return list(v.keys())
+            return None
+
+        for node in self._graph.nodes:
+            if node.op == 'placeholder' or node.name not in self._live:
+                continue
+            if node.name in provided:
+                env[node.name] = provided[node.name]
+                continue
+            if node.op == 'get_attr':
+                env[node.name] = self.get_parameter(node.target)
+            elif node.op == 'call_module':
+                sub = self.get_submodule(node.target)
+                first = next(iter(sub.values()))
+                if isinstance(first, MessagePassing):
+                    xin = env[node.args[0].name]
+                    env[node.name] = self._conv(node, xin, ei_dict, plan,
+                                                is_input=node.args[0].name == self._placeholders[0])
+                elif isinstance(first, nn.BatchNorm1d):
+                    y, act, relu, drop = self._bn(node, env[node.args[0].name])
+                    env[node.name] = y
+                    if relu is not None:
+                        provided[drop[0] if drop is not None else relu] = act
+                        if drop is not None:
+                            provided[relu] = None      # consumed only by the fused dropout
+                else:
+                    if not isinstance(first, (Linear, nn.ReLU)):
+                        self._generic_warn(type(first).__name__)
+                    keys = dict_keys(node.args, node.kwargs)
+                    env[node.name] = OrderedDict(
+                        (k, sub[key2str(k)](*load(node.args, k), **load(node.kwargs, k)))
+                        for k in keys)
+            elif _is_log_softmax(node):
+                src = env[node.args[0].name]
+                env[node.name] = OrderedDict((k, AF.log_softmax(v, 1)) for k, v in src.items())
+            elif _is_dropout_fn(node):
+                src = env[node.args[0].name]
+                p = node.kwargs.get('p', node.args[1] if len(node.args) > 1 else 0.5)
+                training = node.kwargs.get('training', node.args[2] if len(node.args) > 2 else True)
+                if not training or (p == 0 and self.dropout_masks is None):
+                    env[node.name] = src
+                else:
+                    env[node.name] = OrderedDict(
+                        (k, AF.dropout_apply(v, self._mask(v.shape, p, v.device, k)))
+                        for k, v in src.items())
+            elif node.op in ('call_function', 'call_method'):
+                keys = dict_keys(node.args, node.kwargs)
+                self._generic_warn(str(node.target))
+
+                def run(k):
+                    a, kw = load(node.args, k), load(node.kwargs, k)
+                    if node.op == 'call_function':
+                        return node.target(*a, **kw)
+                    return getattr(a[0], node.target)(*a[1:], **kw)
+                env[node.name] = run(None) if keys is None else OrderedDict((k, run(k)) for k in keys)
+            elif node.op == 'output':
+                return load(node.args[0])
+        raise RuntimeError('fx graph without output node')
+
+
+def to_hetero(module: nn.Module, metadata, aggr: str = 'sum', **kwargs) -> HeteroModule:
+    return HeteroModule(module, metadata, aggr, **kwargs)

@@ -1,0 +1,360 @@
+"""Tensor-level wrappers over the C ABI (include/agx.h): every function takes CUDA torch tensors,
+passes raw device pointers + the current stream to ``libagx.so`` and returns torch tensors.
+torch is used for allocation and stream plumbing only."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from ._lib import check, lib, ptr, stream_ptr
+
+
+# ------------------------------------------------------------------------------------------------
+# K1: CSR / CSC
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class CSR:
+    """Compressed rows of one relation: ``col[rowptr[i]:rowptr[i+1]]`` are row i's neighbours in
+    edge-list order; ``eid`` is the stable permutation; ``cnt = max(degree, 1)`` as float."""
+    rowptr: torch.Tensor
+    col: torch.Tensor
+    eid: torch.Tensor
+    cnt: torch.Tensor
+    n_rows: int
+    n_cols: int
+    n_edges: int
+
+    @property
+    def avg_degree(self) -> float:
+        return self.n_edges / max(self.n_rows, 1)
+
+
+def csr_build(edge_lists: Sequence[Tuple[torch.Tensor, torch.Tensor, int, int]],
+              check_range: bool = True) -> List[CSR]:
+    """``edge_lists``: (keys int64 [E], vals int64 [E], n_rows, n_cols) per relation.  One batched
+    stable radix sort (K1) for all of them.  Raises IndexError for out-of-range indices, like the
+    reference's ``index_select`` / ``scatter_add_``."""
+    out: List[CSR] = []
+    for base in range(0, len(edge_lists), L.MAX_CSR_RELS):
+        out.extend(_csr_build_batch(edge_lists[base:base + L.MAX_CSR_RELS], check_range))
+    return out
+
+
+def _csr_build_batch(edge_lists, check_range) -> List[CSR]:
+    n = len(edge_lists)
+    dev = edge_lists[0][0].device
+    arr = (L.EdgeList * n)()
+    keep = []
+    tot_e = tot_r = 0
+    for i, (keys, vals, n_rows, n_cols) in enumerate(edge_lists):
+        L.require_cuda(keys, 'edge keys')
+        if keys.dtype != torch.int64 or vals.dtype != torch.int64:
+            raise TypeError('edge_index must be int64')
+        keys = keys.contiguous()
+        vals = vals.contiguous()
+        keep += [keys, vals]
+        arr[i] = L.EdgeList(ptr(keys), ptr(vals), keys.numel(), int(n_rows), int(n_cols))
+        tot_e += keys.numel()
+        tot_r += int(n_rows)
+    rowptr = torch.empty(tot_r + n, dtype=torch.int32, device=dev)
+    col = torch.empty(max(tot_e, 1), dtype=torch.int32, device=dev)
+    eid = torch.empty(max(tot_e, 1), dtype=torch.int32, device=dev)
+    cnt = torch.empty(max(tot_r, 1), dtype=torch.float32, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_bytes = lib().agx_csr_workspace_bytes(tot_e, tot_r)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(lib().agx_csr_build(arr, n, ptr(rowptr), ptr(col), ptr(eid), ptr(cnt), ptr(err), ptr(ws),
+                              ws_bytes, stream_ptr()), 'agx_csr_build')
+    if check_range and int(err.item()) != 0:
+        raise IndexError('edge_index contains node ids outside [0, num_nodes)')
+    res = []
+    e0 = r0 = 0
+    for i, (keys, vals, n_rows, n_cols) in enumerate(edge_lists):
+        e, r = keys.numel(), int(n_rows)
+        res.append(CSR(rowptr[r0 + i:r0 + i + r + 1], col[e0:e0 + e], eid[e0:e0 + e],
+                       cnt[r0:r0 + r], r, int(n_cols), e))
+        e0 += e
+        r0 += r
+    return res
+
+
+def coalesce_undirected(row: torch.Tensor, col: torch.Tensor, n_nodes: int) -> torch.Tensor:
+    """a-2, non-bipartite store: unique (row, col) pairs of the symmetrised list, ascending."""
+    L.require_cuda(row, 'edge_index')
+    e = row.numel()
+    dev = row.device
+    out_r = torch.empty(max(2 * e, 1), dtype=torch.int64, device=dev)
+    out_c = torch.empty(max(2 * e, 1), dtype=torch.int64, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws_bytes = lib().agx_coalesce_workspace_bytes(e)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    row, col = row.contiguous(), col.contiguous()
+    check(lib().agx_coalesce_undirected(ptr(row), ptr(col), e, int(n_nodes), ptr(out_r), ptr(out_c),
+                                        ptr(count), ptr(ws), ws_bytes, stream_ptr()),
+          'agx_coalesce_undirected')
+    k = int(count.item())
+    return torch.stack([out_r[:k], out_c[:k]], dim=0)
+
+
+# ------------------------------------------------------------------------------------------------
+# K2/K3: aggregation
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class RelArg:
+    csr: CSR
+    x: torch.Tensor
+    mean_rows: bool = False          # divide by the row's own count (forward scatter-mean)
+    nbr_scale: Optional[torch.Tensor] = None   # per-neighbour counts (transpose of scatter-mean)
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return L.F32
+    if t.dtype == torch.bfloat16:
+        return L.BF16
+    raise TypeError(f'unsupported feature dtype {t.dtype}')
+
+
+def _rel_struct(a: RelArg) -> L.Rel:
+    if a.x.stride(-1) != 1:
+        raise ValueError('feature rows must be contiguous')
+    return L.Rel(ptr(a.csr.rowptr), ptr(a.csr.col), ptr(a.x), a.x.stride(0),
+                 ptr(a.csr.cnt) if a.mean_rows else None, ptr(a.nbr_scale))
+
+
+def aggregate_rows(groups: Sequence[Tuple[torch.Tensor, Sequence[RelArg], bool]], F: int):
+    """``groups``: (out [n_rows, F], relations, accumulate).  One launch per <=24 groups; each output
+    row is the sum over the group's relations of the (scaled) neighbour sums."""
+    if not groups:
+        return
+    dt = _dtype_code(groups[0][0])
+    for base in range(0, len(groups), L.MAX_GROUPS):
+        part = groups[base:base + L.MAX_GROUPS]
+        arr = (L.RowGroup * len(part))()
+        for i, (out, rels, acc) in enumerate(part):
+            if len(rels) > L.MAX_REL_PER_GROUP:
+                raise ValueError('more than 8 relations in one aggregation group')
+            g = arr[i]
+            g.out, g.ldo, g.n_rows, g.n_rel, g.accumulate = ptr(out), out.stride(0), out.shape[0], \
+                len(rels), int(acc)
+            for j, a in enumerate(rels):
+                g.rel[j] = _rel_struct(a)
+        check(lib().agx_aggregate_rows(arr, len(part), F, dt, stream_ptr()), 'agx_aggregate_rows')
+
+
+def aggregate_chunks(segs: Sequence[Tuple[torch.Tensor, RelArg]], F: int):
+    """Edge-balanced aggregation for long-row relations; ``segs``: (out [n_rows, F], relation)."""
+    if not segs:
+        return
+    dt = _dtype_code(segs[0][0])
+    dev = segs[0][0].device
+    for base in range(0, len(segs), L.MAX_CHUNK_SEGS):
+        part = segs[base:base + L.MAX_CHUNK_SEGS]
+        arr = (L.ChunkSeg * len(part))()
+        sizes = [lib().agx_chunk_frag_floats(a.csr.n_edges, F) for _, a in part]
+        frag = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        off = 0
+        for i, (out, a) in enumerate(part):
+            s = arr[i]
+            s.rel = _rel_struct(a)
+            s.out, s.ldo, s.n_rows, s.n_edges = ptr(out), out.stride(0), out.shape[0], a.csr.n_edges
+            s.frag = frag.data_ptr() + 4 * off
+            off += sizes[i]
+        check(lib().agx_aggregate_chunks(arr, len(part), F, dt, stream_ptr()),
+              'agx_aggregate_chunks')
+
+
+LONG_ROW_AVG_DEGREE = 24.0
+
+
+def aggregate(out: torch.Tensor, rel: RelArg, F: int):
+    """Single relation, picks the row-parallel or the edge-balanced kernel from the mean degree."""
+    if rel.csr.avg_degree > LONG_ROW_AVG_DEGREE:
+        aggregate_chunks([(out, rel)], F)
+    else:
+        aggregate_rows([(out, [rel], False)], F)
+
+
+# ------------------------------------------------------------------------------------------------
+# K4: grouped GEMM
+# ------------------------------------------------------------------------------------------------
+class GemmBatch:
+    """Collects problems ``C (+)= sum_s opA_s @ opB_s (+ bias)`` and launches them together.
+    Operands are given as 2-D tensor *views* (any strides): opA [M, K], opB [K, N]."""
+
+    def __init__(self):
+        self.problems: List[L.GemmProblem] = []
+        self.segs: List[L.GemmSeg] = []
+        self._keep = []
+
+    def add(self, C_out: torch.Tensor, segs: Sequence[tuple], bias: Optional[torch.Tensor] = None,
+            accumulate: bool = False, row_scale: Optional[torch.Tensor] = None,
+            split_k: int = 1, skip_flag: Optional[torch.Tensor] = None):
+        """``segs``: (opA [M,K], opB [K,N]) or (opA, opB, A_mask, B_mask)."""
+        M, N = C_out.shape
+        if C_out.stride(1) != 1:
+            raise ValueError('C must be row-major')
+        p = L.GemmProblem()
+        p.C, p.ldc, p.bias, p.row_scale = ptr(C_out), C_out.stride(0), ptr(bias), ptr(row_scale)
+        p.M, p.N, p.accumulate = M, N, int(accumulate)
+        p.seg_begin, p.seg_count = len(self.segs), len(segs)
+        p.split_k = split_k
+        p.skip_flag = ptr(skip_flag)
+        if split_k > 1:
+            part = torch.empty(split_k * M * N, dtype=torch.float32, device=C_out.device)
+            self._keep.append(part)
+            p.partial = ptr(part)
+        for sg in segs:
+            A, B = sg[0], sg[1]
+            Am = sg[2] if len(sg) > 2 else None
+            Bm = sg[3] if len(sg) > 3 else None
+            if A.shape[0] != M or B.shape[1] != N or A.shape[1] != B.shape[0]:
+                raise ValueError(f'gemm shape mismatch: A {tuple(A.shape)} B {tuple(B.shape)} '
+                                 f'C {tuple(C_out.shape)}')
+            if Am is not None and Am.stride() != A.stride():
+                raise ValueError('A_mask must have the strides of A')
+            if Bm is not None and Bm.stride() != B.stride():
+                raise ValueError('B_mask must have the strides of B')
+            s = L.GemmSeg(ptr(A), A.stride(0), A.stride(1), ptr(B), B.stride(0), B.stride(1),
+                          ptr(Am), ptr(Bm), A.shape[1], 0)
+            self.segs.append(s)
+            self._keep += [A, B, Am, Bm]
+        self.problems.append(p)
+        self._keep += [C_out, bias, row_scale, skip_flag]
+
+    def run(self):
+        i = 0
+        n = len(self.problems)
+        while i < n:
+            # take problems while both tables fit
+            j, nseg = i, 0
+            while j < n and j - i < L.MAX_GEMM_PROBLEMS and \
+                    nseg + self.problems[j].seg_count <= L.MAX_GEMM_SEGS:
+                nseg += self.problems[j].seg_count
+                j += 1
+            if j == i:
+                raise ValueError('a GEMM problem has more than 64 segments')
+            parr = (L.GemmProblem * (j - i))()
+            sarr = (L.GemmSeg * max(nseg, 1))()
+            so = 0
+            for k in range(i, j):
+                src = self.problems[k]
+                q = parr[k - i]
+                C.memmove(C.byref(q), C.byref(src), C.sizeof(L.GemmProblem))
+                for t in range(src.seg_count):
+                    sarr[so + t] = self.segs[src.seg_begin + t]
+                q.seg_begin = so
+                so += src.seg_count
+            check(lib().agx_gemm_grouped(parr, j - i, sarr, max(nseg, 1), stream_ptr()),
+                  'agx_gemm_grouped')
+            i = j
+        self.problems, self.segs, self._keep = [], [], []
+
+
+def split_k_for(k_rows: int, slab: int = 1024, max_split: int = 256) -> int:
+    return max(1, min(max_split, (k_rows + slab - 1) // slab))
+
+
+# ------------------------------------------------------------------------------------------------
+# small batched ops
+# ------------------------------------------------------------------------------------------------
+def sum_arrays(items: Sequence[Tuple[torch.Tensor, Sequence[torch.Tensor]]]):
+    """``items``: (out, [in_0..in_k]) -- out = sum of inputs (same numel, contiguous)."""
+    for base in range(0, len(items), L.MAX_TENSORS):
+        part = items[base:base + L.MAX_TENSORS]
+        arr = (L.SumDesc * len(part))()
+        for i, (out, ins) in enumerate(part):
+            d = arr[i]
+            d.out, d.n_in, d.numel = ptr(out), len(ins), out.numel()
+            for k, t in enumerate(ins):
+                if not t.is_contiguous() or t.numel() != out.numel():
+                    raise ValueError('sum_arrays needs contiguous equally sized tensors')
+                d.inp[k] = ptr(t)
+        check(lib().agx_sum_arrays(arr, len(part), stream_ptr()), 'agx_sum_arrays')
+
+
+def colsum(items: Sequence[Tuple[torch.Tensor, torch.Tensor, bool]]):
+    """``items``: (x [rows, F], out [F], accumulate)."""
+    if not items:
+        return
+    dev = items[0][0].device
+    for base in range(0, len(items), L.MAX_TENSORS):
+        part = items[base:base + L.MAX_TENSORS]
+        arr = (L.ColsumDesc * len(part))()
+        rows = sum(x.shape[0] for x, _, _ in part)
+        maxf = max(x.shape[1] for x, _, _ in part)
+        for i, (x, out, acc) in enumerate(part):
+            arr[i] = L.ColsumDesc(ptr(x), x.stride(0), ptr(out), x.shape[0], x.shape[1], int(acc), 0)
+        n_ws = lib().agx_colsum_workspace_floats(rows, len(part), maxf)
+        ws = torch.empty(n_ws, dtype=torch.float32, device=dev)
+        check(lib().agx_colsum(arr, len(part), ptr(ws), n_ws, stream_ptr()), 'agx_colsum')
+
+
+def dropout_mask(shape, p: float, seed_state: torch.Tensor) -> torch.Tensor:
+    """Multiplicative mask ``bernoulli(1-p) / (1-p)`` from Philox; ``seed_state`` = device
+    uint64-as-int64 [2] (key, counter)."""
+    mask = torch.empty(shape, dtype=torch.float32, device=seed_state.device)
+    check(lib().agx_dropout_mask(ptr(mask), mask.numel(), float(p), ptr(seed_state), stream_ptr()),
+          'agx_dropout_mask')
+    return mask
+
+
+def fill_(t: torch.Tensor, v: float):
+    check(lib().agx_fill_f32(ptr(t), t.numel(), float(v), stream_ptr()), 'agx_fill_f32')
+    return t
+
+
+def zeros(shape, device) -> torch.Tensor:
+    return fill_(torch.empty(shape, dtype=torch.float32, device=device), 0.0)
+
+
+def scale_mask(x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    y = torch.empty_like(x)
+    check(lib().agx_scale_mask(ptr(x), ptr(mask), ptr(y), x.numel(), stream_ptr()),
+          'agx_scale_mask')
+    return y
+
+
+def gather_rows(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(idx.numel(), table.shape[1], dtype=torch.float32, device=table.device)
+    check(lib().agx_gather_rows(ptr(table), table.stride(0), ptr(idx), idx.numel(), table.shape[1],
+                                ptr(out), out.stride(0), stream_ptr()), 'agx_gather_rows')
+    return out
+
+
+def is_identity(x: torch.Tensor) -> torch.Tensor:
+    """Device int32 flag: 1 iff ``x`` is a square identity (one-hot node features)."""
+    flag = torch.zeros(2, dtype=torch.int32, device=x.device)
+    if x.dim() != 2 or x.shape[0] != x.shape[1]:
+        return flag[:1]
+    check(lib().agx_is_identity(ptr(x), x.stride(0), x.shape[0], ptr(flag), flag.data_ptr() + 4,
+                                stream_ptr()), 'agx_is_identity')
+    return flag[:1]
+
+
+def transpose_into(out: torch.Tensor, inp: torch.Tensor, only_if_flag: Optional[torch.Tensor] = None):
+    check(lib().agx_transpose(ptr(inp), inp.stride(0), inp.shape[0], inp.shape[1], ptr(out),
+                              out.stride(0), ptr(only_if_flag), stream_ptr()), 'agx_transpose')
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), eps=1e-8,
+              weight_decay=0.0):
+    check(lib().agx_adam_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(),
+                              lr, betas[0], betas[1], eps, weight_decay, ptr(step), stream_ptr()),
+          'agx_adam_step')
+
+
+def pack_rows(x: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(idx.numel(), x.shape[1], dtype=torch.float32, device=x.device)
+    check(lib().agx_pack_rows(ptr(x), x.stride(0), ptr(idx), idx.numel(), x.shape[1], ptr(out),
+                              stream_ptr()), 'agx_pack_rows')
+    return out
+
+
+def unpack_rows_add_(x: torch.Tensor, idx: torch.Tensor, src: torch.Tensor):
+    check(lib().agx_unpack_rows_add(ptr(x), x.stride(0), ptr(idx), idx.numel(), x.shape[1],
+                                    ptr(src), stream_ptr()), 'agx_unpack_rows_add')
