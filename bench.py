@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: one full-graph hetero-GNN training step (forward + nll_loss +
+backward + Adam, the body of ``hetero_training()`` in the reference's train_gnn_embeddings.py)
+on a synthetic ArtGraph-shaped heterograph.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5            # this repo's CUDA path
+    python bench.py --impl reference --steps 3 --warmup 1     # reference semantics on host CPU cores
+    torchrun ... bench.py --gpus N ...                        # one rank per GPU, weak scaling
+
+Prints ONE JSON line (rank 0).  Metric: aggregated edges/s = 5 * sum_r E_r / step time (three
+forward aggregation passes + the two transpose passes of the backward; the count is
+the reference formulation's and does not depend on how this implementation prunes or reorders).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from collections import OrderedDict
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'hetero_gnn_aggregated_edges_per_s'
+UNIT = 'edges/s'
+PASSES = 5                       # aggregation passes per training step
+
+
+def _peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs, copy kernel)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader',
+                                       '-i', str(self.idx), '-lms', '100'], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(',')]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1].split()[0]))
+                mx.append(float(c[2].split()[0]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        return {'sm_mhz': statistics.median(sm) if sm else None,
+                'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference semantics on the host CPU (oracle/; test + baseline infrastructure, never the product)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(size: str, steps: int, warmup: int):
+    from mmac_b200 import synth
+    from oracle import graph_oracle as go
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = synth.make_artgraph(size, features='one-hot')
+    ei = go.to_undirected(g.edge_index_dict)
+    md = (g.node_types, list(ei.keys()))
+    n_edges = sum(int(v.shape[1]) for v in ei.values())
+    model = go.HeteroSGNNOracle(go.SAGEConv, torch.nn.ReLU(), 'sum', 128, 32, md, 2, 0.4, True,
+                                False)
+    with torch.no_grad():
+        model(g.x_dict, ei)
+    opt = torch.optim.Adam([p for p in model.parameters()
+                            if not isinstance(p, torch.nn.parameter.UninitializedParameter)],
+                           lr=0.01)
+    y = g['artwork'].y_style
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        _, out = model(g.x_dict, ei)
+        loss = go.nll_loss_artwork(out[0], y)
+        loss.backward()
+        opt.step()
+        loss.item()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {'value': PASSES * n_edges * len(times) / total, 'ms_per_step': 1e3 * total / len(times),
+            'n_edges': n_edges, 'cores': torch.get_num_threads(),
+            'sample': f"synthetic ArtGraph '{size}' ({g.num_nodes_dict['artwork']} artworks, "
+                      f"{n_edges} directed edges, one-hot features), {len(times)} train steps "
+                      f"after {warmup} warm-up"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    # bounded sample: at most 4 timed steps after 1 warm-up (a full-size step is ~8 s on 8 cores)
+    r = cpu_reference(args.cpu_size, max(1, min(args.steps, 4)), 1)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT,
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': _workload_name(args.size), 'operator': 'SAGEConv', 'label': 'style',
+                   'note': 'PyG 2.0.2 semantics restated on torch ATen CPU kernels (oracle/); PyG '
+                           'itself is not installable here'},
+        'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
+                         'sample': r['sample']},
+        'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def _workload_name(size):
+    return (f"train_gnn_embeddings.py --label style: full-graph SAGEConv to_hetero training step on "
+            f"synthetic ArtGraph '{size}' (one-hot node features as in artgraph.py:93-95)")
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo's CUDA path
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import mmac_b200 as agx
+    from mmac_b200 import ops, synth
+    from mmac_b200.trainer import GNNTrainer
+    from mmac_b200._lib import launch_count
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the product has no CPU path '
+                         '(use --impl reference for the host baseline)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+
+    agx.lib()
+    # ---- inputs: pinned host copies (e2e) + device residents ---------------------------------
+    g = synth.make_artgraph(args.size, features='one-hot', seed=None if world == 1 else 1234 + 2)
+    data = agx.ToUndirected()(g)
+    host_x = OrderedDict((k, v.pin_memory()) for k, v in data.x_dict.items())
+    host_ei = OrderedDict((k, v.pin_memory()) for k, v in data.edge_index_dict.items())
+    x = OrderedDict((k, v.to(dev, non_blocking=True)) for k, v in host_x.items())
+    ei = OrderedDict((k, v.to(dev, non_blocking=True)) for k, v in host_ei.items())
+    y = data['artwork'].y_style.to(dev)
+    n_edges = sum(int(v.shape[1]) for v in ei.values())
+    h2d = sum(v.numel() * v.element_size() for v in host_x.values()) + \
+        sum(v.numel() * v.element_size() for v in host_ei.values())
+
+    torch.manual_seed(0)
+    model = agx.HeteroSGNN(agx.SAGEConv, torch.nn.ReLU(), 'sum', 128, 32, data.metadata(), 2, 0.4,
+                           True, False).to(dev)
+    trainer = GNNTrainer(model, x, ei, y, lr=0.01, use_cuda_graph=not args.no_graph,
+                         dist_group=dist.group.WORLD if dist is not None else None)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing --------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        trainer.train_step()
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = launch_count()
+    ev0.record()
+    for _ in range(args.steps):
+        loss = trainer.train_step()
+    ev1.record()
+    barrier()
+    clk = clocks.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = (launch_count() - l0) if args.no_graph else trainer.launches_per_step * args.steps
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * PASSES * n_edges * args.steps / (ms * 1e-3)
+    final_loss = float(loss.item())
+
+    # ---- end to end: host buffers in, loss out, every step ------------------------------------
+    for _ in range(2):
+        trainer.update_inputs(host_x, host_ei)
+        float(trainer.train_step().item())
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        trainer.update_inputs(host_x, host_ei)          # H2D of x_dict + edge_index_dict, re-sort
+        l_host = float(trainer.train_step().item())     # D2H of the loss
+        trainer.verify_inputs()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e2e_ms, wall_ms)
+    if dist is not None:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * PASSES * n_edges * args.steps / (e2e_ms * 1e-3)
+
+    # ---- roofline of the aggregation kernels: events around every launch, eager steps ----------
+    roofline = None
+    cpu_base = None
+    if rank == 0:
+        peak, peak_src = _peaks()
+        timer = ops.KernelTimer()
+        ops.TIMER = timer
+        for _ in range(3):
+            trainer._step_eager()
+        ops.TIMER = None
+        summ = timer.summary()
+        agg = {k: v for k, v in summ.items() if k.startswith('agg')}
+        dom = max(agg, key=lambda k: agg[k]['ms'])
+        d = agg[dom]
+        achieved = d['bytes'] / (d['ms'] * 1e-3) / 1e9
+        all_b = sum(v['bytes'] for v in agg.values())
+        all_ms = sum(v['ms'] for v in agg.values())
+        roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak,
+                    'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                    'peak_source': peak_src, 'launches_timed': d['launches'],
+                    'avg_launch_us': 1e3 * d['ms'] / d['launches'],
+                    'all_aggregation': {'achieved': all_b / (all_ms * 1e-3) / 1e9,
+                                        'ms_per_step': all_ms / 3,
+                                        'bytes_per_step': all_b / 3},
+                    'gemm': ({'tflops': summ['gemm']['flops'] / (summ['gemm']['ms'] * 1e-3) / 1e12,
+                              'ms_per_step': summ['gemm']['ms'] / 3} if 'gemm' in summ else None)}
+        tr = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.exists(tr):
+            with open(tr) as fh:
+                roofline['traffic'] = json.load(fh).get(dom)
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference(args.cpu_size, 2, 1)
+            cpu_base = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
+                        'sample': r['sample']}
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': _workload_name(args.size), 'operator': 'SAGEConv',
+                       'label': 'style', 'hidden': 128, 'layers': 2,
+                       'artworks_per_gpu': int(x['artwork'].shape[0]),
+                       'directed_edges_per_gpu': n_edges,
+                       'edges_per_step_per_gpu': PASSES * n_edges,
+                       'parallelism': 'single GPU' if world == 1 else
+                                      f'{world} graph blocks, one per GPU; weight-gradient + '
+                                      f'BatchNorm-statistic all-reduce (NCCL)',
+                       'l2_policy': 'inputs larger than L2: features + activations of one step '
+                                    '(~1 GB) exceed the 126 MB L2',
+                       'cuda_graph': not args.no_graph, 'final_loss': final_loss},
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms / args.steps,
+                    'includes': 'pinned-host -> device copy of x_dict and edge_index_dict, CSR/CSC '
+                                're-sort, train step, loss read-back', 'last_loss': l_host},
+            'gpu_launches': int(launches),
+            'clocks': clk,
+            'roofline': roofline,
+            'cpu_baseline': cpu_base,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--size', default='full', help="synthetic graph size of the GPU arm")
+    ap.add_argument('--cpu-size', default='full',
+                    help="graph size of the bounded CPU sample (full: ~8 s per step on 8 cores)")
+    ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA graph')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

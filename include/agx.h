@@ -44,6 +44,8 @@ enum { AGX_SUM = 0, AGX_MEAN = 1 };
 
 int agx_version(void);
 const char* agx_last_error(void);
+/* number of kernels this library has launched (or captured into a CUDA graph) in this process */
+uint64_t agx_launch_count(void);
 /* fills a comma separated list of the __global__ kernels compiled into the library */
 int agx_kernel_inventory(char* h_buf, size_t h_buf_bytes);
 

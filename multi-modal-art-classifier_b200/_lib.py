@@ -82,6 +82,7 @@ class ColsumDesc(C.Structure):
 _SIGS = {
     'agx_version': (C.c_int, []),
     'agx_last_error': (C.c_char_p, []),
+    'agx_launch_count': (C.c_uint64, []),
     'agx_kernel_inventory': (C.c_int, [C.c_char_p, C.c_size_t]),
     'agx_csr_workspace_bytes': (C.c_size_t, [c_i64, c_i64]),
     'agx_csr_build': (C.c_int, [C.POINTER(EdgeList), C.c_int, vp, vp, vp, vp, vp, vp, C.c_size_t,
@@ -163,6 +164,11 @@ def ptr(t: Optional[torch.Tensor]):
     if t is None:
         return None
     return t.data_ptr()
+
+
+def launch_count() -> int:
+    """Kernels launched (or captured) by libagx.so so far in this process."""
+    return int(lib().agx_launch_count())
 
 
 def stream_ptr() -> int:

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "agx_common.cuh"
 
 namespace agx {
@@ -20,7 +22,12 @@ int cuda_fail(cudaError_t e, const char* what) {
     return AGX_ERR_CUDA;
 }
 
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 }  // namespace agx
+
+extern "C" uint64_t agx_launch_count(void) { return agx::g_launches.load(); }
 
 extern "C" int agx_version(void) { return AGX_VERSION; }
 

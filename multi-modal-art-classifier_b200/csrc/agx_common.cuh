@@ -11,6 +11,7 @@ namespace agx {
 
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
+void count_launch();     // bumps the process-wide kernel launch counter (agx_launch_count)
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -37,6 +38,7 @@ constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
     do {                                                            \
         cudaError_t e_ = cudaGetLastError();                        \
         if (e_ != cudaSuccess) return agx::cuda_fail(e_, name);     \
+        agx::count_launch();                                        \
     } while (0)
 
 // 128-bit read-only global load that does not allocate in L1 (streaming gathers)

@@ -76,6 +76,7 @@ class _HeteroConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, spec: ConvSpec, *tensors):
+        ctx.set_materialize_grads(False)      # dead outputs (conv_out of non-artwork types) stay None
         nt = len(spec.node_types)
         xs = {t: tensors[i] for i, t in enumerate(spec.node_types)}
         params = tensors[nt:]
@@ -348,6 +349,7 @@ class _BNActFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, spec: BNSpec, *tensors):
+        ctx.set_materialize_grads(False)
         n, F = spec.n, spec.F
         xs, ws, bs = tensors[:n], tensors[n:2 * n], tensors[2 * n:3 * n]
         dev = xs[0].device

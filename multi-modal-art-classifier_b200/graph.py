@@ -41,8 +41,8 @@ class Relation:
 class HeteroPlan:
     """All relations of one heterograph in device CSR + CSC form."""
 
-    def __init__(self, edge_index_dict, num_nodes: Dict[str, int]):
-        self.num_nodes = dict(num_nodes)
+    def _edge_lists(self, edge_index_dict):
+        num_nodes = self.num_nodes
         lists = []
         keys = list(edge_index_dict.keys())
         for (s, r, d) in keys:
@@ -55,7 +55,29 @@ class HeteroPlan:
         for (s, r, d) in keys:
             ei = edge_index_dict[(s, r, d)]
             lists.append((ei[0], ei[1], num_nodes[s], num_nodes[d]))     # CSC: key = src
-        built = ops.csr_build(lists)
+        return keys, lists
+
+    def rebuild_(self, edge_index_dict):
+        """Re-sort a new edge list of the same shape INTO the existing CSR/CSC tensors (addresses
+        unchanged, nothing synchronises); call ``check()`` afterwards to validate indices."""
+        keys, lists = self._edge_lists(edge_index_dict)
+        if keys != list(self.rels.keys()):
+            raise ValueError('rebuild_: edge types differ from the plan')
+        ops.csr_build(lists, buffers=self._buffers)
+        return self
+
+    def check(self):
+        """Raises IndexError if any sort since construction saw an out-of-range node id (syncs)."""
+        for b in self._buffers:
+            if int(b[4].item()) != 0:
+                raise IndexError('edge_index contains node ids outside [0, num_nodes)')
+
+    def __init__(self, edge_index_dict, num_nodes: Dict[str, int]):
+        self.num_nodes = dict(num_nodes)
+        keys, lists = self._edge_lists(edge_index_dict)
+        self._buffers: list = []
+        built = ops.csr_build(lists, buffers=self._buffers)
+        self.check()
         R = len(keys)
         self.rels: "OrderedDict[EdgeType, Relation]" = OrderedDict()
         for i, (s, r, d) in enumerate(keys):
@@ -76,15 +98,22 @@ def get_plan(edge_index_dict, num_nodes: Dict[str, int], cache: bool = True) -> 
     sorted once, like the reference never re-sorts because it never sorts)."""
     if not cache:
         return HeteroPlan(edge_index_dict, num_nodes)
-    sig = tuple((k, v.data_ptr(), tuple(v.shape), v._version) for k, v in edge_index_dict.items())
+    sig = tuple((k, v.data_ptr(), tuple(v.shape)) for k, v in edge_index_dict.items())
     sig = (sig, tuple(sorted(num_nodes.items())))
+    versions = tuple(v._version for v in edge_index_dict.values())
     plan = _PLAN_CACHE.get(sig)
     if plan is None:
         plan = HeteroPlan(edge_index_dict, num_nodes)
         plan._keepalive = list(edge_index_dict.values())   # pin the addresses the key refers to
+        plan._versions = versions
         _PLAN_CACHE[sig] = plan
         while len(_PLAN_CACHE) > _PLAN_CACHE_MAX:
             _PLAN_CACHE.popitem(last=False)
+    elif plan._versions != versions:
+        # the same tensors were overwritten in place (a new epoch's edge lists copied into static
+        # buffers): re-sort into the plan's existing CSR/CSC tensors, addresses unchanged
+        plan.rebuild_(edge_index_dict)
+        plan._versions = versions
     return plan
 
 

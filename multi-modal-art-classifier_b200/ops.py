@@ -14,6 +14,47 @@ from ._lib import check, lib, ptr, stream_ptr
 
 
 # ------------------------------------------------------------------------------------------------
+# per-kernel-class timing hook (bench.py's roofline leg): CUDA events on the launching stream
+# ------------------------------------------------------------------------------------------------
+class KernelTimer:
+    """When installed as ``ops.TIMER`` every aggregation / GEMM launch group is bracketed by CUDA
+    events on the current stream and its algorithmic bytes / flops are recorded."""
+
+    def __init__(self):
+        self.records = []           # (kind, algorithmic_bytes, flops, start_event, end_event)
+
+    def begin(self):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream())
+        return ev
+
+    def end(self, kind, nbytes, flops, start):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream())
+        self.records.append((kind, nbytes, flops, start, ev))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for kind, nbytes, flops, s, e in self.records:
+            d = out.setdefault(kind, {'launches': 0, 'ms': 0.0, 'bytes': 0, 'flops': 0})
+            d['launches'] += 1
+            d['ms'] += s.elapsed_time(e)
+            d['bytes'] += nbytes
+            d['flops'] += flops
+        return out
+
+
+TIMER: Optional[KernelTimer] = None
+
+
+def aggregation_bytes(n_edges: int, n_rows: int, F: int, elem: int = 4) -> int:
+    """Algorithmic HBM bytes of one relation's aggregation pass:
+    E*(F*s + 4) gathered rows + column ids, (N+1)*4 row pointers, N*F*s output rows."""
+    return n_edges * (F * elem + 4) + (n_rows + 1) * 4 + n_rows * F * elem
+
+
+# ------------------------------------------------------------------------------------------------
 # K1: CSR / CSC
 # ------------------------------------------------------------------------------------------------
 @dataclass
@@ -34,17 +75,29 @@ class CSR:
 
 
 def csr_build(edge_lists: Sequence[Tuple[torch.Tensor, torch.Tensor, int, int]],
-              check_range: bool = True) -> List[CSR]:
+              check_range: bool = True, buffers: Optional[list] = None) -> List[CSR]:
     """``edge_lists``: (keys int64 [E], vals int64 [E], n_rows, n_cols) per relation.  One batched
     stable radix sort (K1) for all of them.  Raises IndexError for out-of-range indices, like the
-    reference's ``index_select`` / ``scatter_add_``."""
+    reference's ``index_select`` / ``scatter_add_``.
+
+    ``buffers``: an (initially empty) list that receives the output / workspace tensors of each
+    batch; passing the same list again re-sorts INTO those tensors (same addresses: a captured
+    CUDA graph that reads the CSR stays valid) and defers the range check to ``buffers`` users
+    (``err`` flags are ``buffers[i][4]``)."""
     out: List[CSR] = []
-    for base in range(0, len(edge_lists), L.MAX_CSR_RELS):
-        out.extend(_csr_build_batch(edge_lists[base:base + L.MAX_CSR_RELS], check_range))
+    for bi, base in enumerate(range(0, len(edge_lists), L.MAX_CSR_RELS)):
+        reuse = None
+        if buffers is not None and bi < len(buffers):
+            reuse = buffers[bi]
+        res, bufs = _csr_build_batch(edge_lists[base:base + L.MAX_CSR_RELS],
+                                     check_range and reuse is None, reuse)
+        if buffers is not None and reuse is None:
+            buffers.append(bufs)
+        out.extend(res)
     return out
 
 
-def _csr_build_batch(edge_lists, check_range) -> List[CSR]:
+def _csr_build_batch(edge_lists, check_range, reuse=None):
     n = len(edge_lists)
     dev = edge_lists[0][0].device
     arr = (L.EdgeList * n)()
@@ -60,13 +113,18 @@ def _csr_build_batch(edge_lists, check_range) -> List[CSR]:
         arr[i] = L.EdgeList(ptr(keys), ptr(vals), keys.numel(), int(n_rows), int(n_cols))
         tot_e += keys.numel()
         tot_r += int(n_rows)
-    rowptr = torch.empty(tot_r + n, dtype=torch.int32, device=dev)
-    col = torch.empty(max(tot_e, 1), dtype=torch.int32, device=dev)
-    eid = torch.empty(max(tot_e, 1), dtype=torch.int32, device=dev)
-    cnt = torch.empty(max(tot_r, 1), dtype=torch.float32, device=dev)
-    err = torch.zeros(1, dtype=torch.int32, device=dev)
     ws_bytes = lib().agx_csr_workspace_bytes(tot_e, tot_r)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    if reuse is not None:
+        rowptr, col, eid, cnt, err, ws = reuse
+        if rowptr.numel() != tot_r + n or col.numel() != max(tot_e, 1) or ws.numel() < ws_bytes:
+            raise ValueError('csr_build: reused buffers do not match the edge lists')
+    else:
+        rowptr = torch.empty(tot_r + n, dtype=torch.int32, device=dev)
+        col = torch.empty(max(tot_e, 1), dtype=torch.int32, device=dev)
+        eid = torch.empty(max(tot_e, 1), dtype=torch.int32, device=dev)
+        cnt = torch.empty(max(tot_r, 1), dtype=torch.float32, device=dev)
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     check(lib().agx_csr_build(arr, n, ptr(rowptr), ptr(col), ptr(eid), ptr(cnt), ptr(err), ptr(ws),
                               ws_bytes, stream_ptr()), 'agx_csr_build')
     if check_range and int(err.item()) != 0:
@@ -79,7 +137,7 @@ def _csr_build_batch(edge_lists, check_range) -> List[CSR]:
                        cnt[r0:r0 + r], r, int(n_cols), e))
         e0 += e
         r0 += r
-    return res
+    return res, [rowptr, col, eid, cnt, err, ws]
 
 
 def coalesce_undirected(row: torch.Tensor, col: torch.Tensor, n_nodes: int) -> torch.Tensor:
@@ -143,7 +201,14 @@ def aggregate_rows(groups: Sequence[Tuple[torch.Tensor, Sequence[RelArg], bool]]
                 len(rels), int(acc)
             for j, a in enumerate(rels):
                 g.rel[j] = _rel_struct(a)
+        t0 = TIMER.begin() if TIMER is not None else None
         check(lib().agx_aggregate_rows(arr, len(part), F, dt, stream_ptr()), 'agx_aggregate_rows')
+        if TIMER is not None:
+            esz = 4 if dt == L.F32 else 2
+            nb = sum(aggregation_bytes(a.csr.n_edges, 0, F, esz) + (out.shape[0] + 1) * 4
+                     for out, rels, _ in part for a in rels)
+            nb += sum(out.shape[0] * F * esz for out, _, _ in part)
+            TIMER.end('agg_rows', nb, 0, t0)
 
 
 def aggregate_chunks(segs: Sequence[Tuple[torch.Tensor, RelArg]], F: int):
@@ -164,8 +229,13 @@ def aggregate_chunks(segs: Sequence[Tuple[torch.Tensor, RelArg]], F: int):
             s.out, s.ldo, s.n_rows, s.n_edges = ptr(out), out.stride(0), out.shape[0], a.csr.n_edges
             s.frag = frag.data_ptr() + 4 * off
             off += sizes[i]
+        t0 = TIMER.begin() if TIMER is not None else None
         check(lib().agx_aggregate_chunks(arr, len(part), F, dt, stream_ptr()),
               'agx_aggregate_chunks')
+        if TIMER is not None:
+            esz = 4 if dt == L.F32 else 2
+            TIMER.end('agg_chunks', sum(aggregation_bytes(a.csr.n_edges, out.shape[0], F, esz)
+                                        for out, a in part), 0, t0)
 
 
 LONG_ROW_AVG_DEGREE = 24.0
@@ -249,8 +319,19 @@ class GemmBatch:
                     sarr[so + t] = self.segs[src.seg_begin + t]
                 q.seg_begin = so
                 so += src.seg_count
+            t0 = TIMER.begin() if TIMER is not None else None
             check(lib().agx_gemm_grouped(parr, j - i, sarr, max(nseg, 1), stream_ptr()),
                   'agx_gemm_grouped')
+            if TIMER is not None:
+                fl = nb = 0
+                for k in range(i, j):
+                    src = self.problems[k]
+                    nb += src.M * src.N * 4
+                    for t in range(src.seg_count):
+                        K = self.segs[src.seg_begin + t].K
+                        fl += 2 * src.M * src.N * K
+                        nb += (src.M + src.N) * K * 4
+                TIMER.end('gemm', nb, fl, t0)
             i = j
         self.problems, self.segs, self._keep = [], [], []
 

