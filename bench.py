@@ -203,6 +203,20 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.ncu:
+        # profiling aid: `ncu --profile-from-start off ... bench.py --ncu` sees exactly one eager
+        # training step (every kernel launched individually, no CUDA graph)
+        trainer.use_cuda_graph = False
+        for _ in range(3):
+            trainer.train_step()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        trainer.train_step()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        print(json.dumps({'ncu_step_done': True, 'loss': float(trainer._loss.item())}))
+        return
+
     # ---- device-resident timing --------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
         trainer.train_step()
@@ -326,6 +340,8 @@ def main():
                     help="graph size of the bounded CPU sample (full: ~8 s per step on 8 cores)")
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA graph')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ncu', action='store_true',
+                    help='run one eager step between cudaProfilerStart/Stop and exit')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -109,33 +109,22 @@ __device__ __forceinline__ void store_vec<__nv_bfloat16, 1>(__nv_bfloat16* p,
 // ------------------------------------------------------------------------------------------------
 // agg_rows
 // ------------------------------------------------------------------------------------------------
+// Direct (un-staged) evaluation of one output row by LPR lanes: the slow path for rows whose
+// neighbour list does not fit the shared-memory staging of agg_rows.
 template <typename T, int VEC, int LPR>
-__global__ void __launch_bounds__(kAggThreads)
-agg_rows(const __grid_constant__ RowGroups P) {
-    constexpr int RPW = 32 / LPR;                  // rows per warp
+__device__ __noinline__ void agg_row_direct(const agx_row_group_t& G, int row, int F, int l) {
     constexpr int U = 4;                           // neighbour rows in flight
-    const int lane = threadIdx.x & 31;
-    const int sub = lane / LPR;
-    const int l = lane % LPR;
-    const int64_t slot = ((int64_t)blockIdx.x * kAggWarps + (threadIdx.x >> 5)) * RPW + sub;
-    if (slot >= P.slot_start[P.n]) return;
-    int gi = 0;
-    while (slot >= P.slot_start[gi + 1]) ++gi;
-    const agx_row_group_t& G = P.g[gi];
-    const int row = (int)(slot - P.slot_start[gi]);
-    const int F = P.F;
-
     for (int c0 = l * VEC; c0 < F; c0 += LPR * VEC) {
         Vec<T, VEC> acc;
         acc.zero();
         for (int r = 0; r < G.n_rel; ++r) {
             const agx_rel_t& R = G.rel[r];
-            const int beg = __ldg(R.rowptr + row), end = __ldg(R.rowptr + row + 1);
             const T* __restrict__ x = reinterpret_cast<const T*>(R.x) + c0;
             Vec<T, VEC> racc;
             racc.zero();
-            int e = beg;
-            for (; e + U <= end; e += U) {
+            const int end_r = __ldg(R.rowptr + row + 1);
+            int e = __ldg(R.rowptr + row);
+            for (; e + U <= end_r; e += U) {
                 int c[U];
                 Vec<T, VEC> v[U];
                 float s[U];
@@ -157,7 +146,7 @@ agg_rows(const __grid_constant__ RowGroups P) {
                         for (int i = 0; i < VEC; ++i) racc.v[i] += v[u].v[i];
                 }
             }
-            for (; e < end; ++e) {
+            for (; e < end_r; ++e) {
                 const int c = __ldg(R.col + e);
                 const Vec<T, VEC> v = load_vec<T, VEC>(x + (int64_t)c * R.ldx);
                 const float s = R.nbr_scale ? 1.0f / __ldg(R.nbr_scale + c) : 1.0f;
@@ -179,6 +168,125 @@ agg_rows(const __grid_constant__ RowGroups P) {
             for (int i = 0; i < VEC; ++i) acc.v[i] += old.v[i];
         }
         store_vec<T, VEC>(o, acc);
+    }
+}
+
+// agg_rows: a warp owns 32 consecutive output rows.
+//   index phase   lane i walks the row extents and neighbour ids of ITS row for every relation of
+//                 the group (coalesced rowptr reads across the warp, all relations issued before
+//                 the first use) and stages up to kRowCap (id, relation, scale) triples in shared
+//                 memory: two dependent memory round trips per 32 rows instead of three per row
+//                 and relation -- short rows are latency-, not bandwidth-bound.
+//   gather phase  the rows are processed one per sub-warp of LPR lanes: ALL feature rows of an
+//                 output row are requested back to back (<= 16 x 512 B in flight per warp), then
+//                 summed in edge order per relation, divided by the relation's count (mean) and
+//                 added in relation order.
+constexpr int kRowCap = 16;
+constexpr int kRowsWarps = 4;
+constexpr int kRowsThreads = kRowsWarps * 32;
+
+template <typename T, int VEC, int LPR>
+__global__ void __launch_bounds__(kRowsThreads)
+agg_rows(const __grid_constant__ RowGroups P) {
+    constexpr int RPW = 32 / LPR;                  // rows gathered concurrently by one warp
+    // per staged edge: address of the source row, multiplier, and "closes its relation" marker
+    // (0 = more edges of the relation follow; d >= 1 = last edge, divide the relation sum by d)
+    __shared__ const T* s_ptr[kRowsWarps][32][kRowCap];
+    __shared__ float s_scl[kRowsWarps][32][kRowCap];
+    __shared__ float s_div[kRowsWarps][32][kRowCap];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int sub = lane / LPR, l = lane % LPR;
+    const int F = P.F;
+    const int64_t slot = ((int64_t)blockIdx.x * kRowsWarps + w) * 32 + lane;
+    const bool valid = slot < P.slot_start[P.n];
+    int gi = 0, row = 0, tot = 0;
+    bool overflow = false;
+    if (valid) {
+        while (slot >= P.slot_start[gi + 1]) ++gi;
+        row = (int)(slot - P.slot_start[gi]);
+        const agx_row_group_t& G = P.g[gi];
+        int beg[AGX_MAX_REL_PER_GROUP], end[AGX_MAX_REL_PER_GROUP];
+#pragma unroll
+        for (int r = 0; r < AGX_MAX_REL_PER_GROUP; ++r) {
+            beg[r] = end[r] = 0;
+            if (r < G.n_rel) {
+                beg[r] = __ldg(G.rel[r].rowptr + row);
+                end[r] = __ldg(G.rel[r].rowptr + row + 1);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < AGX_MAX_REL_PER_GROUP; ++r) {
+            if (r < G.n_rel && beg[r] < end[r]) {
+                const agx_rel_t& R = G.rel[r];
+                const float d = R.row_cnt ? __ldg(R.row_cnt + row) : 1.0f;
+                const T* xb = reinterpret_cast<const T*>(R.x);
+                for (int e = beg[r]; e < end[r]; ++e) {
+                    if (tot < kRowCap) {
+                        const int c = __ldg(R.col + e);
+                        s_ptr[w][lane][tot] = xb + (int64_t)c * R.ldx;
+                        s_scl[w][lane][tot] = R.nbr_scale ? 1.0f / __ldg(R.nbr_scale + c) : 1.0f;
+                        s_div[w][lane][tot] = (e + 1 == end[r]) ? d : 0.f;
+                        ++tot;
+                    } else {
+                        overflow = true;
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+
+    for (int j0 = 0; j0 < 32; j0 += RPW) {
+        const int j = j0 + sub;
+        const bool vj = __shfl_sync(0xffffffffu, valid ? 1 : 0, j) != 0;
+        const bool oj = __shfl_sync(0xffffffffu, overflow ? 1 : 0, j) != 0;
+        const int gj = __shfl_sync(0xffffffffu, gi, j);
+        const int rj = __shfl_sync(0xffffffffu, row, j);
+        const int nj = __shfl_sync(0xffffffffu, tot, j);
+        if (!vj) continue;
+        const agx_row_group_t& G = P.g[gj];
+        if (oj) {
+            agg_row_direct<T, VEC, LPR>(G, rj, F, l);
+            continue;
+        }
+        for (int c0 = l * VEC; c0 < F; c0 += LPR * VEC) {
+            Vec<T, VEC> acc, racc;
+            acc.zero();
+            racc.zero();
+            for (int base = 0; base < nj; base += 8) {          // <= 2 rounds (kRowCap = 16)
+                Vec<T, VEC> v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (base + u < nj) v[u] = load_vec<T, VEC>(s_ptr[w][j][base + u] + c0);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (base + u < nj) {
+                        const float s = s_scl[w][j][base + u];      // 1.0 when unscaled: exact
+                        const float d = s_div[w][j][base + u];
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) racc.v[i] = fmaf(v[u].v[i], s, racc.v[i]);
+                        if (d != 0.f) {                             // last edge of its relation
+                            if (d > 1.f) {
+#pragma unroll
+                                for (int i = 0; i < VEC; ++i) racc.v[i] = racc.v[i] / d;
+                            }
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) {
+                                acc.v[i] += racc.v[i];
+                                racc.v[i] = 0.f;
+                            }
+                        }
+                    }
+                }
+            }
+            T* o = reinterpret_cast<T*>(G.out) + (int64_t)rj * G.ldo + c0;
+            if (G.accumulate) {
+                const Vec<T, VEC> old = load_vec<T, VEC>(o);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc.v[i] += old.v[i];
+            }
+            store_vec<T, VEC>(o, acc);
+        }
     }
 }
 
@@ -282,7 +390,12 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(kAggThreads)
 agg_chunks_fixup(const __grid_constant__ ChunkSegs P) {
     const int lane = threadIdx.x & 31;
-    const int64_t gchunk = (int64_t)blockIdx.x * kAggWarps + (threadIdx.x >> 5);
+    // one CTA per chunk; the (rare) owning CTAs spread the row's fragments over their 8 warps:
+    // warp w adds lead[chunk+1+w], lead[chunk+1+w+8], ... and warp 0 combines trail + the 8 warp
+    // sums in warp order -- a fixed order, so the result is reproducible.
+    __shared__ float wsum[kAggWarps][128 + 4];
+    const int w = threadIdx.x >> 5;
+    const int64_t gchunk = blockIdx.x;
     if (gchunk >= P.chunk_start[P.n]) return;
     int si = 0;
     while (gchunk >= P.chunk_start[si + 1]) ++si;
@@ -296,34 +409,51 @@ agg_chunks_fixup(const __grid_constant__ ChunkSegs P) {
     if (end >= S.n_edges) return;                       // last chunk cannot own a spanning row
     const int row = upper_bound_i32(R.rowptr, S.n_rows + 1, end - 1) - 1;   // row of the last edge
     const int rbeg = __ldg(R.rowptr + row), rend = __ldg(R.rowptr + row + 1);
-    if (!(rend > end && rbeg >= start)) return;
+    if (!(rend > end && rbeg >= start)) return;          // uniform over the CTA
     const int c_last = (rend - 1) / AGX_CHUNK_EDGES;
     const float* lead = S.frag;
     const float* trail = S.frag + (size_t)nchunks * F;
-    for (int c0 = lane * VEC; c0 < F; c0 += 32 * VEC) {
-        float acc[VEC];
+    for (int cb = 0; cb < F; cb += 128) {                // 128 columns per round (smem staging)
+        const int cw = min(128, F - cb);
+        for (int c0 = lane * VEC; c0 < cw; c0 += 32 * VEC) {
+            float acc[VEC];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) acc[i] = trail[(size_t)chunk * F + c0 + i];
-        int c = chunk + 1;
-        for (; c + 4 <= c_last + 1; c += 4) {
-            float t[4][VEC];
+            for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+            int c = chunk + 1 + w;
+            for (; c + 3 * kAggWarps <= c_last; c += 4 * kAggWarps) {
+                float t[4][VEC];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < 4; ++u)
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) t[u][i] = lead[(size_t)(c + u) * F + c0 + i];
+                    for (int i = 0; i < VEC; ++i)
+                        t[u][i] = lead[(size_t)(c + u * kAggWarps) * F + cb + c0 + i];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < 4; ++u)
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) acc[i] += t[u][i];
+                    for (int i = 0; i < VEC; ++i) acc[i] += t[u][i];
+            }
+            for (; c <= c_last; c += kAggWarps)
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[i] += lead[(size_t)c * F + cb + c0 + i];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) wsum[w][c0 + i] = acc[i];
         }
-        for (; c <= c_last; ++c)
+        __syncthreads();
+        if (w == 0) {
+            for (int c0 = lane * VEC; c0 < cw; c0 += 32 * VEC) {
+                Vec<T, VEC> o;
+                const float d = R.row_cnt ? __ldg(R.row_cnt + row) : 1.0f;
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) acc[i] += lead[(size_t)c * F + c0 + i];
-        Vec<T, VEC> o;
-        const float d = R.row_cnt ? __ldg(R.row_cnt + row) : 1.0f;
+                for (int i = 0; i < VEC; ++i) {
+                    float a = trail[(size_t)chunk * F + cb + c0 + i];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) o.v[i] = R.row_cnt ? acc[i] / d : acc[i];
-        store_vec<T, VEC>(reinterpret_cast<T*>(S.out) + (int64_t)row * S.ldo + c0, o);
+                    for (int k = 0; k < kAggWarps; ++k) a += wsum[k][c0 + i];
+                    o.v[i] = R.row_cnt ? a / d : a;
+                }
+                store_vec<T, VEC>(reinterpret_cast<T*>(S.out) + (int64_t)row * S.ldo + cb + c0, o);
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -333,8 +463,8 @@ template <typename T, int VEC>
 static int launch_rows(const RowGroups& P, int lpr, int64_t slots, cudaStream_t st) {
 #define AGX_ROWS_CASE(L)                                                                  \
     case L: {                                                                             \
-        const int64_t per_block = (int64_t)kAggWarps * (32 / L);                          \
-        agg_rows<T, VEC, L><<<(unsigned)ceil_div(slots, per_block), kAggThreads, 0, st>>>(P); \
+        const int64_t per_block = (int64_t)kRowsWarps * 32;   /* 32 row slots per warp */   \
+        agg_rows<T, VEC, L><<<(unsigned)ceil_div(slots, per_block), kRowsThreads, 0, st>>>(P); \
         break;                                                                            \
     }
     switch (lpr) {
@@ -443,21 +573,21 @@ extern "C" int agx_aggregate_chunks(const agx_chunk_seg_t* h_segs, int n_segs, i
         if (vec_ok) {
             agg_chunks<float, 4><<<grid, kAggThreads, 0, st>>>(P);
             AGX_LAUNCH_CHECK("agg_chunks");
-            agg_chunks_fixup<float, 4><<<grid, kAggThreads, 0, st>>>(P);
+            agg_chunks_fixup<float, 4><<<(unsigned)chunks, kAggThreads, 0, st>>>(P);
         } else {
             agg_chunks<float, 1><<<grid, kAggThreads, 0, st>>>(P);
             AGX_LAUNCH_CHECK("agg_chunks");
-            agg_chunks_fixup<float, 1><<<grid, kAggThreads, 0, st>>>(P);
+            agg_chunks_fixup<float, 1><<<(unsigned)chunks, kAggThreads, 0, st>>>(P);
         }
     } else {
         if (vec_ok) {
             agg_chunks<__nv_bfloat16, 8><<<grid, kAggThreads, 0, st>>>(P);
             AGX_LAUNCH_CHECK("agg_chunks");
-            agg_chunks_fixup<__nv_bfloat16, 8><<<grid, kAggThreads, 0, st>>>(P);
+            agg_chunks_fixup<__nv_bfloat16, 8><<<(unsigned)chunks, kAggThreads, 0, st>>>(P);
         } else {
             agg_chunks<__nv_bfloat16, 1><<<grid, kAggThreads, 0, st>>>(P);
             AGX_LAUNCH_CHECK("agg_chunks");
-            agg_chunks_fixup<__nv_bfloat16, 1><<<grid, kAggThreads, 0, st>>>(P);
+            agg_chunks_fixup<__nv_bfloat16, 1><<<(unsigned)chunks, kAggThreads, 0, st>>>(P);
         }
     }
     AGX_LAUNCH_CHECK("agg_chunks_fixup");

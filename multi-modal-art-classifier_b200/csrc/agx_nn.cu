@@ -41,7 +41,7 @@ struct BnParams {
     int32_t slab_start[AGX_MAX_GROUPS + 1];
     int32_t n;
     int32_t F;
-    float* ws;            // [2][total_slabs][F] partials
+    double* ws;           // [total_slabs][F] float64 partials
     int32_t training;
     float momentum, eps;
 };
@@ -54,25 +54,26 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats(const __grid_constant__ B
     const int slab = blockIdx.x - P.slab_start[di];
     const int r0 = slab * kBnSlab, r1 = min(D.n_rows, r0 + kBnSlab);
     const int F = P.F;
-    float* part = P.ws + (size_t)blockIdx.x * F;
-    // thread t owns column (t % F) for F <= 256 lanes-of-columns; row groups stride over t / F
-    __shared__ float red[kBnThreads];
+    double* part = P.ws + (size_t)blockIdx.x * F;
+    // thread t owns column (t % F) for F <= 256 lanes-of-columns; row groups stride over t / F.
+    // float64 accumulation: the reference's CPU BatchNorm accumulates its statistics in double
+    __shared__ double red[kBnThreads];
     for (int c0 = 0; c0 < F; c0 += kBnThreads) {
         const int cols = min(kBnThreads, F - c0);
         const int groups = kBnThreads / cols > 0 ? kBnThreads / cols : 1;   // row groups
         const int c = threadIdx.x % cols, g = threadIdx.x / cols;
-        float s = 0.f;
+        double s = 0.0;
         if (g < groups) {
-            const float m = pass ? D.save_mean[c0 + c] : 0.f;
+            const double m = pass ? (double)D.save_mean[c0 + c] : 0.0;
             for (int r = r0 + g; r < r1; r += groups) {
-                const float v = D.x[(int64_t)r * F + c0 + c] - m;
+                const double v = (double)D.x[(int64_t)r * F + c0 + c] - m;
                 s += pass ? v * v : v;
             }
         }
         red[threadIdx.x] = s;
         __syncthreads();
         if (threadIdx.x < cols) {
-            float t = 0.f;
+            double t = 0.0;
             for (int gg = 0; gg < groups; ++gg) t += red[gg * cols + threadIdx.x];
             part[c0 + threadIdx.x] = t;
         }
@@ -80,21 +81,43 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats(const __grid_constant__ B
     }
 }
 
-// one CTA per descriptor; thread per column, float64 combination of slab partials
-__global__ void __launch_bounds__(256) bn_finalize(const __grid_constant__ BnParams P, int pass) {
+// Ordered float64 total of per-slab partials for 32 consecutive columns: 1024 threads =
+// 32 columns x 32 slab groups; group g adds slabs g, g+32, ... and the 32 group sums are then added
+// in group order by the column's first thread.  part[s * stride + col].  Returns the total in the
+// threads with threadIdx.x < 32 (column = col0 + threadIdx.x).
+__device__ __forceinline__ double slab_total_32x32(const double* __restrict__ part, int slabs,
+                                                   size_t stride, int col0, int ncols,
+                                                   double (*sm)[33]) {
+    const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+    double a = 0.0;
+    if (col0 + c < ncols)
+        for (int s = g; s < slabs; s += 32) a += part[(size_t)s * stride + col0 + c];
+    sm[g][c] = a;
+    __syncthreads();
+    double t = 0.0;
+    if (g == 0)
+        for (int k = 0; k < 32; ++k) t += sm[k][c];
+    __syncthreads();
+    return t;
+}
+
+// grid (descriptor, 32-column block); float64 combination of slab partials
+__global__ void __launch_bounds__(1024) bn_finalize(const __grid_constant__ BnParams P, int pass) {
+    __shared__ double sm[32][33];
     const agx_bn_desc_t& D = P.d[blockIdx.x];
     const int s0 = P.slab_start[blockIdx.x], s1 = P.slab_start[blockIdx.x + 1];
     const int F = P.F;
-    for (int c = threadIdx.x; c < F; c += blockDim.x) {
-        if (!P.training) {
-            if (pass == 0) {
-                D.save_mean[c] = D.running_mean[c];
-                D.save_invstd[c] = (float)(1.0 / sqrt((double)D.running_var[c] + (double)P.eps));
-            }
-            continue;
+    const int col0 = blockIdx.y * 32;
+    const int c = col0 + (int)threadIdx.x;
+    if (!P.training) {
+        if (pass == 0 && threadIdx.x < 32 && c < F) {
+            D.save_mean[c] = D.running_mean[c];
+            D.save_invstd[c] = (float)(1.0 / sqrt((double)D.running_var[c] + (double)P.eps));
         }
-        double acc = 0.0;
-        for (int s = s0; s < s1; ++s) acc += (double)P.ws[(size_t)s * F + c];
+        return;
+    }
+    const double acc = slab_total_32x32(P.ws + (size_t)s0 * F, s1 - s0, F, col0, F, sm);
+    if (threadIdx.x < 32 && c < F) {
         const double n = (double)D.n_rows;
         if (pass == 0) {
             D.save_mean[c] = (float)(acc / n);
@@ -120,6 +143,32 @@ __global__ void __launch_bounds__(256) bn_apply(const __grid_constant__ BnParams
     const int F = P.F;
     const int64_t e0 = (int64_t)slab * kBnSlab * F;
     const int64_t e1 = min((int64_t)D.n_rows * F, e0 + (int64_t)kBnSlab * F);
+    if ((F & 3) == 0) {      // 128-bit path (rows are 16-byte aligned: torch allocations, F % 4 == 0)
+        for (int64_t e = e0 + 4 * (int64_t)threadIdx.x; e < e1; e += 4 * (int64_t)blockDim.x) {
+            const int c = (int)(e % F);
+            const float4 x = *reinterpret_cast<const float4*>(D.x + e);
+            const float4 m = *reinterpret_cast<const float4*>(D.save_mean + c);
+            const float4 is = *reinterpret_cast<const float4*>(D.save_invstd + c);
+            const float4 wv = *reinterpret_cast<const float4*>(D.weight + c);
+            const float4 bv = *reinterpret_cast<const float4*>(D.bias + c);
+            float4 y;
+            y.x = (x.x - m.x) * is.x * wv.x + bv.x;
+            y.y = (x.y - m.y) * is.y * wv.y + bv.y;
+            y.z = (x.z - m.z) * is.z * wv.z + bv.z;
+            y.w = (x.w - m.w) * is.w * wv.w + bv.w;
+            *reinterpret_cast<float4*>(D.y + e) = y;
+            if (D.y_act) {
+                float4 a = make_float4(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f), fmaxf(y.z, 0.f),
+                                       fmaxf(y.w, 0.f));
+                if (D.dmask) {
+                    const float4 k = *reinterpret_cast<const float4*>(D.dmask + e);
+                    a.x *= k.x; a.y *= k.y; a.z *= k.z; a.w *= k.w;
+                }
+                *reinterpret_cast<float4*>(D.y_act + e) = a;
+            }
+        }
+        return;
+    }
     for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
         const int c = (int)(e % F);
         const float xh = (D.x[e] - D.save_mean[c]) * D.save_invstd[c];
@@ -138,7 +187,7 @@ struct BnBwdParams {
     int32_t slab_start[AGX_MAX_GROUPS + 1];
     int32_t n;
     int32_t F;
-    float* ws;            // [total_slabs][2F] partials: sum dy, sum dy*xhat ; then [n][2F] totals
+    double* ws;           // [total_slabs][2F] float64 partials: sum dy, sum dy*xhat
     float* totals;
     int32_t training;
 };
@@ -161,27 +210,27 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce(const __grid_constan
     const int slab = blockIdx.x - P.slab_start[di];
     const int r0 = slab * kBnSlab, r1 = min(D.n_rows, r0 + kBnSlab);
     const int F = P.F;
-    float* part = P.ws + (size_t)blockIdx.x * 2 * F;
-    __shared__ float red0[kBnThreads], red1[kBnThreads];
+    double* part = P.ws + (size_t)blockIdx.x * 2 * F;
+    __shared__ double red0[kBnThreads], red1[kBnThreads];
     for (int c0 = 0; c0 < F; c0 += kBnThreads) {
         const int cols = min(kBnThreads, F - c0);
         const int groups = kBnThreads / cols > 0 ? kBnThreads / cols : 1;
         const int c = threadIdx.x % cols, g = threadIdx.x / cols;
-        float s0 = 0.f, s1 = 0.f;
+        double s0 = 0.0, s1 = 0.0;
         if (g < groups) {
             const float m = D.save_mean[c0 + c], is = D.save_invstd[c0 + c];
             for (int r = r0 + g; r < r1; r += groups) {
                 const int64_t e = (int64_t)r * F + c0 + c;
                 const float gy = bn_dy_total(D, e);
-                s0 += gy;
-                s1 += gy * (D.x[e] - m) * is;
+                s0 += (double)gy;
+                s1 += (double)gy * (double)((D.x[e] - m) * is);
             }
         }
         red0[threadIdx.x] = s0;
         red1[threadIdx.x] = s1;
         __syncthreads();
         if (threadIdx.x < cols) {
-            float t0 = 0.f, t1 = 0.f;
+            double t0 = 0.0, t1 = 0.0;
             for (int gg = 0; gg < groups; ++gg) {
                 t0 += red0[gg * cols + threadIdx.x];
                 t1 += red1[gg * cols + threadIdx.x];
@@ -193,16 +242,17 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce(const __grid_constan
     }
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_finalize(const __grid_constant__ BnBwdParams P) {
+__global__ void __launch_bounds__(1024) bn_bwd_finalize(const __grid_constant__ BnBwdParams P) {
+    __shared__ double sm[32][33];
     const agx_bn_bwd_desc_t& D = P.d[blockIdx.x];
     const int s0 = P.slab_start[blockIdx.x], s1 = P.slab_start[blockIdx.x + 1];
     const int F = P.F;
-    for (int c = threadIdx.x; c < F; c += blockDim.x) {
-        double a0 = 0.0, a1 = 0.0;
-        for (int s = s0; s < s1; ++s) {
-            a0 += (double)P.ws[(size_t)s * 2 * F + c];
-            a1 += (double)P.ws[(size_t)s * 2 * F + F + c];
-        }
+    const int col0 = blockIdx.y * 32;
+    const double* part = P.ws + (size_t)s0 * 2 * F;
+    const double a0 = slab_total_32x32(part, s1 - s0, (size_t)2 * F, col0, F, sm);
+    const double a1 = slab_total_32x32(part + F, s1 - s0, (size_t)2 * F, col0, F, sm);
+    const int c = col0 + (int)threadIdx.x;
+    if (threadIdx.x < 32 && c < F) {
         P.totals[(size_t)blockIdx.x * 2 * F + c] = (float)a0;
         P.totals[(size_t)blockIdx.x * 2 * F + F + c] = (float)a1;
         if (D.dbias) D.dbias[c] += (float)a0;
@@ -244,10 +294,10 @@ struct ColsumParams {
     int32_t slab_start[AGX_MAX_TENSORS + 1];
     int32_t part_start[AGX_MAX_TENSORS + 1];     // float offset of the descriptor's partials
     int32_t n;
-    float* ws;
+    double* ws;
 };
 
-constexpr int kColsumSlab = 512;
+constexpr int kColsumSlab = 128;
 
 __global__ void __launch_bounds__(256) colsum_partial(const __grid_constant__ ColsumParams P) {
     int di = 0;
@@ -256,19 +306,19 @@ __global__ void __launch_bounds__(256) colsum_partial(const __grid_constant__ Co
     const int slab = blockIdx.x - P.slab_start[di];
     const int r0 = slab * kColsumSlab, r1 = min(D.n_rows, r0 + kColsumSlab);
     const int F = D.F;
-    float* part = P.ws + P.part_start[di] + (size_t)slab * F;
-    __shared__ float red[256];
+    double* part = P.ws + P.part_start[di] + (size_t)slab * F;
+    __shared__ double red[256];
     for (int c0 = 0; c0 < F; c0 += 256) {
         const int cols = min(256, F - c0);
         const int groups = 256 / cols > 0 ? 256 / cols : 1;
         const int c = threadIdx.x % cols, g = threadIdx.x / cols;
-        float s = 0.f;
+        double s = 0.0;
         if (g < groups)
-            for (int r = r0 + g; r < r1; r += groups) s += D.x[(int64_t)r * D.ldx + c0 + c];
+            for (int r = r0 + g; r < r1; r += groups) s += (double)D.x[(int64_t)r * D.ldx + c0 + c];
         red[threadIdx.x] = s;
         __syncthreads();
         if (threadIdx.x < cols) {
-            float t = 0.f;
+            double t = 0.0;
             for (int gg = 0; gg < groups; ++gg) t += red[gg * cols + threadIdx.x];
             part[c0 + threadIdx.x] = t;
         }
@@ -276,14 +326,15 @@ __global__ void __launch_bounds__(256) colsum_partial(const __grid_constant__ Co
     }
 }
 
-__global__ void __launch_bounds__(256) colsum_final(const __grid_constant__ ColsumParams P) {
+__global__ void __launch_bounds__(1024) colsum_final(const __grid_constant__ ColsumParams P) {
+    __shared__ double sm[32][33];
     const agx_colsum_desc_t& D = P.d[blockIdx.x];
     const int slabs = P.slab_start[blockIdx.x + 1] - P.slab_start[blockIdx.x];
-    const float* part = P.ws + P.part_start[blockIdx.x];
-    for (int c = threadIdx.x; c < D.F; c += blockDim.x) {
-        double a = 0.0;
-        for (int s = 0; s < slabs; ++s) a += (double)part[(size_t)s * D.F + c];
-        D.out[c] = D.accumulate ? D.out[c] + (float)a : (float)a;
+    const double* part = P.ws + P.part_start[blockIdx.x];
+    for (int col0 = blockIdx.y * 32; col0 < D.F; col0 += gridDim.y * 32) {
+        const double a = slab_total_32x32(part, slabs, D.F, col0, D.F, sm);
+        const int c = col0 + (int)threadIdx.x;
+        if (threadIdx.x < 32 && c < D.F) D.out[c] = D.accumulate ? D.out[c] + (float)a : (float)a;
     }
 }
 
@@ -625,7 +676,7 @@ extern "C" int agx_sum_arrays(const agx_sum_desc_t* h_descs, int n, void* stream
 
 extern "C" size_t agx_bn_workspace_floats(int64_t total_rows, int n_descs, int F) {
     const int64_t slabs = ceil_div(total_rows, kBnSlab) + n_descs;
-    return (size_t)(slabs * 2 * F) + (size_t)n_descs * 2 * F;
+    return 2 * (size_t)(slabs * 2 * F) + (size_t)n_descs * 2 * F;   // float64 partials + float totals
 }
 
 extern "C" int agx_bn_forward(const agx_bn_desc_t* h_descs, int n, int F, int training,
@@ -636,7 +687,7 @@ extern "C" int agx_bn_forward(const agx_bn_desc_t* h_descs, int n, int F, int tr
     BnParams P;
     P.n = n;
     P.F = F;
-    P.ws = workspace;
+    P.ws = reinterpret_cast<double*>(workspace);
     P.training = training;
     P.momentum = momentum;
     P.eps = eps;
@@ -665,14 +716,14 @@ extern "C" int agx_bn_forward(const agx_bn_desc_t* h_descs, int n, int F, int tr
     if (training && slabs > 0) {
         bn_stats<<<slabs, kBnThreads, 0, st>>>(P, 0);
         AGX_LAUNCH_CHECK("bn_stats");
-        bn_finalize<<<n, 256, 0, st>>>(P, 0);
+        bn_finalize<<<dim3(n, (F + 31) / 32), 1024, 0, st>>>(P,0);
         AGX_LAUNCH_CHECK("bn_finalize");
         bn_stats<<<slabs, kBnThreads, 0, st>>>(P, 1);
         AGX_LAUNCH_CHECK("bn_stats");
-        bn_finalize<<<n, 256, 0, st>>>(P, 1);
+        bn_finalize<<<dim3(n, (F + 31) / 32), 1024, 0, st>>>(P,1);
         AGX_LAUNCH_CHECK("bn_finalize");
     } else {
-        bn_finalize<<<n, 256, 0, st>>>(P, 0);
+        bn_finalize<<<dim3(n, (F + 31) / 32), 1024, 0, st>>>(P,0);
         AGX_LAUNCH_CHECK("bn_finalize");
     }
     if (slabs > 0) {
@@ -705,13 +756,13 @@ extern "C" int agx_bn_backward(const agx_bn_bwd_desc_t* h_descs, int n, int F, i
         return AGX_ERR_WORKSPACE;
     }
     const int slabs = P.slab_start[n];
-    P.ws = workspace;
-    P.totals = workspace + (size_t)slabs * 2 * F;
+    P.ws = reinterpret_cast<double*>(workspace);
+    P.totals = workspace + 2 * (size_t)slabs * 2 * F;
     cudaStream_t st = (cudaStream_t)stream;
     if (slabs == 0) return AGX_OK;
     bn_bwd_reduce<<<slabs, kBnThreads, 0, st>>>(P);
     AGX_LAUNCH_CHECK("bn_bwd_reduce");
-    bn_bwd_finalize<<<n, 256, 0, st>>>(P);
+    bn_bwd_finalize<<<dim3(n, (F + 31) / 32), 1024, 0, st>>>(P);
     AGX_LAUNCH_CHECK("bn_bwd_finalize");
     bn_bwd_apply<<<slabs, 256, 0, st>>>(P);
     AGX_LAUNCH_CHECK("bn_bwd_apply");
@@ -719,7 +770,7 @@ extern "C" int agx_bn_backward(const agx_bn_bwd_desc_t* h_descs, int n, int F, i
 }
 
 extern "C" size_t agx_colsum_workspace_floats(int64_t total_rows, int n_descs, int max_F) {
-    return (size_t)(ceil_div(total_rows, kColsumSlab) + n_descs) * (size_t)max_F;
+    return 2 * (size_t)(ceil_div(total_rows, kColsumSlab) + n_descs) * (size_t)max_F;   // float64
 }
 
 extern "C" int agx_colsum(const agx_colsum_desc_t* h_descs, int n, float* workspace,
@@ -727,7 +778,7 @@ extern "C" int agx_colsum(const agx_colsum_desc_t* h_descs, int n, float* worksp
     AGX_CHECK_ARG(h_descs && n >= 1 && n <= AGX_MAX_TENSORS, "agx_colsum: n=%d", n);
     ColsumParams P;
     P.n = n;
-    P.ws = workspace;
+    P.ws = reinterpret_cast<double*>(workspace);
     P.slab_start[0] = 0;
     P.part_start[0] = 0;
     for (int i = 0; i < n; ++i) {
@@ -738,7 +789,7 @@ extern "C" int agx_colsum(const agx_colsum_desc_t* h_descs, int n, float* worksp
         P.slab_start[i + 1] = P.slab_start[i] + slabs;
         P.part_start[i + 1] = P.part_start[i] + slabs * h_descs[i].F;
     }
-    if ((size_t)P.part_start[n] > workspace_floats || (P.part_start[n] > 0 && !workspace)) {
+    if (2 * (size_t)P.part_start[n] > workspace_floats || (P.part_start[n] > 0 && !workspace)) {
         set_error("agx_colsum: workspace too small (%d floats needed)", P.part_start[n]);
         return AGX_ERR_WORKSPACE;
     }
@@ -747,7 +798,7 @@ extern "C" int agx_colsum(const agx_colsum_desc_t* h_descs, int n, float* worksp
         colsum_partial<<<P.slab_start[n], 256, 0, st>>>(P);
         AGX_LAUNCH_CHECK("colsum_partial");
     }
-    colsum_final<<<n, 256, 0, st>>>(P);
+    colsum_final<<<dim3(n, 4), 1024, 0, st>>>(P);
     AGX_LAUNCH_CHECK("colsum_final");
     return AGX_OK;
 }

@@ -22,7 +22,8 @@ from ._lib import check, lib, ptr, stream_ptr
 from .graph import HeteroPlan, Relation
 
 # relative cost model for choosing transform-first vs aggregate-first per relation
-_FLOP_RATE = 40e12      # sustained fp32 FFMA flop/s of the grouped GEMM
+_FLOP_RATE = 40e12      # sustained fp32 FFMA flop/s of the grouped GEMM (whole chip)
+_CTA_FLOP_RATE = 0.25e12  # one CTA's share: latency floor of a problem with a single row tile
 _BYTE_RATE = 5e12       # gather bandwidth
 
 
@@ -45,15 +46,29 @@ class ConvSpec:
     dst_types: List[str] = field(default_factory=list)   # output order
     identity: Dict[str, bool] = field(default_factory=dict)   # type -> x[type] is eye(N)
     planned: bool = False
+    param_refs: Optional[list] = None    # the nn.Parameters behind the flat parameter list
 
     def plan_modes(self, feat_dims: Dict[str, int]):
+        """Per relation: transform-first (Y = X_src W_l^T, gather at width O) or aggregate-first
+        (gather at width F_src, product on the N_dst rows), whichever moves fewer bytes / flops.
+        A GEMM with few output rows runs on few CTAs, so its cost is floored by the serial
+        K-loop of one CTA (~_CTA_FLOP_RATE); one-hot sources make the transform a transposed
+        copy of the weight."""
         O = self.out_channels
         for rs in self.rels:
             r = rs.rel
             fs = feat_dims[r.src]
-            tf = 2.0 * r.n_src * fs * O / _FLOP_RATE + r.n_edges * O * 4.0 / _BYTE_RATE
-            af = r.n_edges * fs * 4.0 / _BYTE_RATE + 2.0 * r.n_dst * fs * O / _FLOP_RATE
-            rs.transform_first = tf < af
+
+            def gemm_cost(m):
+                flops = 2.0 * m * fs * O
+                return max(flops / _FLOP_RATE, 2.0 * min(m, 128) * fs * O / _CTA_FLOP_RATE)
+            if self.identity.get(r.src, False):
+                tf = r.n_src * O * 8.0 / _BYTE_RATE
+            else:
+                tf = gemm_cost(r.n_src)
+            tf += r.n_edges * O * 4.0 / _BYTE_RATE
+            af = r.n_edges * fs * 4.0 / _BYTE_RATE + gemm_cost(r.n_dst)
+            rs.transform_first = tf < af or (tf <= af * 1.05 and r.n_src <= r.n_dst)
         self.dst_types = []
         for rs in self.rels:
             if rs.rel.dst not in self.dst_types:
@@ -139,14 +154,25 @@ class _HeteroConvFn(torch.autograd.Function):
         rows_by_F: Dict[int, list] = {}
         chunks_by_F: Dict[int, list] = {}
         id_root: Dict[str, bool] = {}
+        tf_long: Dict[str, list] = {}
         for t, lst in by_dst.items():
             outs[t] = torch.empty(lst[0].rel.n_dst, O, dtype=torch.float32, device=dev)
             # root product against one-hot features: x[t] W^T = W^T, written first, rest accumulates
             id_root[t] = bool(spec.identity.get(t, False)) and wroot[t] is not None
             if id_root[t]:
                 ops.transpose_into(outs[t], wroot[t])
-            tf = [(k, rs) for k, rs in enumerate(spec.rels) if rs.rel.dst == t and rs.transform_first]
-            has_tf[t] = bool(tf) or id_root[t]
+            tf_all = [(k, rs) for k, rs in enumerate(spec.rels)
+                      if rs.rel.dst == t and rs.transform_first]
+            has_tf[t] = bool(tf_all) or id_root[t]
+            # transform-first relations with long / skewed rows: edge-balanced kernel into a
+            # private [N_dst, O] buffer (N_dst is small there), summed into out[t] afterwards
+            tf = [(k, rs) for k, rs in tf_all if not rs.rel.csr.long_rows]
+            for k, rs in tf_all:
+                if rs.rel.csr.long_rows:
+                    tmp = torch.empty_like(outs[t])
+                    tf_long.setdefault(t, []).append(tmp)
+                    chunks_by_F.setdefault(O, []).append(
+                        (tmp, ops.RelArg(rs.rel.csr, Y[k], mean_rows=rs.mean)))
             for base in range(0, len(tf), L.MAX_REL_PER_GROUP):
                 part = tf[base:base + L.MAX_REL_PER_GROUP]
                 # groups that accumulate onto the same output go to later launches ("waves")
@@ -161,7 +187,7 @@ class _HeteroConvFn(torch.autograd.Function):
             g = torch.empty(r.n_dst, fs, dtype=torch.float32, device=dev)
             G[k] = g
             arg = ops.RelArg(r.csr, xs[r.src], mean_rows=rs.mean)
-            if r.csr.avg_degree > ops.LONG_ROW_AVG_DEGREE:
+            if r.csr.long_rows:
                 chunks_by_F.setdefault(fs, []).append((g, arg))
             else:
                 rows_by_F.setdefault((0, fs), []).append((g, [arg], False))
@@ -169,6 +195,17 @@ class _HeteroConvFn(torch.autograd.Function):
             ops.aggregate_rows(rows_by_F[(wave, F)], F)
         for F, segs in chunks_by_F.items():
             ops.aggregate_chunks(segs, F)
+        if tf_long:
+            items = []
+            for t, temps in tf_long.items():
+                already = id_root[t] or any(rs.transform_first and not rs.rel.csr.long_rows
+                                            for rs in by_dst[t])
+                ins = ([outs[t]] if already else []) + temps
+                while len(ins) > 8:                       # chain (in place, elementwise)
+                    ops.sum_arrays([(outs[t], ins[:8])])
+                    ins = [outs[t]] + ins[8:]
+                items.append((outs[t], ins))
+            ops.sum_arrays(items)
 
         # s3: one multi-segment GEMM per destination type
         gb = ops.GemmBatch()
@@ -243,7 +280,7 @@ class _HeteroConvFn(torch.autograd.Function):
             dY[k] = dy
             arg = ops.RelArg(r.csc, dout[r.dst], mean_rows=False,
                              nbr_scale=r.csr.cnt if rs.mean else None)
-            if r.csc.avg_degree > ops.LONG_ROW_AVG_DEGREE:
+            if r.csc.long_rows:
                 chunks.append((dy, arg))
             else:
                 rows.append((dy, [arg], False))
@@ -287,6 +324,8 @@ class _HeteroConvFn(torch.autograd.Function):
 
         # b5: input gradients per source type
         groups = {}
+        long_chunks: Dict[int, list] = {}
+        long_sums: list = []
         for t in spec.node_types:
             if not need_x[t]:
                 continue
@@ -297,11 +336,24 @@ class _HeteroConvFn(torch.autograd.Function):
                 continue
             dx = torch.empty_like(xs[t])
             grads[spec.node_types.index(t)] = dx
-            for base in range(0, len(af), L.MAX_REL_PER_GROUP):
-                part = af[base:base + L.MAX_REL_PER_GROUP]
-                groups.setdefault((base // L.MAX_REL_PER_GROUP, xs[t].shape[1]), []).append(
+            fs = xs[t].shape[1]
+            af_short = [(k, rs) for k, rs in af if not rs.rel.csc.long_rows]
+            af_long = [(k, rs) for k, rs in af if rs.rel.csc.long_rows]
+            for base in range(0, len(af_short), L.MAX_REL_PER_GROUP):
+                part = af_short[base:base + L.MAX_REL_PER_GROUP]
+                groups.setdefault((base // L.MAX_REL_PER_GROUP, fs), []).append(
                     (dx, [ops.RelArg(rs.rel.csc, dG[k], nbr_scale=rs.rel.csr.cnt if rs.mean else None)
                           for k, rs in part], base > 0))
+            # skewed source rows (a source node feeding thousands of destinations): edge-balanced
+            # kernel into a private buffer, summed into dx afterwards
+            temps = []
+            for k, rs in af_long:
+                tmp = torch.empty_like(dx)
+                temps.append(tmp)
+                long_chunks.setdefault(fs, []).append(
+                    (tmp, ops.RelArg(rs.rel.csc, dG[k], nbr_scale=rs.rel.csr.cnt if rs.mean else None)))
+            if temps:
+                long_sums.append((dx, ([dx] if af_short else []) + temps))
             segs = [(dY[k], params[rs.i_wl]) for k, rs in tf]
             if root:
                 segs.append((dout[t], wroot[t]))
@@ -309,12 +361,40 @@ class _HeteroConvFn(torch.autograd.Function):
         gb = ops.GemmBatch()
         for key in sorted(k for k in groups.keys() if k != ('gemm',)):
             ops.aggregate_rows(groups[key], key[1])
+        for F_, segs_ in long_chunks.items():
+            ops.aggregate_chunks(segs_, F_)
+        for dx_, ins in long_sums:
+            while len(ins) > 8:
+                ops.sum_arrays([(dx_, ins[:8])])
+                ins = [dx_] + ins[8:]
+            ops.sum_arrays([(dx_, ins)])
         for dx, segs, acc in groups.get(('gemm',), []):
             if segs:
                 gb.add(dx, segs, accumulate=acc)
         if gb.problems:
             gb.run()
+        _deliver_param_grads(spec.param_refs, grads, nt)
         return (None, *grads)
+
+
+def _deliver_param_grads(param_refs, grads, offset):
+    """When every parameter already owns a gradient buffer (FlatAdam's flat arena), add the fresh
+    gradients into those buffers with ONE batched agx launch and hand autograd ``None`` -- instead
+    of ~50 AccumulateGrad element-wise kernels per layer."""
+    if param_refs is None:
+        return
+    todo = [(i, p) for i, p in enumerate(param_refs) if grads[offset + i] is not None]
+    if not todo or any(p.grad is None or not p.grad.is_contiguous() for _, p in todo):
+        return
+    items = []
+    for i, p in todo:
+        g = grads[offset + i]
+        if not g.is_contiguous():
+            return
+        items.append((p.grad, [p.grad, g]))
+    ops.sum_arrays(items)
+    for i, _ in todo:
+        grads[offset + i] = None
 
 
 def _n_params(spec: ConvSpec) -> int:
@@ -341,6 +421,7 @@ class BNSpec:
     running: List[Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]]   # per type buffers
     with_act: bool                           # also produce relu(y) * dmask
     dmasks: Optional[List[Optional[torch.Tensor]]] = None
+    param_refs: Optional[tuple] = None       # ([weight Parameters], [bias Parameters])
 
 
 class _BNActFn(torch.autograd.Function):
@@ -399,13 +480,22 @@ class _BNActFn(torch.autograd.Function):
             arr = (L.BnBwdDesc * len(idx))()
             rows = 0
             keep = []
+            refs = spec.param_refs
+            direct = refs is not None and all(
+                refs[0][i].grad is not None and refs[1][i].grad is not None and
+                refs[0][i].grad.is_contiguous() and refs[1][i].grad.is_contiguous() for i in idx)
+            if not direct:
+                zbuf = ops.zeros(2 * len(idx) * F, dev)          # the kernel accumulates (+=)
             for j, i in enumerate(idx):
                 dy = None if dys[i] is None else dys[i].contiguous()
                 da = None if dacts[i] is None else dacts[i].contiguous()
                 keep += [dy, da]
                 dxs[i] = torch.empty_like(xs[i]) if ctx.needs_input_grad[1 + i] else None
-                dws[i] = ops.zeros(F, dev)
-                dbs[i] = ops.zeros(F, dev)
+                if direct:      # straight into the optimizer's gradient arena, autograd gets None
+                    dws[i], dbs[i] = refs[0][i].grad, refs[1][i].grad
+                else:
+                    dws[i] = zbuf[2 * j * F:(2 * j + 1) * F]
+                    dbs[i] = zbuf[(2 * j + 1) * F:(2 * j + 2) * F]
                 dm = spec.dmasks[i] if (spec.with_act and spec.dmasks is not None) else None
                 arr[j] = L.BnBwdDesc(ptr(xs[i]), ptr(ys[i]), ptr(dy), ptr(da), ptr(dm), ptr(ws[i]),
                                      ptr(means[i]), ptr(invstds[i]), ptr(dxs[i]), ptr(dws[i]),
@@ -415,6 +505,9 @@ class _BNActFn(torch.autograd.Function):
             wsb = torch.empty(n_ws, dtype=torch.float32, device=dev)
             check(lib().agx_bn_backward(arr, len(idx), F, int(spec.training), ptr(wsb), n_ws,
                                         stream_ptr()), 'agx_bn_backward')
+            if direct:
+                dws = [None] * n
+                dbs = [None] * n
         return (None, *dxs, *dws, *dbs)
 
 

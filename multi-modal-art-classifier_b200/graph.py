@@ -78,6 +78,12 @@ class HeteroPlan:
         self._buffers: list = []
         built = ops.csr_build(lists, buffers=self._buffers)
         self.check()
+        # largest row of every CSR/CSC (one stacked read-back): picks the kernel for skewed rows
+        maxdeg = torch.stack([(c.rowptr[1:] - c.rowptr[:-1]).max() if c.n_rows > 0 and c.n_edges > 0
+                              else torch.zeros((), dtype=torch.int32, device=c.rowptr.device)
+                              for c in built]).cpu().tolist()
+        for c, m in zip(built, maxdeg):
+            c.max_degree = int(m)
         R = len(keys)
         self.rels: "OrderedDict[EdgeType, Relation]" = OrderedDict()
         for i, (s, r, d) in enumerate(keys):

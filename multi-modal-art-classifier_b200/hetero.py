@@ -194,6 +194,7 @@ class HeteroModule(nn.Module):
             self._conv_specs[key] = spec
         spec.identity = ({t: _is_identity_input(x_dict[t]) for t in types}
                          if (is_input and self.detect_identity) else {})
+        spec.param_refs = params
         outs = AF.hetero_conv(spec, [x_dict[t].contiguous() for t in types], params)
         return OrderedDict(zip(spec.dst_types, outs))
 
@@ -214,7 +215,8 @@ class HeteroModule(nn.Module):
         spec = BNSpec(n=len(types), F=first.num_features, training=first.training or
                       not first.track_running_stats, momentum=first.momentum, eps=first.eps,
                       running=[(bns[t].running_mean, bns[t].running_var) for t in types],
-                      with_act=relu is not None, dmasks=dmasks)
+                      with_act=relu is not None, dmasks=dmasks,
+                      param_refs=([bns[t].weight for t in types], [bns[t].bias for t in types]))
         res = AF.batch_norm_act(spec, [x_dict[t].contiguous() for t in types],
                                 [bns[t].weight for t in types], [bns[t].bias for t in types])
         n = len(types)

@@ -46,6 +46,7 @@ class KernelTimer:
 
 
 TIMER: Optional[KernelTimer] = None
+_DEBUG = bool(int(__import__('os').environ.get('AGX_DEBUG', '0')))
 
 
 def aggregation_bytes(n_edges: int, n_rows: int, F: int, elem: int = 4) -> int:
@@ -68,10 +69,22 @@ class CSR:
     n_rows: int
     n_cols: int
     n_edges: int
+    max_degree: int = -1             # filled by HeteroPlan (one read-back at plan time); -1 unknown
 
     @property
     def avg_degree(self) -> float:
         return self.n_edges / max(self.n_rows, 1)
+
+    @property
+    def long_rows(self) -> bool:
+        """Few / skewed rows: a warp per row would serialise thousands of gathers behind one warp
+        (artwork -> style has 32 rows of ~3.6k edges; Zipf tags reach 40k), so the edge-balanced
+        kernel is used instead."""
+        return self.avg_degree > LONG_ROW_AVG_DEGREE or self.max_degree > LONG_ROW_MAX_DEGREE
+
+
+LONG_ROW_AVG_DEGREE = 12.0     # agg_rows stages <= 16 neighbours per output row
+LONG_ROW_MAX_DEGREE = 256
 
 
 def csr_build(edge_lists: Sequence[Tuple[torch.Tensor, torch.Tensor, int, int]],
@@ -190,6 +203,12 @@ def aggregate_rows(groups: Sequence[Tuple[torch.Tensor, Sequence[RelArg], bool]]
     if not groups:
         return
     dt = _dtype_code(groups[0][0])
+    if _DEBUG:
+        for out, rels, acc in groups:
+            print(f'[agx] agg_rows F={F} rows={out.shape[0]} acc={acc} rels=' + ', '.join(
+                f'(E={a.csr.n_edges} avg={a.csr.avg_degree:.1f} max={a.csr.max_degree} '
+                f'mean={a.mean_rows} scale={a.nbr_scale is not None} x={tuple(a.x.shape)})'
+                for a in rels), flush=True)
     for base in range(0, len(groups), L.MAX_GROUPS):
         part = groups[base:base + L.MAX_GROUPS]
         arr = (L.RowGroup * len(part))()
@@ -238,12 +257,9 @@ def aggregate_chunks(segs: Sequence[Tuple[torch.Tensor, RelArg]], F: int):
                                         for out, a in part), 0, t0)
 
 
-LONG_ROW_AVG_DEGREE = 24.0
-
-
 def aggregate(out: torch.Tensor, rel: RelArg, F: int):
     """Single relation, picks the row-parallel or the edge-balanced kernel from the mean degree."""
-    if rel.csr.avg_degree > LONG_ROW_AVG_DEGREE:
+    if rel.csr.long_rows:
         aggregate_chunks([(out, rel)], F)
     else:
         aggregate_rows([(out, [rel], False)], F)
