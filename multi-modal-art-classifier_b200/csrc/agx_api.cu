@@ -38,7 +38,7 @@ extern "C" int agx_kernel_inventory(char* h_buf, size_t h_buf_bytes) {
         "csr_make_keys,radix_hist,radix_scatter,scan_reduce,scan_spine,scan_apply,csr_finalize,"
         "csr_rowptr,coalesce_prepare,coalesce_flag,coalesce_compact,"
         "agg_rows,agg_chunks,agg_chunks_fixup,"
-        "gemm_f32,gemm_splitk_reduce,"
+        "gemm_f32,gemm_splitk_reduce,gemm_tf32x3_tc,"
         "sum_arrays,bn_stats,bn_apply,bn_bwd_reduce,bn_bwd_apply,colsum,"
         "log_softmax_nll,log_softmax_nll_bwd,adam_step,head_forward,ce_forward,ce_finish,"
         "smooth_l1,fill_f32,scale_mask,gather_rows,is_identity,transpose,pack_rows,"

@@ -12,9 +12,15 @@
 // This is the exact-fp32 path required by the 1e-5 parity bound (TF32 tensor-core products are
 // 1e-3).  128x128x16 (or 128x32x16) CTA tiles, 8x8 (4x4... ) register micro-tiles, 128-bit shared
 // memory reads, register-staged global prefetch of the next k-tile.
+#include <stdlib.h>
+
 #include "agx_common.cuh"
 
 namespace agx {
+
+// agx_gemm_tc.cu: tcgen05 path for X W^T problems with many rows
+bool gemm_tc_eligible(const agx_gemm_problem_t& Q, const agx_gemm_seg_t* segs);
+int gemm_tc_launch(const agx_gemm_problem_t& Q, const agx_gemm_seg_t* segs, cudaStream_t st);
 
 constexpr int kGemmThreads = 256;
 constexpr int BK = 16;
@@ -315,6 +321,8 @@ extern "C" int agx_gemm_grouped(const agx_gemm_problem_t* h_problems, int n_prob
                   "agx_gemm_grouped: n_segs=%d out of [1,%d]", n_segs, AGX_MAX_GEMM_SEGS);
     cudaStream_t st = (cudaStream_t)stream;
     int wide[AGX_MAX_GEMM_PROBLEMS], narrow[AGX_MAX_GEMM_PROBLEMS], nw = 0, nn = 0;
+    int tc[AGX_MAX_GEMM_PROBLEMS], ntc = 0;
+    static const bool use_tc = getenv("AGX_DISABLE_TC") == nullptr;   // A/B switch for tests
     bool any_split = false;
     for (int i = 0; i < n_problems; ++i) {
         const agx_gemm_problem_t& Q = h_problems[i];
@@ -334,7 +342,15 @@ extern "C" int agx_gemm_grouped(const agx_gemm_problem_t* h_problems, int n_prob
                           "agx_gemm_grouped: problem %d segment %d: null operand", i, s);
         }
         if (Q.M == 0 || Q.N == 0) continue;
+        if (use_tc && gemm_tc_eligible(Q, h_segs)) {      // tall X W^T products: tcgen05 3xTF32
+            tc[ntc++] = i;
+            continue;
+        }
         if (Q.N <= 48) narrow[nn++] = i; else wide[nw++] = i;
+    }
+    for (int i = 0; i < ntc; ++i) {
+        const int rc_tc = gemm_tc_launch(h_problems[tc[i]], h_segs, st);
+        if (rc_tc) return rc_tc;
     }
     int rc = launch_class<128, 128, 8, 8>(h_problems, wide, nw, h_segs, n_segs, st);
     if (rc) return rc;

@@ -1,0 +1,446 @@
+// K4-TC: the dense transforms on the 5th-generation tensor cores (tcgen05), float32-accurate.
+//
+//   C[M,N] (+)= sum_s A_s[M,K_s] * W_s[N,K_s]^T (+ bias)        A_s, W_s row-major, K contiguous
+//
+// The parity bound of the hot path is rel 1e-5 in float32; a single TF32 product is 1e-3.  Each
+// operand is therefore split in shared memory into hi = x with the low 13 mantissa bits cleared
+// (exactly a TF32 value) and lo = x - hi (exact in float32), and three tcgen05.mma kind::tf32
+// products  hi*hi + lo*hi + hi*lo  accumulate in TMEM in float32 ("3xTF32"): error ~2^-21.
+// The kernel stays HBM-bound (AI of [N,128]x[128,128] is 32 flop/B, a third of the TF32 tensor
+// peak still exceeds what HBM can feed).
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0      TMA producer: cp.async.bulk.tensor (128B swizzle) of A / W k-blocks [128 x 32 f32]
+//   warp 1      MMA issuer: one elected lane issues the tcgen05.mma's, commits to mbarriers
+//   warps 2-5   splitters: hi/lo split of the landed tiles (generic proxy -> fence.proxy.async)
+//   warps 6-9   epilogue: tcgen05.ld of the accumulator (double-buffered in TMEM), bias /
+//               accumulate, 128-bit global stores
+// Pipelines: smem ring (TMA -> split -> MMA, kStages deep), TMEM ring (MMA -> epilogue, 2 deep).
+#include <cuda.h>
+
+#include "agx_common.cuh"
+
+namespace agx {
+
+constexpr int kTcBM = 128;                 // rows per tile
+constexpr int kTcBK = 32;                  // float32 per k-block = one 128 B swizzle span
+constexpr int kTcStages = 3;
+constexpr int kTcMaxSegs = 8;
+constexpr int kTcMaxBN = 128;               // output columns per tile (UMMA N), TMEM: 2 x 128 columns
+constexpr int kTcThreads = 320;            // 10 warps
+constexpr int kTileBytes = kTcBM * kTcBK * 4;   // 16 KB
+
+struct TcSeg {
+    CUtensorMap map_a;                     // [M, K] f32, box [32, 128], swizzle 128B
+    CUtensorMap map_w;                     // [N, K] f32, box [32, BN]
+    int32_t k_blocks;
+    int32_t pad_[15];
+};
+
+struct TcParams {
+    TcSeg seg[kTcMaxSegs];
+    CUtensorMap map_c;                     // [M, N] f32, box [32, 128], swizzle 128B (TMA store)
+    int32_t n_seg;
+    int32_t M, N, BN;                      // BN = N rounded up to 16 (UMMA N), <= kTcMaxBN
+    float* C;
+    int64_t ldc;
+    const float* bias;
+    int32_t accumulate;
+    int32_t m_tiles;
+};
+
+// ---- PTX helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int x,
+                                            int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+        "{%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major operand tile, 128 B rows, 128B swizzle, 8-row groups 1024 B apart (SBO), version 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address      [0,14)
+    d |= (uint64_t)1 << 16;                           // LBO (unused)       [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;                 // SBO = 1024 B       [32,46)
+    d |= (uint64_t)1 << 46;                           // descriptor version [46,48)
+    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B       [61,64)
+    return d;
+}
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+    uint32_t d = 0;
+    d |= 1u << 4;                    // D format  : F32
+    d |= 2u << 7;                    // A format  : TF32
+    d |= 2u << 10;                   // B format  : TF32
+    d |= (uint32_t)(N >> 3) << 17;   // N
+    d |= (uint32_t)(M >> 4) << 24;   // M
+    return d;                        // A, B K-major, no negate, dense
+}
+
+struct __align__(1024) TcSmem {
+    float a_hi[kTcStages][kTcBM * kTcBK];
+    float a_lo[kTcStages][kTcBM * kTcBK];
+    float w_hi[kTcStages][kTcMaxBN * kTcBK];
+    float w_lo[kTcStages][kTcMaxBN * kTcBK];
+    float stage[2][kTcBM * 32];             // epilogue staging: 128 rows x 32 columns, 128B swizzle
+    uint64_t full[kTcStages];               // TMA landed
+    uint64_t split[kTcStages];              // hi/lo written
+    uint64_t empty[kTcStages];              // MMAs of the stage retired
+    uint64_t acc_full[2];                   // accumulator complete
+    uint64_t acc_empty[2];                  // accumulator drained by the epilogue
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tf32x3_tc(const __grid_constant__ TcParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    TcSmem& S = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int BN = P.BN;
+    const uint32_t w_tile_bytes = (uint32_t)BN * kTcBK * 4;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kTcStages; ++s) {
+            mbar_init(&S.full[s], 1);
+            mbar_init(&S.split[s], 128);
+            mbar_init(&S.empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&S.acc_full[a], 1);
+            mbar_init(&S.acc_empty[a], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // TMEM: 2 accumulators x 128 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(
+            smem_u32(&S.tmem_base)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S.tmem_base;
+
+    int total_kb = 0;
+    for (int s = 0; s < P.n_seg; ++s) total_kb += P.seg[s].k_blocks;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < P.m_tiles; tile += gridDim.x) {
+                for (int s = 0; s < P.n_seg; ++s) {
+                    for (int kb = 0; kb < P.seg[s].k_blocks; ++kb, ++it) {
+                        const int st = it % kTcStages;
+                        const uint32_t ph = (it / kTcStages) & 1;
+                        mbar_wait(&S.empty[st], ph ^ 1);
+                        mbar_expect_tx(&S.full[st], kTileBytes + w_tile_bytes);
+                        tma_load_2d(&P.seg[s].map_a, &S.full[st], S.a_hi[st], kb * kTcBK,
+                                    tile * kTcBM);
+                        tma_load_2d(&P.seg[s].map_w, &S.full[st], S.w_hi[st], kb * kTcBK, 0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        const uint32_t idesc = make_idesc(kTcBM, BN);
+        uint32_t it = 0, tl = 0;
+        for (int tile = blockIdx.x; tile < P.m_tiles; tile += gridDim.x, ++tl) {
+            const int acc = tl & 1;
+            const uint32_t acc_ph = (tl >> 1) & 1;
+            mbar_wait(&S.acc_empty[acc], acc_ph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem + (uint32_t)acc * kTcMaxBN;
+            for (int kbt = 0; kbt < total_kb; ++kbt, ++it) {
+                const int st = it % kTcStages;
+                const uint32_t ph = (it / kTcStages) & 1;
+                mbar_wait(&S.split[st], ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_hi = smem_u32(S.a_hi[st]), a_lo = smem_u32(S.a_lo[st]);
+                    const uint32_t w_hi = smem_u32(S.w_hi[st]), w_lo = smem_u32(S.w_lo[st]);
+#pragma unroll
+                    for (int k = 0; k < kTcBK / 8; ++k) {       // 8 tf32 = 32 B per MMA
+                        const uint32_t off = k * 32;
+                        const uint32_t first = (kbt == 0 && k == 0) ? 0u : 1u;
+                        tc_mma_tf32(d_tmem, make_desc(a_lo + off), make_desc(w_hi + off), idesc, first);
+                        tc_mma_tf32(d_tmem, make_desc(a_hi + off), make_desc(w_lo + off), idesc, 1u);
+                        tc_mma_tf32(d_tmem, make_desc(a_hi + off), make_desc(w_hi + off), idesc, 1u);
+                    }
+                    tc_commit(&S.empty[st]);                     // frees the smem stage
+                    if (kbt == total_kb - 1) tc_commit(&S.acc_full[acc]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp < 6) {
+        // ================= splitters (128 threads) =================
+        const int t = threadIdx.x - 64;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < P.m_tiles; tile += gridDim.x) {
+            for (int kbt = 0; kbt < total_kb; ++kbt, ++it) {
+                const int st = it % kTcStages;
+                const uint32_t ph = (it / kTcStages) & 1;
+                mbar_wait(&S.full[st], ph);
+                // elementwise, layout-agnostic: the swizzled byte order is kept as it landed
+                float4* ah = reinterpret_cast<float4*>(S.a_hi[st]);
+                float4* al = reinterpret_cast<float4*>(S.a_lo[st]);
+#pragma unroll 4
+                for (int i = t; i < kTcBM * kTcBK / 4; i += 128) {
+                    const float4 x = ah[i];
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); l.x = x.x - h.x;
+                    h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = x.y - h.y;
+                    h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = x.z - h.z;
+                    h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = x.w - h.w;
+                    ah[i] = h;
+                    al[i] = l;
+                }
+                float4* wh = reinterpret_cast<float4*>(S.w_hi[st]);
+                float4* wl = reinterpret_cast<float4*>(S.w_lo[st]);
+                for (int i = t; i < BN * kTcBK / 4; i += 128) {
+                    const float4 x = wh[i];
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); l.x = x.x - h.x;
+                    h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = x.y - h.y;
+                    h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = x.z - h.z;
+                    h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = x.w - h.w;
+                    wh[i] = h;
+                    wl[i] = l;
+                }
+                fence_proxy_async();             // generic-proxy writes -> visible to tcgen05.mma
+                mbar_arrive(&S.split[st]);
+            }
+        }
+    } else {
+        // ================= epilogue (warps 6..9; TMEM lane quarter = warp % 4) =================
+        // accumulator row r of the tile lives in TMEM lane r: thread (q, lane) owns row 32q+lane.
+        // Each 32-column slab goes registers -> swizzled smem -> one TMA store (or TMA reduce-add
+        // when accumulating): full 128 B lines leave the SM instead of 32 scattered 16 B pieces.
+        const int q = warp & 3;
+        const int r_in_tile = q * 32 + lane;
+        const bool store_thread = (warp == 6 && lane == 0);
+        uint32_t tl = 0, chunk_ctr = 0;
+        for (int tile = blockIdx.x; tile < P.m_tiles; tile += gridDim.x, ++tl) {
+            const int acc = tl & 1;
+            const uint32_t acc_ph = (tl >> 1) & 1;
+            mbar_wait(&S.acc_full[acc], acc_ph);
+            tc_fence_after();
+            for (int c0 = 0; c0 < BN; c0 += 32, ++chunk_ctr) {
+                float* stg = S.stage[chunk_ctr & 1];
+                // the bulk store that last read this staging buffer must have drained it
+                if (store_thread) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                uint32_t v[32];
+                const uint32_t taddr = tmem + (uint32_t)acc * kTcMaxBN + (uint32_t)c0 + ((uint32_t)(q * 32) << 16);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, "
+                    "[%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]),
+                      "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
+                      "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]),
+                      "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+                      "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c0 + 32 >= BN) {             // last slab read: hand the accumulator back
+                    tc_fence_before();
+                    mbar_arrive(&S.acc_empty[acc]);
+                }
+                // row r_in_tile, 16-byte chunk j -> physical chunk j ^ (row % 8)  (128B swizzle)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                    if (P.bias) {
+                        const int c = c0 + 4 * j;
+                        o.x += c + 0 < P.N ? P.bias[c + 0] : 0.f;
+                        o.y += c + 1 < P.N ? P.bias[c + 1] : 0.f;
+                        o.z += c + 2 < P.N ? P.bias[c + 2] : 0.f;
+                        o.w += c + 3 < P.N ? P.bias[c + 3] : 0.f;
+                    }
+                    *reinterpret_cast<float4*>(stg + r_in_tile * 32 + ((j ^ (r_in_tile & 7)) << 2)) = o;
+                }
+                fence_proxy_async();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (store_thread) {
+                    if (P.accumulate)
+                        asm volatile(
+                            "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group "
+                            "[%0, {%2, %3}], [%1];" ::"l"(&P.map_c),
+                            "r"(smem_u32(stg)), "r"(c0), "r"(tile * kTcBM)
+                            : "memory");
+                    else
+                        asm volatile(
+                            "cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group "
+                            "[%0, {%2, %3}], [%1];" ::"l"(&P.map_c),
+                            "r"(smem_u32(stg)), "r"(c0), "r"(tile * kTcBM)
+                            : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+        }
+        if (store_thread) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
+    }
+}
+
+// ---- host ----------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                        const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                        const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_tmapEncodeTiled)p;
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld,
+                    int box_rows) {
+    PFN_tmapEncodeTiled enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return AGX_ERR_CUDA;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
+                  (long long)rows, (long long)cols, (long long)ld);
+        return AGX_ERR_CUDA;
+    }
+    return AGX_OK;
+}
+
+static bool tc_seg_ok(const agx_gemm_seg_t& S) {
+    // A[M,K] K-contiguous, B[k][n] = W[n][k] K-contiguous, 16-byte aligned rows, no masks
+    return S.a_cs == 1 && S.b_rs == 1 && !S.A_mask && !S.B_mask && S.K >= 8 && (S.a_rs % 4) == 0 &&
+           (S.b_cs % 4) == 0 && (reinterpret_cast<uintptr_t>(S.A) % 16) == 0 &&
+           (reinterpret_cast<uintptr_t>(S.B) % 16) == 0;
+}
+
+bool gemm_tc_eligible(const agx_gemm_problem_t& Q, const agx_gemm_seg_t* segs) {
+    if (Q.split_k > 1 || Q.row_scale || Q.skip_flag || Q.seg_count < 1 || Q.seg_count > kTcMaxSegs)
+        return false;
+    if (Q.N < 8 || Q.N > kTcMaxBN || Q.M < 512) return false;
+    if ((reinterpret_cast<uintptr_t>(Q.C) % 16) != 0 || (Q.ldc % 4) != 0) return false;
+    for (int s = 0; s < Q.seg_count; ++s)
+        if (!tc_seg_ok(segs[Q.seg_begin + s])) return false;
+    return true;
+}
+
+int gemm_tc_launch(const agx_gemm_problem_t& Q, const agx_gemm_seg_t* segs, cudaStream_t st) {
+    static bool attr_set = false;
+    const size_t smem = sizeof(TcSmem) + 1024;
+    if (!attr_set) {
+        AGX_CUDA(cudaFuncSetAttribute(gemm_tf32x3_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+        attr_set = true;
+    }
+    TcParams P;
+    P.n_seg = Q.seg_count;
+    P.M = Q.M;
+    P.N = Q.N;
+    P.BN = (Q.N + 15) / 16 * 16;
+    P.C = Q.C;
+    P.ldc = Q.ldc;
+    P.bias = Q.bias;
+    P.accumulate = Q.accumulate;
+    P.m_tiles = (Q.M + kTcBM - 1) / kTcBM;
+    {
+        const int rc = make_map(&P.map_c, Q.C, Q.M, Q.N, Q.ldc, kTcBM);
+        if (rc) return rc;
+    }
+    for (int s = 0; s < Q.seg_count; ++s) {
+        const agx_gemm_seg_t& G = segs[Q.seg_begin + s];
+        int rc = make_map(&P.seg[s].map_a, G.A, Q.M, G.K, G.a_rs, kTcBM);
+        if (rc) return rc;
+        rc = make_map(&P.seg[s].map_w, G.B, Q.N, G.K, G.b_cs, P.BN);
+        if (rc) return rc;
+        P.seg[s].k_blocks = (G.K + kTcBK - 1) / kTcBK;
+    }
+    const int grid = P.m_tiles < kNumSMs ? P.m_tiles : kNumSMs;
+    gemm_tf32x3_tc<<<grid, kTcThreads, smem, st>>>(P);
+    AGX_LAUNCH_CHECK("gemm_tf32x3_tc");
+    return AGX_OK;
+}
+
+}  // namespace agx

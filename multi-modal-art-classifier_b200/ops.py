@@ -268,6 +268,9 @@ def aggregate(out: torch.Tensor, rel: RelArg, F: int):
 # ------------------------------------------------------------------------------------------------
 # K4: grouped GEMM
 # ------------------------------------------------------------------------------------------------
+TC_MIN_ROWS = 512        # agx_gemm_tc.cu takes problems with at least this many output rows
+
+
 class GemmBatch:
     """Collects problems ``C (+)= sum_s opA_s @ opB_s (+ bias)`` and launches them together.
     Operands are given as 2-D tensor *views* (any strides): opA [M, K], opB [K, N]."""
@@ -298,6 +301,14 @@ class GemmBatch:
             A, B = sg[0], sg[1]
             Am = sg[2] if len(sg) > 2 else None
             Bm = sg[3] if len(sg) > 3 else None
+            if (M >= TC_MIN_ROWS and split_k <= 1 and Bm is None and B.stride(1) == 1 and
+                    B.stride(0) != 1 and B.shape[0] * B.shape[1] <= (1 << 20)):
+                # dY @ W with W given [K, N] row-major: the tensor-core kernel wants both operands
+                # K-contiguous, so hand it a transposed copy of the (small) weight
+                Bt = torch.empty(B.shape[1], B.shape[0], dtype=torch.float32, device=B.device)
+                transpose_into(Bt, B)
+                self._keep.append(Bt)
+                B = Bt.t()
             if A.shape[0] != M or B.shape[1] != N or A.shape[1] != B.shape[0]:
                 raise ValueError(f'gemm shape mismatch: A {tuple(A.shape)} B {tuple(B.shape)} '
                                  f'C {tuple(C_out.shape)}')

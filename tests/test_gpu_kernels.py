@@ -204,6 +204,37 @@ def test_gemm_nt_nn_tn(M, K, N):
     assert rel_err(dW1, G64.t() @ A64 + 1.0) <= RTOL_F32
 
 
+@pytest.mark.parametrize('M,N,Ks', [(4096, 128, [128]), (5000, 128, [128, 128, 64]),
+                                    (3001, 32, [128]), (2049, 18, [128, 96]), (1500, 72, [200])])
+def test_gemm_tensor_core_3xtf32(M, N, Ks):
+    """Tall X W^T problems take the tcgen05 path (agx_gemm_tc.cu): three TF32 products per
+    element must reproduce float32 accuracy (rel 1e-5 against float64)."""
+    gen = torch.Generator().manual_seed(M + N)
+    As = [torch.randn(M, K, generator=gen) for K in Ks]
+    Ws = [torch.randn(N, K, generator=gen) / 8 for K in Ks]
+    b = torch.randn(N, generator=gen)
+    C0 = torch.randn(M, N, generator=gen)
+    ref = sum(a.double() @ w.double().t() for a, w in zip(As, Ws)) + b.double()
+    Ad = [a.to(DEV) for a in As]
+    Wd = [w.to(DEV) for w in Ws]
+    C = torch.full((M, N), float('nan'), device=DEV)
+    gb = ops.GemmBatch()
+    gb.add(C, [(a, w.t()) for a, w in zip(Ad, Wd)], bias=b.to(DEV))
+    Cacc = C0.to(DEV).clone()
+    gb.add(Cacc, [(a, w.t()) for a, w in zip(Ad, Wd)], bias=b.to(DEV), accumulate=True)
+    gb.run()
+    assert rel_err(C, ref) <= RTOL_F32
+    assert rel_err(Cacc, ref + C0.double()) <= RTOL_F32
+    # an ill-conditioned case: large common offset, the lo terms matter
+    A2 = (torch.randn(M, Ks[0], generator=gen) * 1e-3 + 7.0)
+    W2 = torch.randn(N, Ks[0], generator=gen)
+    C2 = torch.empty(M, N, device=DEV)
+    gb = ops.GemmBatch()
+    gb.add(C2, [(A2.to(DEV), W2.to(DEV).t())])
+    gb.run()
+    assert rel_err(C2, A2.double() @ W2.double().t()) <= RTOL_F32
+
+
 def test_gemm_multi_segment_masks_and_slices():
     gen = torch.Generator().manual_seed(1)
     B, Fv, Fe, Cn = 200, 768, 128, 32
