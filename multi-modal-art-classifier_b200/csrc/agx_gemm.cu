@@ -20,7 +20,8 @@ namespace agx {
 
 // agx_gemm_tc.cu: tcgen05 path for X W^T problems with many rows
 bool gemm_tc_eligible(const agx_gemm_problem_t& Q, const agx_gemm_seg_t* segs);
-int gemm_tc_launch(const agx_gemm_problem_t& Q, const agx_gemm_seg_t* segs, cudaStream_t st);
+int gemm_tc_launch(const agx_gemm_problem_t* probs, const int* idx, int cnt,
+                   const agx_gemm_seg_t* segs, cudaStream_t st);
 
 constexpr int kGemmThreads = 256;
 constexpr int BK = 16;
@@ -348,8 +349,8 @@ extern "C" int agx_gemm_grouped(const agx_gemm_problem_t* h_problems, int n_prob
         }
         if (Q.N <= 48) narrow[nn++] = i; else wide[nw++] = i;
     }
-    for (int i = 0; i < ntc; ++i) {
-        const int rc_tc = gemm_tc_launch(h_problems[tc[i]], h_segs, st);
+    if (ntc > 0) {
+        const int rc_tc = gemm_tc_launch(h_problems, tc, ntc, h_segs, st);
         if (rc_tc) return rc_tc;
     }
     int rc = launch_class<128, 128, 8, 8>(h_problems, wide, nw, h_segs, n_segs, st);
