@@ -221,6 +221,22 @@ typedef struct {
 int agx_bn_backward(const agx_bn_bwd_desc_t* h_descs, int n, int F, int training, float* workspace,
                     size_t workspace_floats, void* stream);
 
+/* Multi-GPU BatchNorm (the node type's rows are spread over the ranks; statistics over ALL rows,
+ * as on one GPU).  phases is a bit mask; between phases the caller all-reduces the float64 buffer:
+ *   forward : 1 -> sums[n][F] = local column sums            (all-reduce sums)
+ *             2 -> mean from sums/counts; sums = local centred second moments   (all-reduce sums)
+ *             4 -> invstd + running stats from sums/counts; normalise (+ReLU, dropout)
+ *   backward: 1 -> totals[n][2F] = local (sum dy, sum dy*xhat); dweight/dbias += local sums
+ *                                                                             (all-reduce totals)
+ *             2 -> dx with the global totals / counts
+ * counts[n] = global row count per descriptor (float64, device). */
+int agx_bn_forward_phase(const agx_bn_desc_t* h_descs, int n, int F, int training, float momentum,
+                         float eps, float* workspace, size_t workspace_floats, int phases,
+                         double* sums, const double* counts, void* stream);
+int agx_bn_backward_phase(const agx_bn_bwd_desc_t* h_descs, int n, int F, int training,
+                          float* workspace, size_t workspace_floats, int phases, double* totals,
+                          const double* counts, void* stream);
+
 /* column sums: out[F] (+)= sum_rows x[rows, F] (bias gradients) */
 typedef struct { const float* x; int64_t ldx; float* out; int32_t n_rows; int32_t F; int32_t accumulate; int32_t pad_; } agx_colsum_desc_t;
 size_t agx_colsum_workspace_floats(int64_t total_rows, int n_descs, int max_F);

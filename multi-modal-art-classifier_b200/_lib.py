@@ -100,6 +100,10 @@ _SIGS = {
                                  C.c_size_t, vp]),
     'agx_bn_backward': (C.c_int, [C.POINTER(BnBwdDesc), C.c_int, C.c_int, C.c_int, vp, C.c_size_t,
                                   vp]),
+    'agx_bn_forward_phase': (C.c_int, [C.POINTER(BnDesc), C.c_int, C.c_int, C.c_int, c_f32, c_f32,
+                                       vp, C.c_size_t, C.c_int, vp, vp, vp]),
+    'agx_bn_backward_phase': (C.c_int, [C.POINTER(BnBwdDesc), C.c_int, C.c_int, C.c_int, vp,
+                                        C.c_size_t, C.c_int, vp, vp, vp]),
     'agx_colsum_workspace_floats': (C.c_size_t, [c_i64, C.c_int, C.c_int]),
     'agx_colsum': (C.c_int, [C.POINTER(ColsumDesc), C.c_int, vp, C.c_size_t, vp]),
     'agx_log_softmax_nll': (C.c_int, [vp, c_i64, c_i32, c_i32, vp, vp, vp, c_i64, vp, vp, vp]),

@@ -44,6 +44,11 @@ struct BnParams {
     double* ws;           // [total_slabs][F] float64 partials
     int32_t training;
     float momentum, eps;
+    // multi-GPU (SyncBN): mode 1 = only reduce the slab partials into sums[n][F]; mode 2 = finalize
+    // from sums (already all-reduced across ranks) with the global row counts; mode 0 = fused
+    int32_t mode;
+    double* sums;
+    const double* counts;
 };
 
 // pass: 0 -> sum x ; 1 -> sum (x - mean)^2
@@ -116,16 +121,25 @@ __global__ void __launch_bounds__(1024) bn_finalize(const __grid_constant__ BnPa
         }
         return;
     }
-    const double acc = slab_total_32x32(P.ws + (size_t)s0 * F, s1 - s0, F, col0, F, sm);
+    double acc = 0.0;
+    if (P.mode == 2) {
+        if (threadIdx.x < 32 && c < F) acc = P.sums[(size_t)blockIdx.x * F + c];
+    } else {
+        acc = slab_total_32x32(P.ws + (size_t)s0 * F, s1 - s0, F, col0, F, sm);
+    }
+    if (P.mode == 1) {
+        if (threadIdx.x < 32 && c < F) P.sums[(size_t)blockIdx.x * F + c] = acc;
+        return;
+    }
     if (threadIdx.x < 32 && c < F) {
-        const double n = (double)D.n_rows;
+        const double n = P.counts ? P.counts[blockIdx.x] : (double)D.n_rows;
         if (pass == 0) {
             D.save_mean[c] = (float)(acc / n);
         } else {
             const double var = acc / n;
             D.save_invstd[c] = (float)(1.0 / sqrt(var + (double)P.eps));
             if (D.running_mean) {
-                const double unbiased = D.n_rows > 1 ? acc / (n - 1.0) : var;
+                const double unbiased = n > 1.0 ? acc / (n - 1.0) : var;
                 D.running_mean[c] = (float)((1.0 - P.momentum) * D.running_mean[c] +
                                             P.momentum * (double)D.save_mean[c]);
                 D.running_var[c] = (float)((1.0 - P.momentum) * D.running_var[c] +
@@ -188,7 +202,8 @@ struct BnBwdParams {
     int32_t n;
     int32_t F;
     double* ws;           // [total_slabs][2F] float64 partials: sum dy, sum dy*xhat
-    float* totals;
+    double* totals;       // [n][2F] column totals (all-reduced across ranks for SyncBN)
+    const double* counts; // nullable: global rows per descriptor
     int32_t training;
 };
 
@@ -253,8 +268,8 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize(const __grid_constant__ 
     const double a1 = slab_total_32x32(part + F, s1 - s0, (size_t)2 * F, col0, F, sm);
     const int c = col0 + (int)threadIdx.x;
     if (threadIdx.x < 32 && c < F) {
-        P.totals[(size_t)blockIdx.x * 2 * F + c] = (float)a0;
-        P.totals[(size_t)blockIdx.x * 2 * F + F + c] = (float)a1;
+        P.totals[(size_t)blockIdx.x * 2 * F + c] = a0;
+        P.totals[(size_t)blockIdx.x * 2 * F + F + c] = a1;
         if (D.dbias) D.dbias[c] += (float)a0;
         if (D.dweight) D.dweight[c] += (float)a1;
     }
@@ -267,8 +282,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply(const __grid_constant__ BnBw
     if (!D.dx) return;
     const int slab = blockIdx.x - P.slab_start[di];
     const int F = P.F;
-    const float* tot = P.totals + (size_t)di * 2 * F;
-    const float inv_n = 1.0f / (float)D.n_rows;
+    const double* tot = P.totals + (size_t)di * 2 * F;
+    const float inv_n = (float)(1.0 / (P.counts ? P.counts[di] : (double)D.n_rows));
     const int64_t e0 = (int64_t)slab * kBnSlab * F;
     const int64_t e1 = min((int64_t)D.n_rows * F, e0 + (int64_t)kBnSlab * F);
     for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
@@ -278,7 +293,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply(const __grid_constant__ BnBw
         float dx;
         if (P.training) {
             const float xh = (D.x[e] - D.save_mean[c]) * is;
-            dx = D.weight[c] * is * (gy - tot[c] * inv_n - xh * tot[F + c] * inv_n);
+            dx = D.weight[c] * is * (gy - (float)tot[c] * inv_n - xh * (float)tot[F + c] * inv_n);
         } else {
             dx = D.weight[c] * is * gy;
         }
@@ -676,18 +691,25 @@ extern "C" int agx_sum_arrays(const agx_sum_desc_t* h_descs, int n, void* stream
 
 extern "C" size_t agx_bn_workspace_floats(int64_t total_rows, int n_descs, int F) {
     const int64_t slabs = ceil_div(total_rows, kBnSlab) + n_descs;
-    return 2 * (size_t)(slabs * 2 * F) + (size_t)n_descs * 2 * F;   // float64 partials + float totals
+    return 2 * (size_t)(slabs * 2 * F) + 2 * (size_t)n_descs * 2 * F;   // float64 partials + totals
 }
 
-extern "C" int agx_bn_forward(const agx_bn_desc_t* h_descs, int n, int F, int training,
-                              float momentum, float eps, float* workspace, size_t workspace_floats,
-                              void* stream) {
+// phases (bit mask): 1 = first-moment pass, 2 = second-moment pass, 4 = normalise.  With `sums`
+// (multi-GPU SyncBN) each statistics phase ends by writing the per-type float64 column sums to
+// sums[n][F]; the caller all-reduces them and the next phase finalises from them with the global
+// row `counts`.  Without `sums` the phases run back to back and finalise from local partials.
+static int bn_forward_impl(const agx_bn_desc_t* h_descs, int n, int F, int training, float momentum,
+                           float eps, float* workspace, size_t workspace_floats, int phases,
+                           double* sums, const double* counts, cudaStream_t st) {
     AGX_CHECK_ARG(h_descs && n >= 1 && n <= AGX_MAX_GROUPS, "agx_bn_forward: n=%d", n);
     AGX_CHECK_ARG(F >= 1, "agx_bn_forward: F=%d", F);
     BnParams P;
     P.n = n;
     P.F = F;
     P.ws = reinterpret_cast<double*>(workspace);
+    P.mode = 0;
+    P.sums = sums;
+    P.counts = counts;
     P.training = training;
     P.momentum = momentum;
     P.eps = eps;
@@ -700,7 +722,7 @@ extern "C" int agx_bn_forward(const agx_bn_desc_t* h_descs, int n, int F, int tr
                       "agx_bn_forward: desc %d has null pointers", i);
         AGX_CHECK_ARG(training || (D.running_mean && D.running_var),
                       "agx_bn_forward: desc %d: eval mode needs running stats", i);
-        AGX_CHECK_ARG(!training || D.n_rows > 1,
+        AGX_CHECK_ARG(!training || D.n_rows > 1 || counts,
                       "agx_bn_forward: desc %d: Expected more than 1 value per channel when "
                       "training, got input size [%d, %d]", i, D.n_rows, F);
         P.d[i] = D;
@@ -711,30 +733,70 @@ extern "C" int agx_bn_forward(const agx_bn_desc_t* h_descs, int n, int F, int tr
         set_error("agx_bn_forward: workspace too small");
         return AGX_ERR_WORKSPACE;
     }
-    cudaStream_t st = (cudaStream_t)stream;
     const int slabs = P.slab_start[n];
-    if (training && slabs > 0) {
-        bn_stats<<<slabs, kBnThreads, 0, st>>>(P, 0);
-        AGX_LAUNCH_CHECK("bn_stats");
-        bn_finalize<<<dim3(n, (F + 31) / 32), 1024, 0, st>>>(P,0);
-        AGX_LAUNCH_CHECK("bn_finalize");
-        bn_stats<<<slabs, kBnThreads, 0, st>>>(P, 1);
-        AGX_LAUNCH_CHECK("bn_stats");
-        bn_finalize<<<dim3(n, (F + 31) / 32), 1024, 0, st>>>(P,1);
-        AGX_LAUNCH_CHECK("bn_finalize");
+    const dim3 fgrid(n, (F + 31) / 32);
+    if (!training) {
+        if (phases & 4) {
+            bn_finalize<<<fgrid, 1024, 0, st>>>(P, 0);
+            AGX_LAUNCH_CHECK("bn_finalize");
+        }
     } else {
-        bn_finalize<<<dim3(n, (F + 31) / 32), 1024, 0, st>>>(P,0);
-        AGX_LAUNCH_CHECK("bn_finalize");
+        if (phases & 1) {
+            if (slabs > 0) {
+                bn_stats<<<slabs, kBnThreads, 0, st>>>(P, 0);
+                AGX_LAUNCH_CHECK("bn_stats");
+            }
+            P.mode = sums ? 1 : 0;
+            bn_finalize<<<fgrid, 1024, 0, st>>>(P, 0);
+            AGX_LAUNCH_CHECK("bn_finalize");
+        }
+        if (phases & 2) {
+            if (sums) {
+                P.mode = 2;
+                bn_finalize<<<fgrid, 1024, 0, st>>>(P, 0);
+                AGX_LAUNCH_CHECK("bn_finalize");
+            }
+            if (slabs > 0) {
+                bn_stats<<<slabs, kBnThreads, 0, st>>>(P, 1);
+                AGX_LAUNCH_CHECK("bn_stats");
+            }
+            P.mode = sums ? 1 : 0;
+            bn_finalize<<<fgrid, 1024, 0, st>>>(P, 1);
+            AGX_LAUNCH_CHECK("bn_finalize");
+        }
+        if ((phases & 4) && sums) {
+            P.mode = 2;
+            bn_finalize<<<fgrid, 1024, 0, st>>>(P, 1);
+            AGX_LAUNCH_CHECK("bn_finalize");
+        }
     }
-    if (slabs > 0) {
+    if ((phases & 4) && slabs > 0) {
         bn_apply<<<slabs, 256, 0, st>>>(P);
         AGX_LAUNCH_CHECK("bn_apply");
     }
     return AGX_OK;
 }
 
-extern "C" int agx_bn_backward(const agx_bn_bwd_desc_t* h_descs, int n, int F, int training,
-                               float* workspace, size_t workspace_floats, void* stream) {
+extern "C" int agx_bn_forward(const agx_bn_desc_t* h_descs, int n, int F, int training,
+                              float momentum, float eps, float* workspace, size_t workspace_floats,
+                              void* stream) {
+    return bn_forward_impl(h_descs, n, F, training, momentum, eps, workspace, workspace_floats, 7,
+                           nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int agx_bn_forward_phase(const agx_bn_desc_t* h_descs, int n, int F, int training,
+                                    float momentum, float eps, float* workspace,
+                                    size_t workspace_floats, int phases, double* sums,
+                                    const double* counts, void* stream) {
+    AGX_CHECK_ARG(sums && counts, "agx_bn_forward_phase: sums/counts must not be null");
+    return bn_forward_impl(h_descs, n, F, training, momentum, eps, workspace, workspace_floats,
+                           phases, sums, counts, (cudaStream_t)stream);
+}
+
+// phases: 1 = column totals (sum dy, sum dy*xhat) into `totals` + local dweight/dbias, 2 = dx
+static int bn_backward_impl(const agx_bn_bwd_desc_t* h_descs, int n, int F, int training,
+                            float* workspace, size_t workspace_floats, int phases, double* totals,
+                            const double* counts, cudaStream_t st) {
     AGX_CHECK_ARG(h_descs && n >= 1 && n <= AGX_MAX_GROUPS, "agx_bn_backward: n=%d", n);
     BnBwdParams P;
     P.n = n;
@@ -757,16 +819,35 @@ extern "C" int agx_bn_backward(const agx_bn_bwd_desc_t* h_descs, int n, int F, i
     }
     const int slabs = P.slab_start[n];
     P.ws = reinterpret_cast<double*>(workspace);
-    P.totals = workspace + 2 * (size_t)slabs * 2 * F;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (slabs == 0) return AGX_OK;
-    bn_bwd_reduce<<<slabs, kBnThreads, 0, st>>>(P);
-    AGX_LAUNCH_CHECK("bn_bwd_reduce");
-    bn_bwd_finalize<<<dim3(n, (F + 31) / 32), 1024, 0, st>>>(P);
-    AGX_LAUNCH_CHECK("bn_bwd_finalize");
-    bn_bwd_apply<<<slabs, 256, 0, st>>>(P);
-    AGX_LAUNCH_CHECK("bn_bwd_apply");
+    P.totals = totals ? totals : reinterpret_cast<double*>(workspace) + (size_t)slabs * 2 * F;
+    P.counts = counts;
+    if (phases & 1) {
+        if (slabs > 0) {
+            bn_bwd_reduce<<<slabs, kBnThreads, 0, st>>>(P);
+            AGX_LAUNCH_CHECK("bn_bwd_reduce");
+        }
+        bn_bwd_finalize<<<dim3(n, (F + 31) / 32), 1024, 0, st>>>(P);
+        AGX_LAUNCH_CHECK("bn_bwd_finalize");
+    }
+    if ((phases & 2) && slabs > 0) {
+        bn_bwd_apply<<<slabs, 256, 0, st>>>(P);
+        AGX_LAUNCH_CHECK("bn_bwd_apply");
+    }
     return AGX_OK;
+}
+
+extern "C" int agx_bn_backward(const agx_bn_bwd_desc_t* h_descs, int n, int F, int training,
+                               float* workspace, size_t workspace_floats, void* stream) {
+    return bn_backward_impl(h_descs, n, F, training, workspace, workspace_floats, 3, nullptr, nullptr,
+                            (cudaStream_t)stream);
+}
+
+extern "C" int agx_bn_backward_phase(const agx_bn_bwd_desc_t* h_descs, int n, int F, int training,
+                                     float* workspace, size_t workspace_floats, int phases,
+                                     double* totals, const double* counts, void* stream) {
+    AGX_CHECK_ARG(totals && counts, "agx_bn_backward_phase: totals/counts must not be null");
+    return bn_backward_impl(h_descs, n, F, training, workspace, workspace_floats, phases, totals,
+                            counts, (cudaStream_t)stream);
 }
 
 extern "C" size_t agx_colsum_workspace_floats(int64_t total_rows, int n_descs, int max_F) {

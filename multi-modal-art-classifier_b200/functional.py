@@ -422,6 +422,8 @@ class BNSpec:
     with_act: bool                           # also produce relu(y) * dmask
     dmasks: Optional[List[Optional[torch.Tensor]]] = None
     param_refs: Optional[tuple] = None       # ([weight Parameters], [bias Parameters])
+    group: object = None                     # torch.distributed process group -> SyncBN
+    counts: Optional[torch.Tensor] = None    # float64 [n] global row counts (with group)
 
 
 class _BNActFn(torch.autograd.Function):
@@ -454,8 +456,19 @@ class _BNActFn(torch.autograd.Function):
             rows += x.shape[0]
         n_ws = lib().agx_bn_workspace_floats(rows, n, F)
         wsb = torch.empty(n_ws, dtype=torch.float32, device=dev)
-        check(lib().agx_bn_forward(arr, n, F, int(spec.training), spec.momentum, spec.eps, ptr(wsb),
-                                   n_ws, stream_ptr()), 'agx_bn_forward')
+        if spec.group is not None and spec.training:
+            # SyncBN: statistics over the rows of ALL ranks (two float64 all-reduces of [n, F])
+            import torch.distributed as dist
+            sums = torch.empty(n * F, dtype=torch.float64, device=dev)
+            for phase in (1, 2, 4):
+                check(lib().agx_bn_forward_phase(arr, n, F, 1, spec.momentum, spec.eps, ptr(wsb),
+                                                 n_ws, phase, ptr(sums), ptr(spec.counts),
+                                                 stream_ptr()), 'agx_bn_forward_phase')
+                if phase != 4:
+                    dist.all_reduce(sums, group=spec.group)
+        else:
+            check(lib().agx_bn_forward(arr, n, F, int(spec.training), spec.momentum, spec.eps,
+                                       ptr(wsb), n_ws, stream_ptr()), 'agx_bn_forward')
         ctx.spec = spec
         ctx.save_for_backward(*xs, *ws, *ys, *means, *invstds)
         if spec.with_act:
@@ -503,8 +516,18 @@ class _BNActFn(torch.autograd.Function):
                 rows += xs[i].shape[0]
             n_ws = lib().agx_bn_workspace_floats(rows, len(idx), F)
             wsb = torch.empty(n_ws, dtype=torch.float32, device=dev)
-            check(lib().agx_bn_backward(arr, len(idx), F, int(spec.training), ptr(wsb), n_ws,
-                                        stream_ptr()), 'agx_bn_backward')
+            if spec.group is not None and spec.training:
+                import torch.distributed as dist
+                totals = torch.empty(len(idx) * 2 * F, dtype=torch.float64, device=dev)
+                counts = spec.counts[idx].contiguous() if len(idx) != n else spec.counts
+                check(lib().agx_bn_backward_phase(arr, len(idx), F, 1, ptr(wsb), n_ws, 1, ptr(totals),
+                                                  ptr(counts), stream_ptr()), 'agx_bn_backward_phase')
+                dist.all_reduce(totals, group=spec.group)
+                check(lib().agx_bn_backward_phase(arr, len(idx), F, 1, ptr(wsb), n_ws, 2, ptr(totals),
+                                                  ptr(counts), stream_ptr()), 'agx_bn_backward_phase')
+            else:
+                check(lib().agx_bn_backward(arr, len(idx), F, int(spec.training), ptr(wsb), n_ws,
+                                            stream_ptr()), 'agx_bn_backward')
             if direct:
                 dws = [None] * n
                 dbs = [None] * n
@@ -552,7 +575,7 @@ class _SoftmaxNLLFn(torch.autograd.Function):
     """coef * weighted-mean nll(log_softmax(logits), labels); also returns log-probabilities."""
 
     @staticmethod
-    def forward(ctx, logits, labels, class_w, coef):
+    def forward(ctx, logits, labels, class_w, coef, group=None):
         L.require_cuda(logits, 'logits')
         logits = logits.contiguous()
         n, c = logits.shape
@@ -565,6 +588,9 @@ class _SoftmaxNLLFn(torch.autograd.Function):
         check(lib().agx_log_softmax_nll(ptr(logits), logits.stride(0), n, c, ptr(labels),
                                         ptr(class_w), ptr(logp), logp.stride(0), ptr(loss_sum),
                                         ptr(row_ws), stream_ptr()), 'agx_log_softmax_nll')
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(loss_sum, group=group)
         check(lib().agx_loss_finish(ptr(loss_sum), coef, ptr(loss), 0, stream_ptr()),
               'agx_loss_finish')
         ctx.save_for_backward(logp, labels, loss_sum, class_w if class_w is not None else logp)
@@ -582,17 +608,19 @@ class _SoftmaxNLLFn(torch.autograd.Function):
                                             ptr(labels), ptr(cw) if ctx.has_w else None,
                                             ptr(loss_sum), ptr(gs), ctx.coef, None, 0, ptr(dx),
                                             dx.stride(0), stream_ptr()), 'agx_log_softmax_nll_bwd')
-        return dx, None, None, None
+        return dx, None, None, None, None
 
 
-def cross_entropy(logits, labels, weight: Optional[torch.Tensor] = None, coef: float = 1.0):
-    """``coef * F.cross_entropy(logits, labels, weight)`` (weighted mean), fused fwd/bwd."""
-    return _SoftmaxNLLFn.apply(logits, labels, weight, coef)[0]
+def cross_entropy(logits, labels, weight: Optional[torch.Tensor] = None, coef: float = 1.0,
+                  group=None):
+    """``coef * F.cross_entropy(logits, labels, weight)`` (weighted mean), fused fwd/bwd.  With
+    ``group`` the weighted mean is taken over the batch shards of all ranks."""
+    return _SoftmaxNLLFn.apply(logits, labels, weight, coef, group)[0]
 
 
-def softmax_nll(logits, labels, weight=None, coef: float = 1.0):
+def softmax_nll(logits, labels, weight=None, coef: float = 1.0, group=None):
     """Returns (loss, log_softmax(logits)) -- the GNN's output + loss in one pass."""
-    return _SoftmaxNLLFn.apply(logits, labels, weight, coef)
+    return _SoftmaxNLLFn.apply(logits, labels, weight, coef, group)
 
 
 class _NLLFromLogpFn(torch.autograd.Function):
@@ -600,7 +628,7 @@ class _NLLFromLogpFn(torch.autograd.Function):
     src/train_gnn_embeddings.py:29-30)."""
 
     @staticmethod
-    def forward(ctx, logp, labels):
+    def forward(ctx, logp, labels, group=None):
         L.require_cuda(logp, 'nll_loss input')
         n, c = logp.shape
         dev = logp.device
@@ -611,6 +639,9 @@ class _NLLFromLogpFn(torch.autograd.Function):
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         check(lib().agx_nll_forward(ptr(lp), lp.stride(0), n, c, ptr(labels), None, ptr(loss_sum),
                                     ptr(row_ws), stream_ptr()), 'agx_nll_forward')
+        if group is not None:        # mean over the rows of ALL ranks: (sum nll, count) all-reduced
+            import torch.distributed as dist
+            dist.all_reduce(loss_sum, group=group)
         check(lib().agx_loss_finish(ptr(loss_sum), 1.0, ptr(loss), 0, stream_ptr()),
               'agx_loss_finish')
         ctx.save_for_backward(labels, loss_sum)
@@ -625,11 +656,13 @@ class _NLLFromLogpFn(torch.autograd.Function):
         gs = g.reshape(1).to(torch.float32).contiguous()
         check(lib().agx_nll_backward(n, c, ptr(labels), None, ptr(loss_sum), ptr(gs), 1.0, ptr(dlp),
                                      c, stream_ptr()), 'agx_nll_backward')
-        return dlp, None
+        return dlp, None, None
 
 
-def nll_loss(logp: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
-    return _NLLFromLogpFn.apply(logp, labels)
+def nll_loss(logp: torch.Tensor, labels: torch.Tensor, group=None) -> torch.Tensor:
+    """``F.nll_loss(logp, labels)``; with ``group`` the mean runs over the rows of all ranks (each
+    rank then holds the gradient of the GLOBAL loss w.r.t. its own rows)."""
+    return _NLLFromLogpFn.apply(logp, labels, group)
 
 
 # ------------------------------------------------------------------------------------------------
