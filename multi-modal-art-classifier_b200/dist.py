@@ -1,0 +1,275 @@
+"""Multi-GPU execution of the path (nothing like it exists in the reference, which is
+single-process): one process per GPU, ``torch.distributed`` (NCCL over NVLink / NVSwitch) for the
+plumbing.
+
+GNN: the graph is partitioned **by destination node**.  Every node type is cut into ``world``
+contiguous id ranges; rank p owns the destination rows of its ranges and every edge that points at
+them, so the per-row neighbour lists -- and their order -- are those of the single-GPU CSR.  Source
+rows owned by another rank are *boundary* ("halo") rows: before each conv layer every rank packs
+the rows some other rank needs (``agx_pack_rows``) and one NCCL **all-gather** per node type appends
+all ranks' boundary rows to the local feature table; in the backward pass the gradient of that
+gathered region is **reduce-scattered** back to the owners (``agx_unpack_rows_add``).  Weights are
+replicated; their gradients (one flat arena, ``FlatAdam``) take one **all-reduce**; BatchNorm
+statistics over the rows of all ranks take two small float64 all-reduces per layer
+(``agx_bn_forward_phase``), the loss one.  With these the N-GPU step is arithmetically the
+single-GPU step on the whole graph.
+
+For the block-diagonal N-times replicated graph of BASELINE config 5 partitioned block by block no
+edge is cut, every boundary list is empty and no feature rows move.
+
+Heads: batch-sharded data parallel, one all-reduce of the gradient arena per step, and the class
+weighted CE normaliser (sum of w_y) all-reduced so the weighted mean equals the single-GPU one
+(``functional.cross_entropy(..., group=)``).
+
+``GraphPartition`` is host-side index arithmetic in plain torch (runs on CPU or CUDA tensors, no
+kernels): it is covered by world_size-2 ``gloo`` tests on CPU.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from ._lib import check, lib, ptr, stream_ptr
+
+
+def split_bounds(n: int, world: int) -> List[int]:
+    """``world + 1`` boundaries of contiguous ranges whose sizes differ by at most one."""
+    base, rem = divmod(int(n), int(world))
+    out = [0]
+    for q in range(world):
+        out.append(out[-1] + base + (1 if q < rem else 0))
+    return out
+
+
+class GraphPartition:
+    """Destination-node partition of one heterograph, from the point of view of ``rank``.
+
+    Feature table of node type t on this rank ("extended" table):
+        rows [0, n_owned[t])                                 the rows this rank owns
+        row  n_owned[t] + q * max_boundary[t] + j            the j-th boundary row of rank q
+    (the second region exists only if some rank has boundary rows of type t).
+
+    ``edge_index[(s, rel, d)]``: the edges whose destination this rank owns, in their original
+    order, row 0 = source index into the extended table of s, row 1 = destination index into the
+    owned rows of d.
+    """
+
+    def __init__(self, edge_index_dict, num_nodes: Dict[str, int], world: int, rank: int,
+                 bounds: Optional[Dict[str, List[int]]] = None):
+        self.world, self.rank = int(world), int(rank)
+        self.num_nodes = OrderedDict((t, int(n)) for t, n in num_nodes.items())
+        self.bounds = {t: list(bounds[t]) if bounds and t in bounds else split_bounds(n, world)
+                       for t, n in self.num_nodes.items()}
+        for t, b in self.bounds.items():
+            if len(b) != world + 1 or b[0] != 0 or b[-1] != self.num_nodes[t] or \
+                    any(b[i] > b[i + 1] for i in range(world)):
+                raise ValueError(f'bounds of {t} must be {world + 1} ascending ids from 0 to N')
+        dev = next(iter(edge_index_dict.values())).device
+        bt = {t: torch.tensor(b, dtype=torch.int64, device=dev) for t, b in self.bounds.items()}
+
+        def owner(t, ids):
+            return torch.bucketize(ids, bt[t][1:], right=True)
+
+        # 1. boundary rows: sources of edges whose destination lives on another rank
+        is_b = {t: torch.zeros(n, dtype=torch.bool, device=dev) for t, n in self.num_nodes.items()}
+        own_dst = {}
+        for (s, r, d), ei in edge_index_dict.items():
+            if ei.numel() and (int(ei[0].max()) >= self.num_nodes[s] or int(ei[0].min()) < 0 or
+                               int(ei[1].max()) >= self.num_nodes[d] or int(ei[1].min()) < 0):
+                raise IndexError('edge_index contains node ids outside [0, num_nodes)')
+            od = owner(d, ei[1])
+            own_dst[(s, r, d)] = od
+            is_b[s][ei[0][owner(s, ei[0]) != od]] = True
+
+        # 2. slots of the boundary rows inside their owner's packed send buffer
+        self.n_owned: Dict[str, int] = {}
+        self.n_ext: Dict[str, int] = {}
+        self.max_boundary: Dict[str, int] = {}
+        self.n_boundary: Dict[str, List[int]] = {}
+        self.boundary_idx: Dict[str, torch.Tensor] = {}
+        self.ext_global: Dict[str, torch.Tensor] = {}
+        ext_of_global = {}
+        for t, n in self.num_nodes.items():
+            lo, hi = self.bounds[t][rank], self.bounds[t][rank + 1]
+            csum0 = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev),
+                               torch.cumsum(is_b[t].to(torch.int64), 0)])
+            at_bounds = csum0[bt[t]]
+            cnt = (at_bounds[1:] - at_bounds[:-1]).tolist()
+            B = max(cnt) if cnt else 0
+            self.n_boundary[t] = [int(c) for c in cnt]
+            self.max_boundary[t] = int(B)
+            self.n_owned[t] = hi - lo
+            self.n_ext[t] = (hi - lo) + (world * B if B > 0 else 0)
+            self.boundary_idx[t] = torch.nonzero(is_b[t][lo:hi]).flatten().to(torch.int32)
+            ids = torch.arange(n, dtype=torch.int64, device=dev)
+            own = owner(t, ids)
+            slot = csum0[1:] - 1 - at_bounds[own]
+            ext_of_global[t] = torch.where(own == rank, ids - lo, (hi - lo) + own * B + slot)
+            eg = torch.full((self.n_ext[t],), -1, dtype=torch.int64, device=dev)
+            eg[:hi - lo] = ids[lo:hi]
+            if B > 0:
+                bi = torch.nonzero(is_b[t]).flatten()
+                eg[(hi - lo) + own[bi] * B + slot[bi]] = bi
+            self.ext_global[t] = eg
+
+        # 3. the edges this rank owns, re-indexed, original order kept
+        self.edge_index = OrderedDict()
+        for (s, r, d), ei in edge_index_dict.items():
+            m = own_dst[(s, r, d)] == rank
+            self.edge_index[(s, r, d)] = torch.stack(
+                [ext_of_global[s][ei[0][m]], ei[1][m] - self.bounds[d][rank]], dim=0).contiguous()
+
+    @property
+    def has_halo(self) -> bool:
+        return any(b > 0 for b in self.max_boundary.values())
+
+    def owned(self, t: str, x_global: torch.Tensor) -> torch.Tensor:
+        """This rank's rows of a per-node tensor of type t (features, labels)."""
+        return x_global[self.bounds[t][self.rank]:self.bounds[t][self.rank + 1]]
+
+    def halo_rows(self) -> int:
+        """Rows this rank receives per exchange (all types)."""
+        return sum(self.world * b for b in self.max_boundary.values())
+
+
+class _HaloFn(torch.autograd.Function):
+    """x_owned [n, F] -> extended table [n + world * B, F] (pack, all-gather); backward:
+    reduce-scatter of the gathered region's gradient + scatter-add into the owned rows."""
+
+    @staticmethod
+    def forward(ctx, x, idx, B, group):
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        n, F = x.shape
+        x = x.contiguous()
+        ext = torch.empty(n + world * B, F, dtype=torch.float32, device=x.device)
+        ext[:n].copy_(x)
+        send = ops.zeros((B, F), x.device) if idx.numel() < B else \
+            torch.empty(B, F, dtype=torch.float32, device=x.device)
+        check(lib().agx_pack_rows(ptr(x), x.stride(0), ptr(idx), idx.numel(), F, ptr(send),
+                                  stream_ptr()), 'agx_pack_rows')
+        dist.all_gather_into_tensor(ext[n:], send, group=group)
+        ctx.save_for_backward(idx)
+        ctx.meta = (n, F, B, group)
+        return ext
+
+    @staticmethod
+    def backward(ctx, d_ext):
+        import torch.distributed as dist
+        (idx,) = ctx.saved_tensors
+        n, F, B, group = ctx.meta
+        d_ext = d_ext.contiguous()
+        dx = d_ext[:n].clone()
+        recv = torch.empty(B, F, dtype=torch.float32, device=d_ext.device)
+        dist.reduce_scatter_tensor(recv, d_ext[n:], group=group)
+        check(lib().agx_unpack_rows_add(ptr(dx), dx.stride(0), ptr(idx), idx.numel(), F, ptr(recv),
+                                        stream_ptr()), 'agx_unpack_rows_add')
+        return dx, None, None, None
+
+
+class HaloExchange:
+    """Runtime side of a ``GraphPartition``: extends owned feature tables by the boundary rows of
+    all ranks.  Input features that do not change between steps are exchanged once (cached on
+    tensor identity + version)."""
+
+    def __init__(self, part: GraphPartition, group, device):
+        self.group = group
+        self.n_owned = dict(part.n_owned)
+        self.n_ext = dict(part.n_ext)
+        self.max_boundary = dict(part.max_boundary)
+        self.idx = {t: part.boundary_idx[t].to(device=device, dtype=torch.int32).contiguous()
+                    for t in part.boundary_idx}
+        self._cache: Dict[str, tuple] = {}
+        self.rows_exchanged = 0
+
+    def extend(self, x_dict, cache: bool = False):
+        out = OrderedDict()
+        for t, x in x_dict.items():
+            B = self.max_boundary.get(t, 0)
+            if B == 0:
+                out[t] = x
+                continue
+            if x.shape[0] != self.n_owned[t]:
+                raise ValueError(f"x['{t}'] has {x.shape[0]} rows, this rank owns {self.n_owned[t]}")
+            if cache and not x.requires_grad:
+                key = (x.data_ptr(), tuple(x.shape), x._version)
+                hit = self._cache.get(t)
+                if hit is not None and hit[0] == key:
+                    out[t] = hit[1]
+                    continue
+            ext = _HaloFn.apply(x, self.idx[t], B, self.group)
+            self.rows_exchanged += ext.shape[0] - x.shape[0]
+            if cache and not x.requires_grad:
+                self._cache[t] = (key, ext)
+            out[t] = ext
+        return out
+
+
+    @torch.no_grad()
+    def refresh(self, x_dict):
+        """New values were copied into cached (static) input tables: redo their exchange INTO the
+        cached extended tables (addresses unchanged, so a captured CUDA graph reads the new rows)."""
+        for t, x in x_dict.items():
+            hit = self._cache.get(t)
+            if hit is None or self.max_boundary.get(t, 0) == 0:
+                continue
+            key = (x.data_ptr(), tuple(x.shape), x._version)
+            if hit[0] != key:
+                hit[1].copy_(_HaloFn.apply(x, self.idx[t], self.max_boundary[t], self.group))
+                self._cache[t] = (key, hit[1])
+
+
+@dataclass
+class DistContext:
+    """What the hetero module and the trainers need to run one rank of a multi-GPU job."""
+    group: object
+    rank: int
+    world: int
+    num_nodes_global: Dict[str, int]            # rows of every node type over all ranks
+    halo: Optional[HaloExchange] = None
+    _counts: Optional[dict] = None
+
+    def __deepcopy__(self, memo):           # process groups are not copyable; share the context
+        return self
+
+    def counts(self, types, device) -> torch.Tensor:
+        """float64 [len(types)] global row counts (BatchNorm over the rows of all ranks)."""
+        if self._counts is None:
+            self._counts = {}
+        key = (tuple(types), str(device))
+        c = self._counts.get(key)
+        if c is None:
+            c = torch.tensor([float(self.num_nodes_global[t]) for t in types], dtype=torch.float64,
+                             device=device)
+            self._counts[key] = c
+        return c
+
+
+def block_context(group, num_nodes_block: Dict[str, int]) -> DistContext:
+    """Context of the block-diagonal replicated graph, one block per rank (no edge is cut)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    return DistContext(group, dist.get_rank(group), world,
+                       {t: int(n) * world for t, n in num_nodes_block.items()}, None)
+
+
+def partition_context(part: GraphPartition, group, device) -> DistContext:
+    halo = HaloExchange(part, group, device) if part.has_halo else None
+    return DistContext(group, part.rank, part.world, dict(part.num_nodes), halo)
+
+
+def all_reduce_(t: torch.Tensor, group) -> torch.Tensor:
+    import torch.distributed as dist
+    dist.all_reduce(t, group=group)
+    return t
+
+
+def broadcast_(t: torch.Tensor, group, src: int = 0) -> torch.Tensor:
+    import torch.distributed as dist
+    dist.broadcast(t, src=dist.get_global_rank(group, src) if group is not None else src,
+                   group=group)
+    return t

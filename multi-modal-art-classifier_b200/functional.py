@@ -106,6 +106,7 @@ class _HeteroConvFn(torch.autograd.Function):
         by_dst: Dict[str, List[RelSpec]] = {t: [] for t in spec.dst_types}
         for rs in spec.rels:
             by_dst[rs.rel.dst].append(rs)
+        xd = _dst_views(spec, xs)
 
         # s0: per destination type, the sum of root weights and of biases
         wroot: Dict[str, Optional[torch.Tensor]] = {}
@@ -158,7 +159,8 @@ class _HeteroConvFn(torch.autograd.Function):
         for t, lst in by_dst.items():
             outs[t] = torch.empty(lst[0].rel.n_dst, O, dtype=torch.float32, device=dev)
             # root product against one-hot features: x[t] W^T = W^T, written first, rest accumulates
-            id_root[t] = bool(spec.identity.get(t, False)) and wroot[t] is not None
+            id_root[t] = bool(spec.identity.get(t, False)) and wroot[t] is not None and \
+                xd[t] is xs[t]
             if id_root[t]:
                 ops.transpose_into(outs[t], wroot[t])
             tf_all = [(k, rs) for k, rs in enumerate(spec.rels)
@@ -215,7 +217,7 @@ class _HeteroConvFn(torch.autograd.Function):
                 if rs.rel.dst == t and not rs.transform_first:
                     segs.append((G[k], _t(params[rs.i_wl])))
             if wroot[t] is not None and not id_root[t]:
-                segs.append((xs[t], _t(wroot[t])))
+                segs.append((xd[t], _t(wroot[t])))
             if not segs and bsum[t] is not None:
                 # bias only (no dense segment left): rank-1 product ones[N,1] @ bias[1,O]
                 ones = ops.fill_(torch.empty(outs[t].shape[0], 1, dtype=torch.float32, device=dev), 1.0)
@@ -246,6 +248,7 @@ class _HeteroConvFn(torch.autograd.Function):
         params = tensors[nt:]
         G = {k: saved[n_in + i] for i, k in enumerate(ctx.g_keys)}
         wroot = {t: saved[n_in + len(G) + i] for i, t in enumerate(ctx.wroot_types)}
+        xd = _dst_views(spec, xs)
         O = spec.out_channels
         dev = tensors[0].device
         dout: Dict[str, Optional[torch.Tensor]] = {}
@@ -293,10 +296,10 @@ class _HeteroConvFn(torch.autograd.Function):
         for t in spec.dst_types:
             if dout[t] is None or t not in wroot:
                 continue
-            x = xs[t]
+            x = xd[t]
             dw = torch.empty(O, x.shape[1], dtype=torch.float32, device=dev)
             dwroot[t] = dw
-            if spec.identity.get(t, False):
+            if spec.identity.get(t, False) and x is xs[t]:
                 ops.transpose_into(dw, dout[t])                  # dout^T I
             else:
                 gb.add(dw, [(_t(dout[t]), x)], split_k=ops.split_k_for(x.shape[0]))
@@ -324,6 +327,7 @@ class _HeteroConvFn(torch.autograd.Function):
 
         # b5: input gradients per source type
         groups = {}
+        late_root: list = []
         long_chunks: Dict[int, list] = {}
         long_sums: list = []
         for t in spec.node_types:
@@ -355,8 +359,14 @@ class _HeteroConvFn(torch.autograd.Function):
             if temps:
                 long_sums.append((dx, ([dx] if af_short else []) + temps))
             segs = [(dY[k], params[rs.i_wl]) for k, rs in tf]
-            if root:
+            if root and xd[t] is xs[t]:
                 segs.append((dout[t], wroot[t]))
+            elif root:
+                # partitioned graph: the table carries other ranks' boundary rows behind the owned
+                # rows; the root term only reaches the owned ones (second, accumulating launch)
+                if not (af or tf):
+                    ops.fill_(dx, 0.0)
+                late_root.append((dx[:xd[t].shape[0]], [(dout[t], wroot[t])], True))
             groups.setdefault(('gemm',), []).append((dx, segs, bool(af)))
         gb = ops.GemmBatch()
         for key in sorted(k for k in groups.keys() if k != ('gemm',)):
@@ -373,8 +383,28 @@ class _HeteroConvFn(torch.autograd.Function):
                 gb.add(dx, segs, accumulate=acc)
         if gb.problems:
             gb.run()
+        for dx, segs, acc in late_root:
+            gb.add(dx, segs, accumulate=acc)
+        if gb.problems:
+            gb.run()
         _deliver_param_grads(spec.param_refs, grads, nt)
         return (None, *grads)
+
+
+def _dst_views(spec: ConvSpec, xs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """x[t] as seen by the root (``lin_r``) term: the rows of the destination nodes.  Single GPU:
+    the whole table; on a rank of a partitioned graph (dist.GraphPartition) the owned rows, which
+    precede the gathered boundary rows."""
+    out = {}
+    for rs in spec.rels:
+        t = rs.rel.dst
+        if t in out or t not in xs:
+            continue
+        x = xs[t]
+        if x.shape[0] < rs.rel.n_dst:
+            raise ValueError(f"x['{t}'] has {x.shape[0]} rows, the graph has {rs.rel.n_dst}")
+        out[t] = x if x.shape[0] == rs.rel.n_dst else x[:rs.rel.n_dst]
+    return out
 
 
 def _deliver_param_grads(param_refs, grads, offset):
@@ -424,6 +454,7 @@ class BNSpec:
     param_refs: Optional[tuple] = None       # ([weight Parameters], [bias Parameters])
     group: object = None                     # torch.distributed process group -> SyncBN
     counts: Optional[torch.Tensor] = None    # float64 [n] global row counts (with group)
+    counts_of: Optional[object] = None       # callable(indices) -> counts of a subset (cached)
 
 
 class _BNActFn(torch.autograd.Function):
@@ -519,7 +550,7 @@ class _BNActFn(torch.autograd.Function):
             if spec.group is not None and spec.training:
                 import torch.distributed as dist
                 totals = torch.empty(len(idx) * 2 * F, dtype=torch.float64, device=dev)
-                counts = spec.counts[idx].contiguous() if len(idx) != n else spec.counts
+                counts = spec.counts_of(tuple(idx)) if len(idx) != n else spec.counts
                 check(lib().agx_bn_backward_phase(arr, len(idx), F, 1, ptr(wsb), n_ws, 1, ptr(totals),
                                                   ptr(counts), stream_ptr()), 'agx_bn_backward_phase')
                 dist.all_reduce(totals, group=spec.group)

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 from collections import OrderedDict
 from dataclasses import dataclass
-from typing import Dict, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 
@@ -42,7 +42,7 @@ class HeteroPlan:
     """All relations of one heterograph in device CSR + CSC form."""
 
     def _edge_lists(self, edge_index_dict):
-        num_nodes = self.num_nodes
+        num_nodes, num_dst = self.num_nodes, self.num_dst
         lists = []
         keys = list(edge_index_dict.keys())
         for (s, r, d) in keys:
@@ -51,10 +51,10 @@ class HeteroPlan:
                 raise AgxError('edge_index must be a CUDA tensor: this package has no CPU path')
             if ei.dim() != 2 or ei.shape[0] != 2 or ei.dtype != torch.int64:
                 raise ValueError(f'edge_index of {(s, r, d)} must be int64 [2, E]')
-            lists.append((ei[1], ei[0], num_nodes[d], num_nodes[s]))     # CSR: key = dst
+            lists.append((ei[1], ei[0], num_dst[d], num_nodes[s]))       # CSR: key = dst
         for (s, r, d) in keys:
             ei = edge_index_dict[(s, r, d)]
-            lists.append((ei[0], ei[1], num_nodes[s], num_nodes[d]))     # CSC: key = src
+            lists.append((ei[0], ei[1], num_nodes[s], num_dst[d]))       # CSC: key = src
         return keys, lists
 
     def rebuild_(self, edge_index_dict):
@@ -72,8 +72,13 @@ class HeteroPlan:
             if int(b[4].item()) != 0:
                 raise IndexError('edge_index contains node ids outside [0, num_nodes)')
 
-    def __init__(self, edge_index_dict, num_nodes: Dict[str, int]):
+    def __init__(self, edge_index_dict, num_nodes: Dict[str, int],
+                 num_dst: Optional[Dict[str, int]] = None):
+        # num_nodes: rows of every type's feature table as a SOURCE; num_dst: rows it has as a
+        # DESTINATION (fewer on a rank of a partitioned graph, whose source tables carry the
+        # boundary rows of the other ranks behind the owned rows -- dist.GraphPartition)
         self.num_nodes = dict(num_nodes)
+        self.num_dst = dict(num_dst) if num_dst is not None else self.num_nodes
         keys, lists = self._edge_lists(edge_index_dict)
         self._buffers: list = []
         built = ops.csr_build(lists, buffers=self._buffers)
@@ -87,7 +92,7 @@ class HeteroPlan:
         R = len(keys)
         self.rels: "OrderedDict[EdgeType, Relation]" = OrderedDict()
         for i, (s, r, d) in enumerate(keys):
-            self.rels[(s, r, d)] = Relation(s, r, d, num_nodes[s], num_nodes[d],
+            self.rels[(s, r, d)] = Relation(s, r, d, self.num_nodes[s], self.num_dst[d],
                                             built[i].n_edges, built[i], built[R + i])
         self.n_edges = sum(r.n_edges for r in self.rels.values())
 
@@ -99,17 +104,19 @@ _PLAN_CACHE: "OrderedDict[tuple, HeteroPlan]" = OrderedDict()
 _PLAN_CACHE_MAX = 8
 
 
-def get_plan(edge_index_dict, num_nodes: Dict[str, int], cache: bool = True) -> HeteroPlan:
+def get_plan(edge_index_dict, num_nodes: Dict[str, int], cache: bool = True,
+             num_dst: Optional[Dict[str, int]] = None) -> HeteroPlan:
     """Plans are cached on the identity + version of the edge_index tensors (a static graph is
     sorted once, like the reference never re-sorts because it never sorts)."""
     if not cache:
-        return HeteroPlan(edge_index_dict, num_nodes)
+        return HeteroPlan(edge_index_dict, num_nodes, num_dst)
     sig = tuple((k, v.data_ptr(), tuple(v.shape)) for k, v in edge_index_dict.items())
-    sig = (sig, tuple(sorted(num_nodes.items())))
+    sig = (sig, tuple(sorted(num_nodes.items())),
+           None if num_dst is None else tuple(sorted(num_dst.items())))
     versions = tuple(v._version for v in edge_index_dict.values())
     plan = _PLAN_CACHE.get(sig)
     if plan is None:
-        plan = HeteroPlan(edge_index_dict, num_nodes)
+        plan = HeteroPlan(edge_index_dict, num_nodes, num_dst)
         plan._keepalive = list(edge_index_dict.values())   # pin the addresses the key refers to
         plan._versions = versions
         _PLAN_CACHE[sig] = plan

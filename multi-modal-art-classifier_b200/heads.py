@@ -96,17 +96,22 @@ class LabelProjectorHead(nn.Module):
         return AF.fused_linear([visual_features], self.encoder.weight, self.encoder.bias)
 
 
-def multitask_loss(out, style_labels, genre_labels, w_style=None, w_genre=None):
+def multitask_loss(out, style_labels, genre_labels, w_style=None, w_genre=None, group=None):
     """``0.5*CE(out[0], y_style; w) + 0.5*CE(out[1], y_genre; w)``
-    (src/train_new_multimodal_multitask.py:48-55,79-81), fused softmax+nll per head."""
-    style_loss = AF.cross_entropy(out[0], style_labels, w_style, coef=0.5)
-    genre_loss = AF.cross_entropy(out[1], genre_labels, w_genre, coef=0.5)
+    (src/train_new_multimodal_multitask.py:48-55,79-81), fused softmax+nll per head.  With
+    ``group`` (batch-sharded heads) both weighted means run over the batch shards of all ranks."""
+    style_loss = AF.cross_entropy(out[0], style_labels, w_style, coef=0.5, group=group)
+    genre_loss = AF.cross_entropy(out[1], genre_labels, w_genre, coef=0.5, group=group)
     return style_loss + genre_loss
 
 
-def projector_loss(out, embedding):
-    """``SmoothL1Loss()(out, embedding)`` (src/train_projector.py:33,52)."""
-    return AF.smooth_l1_loss(out, embedding)
+def projector_loss(out, embedding, global_rows: Optional[int] = None):
+    """``SmoothL1Loss()(out, embedding)`` (src/train_projector.py:33,52).  ``global_rows``: batch
+    rows over all ranks -- this rank's term of the global mean (the terms sum to the loss)."""
+    loss = AF.smooth_l1_loss(out, embedding)
+    if global_rows is not None and global_rows != out.shape[0]:
+        loss = loss * (out.shape[0] / float(global_rows))
+    return loss
 
 
 def select_embeddings(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:

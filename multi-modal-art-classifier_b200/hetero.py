@@ -107,6 +107,15 @@ class HeteroModule(nn.Module):
         self._warned = set()
         self.dropout_masks: Optional[Dict[str, torch.Tensor]] = None   # test hook (injected masks)
         self._seed = None
+        self._dist = None            # dist.DistContext: this module runs one rank of a multi-GPU job
+
+    def set_distributed(self, ctx):
+        """Run as one rank of a destination-partitioned multi-GPU job (dist.DistContext):
+        BatchNorm statistics over the rows of all ranks, boundary-row exchange before every conv,
+        a different dropout stream per rank.  ``None`` restores single-GPU behaviour."""
+        self._dist = ctx
+        self._seed = None
+        return self
 
     # ---- static analysis ----------------------------------------------------------------------
     def _liveness(self):
@@ -150,7 +159,10 @@ class HeteroModule(nn.Module):
     # ---- execution ----------------------------------------------------------------------------
     def _seed_state(self, device):
         if self._seed is None or self._seed.device != device:
-            s = torch.initial_seed() & 0x7fffffffffffffff
+            s = torch.initial_seed()
+            if self._dist is not None:
+                s += 0x9E3779B97F4A7C15 * (self._dist.rank + 1)
+            s &= 0x7fffffffffffffff
             self._seed = torch.tensor([s, 0], dtype=torch.int64, device=device)
         return self._seed
 
@@ -166,6 +178,9 @@ class HeteroModule(nn.Module):
     def _conv(self, node, x_dict, ei_dict, plan, is_input):
         convs = self.get_submodule(node.target)
         key = (node.target, id(plan))
+        if self._dist is not None and self._dist.halo is not None:
+            # boundary rows of the other ranks behind the owned rows (static inputs: once)
+            x_dict = self._dist.halo.extend(x_dict, cache=is_input)
         types = [t for t in self.node_types if t in x_dict]
         dev = x_dict[types[0]].device
         params: List[torch.Tensor] = []
@@ -217,6 +232,11 @@ class HeteroModule(nn.Module):
                       running=[(bns[t].running_mean, bns[t].running_var) for t in types],
                       with_act=relu is not None, dmasks=dmasks,
                       param_refs=([bns[t].weight for t in types], [bns[t].bias for t in types]))
+        if self._dist is not None:
+            spec.group = self._dist.group
+            ctx, dev = self._dist, x_dict[types[0]].device
+            spec.counts = ctx.counts(types, dev)
+            spec.counts_of = lambda idx: ctx.counts([types[i] for i in idx], dev)
         res = AF.batch_norm_act(spec, [x_dict[t].contiguous() for t in types],
                                 [bns[t].weight for t in types], [bns[t].bias for t in types])
         n = len(types)
@@ -234,7 +254,12 @@ class HeteroModule(nn.Module):
         x_dict, ei_dict = x, edge_index
         num_nodes = {t: v.shape[0] for t, v in x_dict.items()}
         ei_dict = OrderedDict((tuple(k), v) for k, v in ei_dict.items())
-        plan = get_plan(OrderedDict((et, ei_dict[et]) for et in self.edge_types), num_nodes)
+        num_dst = None
+        if self._dist is not None and self._dist.halo is not None:
+            num_dst, num_nodes = num_nodes, {t: self._dist.halo.n_ext.get(t, n)
+                                             for t, n in num_nodes.items()}
+        plan = get_plan(OrderedDict((et, ei_dict[et]) for et in self.edge_types), num_nodes,
+                        num_dst=num_dst)
         env = {self._placeholders[0]: x_dict, self._placeholders[1]: ei_dict}
         provided = {}
 

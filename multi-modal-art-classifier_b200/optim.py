@@ -63,6 +63,12 @@ class FlatAdam:
         self._members = members
         self._member_ids = {id(p) for p in members}
 
+    def flatten(self):
+        """Move the parameters into the flat arena now (otherwise done by the first step)."""
+        if self.flat is None:
+            self._flatten()
+        return self
+
     def _ensure(self):
         if self.flat is None:
             self._flatten()

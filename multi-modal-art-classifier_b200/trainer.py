@@ -30,11 +30,22 @@ def _accuracy(logp: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
 
 
 class GNNTrainer:
+    """``dist_ctx`` (dist.DistContext) makes this one rank of a multi-GPU job: ``x_dict`` / ``labels``
+    are the rows this rank owns, ``edge_index_dict`` its edges (dist.GraphPartition.edge_index, or
+    its own block of the replicated graph); the loss, BatchNorm statistics and weight gradients are
+    those of the whole graph (NCCL all-reduces inside the captured step)."""
+
     def __init__(self, model: torch.nn.Module, x_dict, edge_index_dict, labels: torch.Tensor,
                  lr: float = 0.01, use_cuda_graph: bool = True, node_type: str = 'artwork',
-                 dist_group=None):
+                 dist_ctx=None):
         self.model = model
-        self.group = dist_group
+        self.ctx = dist_ctx
+        self.group = dist_ctx.group if dist_ctx is not None else None
+        if dist_ctx is not None:
+            from .hetero import HeteroModule
+            for m in model.modules():
+                if isinstance(m, HeteroModule):
+                    m.set_distributed(dist_ctx)
         self._id_flags = {}
         self._identity_seen = {}
         self._plan = None
@@ -55,8 +66,11 @@ class GNNTrainer:
     def _step_eager(self):
         self.opt.zero_grad()
         emb, out = self.model(self.x, self.ei)
-        loss = AF.nll_loss(out[0][self.node_type], self.y)
+        loss = AF.nll_loss(out[0][self.node_type], self.y, self.group)
         loss.backward()
+        if self.group is not None:          # every rank holds d(global loss)/dW of its own rows
+            from .dist import all_reduce_
+            all_reduce_(self.opt.grad, self.group)
         self.opt.step()
         return loss, emb, out
 
@@ -66,6 +80,10 @@ class GNNTrainer:
             with torch.no_grad():                       # materialise lazy weights (:146-147)
                 self.model(self.x, self.ei)
             self.opt = FlatAdam(self.model.parameters(), lr=self.lr)
+            self.opt.flatten()
+            if self.group is not None:      # replicated weights: rank 0's initialisation
+                from .dist import broadcast_
+                broadcast_(self.opt.flat, self.group)
 
     def train_step(self) -> torch.Tensor:
         """``hetero_training()``: returns the (device) loss of this step."""
@@ -92,7 +110,9 @@ class GNNTrainer:
         torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
         n0 = launch_count()
-        with torch.cuda.graph(self._graph):
+        # NCCL's watchdog thread polls events while this thread captures: thread-local error mode
+        mode = 'thread_local' if self.group is not None else 'global'
+        with torch.cuda.graph(self._graph, capture_error_mode=mode):
             self._loss, self._emb, self._out = self._step_eager()
         self.launches_per_step = launch_count() - n0
 
@@ -107,7 +127,13 @@ class GNNTrainer:
         for k, v in host_ei.items():
             self.ei[k].copy_(v, non_blocking=True)
         num_nodes = {t: v.shape[0] for t, v in self.x.items()}
-        self._plan = get_plan(self.ei, num_nodes)            # version bump -> in-place re-sort
+        num_dst = None
+        if self.ctx is not None and self.ctx.halo is not None:
+            num_dst, num_nodes = num_nodes, {t: self.ctx.halo.n_ext.get(t, n)
+                                             for t, n in num_nodes.items()}
+        self._plan = get_plan(self.ei, num_nodes, num_dst=num_dst)   # version bump -> re-sort
+        if self.ctx is not None and self.ctx.halo is not None:
+            self.ctx.halo.refresh(self.x)
         self._id_flags = {}
         for t, v in self.x.items():
             if v.dim() == 2 and v.shape[0] == v.shape[1] and v.shape[0] >= 2:
@@ -138,7 +164,7 @@ class GNNTrainer:
         y = self.y if labels is None else labels.to(torch.int64)
         _, out = self.model(x, ei)
         logp = out[0][self.node_type]
-        loss = AF.nll_loss(logp, y)
+        loss = AF.nll_loss(logp, y, self.group if x_dict is None else None)
         self.model.train()
         return loss, _accuracy(logp, y)
 
@@ -157,12 +183,21 @@ class HeadTrainer:
     """One fused step per mini-batch on device-resident (or freshly copied) features."""
 
     def __init__(self, head: torch.nn.Module, kind: str = 'multitask', lr: float = 3e-4,
-                 w_style=None, w_genre=None):
+                 w_style=None, w_genre=None, group=None):
+        """``group``: batch-sharded data parallel -- ``step`` gets this rank's shard of the batch;
+        weights are replicated (rank 0's), gradients all-reduced (one NCCL call on the arena)."""
         assert kind in ('multitask', 'projector')
         self.head = head
         self.kind = kind
-        self.opt = FlatAdam(head.parameters(), lr=lr)
+        self.opt = FlatAdam(head.parameters(), lr=lr).flatten()
         self.w_style, self.w_genre = w_style, w_genre
+        self.group = group
+        self.world = 1
+        if group is not None:
+            import torch.distributed as dist
+            from .dist import broadcast_
+            self.world = dist.get_world_size(group)
+            broadcast_(self.opt.flat, group)
 
     def step(self, feat, *rest) -> torch.Tensor:
         self.head.train()
@@ -170,10 +205,15 @@ class HeadTrainer:
         if self.kind == 'multitask':
             emb_s, emb_g, y_s, y_g = rest
             out = self.head(feat, emb_s, emb_g)
-            loss = multitask_loss(out, y_s, y_g, self.w_style, self.w_genre)
+            loss = multitask_loss(out, y_s, y_g, self.w_style, self.w_genre, self.group)
         else:
-            (target,) = rest
-            loss = projector_loss(self.head(feat), target)
+            (target,) = rest             # equal shards: global rows = world * local rows
+            loss = projector_loss(self.head(feat), target, feat.shape[0] * self.world)
         loss.backward()
+        if self.group is not None:
+            from .dist import all_reduce_
+            all_reduce_(self.opt.grad, self.group)
+            if self.kind == 'projector':
+                loss = all_reduce_(loss.detach().clone(), self.group)
         self.opt.step()
         return loss

@@ -1,0 +1,168 @@
+"""Host-side logic of the multi-GPU path (mmac_b200.dist.GraphPartition) on CPU: world_size-2
+``gloo`` processes partition the same heterograph by destination node, exchange boundary rows the
+way the CUDA path does (pack -> all-gather -> extended table; gradient: reduce-scatter ->
+scatter-add; emulated here with plain torch ops, the product uses agx_pack_rows /
+agx_unpack_rows_add + NCCL) and must reproduce the oracle's single-process aggregation of the
+whole graph: bit-exact forward (same in-row neighbour order), gradients to 1e-6."""
+import os
+import socket
+import sys
+import traceback
+from collections import OrderedDict
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import util  # noqa: F401  (sys.path)
+from oracle import graph_oracle as go
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _extend(part, t, x_owned):
+    """pack boundary rows -> all-gather -> [owned ; gathered]  (dist._HaloFn.forward on CPU)."""
+    B = part.max_boundary[t]
+    if B == 0:
+        return x_owned
+    send = torch.zeros(B, x_owned.shape[1], dtype=x_owned.dtype)
+    idx = part.boundary_idx[t].long()
+    send[:idx.numel()] = x_owned[idx]
+    bufs = [torch.empty_like(send) for _ in range(part.world)]
+    dist.all_gather(bufs, send)
+    return torch.cat([x_owned] + bufs, dim=0)
+
+
+def _fold_grad(part, t, d_ext):
+    """reduce-scatter of the gathered region + scatter-add (dist._HaloFn.backward on CPU)."""
+    n, B = part.n_owned[t], part.max_boundary[t]
+    if B == 0:
+        return d_ext
+    tail = d_ext[n:].clone()
+    dist.all_reduce(tail)
+    mine = tail[part.rank * B:(part.rank + 1) * B]
+    dx = d_ext[:n].clone()
+    idx = part.boundary_idx[t].long()
+    dx[idx] += mine[:idx.numel()]
+    return dx
+
+
+def _worker(rank, world, port, size, bounds_kind, errq):
+    try:
+        os.environ['MASTER_ADDR'] = '127.0.0.1'
+        os.environ['MASTER_PORT'] = str(port)
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+        import mmac_b200  # noqa: F401
+        from mmac_b200 import synth
+        from mmac_b200.dist import GraphPartition, split_bounds
+        torch.set_num_threads(1)
+        if bounds_kind == 'blocks':
+            g = synth.replicate(synth.make_artgraph(size, features='dense'), world)
+        else:
+            g = synth.make_artgraph(size, features='dense')
+        ei = go.to_undirected(g.edge_index_dict)
+        n = g.num_nodes_dict
+        bounds = None
+        if bounds_kind == 'uneven':            # an empty shard and a lopsided one
+            bounds = {'style': [0, 0, n['style']], 'artwork': [0, n['artwork'] // 5, n['artwork']]}
+        part = GraphPartition(ei, n, world, rank, bounds)
+        for t in n:
+            assert part.bounds[t][0] == 0 and part.bounds[t][-1] == n[t]
+            assert part.n_owned[t] == part.bounds[t][rank + 1] - part.bounds[t][rank]
+        if bounds_kind == 'blocks':
+            assert not part.has_halo and part.halo_rows() == 0
+            for t in n:
+                assert part.n_ext[t] == part.n_owned[t] == n[t] // world
+        else:
+            assert part.has_halo
+
+        # every edge lands on exactly one rank
+        cnt = torch.tensor([sum(v.shape[1] for v in part.edge_index.values())])
+        dist.all_reduce(cnt)
+        assert int(cnt) == sum(v.shape[1] for v in ei.values())
+
+        xg = {t: g.x_dict[t].clone().requires_grad_(True) for t in n}
+        xl = {t: part.owned(t, g.x_dict[t]).clone().requires_grad_(True) for t in n}
+        ext = {t: _extend(part, t, xl[t]) for t in n}
+        for t in n:
+            eg = part.ext_global[t]
+            assert ext[t].shape[0] == part.n_ext[t] == eg.numel()
+            ok = eg >= 0
+            assert torch.equal(ext[t][ok].detach(), g.x_dict[t][eg[ok]])
+        tot_g = 0
+        tot_l = 0
+        for k, ((s, r, d), e) in enumerate(ei.items()):
+            reduce = 'mean' if k % 2 == 0 else 'sum'
+            ref = go.propagate(xg[s], e, n[d], reduce)
+            le = part.edge_index[(s, r, d)]
+            if le.numel():
+                assert int(le[0].max()) < part.n_ext[s] and int(le[1].max()) < part.n_owned[d]
+            out = go.propagate(ext[s], le, part.n_owned[d], reduce)
+            assert torch.equal(out.detach(), part.owned(d, ref).detach()), (s, r, d)
+            w = torch.cos(torch.arange(ref.numel(), dtype=torch.float32)).view_as(ref) * (1 + k)
+            tot_g = tot_g + (ref * w).sum()
+            tot_l = tot_l + (out * part.owned(d, w)).sum()
+        tot_g.backward()
+        d_ext = torch.autograd.grad(tot_l, [ext[t] for t in n], allow_unused=True)
+        for t, de in zip(n, d_ext):
+            if de is None:
+                de = torch.zeros_like(ext[t])
+            dx = _fold_grad(part, t, de)
+            ref = part.owned(t, xg[t].grad)
+            err = float((dx - ref).abs().max()) / max(float(ref.abs().max()), 1e-30) \
+                if ref.numel() else 0.0
+            assert err < 1e-6, (t, err)
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        errq.put(f'rank {rank}:\n{traceback.format_exc()}')
+        raise
+
+
+@pytest.mark.parametrize('bounds_kind', ['even', 'uneven', 'blocks'])
+def test_partition_halo_exchange_world2_gloo(bounds_kind):
+    world = 2
+    ctx = mp.get_context('spawn')
+    errq = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 'tiny', bounds_kind, errq))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+    msgs = []
+    while not errq.empty():
+        msgs.append(errq.get())
+    assert not msgs, '\n'.join(msgs)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+
+
+def test_split_bounds():
+    import mmac_b200  # noqa: F401
+    from mmac_b200.dist import split_bounds
+    assert split_bounds(10, 4) == [0, 3, 6, 8, 10]
+    assert split_bounds(2, 4) == [0, 1, 2, 2, 2]
+    assert split_bounds(0, 2) == [0, 0, 0]
+    for n in (1, 7, 18, 32, 116475):
+        for w in (1, 2, 4, 8):
+            b = split_bounds(n, w)
+            sizes = [b[i + 1] - b[i] for i in range(w)]
+            assert b[0] == 0 and b[-1] == n and max(sizes) - min(sizes) <= 1
+
+
+def test_partition_single_rank_is_identity():
+    import mmac_b200  # noqa: F401
+    from mmac_b200 import synth
+    from mmac_b200.dist import GraphPartition
+    g = synth.make_artgraph('tiny', features='dense')
+    ei = go.to_undirected(g.edge_index_dict)
+    part = GraphPartition(ei, g.num_nodes_dict, 1, 0)
+    assert not part.has_halo
+    for k, v in ei.items():
+        assert torch.equal(part.edge_index[k], v)
