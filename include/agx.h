@@ -132,11 +132,15 @@ typedef struct {
     int32_t n_rows;
     int32_t n_edges;
     float* frag;              /* [agx_chunk_frag_floats(n_edges, F)] scratch                     */
+    int32_t* counters;        /* [agx_chunk_counters(n_edges)] arrival counters: ALL ZERO on entry,
+                                 all zero again when the kernel has finished                      */
 } agx_chunk_seg_t;
 
 size_t agx_chunk_frag_floats(int64_t n_edges, int F);
-/* edge-balanced variant for relations with long rows (few destination rows, many edges):
- * one warp per 128 consecutive CSR edges, row fragments combined in fixed chunk order */
+size_t agx_chunk_counters(int64_t n_edges);
+/* edge-balanced variant for relations with long rows (few destination rows, many edges): one warp
+ * per 128 consecutive CSR edges; rows that cross chunks are completed, in fixed chunk order, by the
+ * last warp to deliver a fragment (one launch, no float atomics, reproducible) */
 int agx_aggregate_chunks(const agx_chunk_seg_t* h_segs, int n_segs, int F, int dtype,
                          void* stream);
 

@@ -44,7 +44,7 @@ class RowGroup(C.Structure):
 
 class ChunkSeg(C.Structure):
     _fields_ = [('rel', Rel), ('out', vp), ('ldo', c_i64), ('n_rows', c_i32), ('n_edges', c_i32),
-                ('frag', vp)]
+                ('frag', vp), ('counters', vp)]
 
 
 class GemmSeg(C.Structure):
@@ -91,6 +91,7 @@ _SIGS = {
     'agx_coalesce_undirected': (C.c_int, [vp, vp, c_i64, c_i64, vp, vp, vp, vp, C.c_size_t, vp]),
     'agx_aggregate_rows': (C.c_int, [C.POINTER(RowGroup), C.c_int, C.c_int, C.c_int, vp]),
     'agx_chunk_frag_floats': (C.c_size_t, [c_i64, C.c_int]),
+    'agx_chunk_counters': (C.c_size_t, [c_i64]),
     'agx_aggregate_chunks': (C.c_int, [C.POINTER(ChunkSeg), C.c_int, C.c_int, C.c_int, vp]),
     'agx_gemm_grouped': (C.c_int, [C.POINTER(GemmProblem), C.c_int, C.POINTER(GemmSeg), C.c_int,
                                    vp]),

@@ -291,51 +291,71 @@ agg_rows(const __grid_constant__ RowGroups P) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// agg_chunks: warp per 128 CSR edges.  frag layout per segment: lead[chunks][F], trail[chunks][F]
+// agg_chunks: edge-balanced, ONE launch.  A warp owns 128 consecutive CSR edges of one relation.
+//
+//   * the chunk's neighbour ids (and 1/nbr_scale) are staged once in shared memory, the first row
+//     is found by a warp-wide 32-ary search, row extents are read 32 rows at a time;
+//   * LPR = F/VEC lanes cover one feature row; the 32/LPR sub-warps take alternating edges of a row
+//     segment (F=32: four 128 B gathers per load instruction instead of one) and their partial
+//     sums are added in sub-warp order -- for LPR = 32 (F >= 128) that is plain edge order;
+//   * a row that lies inside the chunk is written directly (mean: divided by its count); a row
+//     that crosses chunk boundaries leaves per-chunk fragments (lead[chunk] = the part of a row
+//     that started in an earlier chunk, trail[chunk] = the start of a row that continues), and
+//     the LAST warp to deliver a fragment of that row (one counter per row, self-resetting) adds
+//     them up in chunk order: trail[c0] + lead[c0+1] + ... -- a fixed order whoever does it, so
+//     results are reproducible; no float atomics, no second kernel;
+//   * rows without edges are zero-filled by the chunk that holds the preceding edge (no memset).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int upper_bound_i32(const int32_t* a, int n, int key) {
-    int lo = 0, hi = n;            // first index with a[idx] > key
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(a + mid) <= key) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
+constexpr int kGatherDepth = 8;                    // feature-row loads in flight per lane
 
 template <typename T, int VEC>
-__device__ __forceinline__ void accumulate_edges(Vec<T, VEC>& acc, const agx_rel_t& R, const T* x,
-                                                 int e0, int e1, int lane, bool active) {
-    // sequential (edge order) sum of rows col[e0..e1); neighbour ids fetched 32 at a time
-    for (int e = e0; e < e1; e += 32) {
-        const int n = min(32, e1 - e);
-        int c = lane < n ? __ldg(R.col + e + lane) : 0;
-        float s = 1.0f;
-        if (R.nbr_scale && lane < n) s = 1.0f / __ldg(R.nbr_scale + c);
-        for (int j0 = 0; j0 < n; j0 += 8) {
-            Vec<T, VEC> v[8];
-            float sj[8];
+__device__ __forceinline__ Vec<T, VEC> load_frag(const float* p) {   // L2 (other SMs wrote it)
+    Vec<T, VEC> r;
+    if constexpr (VEC % 4 == 0) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int cj = __shfl_sync(0xffffffffu, c, (j0 + u) & 31);
-                sj[u] = __shfl_sync(0xffffffffu, s, (j0 + u) & 31);
-                if (j0 + u < n && active) v[u] = load_vec<T, VEC>(x + (int64_t)cj * R.ldx);
-                else v[u].zero();
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (j0 + u < n) {
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i) acc.v[i] += v[u].v[i] * sj[u];
-                }
+        for (int i = 0; i < VEC; i += 4) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(p + i));
+            r.v[i] = t.x; r.v[i + 1] = t.y; r.v[i + 2] = t.z; r.v[i + 3] = t.w;
         }
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) r.v[i] = __ldcg(p + i);
     }
+    return r;
 }
 
 template <typename T, int VEC>
+__device__ __forceinline__ void store_frag(float* p, const Vec<T, VEC>& a) {
+    if constexpr (VEC % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; i += 4)
+            *reinterpret_cast<float4*>(p + i) = make_float4(a.v[i], a.v[i + 1], a.v[i + 2], a.v[i + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) p[i] = a.v[i];
+    }
+}
+
+// rows [r0, r1) of the segment's output have no edges: write zeros (whole warp, VEC-wide stores)
+template <typename T, int VEC>
+__device__ __forceinline__ void zero_rows(const agx_chunk_seg_t& S, int F, int r0, int r1, int lane) {
+    Vec<T, VEC> z;
+    z.zero();
+    for (int r = r0; r < r1; ++r)
+        for (int c0 = lane * VEC; c0 < F; c0 += 32 * VEC)
+            store_vec<T, VEC>(reinterpret_cast<T*>(S.out) + (int64_t)r * S.ldo + c0, z);
+}
+
+template <typename T, int VEC, int LPR>
 __global__ void __launch_bounds__(kAggThreads)
 agg_chunks(const __grid_constant__ ChunkSegs P) {
-    const int lane = threadIdx.x & 31;
-    const int64_t gchunk = (int64_t)blockIdx.x * kAggWarps + (threadIdx.x >> 5);
+    constexpr int SUB = 32 / LPR;
+    constexpr int U = kGatherDepth;
+    __shared__ int s_col[kAggWarps][AGX_CHUNK_EDGES];
+    __shared__ float s_scl[kAggWarps][AGX_CHUNK_EDGES];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int sub = lane / LPR, l = lane % LPR;
+    const int64_t gchunk = (int64_t)blockIdx.x * kAggWarps + w;
     if (gchunk >= P.chunk_start[P.n]) return;
     int si = 0;
     while (gchunk >= P.chunk_start[si + 1]) ++si;
@@ -346,114 +366,148 @@ agg_chunks(const __grid_constant__ ChunkSegs P) {
     const int nchunks = P.chunk_start[si + 1] - P.chunk_start[si];
     const int start = chunk * AGX_CHUNK_EDGES;
     const int end = min(S.n_edges, start + AGX_CHUNK_EDGES);
+    const int n_rows = S.n_rows;
     float* lead = S.frag;
     float* trail = S.frag + (size_t)nchunks * F;
 
-    for (int c0 = lane * VEC; c0 < ((F + 32 * VEC - 1) / (32 * VEC)) * (32 * VEC); c0 += 32 * VEC) {
-        const bool active = c0 < F;
-        const T* x = reinterpret_cast<const T*>(R.x) + c0;
-        int row = upper_bound_i32(R.rowptr, S.n_rows + 1, start) - 1;
-        int e = start;
-        while (e < end) {
-            const int rbeg = __ldg(R.rowptr + row), rend = __ldg(R.rowptr + row + 1);
-            const int e1 = min(rend, end);
+    // ---- stage neighbour ids / scales ----------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < AGX_CHUNK_EDGES / 32; ++k) {
+        const int i = k * 32 + lane;
+        int c = 0;
+        if (start + i < end) c = __ldg(R.col + start + i);
+        s_col[w][i] = c;
+        s_scl[w][i] = (R.nbr_scale && start + i < end) ? 1.0f / __ldg(R.nbr_scale + c) : 1.0f;
+    }
+    // ---- row of the first edge: largest r with rowptr[r] <= start (32-ary search) ---------------
+    int lo = 0, hi = n_rows;                       // rowptr[lo] <= start < rowptr[hi]
+    while (hi - lo > 1) {
+        const int step = (hi - lo + 31) >> 5;
+        const int p = lo + (lane + 1) * step;
+        const int v = p < hi ? __ldg(R.rowptr + p) : INT_MAX;
+        const int cnt = __popc(__ballot_sync(0xffffffffu, v <= start));
+        lo += cnt * step;
+        hi = min(hi, lo + step);
+    }
+    int row = lo;
+    __syncwarp();
+    if (chunk == 0) zero_rows<T, VEC>(S, F, 0, row, lane);
+
+    int wrow = row;                                // row-extent window: lane i holds rowptr[wrow+1+i]
+    int rp = wrow + 1 + lane <= n_rows ? __ldg(R.rowptr + wrow + 1 + lane) : INT_MAX;
+    int rbeg = __ldg(R.rowptr + row);
+    int e = start;
+    while (true) {
+        if (row - wrow >= 32) {
+            wrow = row;
+            rp = wrow + 1 + lane <= n_rows ? __ldg(R.rowptr + wrow + 1 + lane) : INT_MAX;
+        }
+        const int rend = __shfl_sync(0xffffffffu, rp, row - wrow);
+        const int e1 = min(rend, end);
+        const bool starts_here = rbeg >= start, ends_here = rend <= end;
+        const int i0 = e - start, i1 = e1 - start;
+        // ---- the row segment [e, e1), one block of LPR*VEC columns at a time ---------------------
+        for (int cb = 0; cb < F; cb += LPR * VEC) {
+            const int c0 = cb + l * VEC;
+            const bool active = c0 < F;
+            const T* x = reinterpret_cast<const T*>(R.x) + c0;
             Vec<T, VEC> acc;
             acc.zero();
-            accumulate_edges<T, VEC>(acc, R, x, e, e1, lane, active);
-            const bool starts_here = rbeg >= start, ends_here = rend <= end;
-            if (active) {
+            for (int base = i0; base < i1; base += SUB * U) {
+                Vec<T, VEC> v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = base + u * SUB + sub;
+                    if (i < i1 && active) v[u] = load_vec<T, VEC>(x + (int64_t)s_col[w][i] * R.ldx);
+                    else v[u].zero();
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = base + u * SUB + sub;
+                    if (i < i1) {
+                        const float sc = s_scl[w][i];
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k) acc.v[k] += v[u].v[k] * sc;
+                    }
+                }
+            }
+            if (SUB > 1) {                         // partial sums of the sub-warps, in sub-warp order
+                Vec<T, VEC> tot;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) tot.v[k] = __shfl_sync(0xffffffffu, acc.v[k], l);
+#pragma unroll
+                for (int sw = 1; sw < SUB; ++sw)
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k)
+                        tot.v[k] += __shfl_sync(0xffffffffu, acc.v[k], sw * LPR + l);
+                acc = tot;
+            }
+            if (active && sub == 0) {
                 if (starts_here && ends_here) {
                     if (R.row_cnt) {
                         const float d = __ldg(R.row_cnt + row);
 #pragma unroll
-                        for (int i = 0; i < VEC; ++i) acc.v[i] = acc.v[i] / d;
+                        for (int k = 0; k < VEC; ++k) acc.v[k] = acc.v[k] / d;
                     }
                     store_vec<T, VEC>(reinterpret_cast<T*>(S.out) + (int64_t)row * S.ldo + c0, acc);
                 } else {
-                    float* f = (starts_here ? trail : lead) + (size_t)chunk * F + c0;
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i) f[i] = acc.v[i];
+                    store_frag<T, VEC>((starts_here ? trail : lead) + (size_t)chunk * F + c0, acc);
                 }
             }
-            e = e1;
-            if (e < end) {
-                ++row;
-                while (__ldg(R.rowptr + row + 1) <= e) ++row;     // skip empty rows
-            }
         }
-    }
-}
-
-// One warp per chunk that owns a spanning row (the row starts in the chunk and runs past its end):
-// total = trail[c] + lead[c+1] + ... + lead[c_last], in chunk order.
-template <typename T, int VEC>
-__global__ void __launch_bounds__(kAggThreads)
-agg_chunks_fixup(const __grid_constant__ ChunkSegs P) {
-    const int lane = threadIdx.x & 31;
-    // one CTA per chunk; the (rare) owning CTAs spread the row's fragments over their 8 warps:
-    // warp w adds lead[chunk+1+w], lead[chunk+1+w+8], ... and warp 0 combines trail + the 8 warp
-    // sums in warp order -- a fixed order, so the result is reproducible.
-    __shared__ float wsum[kAggWarps][128 + 4];
-    const int w = threadIdx.x >> 5;
-    const int64_t gchunk = blockIdx.x;
-    if (gchunk >= P.chunk_start[P.n]) return;
-    int si = 0;
-    while (gchunk >= P.chunk_start[si + 1]) ++si;
-    const agx_chunk_seg_t& S = P.s[si];
-    const agx_rel_t& R = S.rel;
-    const int F = P.F;
-    const int chunk = (int)(gchunk - P.chunk_start[si]);
-    const int nchunks = P.chunk_start[si + 1] - P.chunk_start[si];
-    const int start = chunk * AGX_CHUNK_EDGES;
-    const int end = min(S.n_edges, start + AGX_CHUNK_EDGES);
-    if (end >= S.n_edges) return;                       // last chunk cannot own a spanning row
-    const int row = upper_bound_i32(R.rowptr, S.n_rows + 1, end - 1) - 1;   // row of the last edge
-    const int rbeg = __ldg(R.rowptr + row), rend = __ldg(R.rowptr + row + 1);
-    if (!(rend > end && rbeg >= start)) return;          // uniform over the CTA
-    const int c_last = (rend - 1) / AGX_CHUNK_EDGES;
-    const float* lead = S.frag;
-    const float* trail = S.frag + (size_t)nchunks * F;
-    for (int cb = 0; cb < F; cb += 128) {                // 128 columns per round (smem staging)
-        const int cw = min(128, F - cb);
-        for (int c0 = lane * VEC; c0 < cw; c0 += 32 * VEC) {
-            float acc[VEC];
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
-            int c = chunk + 1 + w;
-            for (; c + 3 * kAggWarps <= c_last; c += 4 * kAggWarps) {
-                float t[4][VEC];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i)
-                        t[u][i] = lead[(size_t)(c + u * kAggWarps) * F + cb + c0 + i];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i) acc[i] += t[u][i];
-            }
-            for (; c <= c_last; c += kAggWarps)
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) acc[i] += lead[(size_t)c * F + cb + c0 + i];
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) wsum[w][c0 + i] = acc[i];
-        }
-        __syncthreads();
-        if (w == 0) {
-            for (int c0 = lane * VEC; c0 < cw; c0 += 32 * VEC) {
-                Vec<T, VEC> o;
+        // ---- a fragment of a row that crosses chunks: the last one to arrive adds them up ----------
+        if (!(starts_here && ends_here)) {
+            const int c_first = rbeg / AGX_CHUNK_EDGES, c_last = (rend - 1) / AGX_CHUNK_EDGES;
+            __threadfence();
+            __syncwarp();
+            int old = 0;
+            if (lane == 0) old = atomicAdd(S.counters + c_first, 1);
+            old = __shfl_sync(0xffffffffu, old, 0);
+            if (old == c_last - c_first) {
+                __threadfence();
                 const float d = R.row_cnt ? __ldg(R.row_cnt + row) : 1.0f;
+                for (int c0 = lane * VEC; c0 < F; c0 += 32 * VEC) {
+                    Vec<T, VEC> tot = load_frag<T, VEC>(trail + (size_t)c_first * F + c0);
+                    for (int c = c_first + 1; c <= c_last; c += U) {
+                        Vec<T, VEC> v[U];
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) {
-                    float a = trail[(size_t)chunk * F + cb + c0 + i];
+                        for (int u = 0; u < U; ++u)
+                            if (c + u <= c_last) v[u] = load_frag<T, VEC>(lead + (size_t)(c + u) * F + c0);
 #pragma unroll
-                    for (int k = 0; k < kAggWarps; ++k) a += wsum[k][c0 + i];
-                    o.v[i] = R.row_cnt ? a / d : a;
+                        for (int u = 0; u < U; ++u)
+                            if (c + u <= c_last) {
+#pragma unroll
+                                for (int k = 0; k < VEC; ++k) tot.v[k] += v[u].v[k];
+                            }
+                    }
+                    if (R.row_cnt) {
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k) tot.v[k] = tot.v[k] / d;
+                    }
+                    store_vec<T, VEC>(reinterpret_cast<T*>(S.out) + (int64_t)row * S.ldo + c0, tot);
                 }
-                store_vec<T, VEC>(reinterpret_cast<T*>(S.out) + (int64_t)row * S.ldo + cb + c0, o);
+                if (lane == 0) S.counters[c_first] = 0;          // ready for the next launch
             }
         }
-        __syncthreads();
+        e = e1;
+        if (rend > end) break;                     // the row continues in the next chunk
+        // ---- next row with edges; the empty rows in between are this chunk's to clear -------------
+        int nr = row + 1;
+        while (nr < n_rows) {
+            if (nr - wrow >= 32) {
+                wrow = nr;
+                rp = wrow + 1 + lane <= n_rows ? __ldg(R.rowptr + wrow + 1 + lane) : INT_MAX;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, rp > rend) & (0xffffffffu << (nr - wrow));
+            const int stop = m ? wrow + (__ffs(m) - 1) : wrow + 32;
+            const int upto = min(stop, n_rows);
+            zero_rows<T, VEC>(S, F, nr, upto, lane);
+            nr = upto;
+            if (m) break;
+        }
+        if (e >= end || nr >= n_rows) break;
+        row = nr;
+        rbeg = rend;
     }
 }
 
@@ -535,6 +589,21 @@ extern "C" size_t agx_chunk_frag_floats(int64_t n_edges, int F) {
     return (size_t)2 * (size_t)ceil_div(n_edges > 0 ? n_edges : 1, AGX_CHUNK_EDGES) * (size_t)F;
 }
 
+extern "C" size_t agx_chunk_counters(int64_t n_edges) {
+    return (size_t)ceil_div(n_edges > 0 ? n_edges : 1, AGX_CHUNK_EDGES);
+}
+
+template <typename T, int VEC>
+static int launch_chunks(const ChunkSegs& P, int lpr, unsigned grid, cudaStream_t st) {
+    switch (lpr) {
+        case 32: agg_chunks<T, VEC, 32><<<grid, kAggThreads, 0, st>>>(P); break;
+        case 16: agg_chunks<T, VEC, 16><<<grid, kAggThreads, 0, st>>>(P); break;
+        default: agg_chunks<T, VEC, 8><<<grid, kAggThreads, 0, st>>>(P); break;
+    }
+    AGX_LAUNCH_CHECK("agg_chunks");
+    return AGX_OK;
+}
+
 extern "C" int agx_aggregate_chunks(const agx_chunk_seg_t* h_segs, int n_segs, int F, int dtype,
                                     void* stream) {
     AGX_CHECK_ARG(h_segs && n_segs >= 1 && n_segs <= AGX_MAX_CHUNK_SEGS,
@@ -555,14 +624,15 @@ extern "C" int agx_aggregate_chunks(const agx_chunk_seg_t* h_segs, int n_segs, i
         AGX_CHECK_ARG(S.n_rows >= 0 && S.n_edges >= 0, "agx_aggregate_chunks: seg %d sizes", s);
         AGX_CHECK_ARG(S.rel.rowptr && S.rel.x && (S.out || S.n_rows == 0),
                       "agx_aggregate_chunks: seg %d: null pointer", s);
-        AGX_CHECK_ARG(S.n_edges == 0 || (S.rel.col && S.frag),
-                      "agx_aggregate_chunks: seg %d: null col/frag", s);
+        AGX_CHECK_ARG(S.n_edges == 0 || (S.rel.col && S.frag && S.counters),
+                      "agx_aggregate_chunks: seg %d: null col/frag/counters", s);
         vec_ok = vec_ok && aligned_to(S.out, 16) && (S.ldo * esz) % 16 == 0 &&
-                 aligned_to(S.rel.x, 16) && (S.rel.ldx * esz) % 16 == 0;
+                 aligned_to(S.rel.x, 16) && (S.rel.ldx * esz) % 16 == 0 &&
+                 (S.n_edges == 0 || aligned_to(S.frag, 16));
         P.s[s] = S;
         P.chunk_start[s + 1] = P.chunk_start[s] + (int32_t)ceil_div(S.n_edges, AGX_CHUNK_EDGES);
-        // rows without edges are never visited by a chunk: clear the output first
-        if (S.n_rows > 0)
+        // a relation without edges is visited by no chunk: clear its output here
+        if (S.n_edges == 0 && S.n_rows > 0)
             AGX_CUDA(cudaMemset2DAsync(S.out, (size_t)S.ldo * esz, 0, (size_t)F * esz,
                                        (size_t)S.n_rows, st));
     }
@@ -570,26 +640,10 @@ extern "C" int agx_aggregate_chunks(const agx_chunk_seg_t* h_segs, int n_segs, i
     if (chunks == 0) return AGX_OK;
     const unsigned grid = (unsigned)ceil_div(chunks, kAggWarps);
     if (dtype == AGX_F32) {
-        if (vec_ok) {
-            agg_chunks<float, 4><<<grid, kAggThreads, 0, st>>>(P);
-            AGX_LAUNCH_CHECK("agg_chunks");
-            agg_chunks_fixup<float, 4><<<(unsigned)chunks, kAggThreads, 0, st>>>(P);
-        } else {
-            agg_chunks<float, 1><<<grid, kAggThreads, 0, st>>>(P);
-            AGX_LAUNCH_CHECK("agg_chunks");
-            agg_chunks_fixup<float, 1><<<(unsigned)chunks, kAggThreads, 0, st>>>(P);
-        }
-    } else {
-        if (vec_ok) {
-            agg_chunks<__nv_bfloat16, 8><<<grid, kAggThreads, 0, st>>>(P);
-            AGX_LAUNCH_CHECK("agg_chunks");
-            agg_chunks_fixup<__nv_bfloat16, 8><<<(unsigned)chunks, kAggThreads, 0, st>>>(P);
-        } else {
-            agg_chunks<__nv_bfloat16, 1><<<grid, kAggThreads, 0, st>>>(P);
-            AGX_LAUNCH_CHECK("agg_chunks");
-            agg_chunks_fixup<__nv_bfloat16, 1><<<(unsigned)chunks, kAggThreads, 0, st>>>(P);
-        }
+        if (vec_ok) return launch_chunks<float, 4>(P, max(8, min(32, pow2_ceil(F / 4))), grid, st);
+        return launch_chunks<float, 1>(P, max(8, min(32, pow2_ceil(F))), grid, st);
     }
-    AGX_LAUNCH_CHECK("agg_chunks_fixup");
-    return AGX_OK;
+    if (vec_ok)
+        return launch_chunks<__nv_bfloat16, 8>(P, max(8, min(32, pow2_ceil(F / 8))), grid, st);
+    return launch_chunks<__nv_bfloat16, 1>(P, max(8, min(32, pow2_ceil(F))), grid, st);
 }

@@ -147,7 +147,7 @@ struct TileLoader {
 // BM x BN CTA tile; each thread owns TM x TN outputs split in two halves per dimension
 // (rows ty*TM/2 + {0..TM/2-1} and BM/2 + ty*TM/2 + ..) so that float4 smem reads are conflict-free.
 template <int BM, int BN, int TM, int TN>
-__global__ void __launch_bounds__(kGemmThreads)
+__global__ void __launch_bounds__(kGemmThreads, 2)
 gemm_f32(const __grid_constant__ GemmParams P) {
     static_assert((BM / TM) * (BN / TN) == kGemmThreads, "thread tiling");
     constexpr int LDA = BM + 4, LDB = BN + 4;

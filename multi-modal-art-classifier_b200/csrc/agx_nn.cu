@@ -63,6 +63,40 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats(const __grid_constant__ B
     // thread t owns column (t % F) for F <= 256 lanes-of-columns; row groups stride over t / F.
     // float64 accumulation: the reference's CPU BatchNorm accumulates its statistics in double
     __shared__ double red[kBnThreads];
+    if ((F & 3) == 0 && F <= 4 * kBnThreads) {
+        // 128-bit path: thread owns 4 consecutive columns, row groups stride over t / (F/4);
+        // per column the same float64 sum order as below with `groups` row groups
+        __shared__ double red4[4][kBnThreads];
+        const int cols4 = F >> 2;
+        const int groups = kBnThreads / cols4;
+        const int c = (threadIdx.x % cols4) * 4, g = threadIdx.x / cols4;
+        double s[4] = {0.0, 0.0, 0.0, 0.0};
+        if (g < groups) {
+            float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pass) m = *reinterpret_cast<const float4*>(D.save_mean + c);
+            for (int r = r0 + g; r < r1; r += groups) {
+                const float4 x = *reinterpret_cast<const float4*>(D.x + (int64_t)r * F + c);
+                const double v0 = (double)x.x - (double)m.x, v1 = (double)x.y - (double)m.y;
+                const double v2 = (double)x.z - (double)m.z, v3 = (double)x.w - (double)m.w;
+                s[0] += pass ? v0 * v0 : v0;
+                s[1] += pass ? v1 * v1 : v1;
+                s[2] += pass ? v2 * v2 : v2;
+                s[3] += pass ? v3 * v3 : v3;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) red4[i][threadIdx.x] = s[i];
+        __syncthreads();
+        if (threadIdx.x < cols4) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double t = 0.0;
+                for (int gg = 0; gg < groups; ++gg) t += red4[i][gg * cols4 + threadIdx.x];
+                part[4 * threadIdx.x + i] = t;
+            }
+        }
+        return;
+    }
     for (int c0 = 0; c0 < F; c0 += kBnThreads) {
         const int cols = min(kBnThreads, F - c0);
         const int groups = kBnThreads / cols > 0 ? kBnThreads / cols : 1;   // row groups
@@ -218,6 +252,23 @@ __device__ __forceinline__ float bn_dy_total(const agx_bn_bwd_desc_t& D, int64_t
     return g;
 }
 
+__device__ __forceinline__ float4 bn_dy_total4(const agx_bn_bwd_desc_t& D, int64_t e) {
+    float4 g = D.dy ? *reinterpret_cast<const float4*>(D.dy + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (D.dy_act) {
+        float4 a = *reinterpret_cast<const float4*>(D.dy_act + e);
+        if (D.dmask) {
+            const float4 k = *reinterpret_cast<const float4*>(D.dmask + e);
+            a.x *= k.x; a.y *= k.y; a.z *= k.z; a.w *= k.w;
+        }
+        const float4 y = *reinterpret_cast<const float4*>(D.y + e);
+        g.x += y.x > 0.f ? a.x : 0.f;
+        g.y += y.y > 0.f ? a.y : 0.f;
+        g.z += y.z > 0.f ? a.z : 0.f;
+        g.w += y.w > 0.f ? a.w : 0.f;
+    }
+    return g;
+}
+
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce(const __grid_constant__ BnBwdParams P) {
     int di = 0;
     while ((int)blockIdx.x >= P.slab_start[di + 1]) ++di;
@@ -227,6 +278,45 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce(const __grid_constan
     const int F = P.F;
     double* part = P.ws + (size_t)blockIdx.x * 2 * F;
     __shared__ double red0[kBnThreads], red1[kBnThreads];
+    if ((F & 3) == 0 && F <= 4 * kBnThreads) {
+        __shared__ double r40[4][kBnThreads], r41[4][kBnThreads];
+        const int cols4 = F >> 2;
+        const int groups = kBnThreads / cols4;
+        const int c = (threadIdx.x % cols4) * 4, g = threadIdx.x / cols4;
+        double s0[4] = {0.0, 0.0, 0.0, 0.0}, s1[4] = {0.0, 0.0, 0.0, 0.0};
+        if (g < groups) {
+            const float4 m = *reinterpret_cast<const float4*>(D.save_mean + c);
+            const float4 is = *reinterpret_cast<const float4*>(D.save_invstd + c);
+            for (int r = r0 + g; r < r1; r += groups) {
+                const int64_t e = (int64_t)r * F + c;
+                const float4 gy = bn_dy_total4(D, e);
+                const float4 x = *reinterpret_cast<const float4*>(D.x + e);
+                s0[0] += (double)gy.x; s1[0] += (double)gy.x * (double)((x.x - m.x) * is.x);
+                s0[1] += (double)gy.y; s1[1] += (double)gy.y * (double)((x.y - m.y) * is.y);
+                s0[2] += (double)gy.z; s1[2] += (double)gy.z * (double)((x.z - m.z) * is.z);
+                s0[3] += (double)gy.w; s1[3] += (double)gy.w * (double)((x.w - m.w) * is.w);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            r40[i][threadIdx.x] = s0[i];
+            r41[i][threadIdx.x] = s1[i];
+        }
+        __syncthreads();
+        if (threadIdx.x < cols4) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double t0 = 0.0, t1 = 0.0;
+                for (int gg = 0; gg < groups; ++gg) {
+                    t0 += r40[i][gg * cols4 + threadIdx.x];
+                    t1 += r41[i][gg * cols4 + threadIdx.x];
+                }
+                part[4 * threadIdx.x + i] = t0;
+                part[F + 4 * threadIdx.x + i] = t1;
+            }
+        }
+        return;
+    }
     for (int c0 = 0; c0 < F; c0 += kBnThreads) {
         const int cols = min(kBnThreads, F - c0);
         const int groups = kBnThreads / cols > 0 ? kBnThreads / cols : 1;
@@ -275,6 +365,8 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize(const __grid_constant__ 
     }
 }
 
+constexpr int kBnApplyMaxF = 512;      // per-column coefficients staged in shared memory up to this F
+
 __global__ void __launch_bounds__(256) bn_bwd_apply(const __grid_constant__ BnBwdParams P) {
     int di = 0;
     while ((int)blockIdx.x >= P.slab_start[di + 1]) ++di;
@@ -286,6 +378,44 @@ __global__ void __launch_bounds__(256) bn_bwd_apply(const __grid_constant__ BnBw
     const float inv_n = (float)(1.0 / (P.counts ? P.counts[di] : (double)D.n_rows));
     const int64_t e0 = (int64_t)slab * kBnSlab * F;
     const int64_t e1 = min((int64_t)D.n_rows * F, e0 + (int64_t)kBnSlab * F);
+    if ((F & 3) == 0 && F <= kBnApplyMaxF) {
+        // dx = a*gy - b - xh*c  with per-column a = w*invstd, b = a*sum(dy)/n, c = a*sum(dy*xh)/n
+        // (same float operations per element as the scalar path below, in the same order)
+        __shared__ __align__(16) float s_is[kBnApplyMaxF], s_m[kBnApplyMaxF], s_w[kBnApplyMaxF],
+            s_t0[kBnApplyMaxF], s_t1[kBnApplyMaxF];
+        for (int c = threadIdx.x; c < F; c += blockDim.x) {
+            s_is[c] = D.save_invstd[c];
+            s_m[c] = D.save_mean[c];
+            s_w[c] = D.weight[c];
+            s_t0[c] = P.training ? (float)tot[c] * inv_n : 0.f;
+            s_t1[c] = P.training ? (float)tot[F + c] * inv_n : 0.f;
+        }
+        __syncthreads();
+        for (int64_t e = e0 + 4 * (int64_t)threadIdx.x; e < e1; e += 4 * (int64_t)blockDim.x) {
+            const int c = (int)(e % F);
+            const float4 gy = bn_dy_total4(D, e);
+            const float4 is = *reinterpret_cast<const float4*>(s_is + c);
+            const float4 w = *reinterpret_cast<const float4*>(s_w + c);
+            float4 dx;
+            if (P.training) {
+                const float4 x = *reinterpret_cast<const float4*>(D.x + e);
+                const float4 m = *reinterpret_cast<const float4*>(s_m + c);
+                const float4 t0 = *reinterpret_cast<const float4*>(s_t0 + c);
+                const float4 t1 = *reinterpret_cast<const float4*>(s_t1 + c);
+                dx.x = w.x * is.x * (gy.x - t0.x - (x.x - m.x) * is.x * t1.x);
+                dx.y = w.y * is.y * (gy.y - t0.y - (x.y - m.y) * is.y * t1.y);
+                dx.z = w.z * is.z * (gy.z - t0.z - (x.z - m.z) * is.z * t1.z);
+                dx.w = w.w * is.w * (gy.w - t0.w - (x.w - m.w) * is.w * t1.w);
+            } else {
+                dx.x = w.x * is.x * gy.x;
+                dx.y = w.y * is.y * gy.y;
+                dx.z = w.z * is.z * gy.z;
+                dx.w = w.w * is.w * gy.w;
+            }
+            *reinterpret_cast<float4*>(D.dx + e) = dx;
+        }
+        return;
+    }
     for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
         const int c = (int)(e % F);
         const float gy = bn_dy_total(D, e);

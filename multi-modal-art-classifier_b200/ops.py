@@ -230,6 +230,23 @@ def aggregate_rows(groups: Sequence[Tuple[torch.Tensor, Sequence[RelArg], bool]]
             TIMER.end('agg_rows', nb, 0, t0)
 
 
+# Arrival counters of agg_chunks: the kernel needs them zero on entry and leaves them zero, so one
+# zero-initialised buffer per device is handed out in slices, round robin (launches on one stream
+# are ordered; concurrent launches on different streams get different slices until the ring wraps).
+_COUNTER_RING = {}
+_COUNTER_RING_INTS = 1 << 20
+
+
+def _counter_slice(dev: torch.device, n: int) -> torch.Tensor:
+    buf, off = _COUNTER_RING.get(dev, (None, 0))
+    if buf is None or n > buf.numel():
+        buf, off = torch.zeros(max(_COUNTER_RING_INTS, 2 * n), dtype=torch.int32, device=dev), 0
+    if off + n > buf.numel():
+        off = 0
+    _COUNTER_RING[dev] = (buf, off + n)
+    return buf[off:off + n]
+
+
 def aggregate_chunks(segs: Sequence[Tuple[torch.Tensor, RelArg]], F: int):
     """Edge-balanced aggregation for long-row relations; ``segs``: (out [n_rows, F], relation)."""
     if not segs:
@@ -240,14 +257,23 @@ def aggregate_chunks(segs: Sequence[Tuple[torch.Tensor, RelArg]], F: int):
         part = segs[base:base + L.MAX_CHUNK_SEGS]
         arr = (L.ChunkSeg * len(part))()
         sizes = [lib().agx_chunk_frag_floats(a.csr.n_edges, F) for _, a in part]
+        ncnt = [lib().agx_chunk_counters(a.csr.n_edges) for _, a in part]
         frag = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
-        off = 0
+        counters = _counter_slice(dev, sum(ncnt))
+        off = coff = 0
         for i, (out, a) in enumerate(part):
             s = arr[i]
             s.rel = _rel_struct(a)
             s.out, s.ldo, s.n_rows, s.n_edges = ptr(out), out.stride(0), out.shape[0], a.csr.n_edges
             s.frag = frag.data_ptr() + 4 * off
+            s.counters = counters.data_ptr() + 4 * coff
             off += sizes[i]
+            coff += ncnt[i]
+        if _DEBUG:
+            print(f'[agx] agg_chunks F={F} ' + ', '.join(
+                f'(rows={out.shape[0]} E={a.csr.n_edges} max={a.csr.max_degree} '
+                f'mean={a.mean_rows} scale={a.nbr_scale is not None})' for out, a in part),
+                flush=True)
         t0 = TIMER.begin() if TIMER is not None else None
         check(lib().agx_aggregate_chunks(arr, len(part), F, dt, stream_ptr()),
               'agx_aggregate_chunks')
@@ -346,6 +372,13 @@ class GemmBatch:
                     sarr[so + t] = self.segs[src.seg_begin + t]
                 q.seg_begin = so
                 so += src.seg_count
+            if _DEBUG:
+                for k in range(i, j):
+                    src = self.problems[k]
+                    ks = [self.segs[src.seg_begin + t].K for t in range(src.seg_count)]
+                    print(f'[agx] gemm M={src.M} N={src.N} K={ks} split_k={src.split_k} '
+                          f'acc={src.accumulate}', flush=True)
+                print('[agx] gemm launch', flush=True)
             t0 = TIMER.begin() if TIMER is not None else None
             check(lib().agx_gemm_grouped(parr, j - i, sarr, max(nseg, 1), stream_ptr()),
                   'agx_gemm_grouped')
@@ -363,7 +396,7 @@ class GemmBatch:
         self.problems, self.segs, self._keep = [], [], []
 
 
-def split_k_for(k_rows: int, slab: int = 1024, max_split: int = 256) -> int:
+def split_k_for(k_rows: int, slab: int = 384, max_split: int = 512) -> int:
     return max(1, min(max_split, (k_rows + slab - 1) // slab))
 
 

@@ -136,6 +136,50 @@ def test_aggregate_chunks_long_rows(F, reduce):
     assert torch.equal(out, out2)                                      # run-to-run reproducible
 
 
+@pytest.mark.parametrize('F', [128, 64, 32, 200, 260, 18])
+def test_aggregate_chunks_many_segments_empty_rows_and_counter_reset(F):
+    """One launch over several relations: leading / interior / trailing rows without edges (the
+    kernel, not a memset, clears them), rows spanning hundreds of chunks next to 1-edge rows, a
+    relation without any edge; repeated launches reuse the self-resetting arrival counters and
+    must be bit-identical."""
+    gen = torch.Generator().manual_seed(300 + F)
+    specs = [(3000, 60, 50000, 'zipf'), (64, 7, 9000, 'uniform'), (500, 300, 1200, 'sparse'),
+             (40, 25, 0, 'uniform'), (2000, 3, 130, 'uniform'), (900, 1, 129, 'uniform')]
+    segs, refs, keep = [], [], []
+    for n_src, n_dst, e, kind in specs:
+        if kind == 'zipf':                      # rows 0-2 and the last 4 rows empty, rest Zipf
+            p = torch.zeros(n_dst, dtype=torch.float64)
+            p[3:n_dst - 4] = 1.0 / torch.arange(1, n_dst - 6, dtype=torch.float64)
+            dst = torch.multinomial(p / p.sum(), e, replacement=True, generator=gen)
+        elif kind == 'sparse':                  # most rows empty, runs of empty rows > 32
+            live = torch.randperm(n_dst, generator=gen)[:40]
+            dst = live[torch.randint(0, 40, (e,), generator=gen)]
+        else:
+            dst = torch.randint(0, n_dst, (e,), generator=gen)
+        ei = torch.stack([torch.randint(0, n_src, (e,), generator=gen), dst])
+        x = torch.randn(n_src, F, generator=gen)
+        mean = (len(segs) % 2 == 0)
+        refs.append(go.propagate(x, ei, n_dst, 'mean' if mean else 'add'))
+        (csr,) = ops.csr_build([(ei[1].to(DEV), ei[0].to(DEV), n_dst, n_src)])
+        csr.max_degree = int(torch.bincount(dst, minlength=n_dst).max()) if e else 0
+        out = torch.full((n_dst, F), float('nan'), device=DEV)
+        segs.append((out, ops.RelArg(csr, x.to(DEV), mean_rows=mean)))
+        keep.append((x, ei))
+    ops.aggregate_chunks(segs, F)
+    first = [o.clone() for o, _ in segs]
+    for (out, _), ref in zip(segs, refs):
+        assert not torch.isnan(out).any()
+        assert rel_err(out, ref) <= RTOL_F32
+        empty = ref.abs().sum(1) == 0
+        assert torch.all(out.cpu()[empty] == 0)
+    for _ in range(3):
+        for o, _a in segs:
+            o.fill_(float('nan'))
+        ops.aggregate_chunks(segs, F)
+        for (o, _a), f in zip(segs, first):
+            assert torch.equal(o, f)
+
+
 def test_aggregate_multi_relation_group_and_transpose_scale():
     gen = torch.Generator().manual_seed(4)
     n_dst, F = 700, 128
