@@ -309,6 +309,9 @@ int agx_is_identity(const float* x, int64_t ld, int32_t n, int32_t* flag, int32_
 /* out[j, i] = in[i, j] ; in [rows, cols]; skipped on device when only_if_flag && *only_if_flag==0 */
 int agx_transpose(const float* in, int64_t ld_in, int32_t rows, int32_t cols, float* out,
                   int64_t ld_out, const int32_t* only_if_flag, void* stream);
+/* up to AGX_MAX_TENSORS transposes in one launch (the W^T copies of a hetero layer) */
+typedef struct { const float* in; int64_t ld_in; float* out; int64_t ld_out; int32_t rows; int32_t cols; } agx_transpose_desc_t;
+int agx_transpose_batched(const agx_transpose_desc_t* h_descs, int n, void* stream);
 
 /* halo exchange support (config 5): pack rows listed in idx into a contiguous send buffer, and
  * scatter-add received gradient rows back (deterministic: idx is unique per call) */

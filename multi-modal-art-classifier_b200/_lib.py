@@ -58,6 +58,11 @@ class GemmProblem(C.Structure):
                 ('split_k', c_i32), ('partial', vp), ('skip_flag', vp)]
 
 
+class TransposeDesc(C.Structure):
+    _fields_ = [('inp', vp), ('ld_in', c_i64), ('out', vp), ('ld_out', c_i64), ('rows', c_i32),
+                ('cols', c_i32)]
+
+
 class SumDesc(C.Structure):
     _fields_ = [('out', vp), ('inp', vp * 8), ('n_in', c_i32), ('numel', c_i64)]
 
@@ -122,6 +127,7 @@ _SIGS = {
     'agx_gather_rows': (C.c_int, [vp, c_i64, vp, c_i64, c_i32, vp, c_i64, vp]),
     'agx_is_identity': (C.c_int, [vp, c_i64, c_i32, vp, vp, vp]),
     'agx_transpose': (C.c_int, [vp, c_i64, c_i32, c_i32, vp, c_i64, vp, vp]),
+    'agx_transpose_batched': (C.c_int, [C.POINTER(TransposeDesc), C.c_int, vp]),
     'agx_pack_rows': (C.c_int, [vp, c_i64, vp, c_i32, c_i32, vp, vp]),
     'agx_unpack_rows_add': (C.c_int, [vp, c_i64, vp, c_i32, c_i32, vp, vp]),
 }

@@ -22,6 +22,10 @@ namespace agx {
 bool gemm_tc_eligible(const agx_gemm_problem_t& Q, const agx_gemm_seg_t* segs);
 int gemm_tc_launch(const agx_gemm_problem_t* probs, const int* idx, int cnt,
                    const agx_gemm_seg_t* segs, cudaStream_t st);
+// agx_gemm_tc.cu: tcgen05 path for A^T B with a very long K (weight gradients), split over CTAs
+bool gemm_tc_longk_eligible(const agx_gemm_problem_t& Q, const agx_gemm_seg_t* segs);
+int gemm_tc_longk_launch(const agx_gemm_problem_t* probs, const int* idx, int cnt,
+                         const agx_gemm_seg_t* segs, int* used_split, cudaStream_t st);
 
 constexpr int kGemmThreads = 256;
 constexpr int BK = 16;
@@ -268,24 +272,47 @@ struct ReduceParams {
     int32_t n;
 };
 
+// 64 consecutive outputs per CTA; thread (g, j) adds slabs g, g+4, ... of output j, the four
+// group sums are then added in group order: a fixed order, independent of the grid.
 __global__ void __launch_bounds__(256)
 gemm_splitk_reduce(const __grid_constant__ ReduceParams P) {
+    __shared__ float part[4][64];
     const int64_t total = P.elem_start[P.n];
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
-         i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = threadIdx.x & 63, g = threadIdx.x >> 6;
+    for (int64_t base = (int64_t)blockIdx.x * 64; base < total; base += (int64_t)gridDim.x * 64) {
+        const int64_t i = base + j;
         int pi = 0;
-        while (i >= P.elem_start[pi + 1]) ++pi;
-        const agx_gemm_problem_t& Q = P.p[pi];
-        if (Q.skip_flag && *Q.skip_flag != 0) continue;
-        const int64_t e = i - P.elem_start[pi];
-        const int m = (int)(e / Q.N), n = (int)(e % Q.N);
         float v = 0.f;
-        for (int s = 0; s < Q.split_k; ++s) v += Q.partial[(size_t)s * Q.M * Q.N + e];
-        if (Q.row_scale) v = v / Q.row_scale[m];
-        if (Q.bias) v += Q.bias[n];
-        float* c = Q.C + (int64_t)m * Q.ldc + n;
-        if (Q.accumulate) v += *c;
-        *c = v;
+        int64_t e = 0;
+        const bool live = i < total;
+        if (live) {
+            while (i >= P.elem_start[pi + 1]) ++pi;
+            const agx_gemm_problem_t& Q = P.p[pi];
+            e = i - P.elem_start[pi];
+            const size_t mn = (size_t)Q.M * Q.N;
+            int s = g;
+            for (; s + 12 < Q.split_k; s += 16) {
+                const float a = Q.partial[(size_t)s * mn + e], b = Q.partial[(size_t)(s + 4) * mn + e];
+                const float c = Q.partial[(size_t)(s + 8) * mn + e], d = Q.partial[(size_t)(s + 12) * mn + e];
+                v += a; v += b; v += c; v += d;
+            }
+            for (; s < Q.split_k; s += 4) v += Q.partial[(size_t)s * mn + e];
+        }
+        part[g][j] = v;
+        __syncthreads();
+        if (g == 0 && live) {
+            const agx_gemm_problem_t& Q = P.p[pi];
+            if (!(Q.skip_flag && *Q.skip_flag != 0)) {
+                float t = ((part[0][j] + part[1][j]) + part[2][j]) + part[3][j];
+                const int m = (int)(e / Q.N), n = (int)(e % Q.N);
+                if (Q.row_scale) t = t / Q.row_scale[m];
+                if (Q.bias) t += Q.bias[n];
+                float* c = Q.C + (int64_t)m * Q.ldc + n;
+                if (Q.accumulate) t += *c;
+                *c = t;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -323,6 +350,7 @@ extern "C" int agx_gemm_grouped(const agx_gemm_problem_t* h_problems, int n_prob
     cudaStream_t st = (cudaStream_t)stream;
     int wide[AGX_MAX_GEMM_PROBLEMS], narrow[AGX_MAX_GEMM_PROBLEMS], nw = 0, nn = 0;
     int tc[AGX_MAX_GEMM_PROBLEMS], ntc = 0;
+    int lk[AGX_MAX_GEMM_PROBLEMS], nlk = 0, lk_used[AGX_MAX_GEMM_PROBLEMS];
     static const bool use_tc = getenv("AGX_DISABLE_TC") == nullptr;   // A/B switch for tests
     bool any_split = false;
     for (int i = 0; i < n_problems; ++i) {
@@ -347,11 +375,19 @@ extern "C" int agx_gemm_grouped(const agx_gemm_problem_t* h_problems, int n_prob
             tc[ntc++] = i;
             continue;
         }
+        if (use_tc && gemm_tc_longk_eligible(Q, h_segs)) { // dOut^T X over 10^5 rows: tcgen05, split-K
+            lk[nlk++] = i;
+            continue;
+        }
         if (Q.N <= 48) narrow[nn++] = i; else wide[nw++] = i;
     }
     if (ntc > 0) {
         const int rc_tc = gemm_tc_launch(h_problems, tc, ntc, h_segs, st);
         if (rc_tc) return rc_tc;
+    }
+    if (nlk > 0) {
+        const int rc_lk = gemm_tc_longk_launch(h_problems, lk, nlk, h_segs, lk_used, st);
+        if (rc_lk) return rc_lk;
     }
     int rc = launch_class<128, 128, 8, 8>(h_problems, wide, nw, h_segs, n_segs, st);
     if (rc) return rc;
@@ -365,13 +401,15 @@ extern "C" int agx_gemm_grouped(const agx_gemm_problem_t* h_problems, int n_prob
             const agx_gemm_problem_t& Q = h_problems[i];
             if (Q.split_k > 1 && Q.M > 0 && Q.N > 0) {
                 R.p[R.n] = Q;
+                for (int k = 0; k < nlk; ++k)               // tensor-core path wrote fewer slabs
+                    if (lk[k] == i) R.p[R.n].split_k = lk_used[k];
                 R.elem_start[R.n + 1] = R.elem_start[R.n] + (int64_t)Q.M * Q.N;
                 ++R.n;
             }
         }
         if (R.n > 0) {
             const int64_t total = R.elem_start[R.n];
-            const int grid = (int)(ceil_div(total, 256) < 148 * 8 ? ceil_div(total, 256) : 148 * 8);
+            const int grid = (int)(ceil_div(total, 64) < 148 * 8 ? ceil_div(total, 64) : 148 * 8);
             gemm_splitk_reduce<<<grid, 256, 0, st>>>(R);
             AGX_LAUNCH_CHECK("gemm_splitk_reduce");
         }

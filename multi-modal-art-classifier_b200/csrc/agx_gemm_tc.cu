@@ -375,6 +375,264 @@ gemm_tf32x3_tc(const __grid_constant__ TcParams P) {
     }
 }
 
+// =================================================================================================
+// Long reductions on the tensor cores: C[M,N] = A^T B with A [K, M], B [K, N] row-major and K the
+// (very long) node dimension -- the weight gradients dW = dOut^T X over 10^5 rows.
+//
+//   * operands are MN-major for the MMA (the contiguous dimension is M resp. N, not K): TMA boxes
+//     of [32 k-rows x 32 floats] land in the 128B-swizzle-with-32B-atoms layout (the only one the
+//     tensor core takes for MN-major TF32), MN blocks 4 KB apart (LBO), 4-row k groups 512 B apart
+//     (SBO); the instruction descriptor carries a_major = b_major = MN;
+//   * split-K over CTAs: each CTA reduces kLkBlocksPerCta k-blocks and writes one [M, N] partial
+//     (combined in split order by gemm_splitk_reduce: deterministic);
+//   * the tensor core's float32 accumulator truncates (error ~1.2e-8 per accumulated K element),
+//     so an accumulator is only trusted for kLkFlush k-blocks (256 rows): the epilogue warps drain
+//     it (double-buffered in TMEM) into round-to-nearest float32 running sums held in registers.
+// =================================================================================================
+constexpr int kLkStages = 3;
+constexpr int kLkFlush = 8;                 // k-blocks (of 32 rows) per TMEM accumulator
+constexpr int kLkBlocksPerCta = 24;         // 768 rows of K per CTA
+constexpr int kLkMaxProbs = 8;
+constexpr int kLkBlockFloats = 32 * 32;     // one TMA box: 32 k-rows x 32 floats = 4 KB
+
+struct LkProb {
+    CUtensorMap map_a;                      // [K, M] f32, box [32, 32], swizzle 128B
+    CUtensorMap map_b;                      // [K, N] f32, box [32, 32]
+    float* partial;                         // [splits][M][N]
+    int32_t M, N, BN;
+    int32_t total_kb, item_begin, n_items, per;     // per = k-blocks per CTA
+    int32_t pad_[7];
+};
+
+struct LkParams {
+    LkProb prob[kLkMaxProbs];
+    int32_t n_prob;
+    int32_t total_items;
+};
+
+struct __align__(1024) LkSmem {
+    float a_hi[kLkStages][4 * kLkBlockFloats];
+    float a_lo[kLkStages][4 * kLkBlockFloats];
+    float b_hi[kLkStages][4 * kLkBlockFloats];
+    float b_lo[kLkStages][4 * kLkBlockFloats];
+    uint64_t full[kLkStages];
+    uint64_t split[kLkStages];
+    uint64_t empty[kLkStages];
+    uint64_t acc_full[2];
+    uint64_t acc_empty[2];
+    uint32_t tmem_base;
+};
+
+// MN-major TF32 operand: the only shared-memory layout the tensor core accepts is the 128B swizzle
+// with 32 B atomicity (SWIZZLE_128B_BASE32B; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) -- atoms of
+// 4 k-rows x 128 B.  LBO = 4096 B between 32-float MN blocks (one TMA box each), SBO = 512 B
+// between 4-row k groups.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(4096 >> 4) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                           // SWIZZLE_128B_BASE32B
+    return d;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tf32x3_tc_longk(const __grid_constant__ LkParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    LkSmem& S = *reinterpret_cast<LkSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    int pi = 0;
+    while (pi + 1 < P.n_prob && (int)blockIdx.x >= P.prob[pi + 1].item_begin) ++pi;
+    const LkProb& Q = P.prob[pi];
+    const int sp = blockIdx.x - Q.item_begin;
+    const int kb0 = sp * Q.per;
+    const int nkb = min(Q.total_kb, kb0 + Q.per) - kb0;      // >= 1 by construction
+    const int nA = (Q.M + 31) / 32, nB = (Q.N + 31) / 32;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kLkStages; ++s) {
+            mbar_init(&S.full[s], 1);
+            mbar_init(&S.split[s], 128);
+            mbar_init(&S.empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&S.acc_full[a], 1);
+            mbar_init(&S.acc_empty[a], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(
+            smem_u32(&S.tmem_base)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (warp >= 2 && warp < 6 && (nA < 4 || nB < 4)) {
+        // MN blocks beyond M / N are never loaded: give the MMA zeros there, not stale shared memory
+        const int t = threadIdx.x - 64;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int st = 0; st < kLkStages; ++st) {
+            for (int i = nA * 256 + t; i < 4 * 256; i += 128) {
+                reinterpret_cast<float4*>(S.a_hi[st])[i] = z;
+                reinterpret_cast<float4*>(S.a_lo[st])[i] = z;
+            }
+            for (int i = nB * 256 + t; i < 4 * 256; i += 128) {
+                reinterpret_cast<float4*>(S.b_hi[st])[i] = z;
+                reinterpret_cast<float4*>(S.b_lo[st])[i] = z;
+            }
+        }
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S.tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < nkb; ++it) {
+                const int st = it % kLkStages;
+                const uint32_t ph = (it / kLkStages) & 1;
+                mbar_wait(&S.empty[st], ph ^ 1);
+                mbar_expect_tx(&S.full[st], (uint32_t)(nA + nB) * kLkBlockFloats * 4);
+                const int krow = (kb0 + it) * 32;
+                for (int b = 0; b < nA; ++b)
+                    tma_load_2d(&Q.map_a, &S.full[st], S.a_hi[st] + b * kLkBlockFloats, b * 32, krow);
+                for (int b = 0; b < nB; ++b)
+                    tma_load_2d(&Q.map_b, &S.full[st], S.b_hi[st] + b * kLkBlockFloats, b * 32, krow);
+            }
+        }
+    } else if (warp == 1) {
+        // M = 128 rows of D, N = BN columns; A and B MN-major (bits 15, 16)
+        const uint32_t idesc = make_idesc(kTcBM, Q.BN) | (1u << 15) | (1u << 16);
+        int it = 0;
+        for (int g = 0; it < nkb; ++g) {
+            const int acc = g & 1;
+            const uint32_t acc_ph = (g >> 1) & 1;
+            mbar_wait(&S.acc_empty[acc], acc_ph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem + (uint32_t)acc * kTcMaxBN;
+            const int gend = min(nkb, it + kLkFlush);
+            for (int j = 0; it < gend; ++it, ++j) {
+                const int st = it % kLkStages;
+                const uint32_t ph = (it / kLkStages) & 1;
+                mbar_wait(&S.split[st], ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_hi = smem_u32(S.a_hi[st]), a_lo = smem_u32(S.a_lo[st]);
+                    const uint32_t b_hi = smem_u32(S.b_hi[st]), b_lo = smem_u32(S.b_lo[st]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {               // 8 k-rows (one 1 KB atom) per MMA
+                        const uint32_t off = k * 1024;
+                        const uint32_t first = (j == 0 && k == 0) ? 0u : 1u;
+                        tc_mma_tf32(d_tmem, make_desc_mn(a_lo + off), make_desc_mn(b_hi + off), idesc, first);
+                        tc_mma_tf32(d_tmem, make_desc_mn(a_hi + off), make_desc_mn(b_lo + off), idesc, 1u);
+                        tc_mma_tf32(d_tmem, make_desc_mn(a_hi + off), make_desc_mn(b_hi + off), idesc, 1u);
+                    }
+                    tc_commit(&S.empty[st]);
+                    if (it == gend - 1) tc_commit(&S.acc_full[acc]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp < 6) {
+        const int t = threadIdx.x - 64;
+        for (int it = 0; it < nkb; ++it) {
+            const int st = it % kLkStages;
+            const uint32_t ph = (it / kLkStages) & 1;
+            mbar_wait(&S.full[st], ph);
+            float4* ah = reinterpret_cast<float4*>(S.a_hi[st]);
+            float4* al = reinterpret_cast<float4*>(S.a_lo[st]);
+#pragma unroll 4
+            for (int i = t; i < nA * 256; i += 128) {
+                const float4 x = ah[i];
+                float4 h, l;
+                h.x = tf32_rn(x.x); l.x = tf32_rn(x.x - h.x);
+                h.y = tf32_rn(x.y); l.y = tf32_rn(x.y - h.y);
+                h.z = tf32_rn(x.z); l.z = tf32_rn(x.z - h.z);
+                h.w = tf32_rn(x.w); l.w = tf32_rn(x.w - h.w);
+                ah[i] = h;
+                al[i] = l;
+            }
+            float4* bh = reinterpret_cast<float4*>(S.b_hi[st]);
+            float4* bl = reinterpret_cast<float4*>(S.b_lo[st]);
+#pragma unroll 4
+            for (int i = t; i < nB * 256; i += 128) {
+                const float4 x = bh[i];
+                float4 h, l;
+                h.x = tf32_rn(x.x); l.x = tf32_rn(x.x - h.x);
+                h.y = tf32_rn(x.y); l.y = tf32_rn(x.y - h.y);
+                h.z = tf32_rn(x.z); l.z = tf32_rn(x.z - h.z);
+                h.w = tf32_rn(x.w); l.w = tf32_rn(x.w - h.w);
+                bh[i] = h;
+                bl[i] = l;
+            }
+            fence_proxy_async();
+            mbar_arrive(&S.split[st]);
+        }
+    } else {
+        // epilogue: thread (q, lane) owns accumulator row 32q + lane; running sums in registers
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int BN = Q.BN;
+        float run[kTcMaxBN];
+#pragma unroll
+        for (int i = 0; i < kTcMaxBN; ++i) run[i] = 0.f;
+        const int groups = (nkb + kLkFlush - 1) / kLkFlush;
+        for (int g = 0; g < groups; ++g) {
+            const int acc = g & 1;
+            const uint32_t acc_ph = (g >> 1) & 1;
+            mbar_wait(&S.acc_full[acc], acc_ph);
+            tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < kTcMaxBN; c0 += 32) {
+                if (c0 < BN) {
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem + (uint32_t)acc * kTcMaxBN + (uint32_t)c0 + ((uint32_t)(q * 32) << 16);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, "
+                        "[%32];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]),
+                          "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
+                          "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]),
+                          "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+                          "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) run[c0 + j] += __uint_as_float(v[j]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&S.acc_empty[acc]);
+        }
+        if (row < Q.M) {
+            float* out = Q.partial + ((size_t)sp * Q.M + row) * Q.N;
+#pragma unroll
+            for (int c = 0; c < kTcMaxBN; c += 4) {
+                if (c + 3 < Q.N && (Q.N & 3) == 0) {
+                    *reinterpret_cast<float4*>(out + c) = make_float4(run[c], run[c + 1], run[c + 2], run[c + 3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (c + i < Q.N) out[c + i] = run[c + i];
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
+    }
+}
+
 // ---- host ----------------------------------------------------------------------------------
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                         const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -396,7 +654,8 @@ static PFN_tmapEncodeTiled get_encode() {
 }
 
 static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld,
-                    int box_rows) {
+                    int box_rows, int box_cols = kTcBK,
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     PFN_tmapEncodeTiled enc = get_encode();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -404,10 +663,10 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
     }
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
@@ -494,6 +753,67 @@ int gemm_tc_launch(const agx_gemm_problem_t* probs, const int* idx, int cnt,
         const int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
         gemm_tf32x3_tc<<<grid, kTcThreads, smem, st>>>(P);
         AGX_LAUNCH_CHECK("gemm_tf32x3_tc");
+    }
+    return AGX_OK;
+}
+
+// ---- long-K (weight gradient) problems --------------------------------------------------------
+bool gemm_tc_longk_eligible(const agx_gemm_problem_t& Q, const agx_gemm_seg_t* segs) {
+    if (Q.split_k <= 1 || Q.seg_count != 1 || Q.skip_flag || !Q.partial) return false;
+    if (Q.M < 1 || Q.M > kTcBM || Q.N < 8 || Q.N > kTcMaxBN) return false;
+    const agx_gemm_seg_t& S = segs[Q.seg_begin];
+    // A^T given as opA[M,K] with element (m,k) at A[m + k*a_cs]; B [K,N] row-major
+    if (S.K < 2048 || S.a_rs != 1 || S.b_cs != 1 || S.A_mask || S.B_mask) return false;
+    if ((S.a_cs % 4) != 0 || (S.b_rs % 4) != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(S.A) % 16) != 0 || (reinterpret_cast<uintptr_t>(S.B) % 16) != 0)
+        return false;
+    // the caller sized the partial buffer for split_k slabs: enough for the splits used here?
+    const int total_kb = (S.K + 31) / 32;
+    const int items = (total_kb + kLkBlocksPerCta - 1) / kLkBlocksPerCta;
+    return items <= Q.split_k && (reinterpret_cast<uintptr_t>(Q.partial) % 16) == 0;
+}
+
+// used_split[i] receives the number of partial slabs written for problem idx[i]
+int gemm_tc_longk_launch(const agx_gemm_problem_t* probs, const int* idx, int cnt,
+                         const agx_gemm_seg_t* segs, int* used_split, cudaStream_t st) {
+    static bool attr_set = false;
+    const size_t smem = sizeof(LkSmem) + 1024;
+    if (!attr_set) {
+        AGX_CUDA(cudaFuncSetAttribute(gemm_tf32x3_tc_longk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+        attr_set = true;
+    }
+    int done = 0;
+    while (done < cnt) {
+        LkParams P;
+        P.n_prob = 0;
+        P.total_items = 0;
+        while (done < cnt && P.n_prob < kLkMaxProbs) {
+            const agx_gemm_problem_t& Q = probs[idx[done]];
+            const agx_gemm_seg_t& G = segs[Q.seg_begin];
+            LkProb& T = P.prob[P.n_prob];
+            T.partial = Q.partial;
+            T.M = Q.M;
+            T.N = Q.N;
+            T.BN = (Q.N + 15) / 16 * 16;
+            T.total_kb = (G.K + 31) / 32;
+            T.n_items = (T.total_kb + kLkBlocksPerCta - 1) / kLkBlocksPerCta;
+            // every CTA must own at least one k-block with the ceil split used by the kernel
+            const int per = (T.total_kb + T.n_items - 1) / T.n_items;
+            T.n_items = (T.total_kb + per - 1) / per;
+            T.per = per;
+            T.item_begin = P.total_items;
+            int rc = make_map(&T.map_a, G.A, G.K, Q.M, G.a_cs, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+            if (rc) return rc;
+            rc = make_map(&T.map_b, G.B, G.K, Q.N, G.b_rs, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+            if (rc) return rc;
+            used_split[done] = T.n_items;
+            P.total_items += T.n_items;
+            ++P.n_prob;
+            ++done;
+        }
+        gemm_tf32x3_tc_longk<<<P.total_items, kTcThreads, smem, st>>>(P);
+        AGX_LAUNCH_CHECK("gemm_tf32x3_tc_longk");
     }
     return AGX_OK;
 }

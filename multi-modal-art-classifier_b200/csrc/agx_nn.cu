@@ -1177,6 +1177,52 @@ extern "C" int agx_is_identity(const float* x, int64_t ld, int32_t n, int32_t* f
     return AGX_OK;
 }
 
+struct TransposeParams {
+    agx_transpose_desc_t d[AGX_MAX_TENSORS];
+    int32_t tile_start[AGX_MAX_TENSORS + 1];
+    int32_t n;
+};
+
+// every matrix of the batch in one launch: CTA -> (descriptor, 32x32 tile)
+__global__ void __launch_bounds__(256) transpose_batched(const __grid_constant__ TransposeParams P) {
+    int di = 0;
+    while ((int)blockIdx.x >= P.tile_start[di + 1]) ++di;
+    const agx_transpose_desc_t& D = P.d[di];
+    const int t = blockIdx.x - P.tile_start[di];
+    const int tiles_x = (D.cols + 31) / 32;
+    const int bx = (t % tiles_x) * 32, by = (t / tiles_x) * 32;
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {
+        const int r = by + j, c = bx + tx;
+        tile[j][tx] = (r < D.rows && c < D.cols) ? D.in[(int64_t)r * D.ld_in + c] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int c = bx + j, r = by + tx;          // out[c][r]
+        if (c < D.cols && r < D.rows) D.out[(int64_t)c * D.ld_out + r] = tile[tx][j];
+    }
+}
+
+extern "C" int agx_transpose_batched(const agx_transpose_desc_t* h_descs, int n, void* stream) {
+    AGX_CHECK_ARG(h_descs && n >= 1 && n <= AGX_MAX_TENSORS, "agx_transpose_batched: n=%d", n);
+    TransposeParams P;
+    P.n = n;
+    P.tile_start[0] = 0;
+    for (int i = 0; i < n; ++i) {
+        const agx_transpose_desc_t& D = h_descs[i];
+        AGX_CHECK_ARG(D.rows >= 0 && D.cols >= 0 && ((D.in && D.out) || D.rows == 0 || D.cols == 0),
+                      "agx_transpose_batched: desc %d: bad arguments", i);
+        P.d[i] = D;
+        P.tile_start[i + 1] = P.tile_start[i] +
+                              (int32_t)(ceil_div(D.rows, 32) * ceil_div(D.cols, 32));
+    }
+    if (P.tile_start[n] == 0) return AGX_OK;
+    transpose_batched<<<P.tile_start[n], 256, 0, (cudaStream_t)stream>>>(P);
+    AGX_LAUNCH_CHECK("transpose_batched");
+    return AGX_OK;
+}
+
 extern "C" int agx_transpose(const float* in, int64_t ld_in, int32_t rows, int32_t cols, float* out,
                              int64_t ld_out, const int32_t* only_if_flag, void* stream) {
     AGX_CHECK_ARG(in && out && rows >= 0 && cols >= 0, "agx_transpose: bad arguments");

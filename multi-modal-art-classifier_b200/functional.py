@@ -136,17 +136,16 @@ class _HeteroConvFn(torch.autograd.Function):
         # s1: transform-first products on the source tables
         Y: Dict[int, torch.Tensor] = {}
         gb = ops.GemmBatch()
+        tr: list = []                 # transposed weight copies, one batched launch
         for k, rs in enumerate(spec.rels):
             if rs.transform_first:
                 r = rs.rel
                 y = torch.empty(r.n_src, O, dtype=torch.float32, device=dev)
                 Y[k] = y
                 if spec.identity.get(r.src, False):
-                    ops.transpose_into(y, params[rs.i_wl])       # X = I  =>  X W^T = W^T exactly
+                    tr.append((y, params[rs.i_wl]))              # X = I  =>  X W^T = W^T exactly
                 else:
                     gb.add(y, [(xs[r.src], _t(params[rs.i_wl]))])
-        if gb.problems:
-            gb.run()
 
         # s2: gathers
         outs: Dict[str, torch.Tensor] = {}
@@ -162,7 +161,7 @@ class _HeteroConvFn(torch.autograd.Function):
             id_root[t] = bool(spec.identity.get(t, False)) and wroot[t] is not None and \
                 xd[t] is xs[t]
             if id_root[t]:
-                ops.transpose_into(outs[t], wroot[t])
+                tr.append((outs[t], wroot[t]))
             tf_all = [(k, rs) for k, rs in enumerate(spec.rels)
                       if rs.rel.dst == t and rs.transform_first]
             has_tf[t] = bool(tf_all) or id_root[t]
@@ -193,6 +192,10 @@ class _HeteroConvFn(torch.autograd.Function):
                 chunks_by_F.setdefault(fs, []).append((g, arg))
             else:
                 rows_by_F.setdefault((0, fs), []).append((g, [arg], False))
+        if tr:
+            ops.transpose_many(tr)
+        if gb.problems:
+            gb.run()
         for (wave, F) in sorted(rows_by_F.keys()):
             ops.aggregate_rows(rows_by_F[(wave, F)], F)
         for F, segs in chunks_by_F.items():
@@ -292,6 +295,7 @@ class _HeteroConvFn(torch.autograd.Function):
 
         # b2/b3: weight gradients and the aggregate-first input gradients dG = dout W_l
         gb = ops.GemmBatch()
+        trb: list = []
         dwroot: Dict[str, torch.Tensor] = {}
         for t in spec.dst_types:
             if dout[t] is None or t not in wroot:
@@ -300,7 +304,7 @@ class _HeteroConvFn(torch.autograd.Function):
             dw = torch.empty(O, x.shape[1], dtype=torch.float32, device=dev)
             dwroot[t] = dw
             if spec.identity.get(t, False) and x is xs[t]:
-                ops.transpose_into(dw, dout[t])                  # dout^T I
+                trb.append((dw, dout[t]))                        # dout^T I
             else:
                 gb.add(dw, [(_t(dout[t]), x)], split_k=ops.split_k_for(x.shape[0]))
         dG: Dict[int, torch.Tensor] = {}
@@ -310,7 +314,7 @@ class _HeteroConvFn(torch.autograd.Function):
             dw = torch.empty(O, x.shape[1], dtype=torch.float32, device=dev)
             grads[pidx(rs.i_wl)] = dw
             if rs.transform_first and spec.identity.get(r.src, False):
-                ops.transpose_into(dw, dY[k])
+                trb.append((dw, dY[k]))
             elif rs.transform_first:
                 gb.add(dw, [(_t(dY[k]), x)], split_k=ops.split_k_for(r.n_src))
             else:
@@ -319,6 +323,8 @@ class _HeteroConvFn(torch.autograd.Function):
                     dg = torch.empty(r.n_dst, x.shape[1], dtype=torch.float32, device=dev)
                     dG[k] = dg
                     gb.add(dg, [(dout[r.dst], params[rs.i_wl])])
+        if trb:
+            ops.transpose_many(trb)
         if gb.problems:
             gb.run()
         for k, rs in live:

@@ -305,6 +305,7 @@ class GemmBatch:
         self.problems: List[L.GemmProblem] = []
         self.segs: List[L.GemmSeg] = []
         self._keep = []
+        self._transposes: list = []
 
     def add(self, C_out: torch.Tensor, segs: Sequence[tuple], bias: Optional[torch.Tensor] = None,
             accumulate: bool = False, row_scale: Optional[torch.Tensor] = None,
@@ -332,7 +333,7 @@ class GemmBatch:
                 # dY @ W with W given [K, N] row-major: the tensor-core kernel wants both operands
                 # K-contiguous, so hand it a transposed copy of the (small) weight
                 Bt = torch.empty(B.shape[1], B.shape[0], dtype=torch.float32, device=B.device)
-                transpose_into(Bt, B)
+                self._transposes.append((Bt, B))
                 self._keep.append(Bt)
                 B = Bt.t()
             if A.shape[0] != M or B.shape[1] != N or A.shape[1] != B.shape[0]:
@@ -350,6 +351,9 @@ class GemmBatch:
         self._keep += [C_out, bias, row_scale, skip_flag]
 
     def run(self):
+        if self._transposes:
+            transpose_many(self._transposes)
+            self._transposes = []
         i = 0
         n = len(self.problems)
         while i < n:
@@ -475,6 +479,19 @@ def is_identity(x: torch.Tensor) -> torch.Tensor:
     check(lib().agx_is_identity(ptr(x), x.stride(0), x.shape[0], ptr(flag), flag.data_ptr() + 4,
                                 stream_ptr()), 'agx_is_identity')
     return flag[:1]
+
+
+def transpose_many(pairs: Sequence[Tuple[torch.Tensor, torch.Tensor]]):
+    """``pairs``: (out [cols, rows], inp [rows, cols]) -- all transposes in one launch per 48."""
+    for base in range(0, len(pairs), L.MAX_TENSORS):
+        part = pairs[base:base + L.MAX_TENSORS]
+        arr = (L.TransposeDesc * len(part))()
+        for i, (out, inp) in enumerate(part):
+            if inp.stride(1) != 1 or out.stride(1) != 1 or out.shape != (inp.shape[1], inp.shape[0]):
+                raise ValueError('transpose_many: row-major [r, c] -> [c, r] expected')
+            arr[i] = L.TransposeDesc(ptr(inp), inp.stride(0), ptr(out), out.stride(0), inp.shape[0],
+                                     inp.shape[1])
+        check(lib().agx_transpose_batched(arr, len(part), stream_ptr()), 'agx_transpose_batched')
 
 
 def transpose_into(out: torch.Tensor, inp: torch.Tensor, only_if_flag: Optional[torch.Tensor] = None):

@@ -248,6 +248,34 @@ def test_gemm_nt_nn_tn(M, K, N):
     assert rel_err(dW1, G64.t() @ A64 + 1.0) <= RTOL_F32
 
 
+@pytest.mark.parametrize('M,N,K', [(128, 128, 20000), (32, 128, 116475), (128, 32, 5000),
+                                   (100, 72, 3001), (128, 128, 2048), (8, 8, 4100)])
+def test_gemm_tensor_core_long_k_weight_gradient(M, N, K):
+    """dW = dOut^T X over a very long row dimension takes the split-K tcgen05 path (MN-major
+    operands, accumulators drained every 256 rows): float32 accuracy (rel 1e-5 against float64),
+    same answer as the exact FFMA kernel to that tolerance, reproducible, accumulate / bias /
+    strided views handled by the split reduction."""
+    gen = torch.Generator().manual_seed(M + N + K)
+    dout = torch.randn(K, M, generator=gen)
+    x = torch.randn(K, N + 8, generator=gen)[:, 4:4 + N]           # a column slice: ld != N
+    c0 = torch.randn(M, N, generator=gen)
+    ref = dout.double().t() @ x.double()
+    dd, xd = dout.to(DEV), x.to(DEV)
+    sk = ops.split_k_for(K)
+    outs = []
+    for _ in range(2):
+        dw = torch.full((M, N), float('nan'), device=DEV)
+        dwa = c0.to(DEV).clone()
+        gb = ops.GemmBatch()
+        gb.add(dw, [(dd.t(), xd)], split_k=sk)
+        gb.add(dwa, [(dd.t(), xd)], split_k=sk, accumulate=True)
+        gb.run()
+        outs.append((dw, dwa))
+    assert rel_err(outs[0][0], ref) <= RTOL_F32
+    assert rel_err(outs[0][1], ref + c0.double()) <= RTOL_F32
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 @pytest.mark.parametrize('M,N,Ks', [(4096, 128, [128]), (5000, 128, [128, 128, 64]),
                                     (3001, 32, [128]), (2049, 18, [128, 96]), (1500, 72, [200])])
 def test_gemm_tensor_core_3xtf32(M, N, Ks):
