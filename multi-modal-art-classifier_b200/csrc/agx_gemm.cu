@@ -349,6 +349,7 @@ extern "C" int agx_gemm_grouped(const agx_gemm_problem_t* h_problems, int n_prob
                   "agx_gemm_grouped: n_segs=%d out of [1,%d]", n_segs, AGX_MAX_GEMM_SEGS);
     cudaStream_t st = (cudaStream_t)stream;
     int wide[AGX_MAX_GEMM_PROBLEMS], narrow[AGX_MAX_GEMM_PROBLEMS], nw = 0, nn = 0;
+    int shortm[AGX_MAX_GEMM_PROBLEMS], ns = 0;
     int tc[AGX_MAX_GEMM_PROBLEMS], ntc = 0;
     int lk[AGX_MAX_GEMM_PROBLEMS], nlk = 0, lk_used[AGX_MAX_GEMM_PROBLEMS];
     static const bool use_tc = getenv("AGX_DISABLE_TC") == nullptr;   // A/B switch for tests
@@ -379,7 +380,11 @@ extern "C" int agx_gemm_grouped(const agx_gemm_problem_t* h_problems, int n_prob
             lk[nlk++] = i;
             continue;
         }
-        if (Q.N <= 48) narrow[nn++] = i; else wide[nw++] = i;
+        // few-row problems (the small node types, weight gradients) would sit on one or two SMs
+        // with 128-row tiles: 32-row tiles spread them over 4x as many CTAs
+        if (Q.N <= 48) narrow[nn++] = i;
+        else if (Q.M <= 256) shortm[ns++] = i;
+        else wide[nw++] = i;
     }
     if (ntc > 0) {
         const int rc_tc = gemm_tc_launch(h_problems, tc, ntc, h_segs, st);
@@ -390,6 +395,8 @@ extern "C" int agx_gemm_grouped(const agx_gemm_problem_t* h_problems, int n_prob
         if (rc_lk) return rc_lk;
     }
     int rc = launch_class<128, 128, 8, 8>(h_problems, wide, nw, h_segs, n_segs, st);
+    if (rc) return rc;
+    rc = launch_class<32, 128, 2, 8>(h_problems, shortm, ns, h_segs, n_segs, st);
     if (rc) return rc;
     rc = launch_class<128, 32, 4, 4>(h_problems, narrow, nn, h_segs, n_segs, st);
     if (rc) return rc;

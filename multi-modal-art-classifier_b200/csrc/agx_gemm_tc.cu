@@ -783,6 +783,11 @@ int gemm_tc_longk_launch(const agx_gemm_problem_t* probs, const int* idx, int cn
                                       (int)smem));
         attr_set = true;
     }
+    // one wave: aim at <= ~144 CTAs over all problems of the launch (at least 24 k-blocks each)
+    int64_t all_kb = 0;
+    for (int i = 0; i < cnt; ++i) all_kb += (segs[probs[idx[i]].seg_begin].K + 31) / 32;
+    const int kb_per_cta = (int)(all_kb / 140 + 1) > kLkBlocksPerCta ? (int)(all_kb / 140 + 1)
+                                                                     : kLkBlocksPerCta;
     int done = 0;
     while (done < cnt) {
         LkParams P;
@@ -797,7 +802,7 @@ int gemm_tc_longk_launch(const agx_gemm_problem_t* probs, const int* idx, int cn
             T.N = Q.N;
             T.BN = (Q.N + 15) / 16 * 16;
             T.total_kb = (G.K + 31) / 32;
-            T.n_items = (T.total_kb + kLkBlocksPerCta - 1) / kLkBlocksPerCta;
+            T.n_items = (T.total_kb + kb_per_cta - 1) / kb_per_cta;
             // every CTA must own at least one k-block with the ceil split used by the kernel
             const int per = (T.total_kb + T.n_items - 1) / T.n_items;
             T.n_items = (T.total_kb + per - 1) / per;
