@@ -276,6 +276,11 @@ def run_ours(args):
     if rank == 0:
         ops.TIMER = timer
     for _ in range(3):                   # every rank steps (the step holds collectives)
+        # an eager step is CPU-bound (~150 launches from Python): park the GPU behind a spin kernel
+        # while the CPU enqueues the whole step, so that the CUDA events around each launch measure
+        # kernel time, not the gaps in which the GPU waits for the next launch
+        torch.cuda.synchronize()
+        torch.cuda._sleep(int(args.park_ms * 1e-3 * 1.9e9))
         trainer._step_eager()
     ops.TIMER = None
     barrier()
@@ -353,6 +358,8 @@ def main():
                     help="graph size of the bounded CPU sample (full: ~8 s per step on 8 cores)")
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA graph')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--park-ms', type=float, default=60.0,
+                    help='device-side delay in front of each per-kernel timing step (roofline leg)')
     ap.add_argument('--ncu', action='store_true',
                     help='run one eager step between cudaProfilerStart/Stop and exit')
     args = ap.parse_args()

@@ -12,6 +12,7 @@
 // Both accumulate in float32, in CSR (= edge list) order inside a row: no float atomics, results
 // are run-to-run reproducible.  HBM-bound: algorithmic traffic per edge = F*sizeof(T) + 4 B.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "agx_common.cuh"
 
@@ -75,6 +76,47 @@ template <>
 __device__ __forceinline__ Vec<__nv_bfloat16, 1> load_vec<__nv_bfloat16, 1>(const __nv_bfloat16* p) {
     Vec<__nv_bfloat16, 1> r;
     r.v[0] = __bfloat162float(*p);
+    return r;
+}
+
+// Gather loads that must stay batched: ptxas interleaves ordinary loads with their consumers
+// (load, use, load, use: two rows in flight per warp); volatile asm keeps the U loads of a batch
+// back to back so that all of them are in flight before the first use.
+template <typename T, int VEC>
+__device__ __forceinline__ Vec<T, VEC> gather_vec(const T* p);
+
+template <>
+__device__ __forceinline__ Vec<float, 4> gather_vec<float, 4>(const float* p) {
+    Vec<float, 4> r;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p));
+    return r;
+}
+template <>
+__device__ __forceinline__ Vec<float, 1> gather_vec<float, 1>(const float* p) {
+    Vec<float, 1> r;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r.v[0]) : "l"(p));
+    return r;
+}
+template <>
+__device__ __forceinline__ Vec<__nv_bfloat16, 8> gather_vec<__nv_bfloat16, 8>(const __nv_bfloat16* p) {
+    uint32_t w[4];
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(p));
+    Vec<__nv_bfloat16, 8> r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        r.v[2 * i] = __uint_as_float(w[i] << 16);
+        r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+    return r;
+}
+template <>
+__device__ __forceinline__ Vec<__nv_bfloat16, 1> gather_vec<__nv_bfloat16, 1>(const __nv_bfloat16* p) {
+    uint16_t h;
+    asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(h) : "l"(p));
+    Vec<__nv_bfloat16, 1> r;
+    r.v[0] = __uint_as_float((uint32_t)h << 16);
     return r;
 }
 
@@ -308,18 +350,19 @@ agg_rows(const __grid_constant__ RowGroups P) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kGatherDepth = 8;                    // feature-row loads in flight per lane
 
+// fragment loads: from L2 (other SMs wrote them), volatile so that a batch stays in flight together
 template <typename T, int VEC>
-__device__ __forceinline__ Vec<T, VEC> load_frag(const float* p) {   // L2 (other SMs wrote it)
+__device__ __forceinline__ Vec<T, VEC> load_frag(const float* p) {
     Vec<T, VEC> r;
     if constexpr (VEC % 4 == 0) {
 #pragma unroll
-        for (int i = 0; i < VEC; i += 4) {
-            const float4 t = __ldcg(reinterpret_cast<const float4*>(p + i));
-            r.v[i] = t.x; r.v[i + 1] = t.y; r.v[i + 2] = t.z; r.v[i + 3] = t.w;
-        }
+        for (int i = 0; i < VEC; i += 4)
+            asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(r.v[i]), "=f"(r.v[i + 1]), "=f"(r.v[i + 2]), "=f"(r.v[i + 3])
+                         : "l"(p + i));
     } else {
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) r.v[i] = __ldcg(p + i);
+        for (int i = 0; i < VEC; ++i) asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(r.v[i]) : "l"(p + i));
     }
     return r;
 }
@@ -346,13 +389,75 @@ __device__ __forceinline__ void zero_rows(const agx_chunk_seg_t& S, int F, int r
             store_vec<T, VEC>(reinterpret_cast<T*>(S.out) + (int64_t)r * S.ldo + c0, z);
 }
 
-template <typename T, int VEC, int LPR>
-__global__ void __launch_bounds__(kAggThreads)
+// ---- TMA row ring (agg_chunks<.., TMA = true>) ------------------------------------------------
+// Feature rows are not gathered through registers but by the TMA engine: per warp a ring of
+// kRingGroups x kRingRows row slots in shared memory, one cp.async.bulk (global -> shared, one whole
+// feature row, <= 512 B) per neighbour, completion counted in bytes on one mbarrier per group.  Up
+// to kRingGroups * kRingRows rows (12 KB at F = 128) are in flight per warp without holding a
+// single register, and the summation reads 16 B per lane from shared memory in edge order.
+constexpr int kRingRows = 8;
+constexpr int kRingGroups = 3;
+constexpr int kRingMaxRowBytes = 512;
+
+__device__ __forceinline__ uint32_t agg_smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void agg_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(agg_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void agg_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(agg_smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void agg_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(agg_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void agg_bulk_row(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            agg_smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(agg_smem_u32(bar))
+        : "memory");
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ Vec<T, VEC> load_smem_vec(const uint8_t* p) {
+    Vec<T, VEC> r;
+    if constexpr (sizeof(T) == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+    } else {
+        const uint4 t = *reinterpret_cast<const uint4*>(p);
+        const uint32_t wd[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            r.v[2 * i] = __uint_as_float(wd[i] << 16);
+            r.v[2 * i + 1] = __uint_as_float(wd[i] & 0xffff0000u);
+        }
+    }
+    return r;
+}
+
+template <typename T, int VEC, int LPR, bool TMA>
+__global__ void __launch_bounds__(kAggThreads, TMA ? 2 : 3)
 agg_chunks(const __grid_constant__ ChunkSegs P) {
     constexpr int SUB = 32 / LPR;
     constexpr int U = kGatherDepth;
     __shared__ int s_col[kAggWarps][AGX_CHUNK_EDGES];
     __shared__ float s_scl[kAggWarps][AGX_CHUNK_EDGES];
+    __shared__ uint64_t s_bar[kAggWarps][kRingGroups];
+    extern __shared__ __align__(128) uint8_t s_ring[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int sub = lane / LPR, l = lane % LPR;
     const int64_t gchunk = (int64_t)blockIdx.x * kAggWarps + w;
@@ -371,13 +476,23 @@ agg_chunks(const __grid_constant__ ChunkSegs P) {
     float* trail = S.frag + (size_t)nchunks * F;
 
     // ---- stage neighbour ids / scales ----------------------------------------------------------
+    // lane i of register k holds edge k*32 + i of the chunk (register path: read by shuffles);
+    // the TMA path issues its copies from the shared-memory copy
+    int cr[AGX_CHUNK_EDGES / 32];
+    float sr[AGX_CHUNK_EDGES / 32];
 #pragma unroll
     for (int k = 0; k < AGX_CHUNK_EDGES / 32; ++k) {
         const int i = k * 32 + lane;
-        int c = 0;
-        if (start + i < end) c = __ldg(R.col + start + i);
-        s_col[w][i] = c;
-        s_scl[w][i] = (R.nbr_scale && start + i < end) ? 1.0f / __ldg(R.nbr_scale + c) : 1.0f;
+        cr[k] = start + i < end ? __ldg(R.col + start + i) : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < AGX_CHUNK_EDGES / 32; ++k) {
+        const int i = k * 32 + lane;
+        sr[k] = (R.nbr_scale && start + i < end) ? 1.0f / __ldg(R.nbr_scale + cr[k]) : 1.0f;
+        if constexpr (TMA) {
+            s_col[w][i] = cr[k];
+            s_scl[w][i] = sr[k];
+        }
     }
     // ---- row of the first edge: largest r with rowptr[r] <= start (32-ary search) ---------------
     int lo = 0, hi = n_rows;                       // rowptr[lo] <= start < rowptr[hi]
@@ -391,6 +506,33 @@ agg_chunks(const __grid_constant__ ChunkSegs P) {
     }
     int row = lo;
     __syncwarp();
+    // ---- TMA ring: start the first kRingGroups groups of row copies -------------------------------
+    const int n_chunk = end - start;
+    const int ngroups = (n_chunk + kRingRows - 1) / kRingRows;
+    const uint32_t RB = (uint32_t)F * sizeof(T);               // bytes per feature row
+    uint8_t* ring = s_ring + (size_t)w * kRingGroups * kRingRows * RB;
+    int waited = 0;                                              // groups whose rows have landed
+    auto issue_group = [&](int g) {
+        const int r0 = g * kRingRows;
+        const int cnt = min(kRingRows, n_chunk - r0);
+        const int slot = g % kRingGroups;
+        if (lane == 0) agg_mbar_expect_tx(&s_bar[w][slot], (uint32_t)cnt * RB);
+        __syncwarp();
+        if (lane < cnt)
+            agg_bulk_row(ring + (size_t)(slot * kRingRows + lane) * RB,
+                         reinterpret_cast<const uint8_t*>(R.x) +
+                             (int64_t)s_col[w][r0 + lane] * R.ldx * (int64_t)sizeof(T),
+                         RB, &s_bar[w][slot]);
+    };
+    if constexpr (TMA) {
+        if (lane == 0) {
+#pragma unroll
+            for (int g = 0; g < kRingGroups; ++g) agg_mbar_init(&s_bar[w][g], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        for (int g = 0; g < kRingGroups && g < ngroups; ++g) issue_group(g);
+    }
     if (chunk == 0) zero_rows<T, VEC>(S, F, 0, row, lane);
 
     int wrow = row;                                // row-extent window: lane i holds rowptr[wrow+1+i]
@@ -410,25 +552,73 @@ agg_chunks(const __grid_constant__ ChunkSegs P) {
         for (int cb = 0; cb < F; cb += LPR * VEC) {
             const int c0 = cb + l * VEC;
             const bool active = c0 < F;
-            const T* x = reinterpret_cast<const T*>(R.x) + c0;
+            // lanes past the last column read column block 0 (in bounds) and drop the result
+            const T* x = reinterpret_cast<const T*>(R.x) + (active ? c0 : 0);
             Vec<T, VEC> acc;
             acc.zero();
-            for (int base = i0; base < i1; base += SUB * U) {
-                Vec<T, VEC> v[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int i = base + u * SUB + sub;
-                    if (i < i1 && active) v[u] = load_vec<T, VEC>(x + (int64_t)s_col[w][i] * R.ldx);
-                    else v[u].zero();
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int i = base + u * SUB + sub;
-                    if (i < i1) {
-                        const float sc = s_scl[w][i];
-#pragma unroll
-                        for (int k = 0; k < VEC; ++k) acc.v[k] += v[u].v[k] * sc;
+            if constexpr (TMA) {
+                // rows arrive in the ring in edge order; one (segment x group) interval at a time
+                int i = i0;
+                while (i < i1) {
+                    const int g = i / kRingRows;
+                    const int b = min(i1, (g + 1) * kRingRows);
+                    if (waited <= g) {
+                        agg_mbar_wait(&s_bar[w][g % kRingGroups], (uint32_t)(g / kRingGroups) & 1u);
+                        waited = g + 1;
                     }
+                    const uint8_t* rows = ring + (size_t)(g % kRingGroups) * kRingRows * RB +
+                                          (size_t)l * VEC * sizeof(T);
+                    Vec<T, VEC> v[kRingRows / SUB];
+#pragma unroll
+                    for (int u = 0; u < kRingRows / SUB; ++u) {
+                        const int e_ = i + u * SUB + sub;
+                        if (e_ < b && active)
+                            v[u] = load_smem_vec<T, VEC>(rows + (size_t)(e_ - g * kRingRows) * RB);
+                    }
+#pragma unroll
+                    for (int u = 0; u < kRingRows / SUB; ++u) {
+                        const int e_ = i + u * SUB + sub;
+                        if (e_ < b && active) {
+                            const float sc = s_scl[w][e_];
+#pragma unroll
+                            for (int k = 0; k < VEC; ++k) acc.v[k] += v[u].v[k] * sc;
+                        }
+                    }
+                    i = b;
+                    if (b == (g + 1) * kRingRows) {              // group drained: refill its slot
+                        __syncwarp();
+                        if (g + kRingGroups < ngroups) issue_group(g + kRingGroups);
+                    }
+                }
+            } else {
+                // batches of SUB*U edges aligned inside the chunk (never straddling a 32-edge
+                // register); slots outside [i0, i1) are loaded too (their ids are valid rows) but
+                // not added, so the U gathers of a batch are unconditional and stay in flight together
+                constexpr int BATCH = SUB * U;
+                for (int base = (i0 / BATCH) * BATCH; base < i1; base += BATCH) {
+                    const int kreg = base >> 5;                  // warp-uniform
+                    const int ck = kreg == 0 ? cr[0] : kreg == 1 ? cr[1] : kreg == 2 ? cr[2] : cr[3];
+                    const float sk = kreg == 0 ? sr[0] : kreg == 1 ? sr[1] : kreg == 2 ? sr[2] : sr[3];
+                    const int j0 = (base & 31) + sub;
+                    int ci[U];
+                    float sc[U];
+                    bool ok[U];
+                    Vec<T, VEC> v[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int idx = base + u * SUB + sub;
+                        ci[u] = __shfl_sync(0xffffffffu, ck, j0 + u * SUB);
+                        sc[u] = __shfl_sync(0xffffffffu, sk, j0 + u * SUB);
+                        ok[u] = idx >= i0 && idx < i1;
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) v[u] = gather_vec<T, VEC>(x + (int64_t)ci[u] * R.ldx);
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (ok[u]) {
+#pragma unroll
+                            for (int k = 0; k < VEC; ++k) acc.v[k] += v[u].v[k] * sc[u];
+                        }
                 }
             }
             if (SUB > 1) {                         // partial sums of the sub-warps, in sub-warp order
@@ -468,13 +658,14 @@ agg_chunks(const __grid_constant__ ChunkSegs P) {
                 const float d = R.row_cnt ? __ldg(R.row_cnt + row) : 1.0f;
                 for (int c0 = lane * VEC; c0 < F; c0 += 32 * VEC) {
                     Vec<T, VEC> tot = load_frag<T, VEC>(trail + (size_t)c_first * F + c0);
-                    for (int c = c_first + 1; c <= c_last; c += U) {
-                        Vec<T, VEC> v[U];
+                    constexpr int UC = 2 * U;          // fragments in flight (slots past the end
+                    for (int c = c_first + 1; c <= c_last; c += UC) {   // re-read the last one, unused)
+                        Vec<T, VEC> v[UC];
 #pragma unroll
-                        for (int u = 0; u < U; ++u)
-                            if (c + u <= c_last) v[u] = load_frag<T, VEC>(lead + (size_t)(c + u) * F + c0);
+                        for (int u = 0; u < UC; ++u)
+                            v[u] = load_frag<T, VEC>(lead + (size_t)min(c + u, c_last) * F + c0);
 #pragma unroll
-                        for (int u = 0; u < U; ++u)
+                        for (int u = 0; u < UC; ++u)
                             if (c + u <= c_last) {
 #pragma unroll
                                 for (int k = 0; k < VEC; ++k) tot.v[k] += v[u].v[k];
@@ -593,15 +784,32 @@ extern "C" size_t agx_chunk_counters(int64_t n_edges) {
     return (size_t)ceil_div(n_edges > 0 ? n_edges : 1, AGX_CHUNK_EDGES);
 }
 
-template <typename T, int VEC>
-static int launch_chunks(const ChunkSegs& P, int lpr, unsigned grid, cudaStream_t st) {
-    switch (lpr) {
-        case 32: agg_chunks<T, VEC, 32><<<grid, kAggThreads, 0, st>>>(P); break;
-        case 16: agg_chunks<T, VEC, 16><<<grid, kAggThreads, 0, st>>>(P); break;
-        default: agg_chunks<T, VEC, 8><<<grid, kAggThreads, 0, st>>>(P); break;
+template <typename T, int VEC, int LPR>
+static int launch_chunks_lpr(const ChunkSegs& P, unsigned grid, bool tma, cudaStream_t st) {
+    if (tma) {
+        const size_t smem = (size_t)kAggWarps * kRingGroups * kRingRows * (size_t)P.F * sizeof(T);
+        static bool attr_set = false;
+        if (!attr_set) {
+            AGX_CUDA(cudaFuncSetAttribute(agg_chunks<T, VEC, LPR, true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          kAggWarps * kRingGroups * kRingRows * kRingMaxRowBytes));
+            attr_set = true;
+        }
+        agg_chunks<T, VEC, LPR, true><<<grid, kAggThreads, smem, st>>>(P);
+    } else {
+        agg_chunks<T, VEC, LPR, false><<<grid, kAggThreads, 0, st>>>(P);
     }
     AGX_LAUNCH_CHECK("agg_chunks");
     return AGX_OK;
+}
+
+template <typename T, int VEC>
+static int launch_chunks(const ChunkSegs& P, int lpr, unsigned grid, bool tma, cudaStream_t st) {
+    switch (lpr) {
+        case 32: return launch_chunks_lpr<T, VEC, 32>(P, grid, tma, st);
+        case 16: return launch_chunks_lpr<T, VEC, 16>(P, grid, tma, st);
+        default: return launch_chunks_lpr<T, VEC, 8>(P, grid, tma, st);
+    }
 }
 
 extern "C" int agx_aggregate_chunks(const agx_chunk_seg_t* h_segs, int n_segs, int F, int dtype,
@@ -639,11 +847,20 @@ extern "C" int agx_aggregate_chunks(const agx_chunk_seg_t* h_segs, int n_segs, i
     const int64_t chunks = P.chunk_start[n_segs];
     if (chunks == 0) return AGX_OK;
     const unsigned grid = (unsigned)ceil_div(chunks, kAggWarps);
+    // whole feature rows of <= 512 B go through the TMA row ring; wider / unaligned rows through
+    // register gathers
+    // Measured on B200 (scratch/gather_probe.cu, 895k random 512 B rows of an L2-resident 60 MB
+    // table): register gathers 15.7 TB/s, TMA row ring 11.7-13.7 TB/s, and the ring costs ~3x the
+    // instructions per row (one UBLKCP per row is issued lane by lane): the ring is kept as an
+    // option (AGX_TMA_GATHER=1), the default is the register path.
+    static const bool want_tma = getenv("AGX_TMA_GATHER") != nullptr;
+    const bool tma = vec_ok && want_tma && (size_t)F * esz <= (size_t)kRingMaxRowBytes;
     if (dtype == AGX_F32) {
-        if (vec_ok) return launch_chunks<float, 4>(P, max(8, min(32, pow2_ceil(F / 4))), grid, st);
-        return launch_chunks<float, 1>(P, max(8, min(32, pow2_ceil(F))), grid, st);
+        if (vec_ok)
+            return launch_chunks<float, 4>(P, max(8, min(32, pow2_ceil(F / 4))), grid, tma, st);
+        return launch_chunks<float, 1>(P, max(8, min(32, pow2_ceil(F))), grid, false, st);
     }
     if (vec_ok)
-        return launch_chunks<__nv_bfloat16, 8>(P, max(8, min(32, pow2_ceil(F / 8))), grid, st);
-    return launch_chunks<__nv_bfloat16, 1>(P, max(8, min(32, pow2_ceil(F))), grid, st);
+        return launch_chunks<__nv_bfloat16, 8>(P, max(8, min(32, pow2_ceil(F / 8))), grid, tma, st);
+    return launch_chunks<__nv_bfloat16, 1>(P, max(8, min(32, pow2_ceil(F))), grid, false, st);
 }
