@@ -129,9 +129,11 @@ class _HeteroConvFn(torch.autograd.Function):
                         sums.append((acc, [acc] + rest[:7]))
                         rest = rest[7:]
                     store[t] = acc
-        if sums:
-            for s in sums:          # chained sums must run in order
-                ops.sum_arrays([s])
+        if sums:                    # independent sums in one launch, chained ones (> 8 inputs) after
+            ops.sum_arrays([s for s in sums if s[1][0] is not s[0]])
+            for s in sums:
+                if s[1][0] is s[0]:
+                    ops.sum_arrays([s])
 
         # s1: transform-first products on the source tables
         Y: Dict[int, torch.Tensor] = {}
@@ -155,8 +157,14 @@ class _HeteroConvFn(torch.autograd.Function):
         chunks_by_F: Dict[int, list] = {}
         id_root: Dict[str, bool] = {}
         tf_long: Dict[str, list] = {}
+        # all destination types' outputs are row blocks of ONE buffer (consumers that run the same
+        # row-wise op on every type -- log_softmax -- then need a single launch)
+        out_rows = [lst[0].rel.n_dst for lst in by_dst.values()]
+        out_all = torch.empty(sum(out_rows), O, dtype=torch.float32, device=dev)
+        row0 = 0
         for t, lst in by_dst.items():
-            outs[t] = torch.empty(lst[0].rel.n_dst, O, dtype=torch.float32, device=dev)
+            outs[t] = out_all[row0:row0 + lst[0].rel.n_dst]
+            row0 += lst[0].rel.n_dst
             # root product against one-hot features: x[t] W^T = W^T, written first, rest accumulates
             id_root[t] = bool(spec.identity.get(t, False)) and wroot[t] is not None and \
                 xd[t] is xs[t]
@@ -379,11 +387,14 @@ class _HeteroConvFn(torch.autograd.Function):
             ops.aggregate_rows(groups[key], key[1])
         for F_, segs_ in long_chunks.items():
             ops.aggregate_chunks(segs_, F_)
+        last = []
         for dx_, ins in long_sums:
             while len(ins) > 8:
                 ops.sum_arrays([(dx_, ins[:8])])
                 ins = [dx_] + ins[8:]
-            ops.sum_arrays([(dx_, ins)])
+            last.append((dx_, ins))
+        if last:
+            ops.sum_arrays(last)
         for dx, segs, acc in groups.get(('gemm',), []):
             if segs:
                 gb.add(dx, segs, accumulate=acc)
@@ -600,6 +611,59 @@ class _LogSoftmaxFn(torch.autograd.Function):
                                             ptr(dx), dx.stride(0), stream_ptr()),
               'agx_log_softmax_nll_bwd')
         return dx
+
+
+class _LogSoftmaxManyFn(torch.autograd.Function):
+    """log_softmax(dim=1) of several [N_t, C] tensors that are adjacent row blocks of one buffer
+    (the outputs of one hetero conv layer): ONE launch over the whole buffer."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        ctx.set_materialize_grads(False)
+        base, rows, c = xs[0], sum(x.shape[0] for x in xs), xs[0].shape[1]
+        out = torch.empty(rows, c, dtype=torch.float32, device=base.device)
+        check(lib().agx_log_softmax_nll(ptr(base), c, rows, c, None, None, ptr(out), c, None, None,
+                                        stream_ptr()), 'agx_log_softmax_nll')
+        outs, r0 = [], 0
+        for x in xs:
+            outs.append(out[r0:r0 + x.shape[0]])
+            r0 += x.shape[0]
+        ctx.save_for_backward(*outs)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        res = []
+        for logp, g in zip(ctx.saved_tensors, gs):
+            if g is None:
+                res.append(None)
+                continue
+            g = g.contiguous()
+            dx = torch.empty(logp.shape, dtype=torch.float32, device=logp.device)
+            check(lib().agx_log_softmax_nll_bwd(ptr(logp), logp.stride(0), logp.shape[0],
+                                                logp.shape[1], None, None, None, None, 1.0, ptr(g),
+                                                g.stride(0), ptr(dx), dx.stride(0), stream_ptr()),
+                  'agx_log_softmax_nll_bwd')
+            res.append(dx)
+        return tuple(res)
+
+
+def log_softmax_many(xs: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    """``[F.log_softmax(x, dim=1) for x in xs]``; one launch when the inputs are consecutive row
+    blocks of one contiguous float32 buffer (as _HeteroConvFn lays its outputs out)."""
+    xs = list(xs)
+    ok = len(xs) > 1 and all(x.dim() == 2 and x.is_cuda and x.dtype == torch.float32 and
+                             x.is_contiguous() and x.shape[1] == xs[0].shape[1] for x in xs)
+    if ok:
+        p = xs[0].data_ptr()
+        for x in xs:
+            if x.data_ptr() != p:
+                ok = False
+                break
+            p += x.numel() * 4
+    if not ok:
+        return [log_softmax(x, 1) for x in xs]
+    return list(_LogSoftmaxManyFn.apply(*xs))
 
 
 def log_softmax(x: torch.Tensor, dim: int = 1) -> torch.Tensor:

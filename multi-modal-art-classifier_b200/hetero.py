@@ -108,6 +108,7 @@ class HeteroModule(nn.Module):
         self.dropout_masks: Optional[Dict[str, torch.Tensor]] = None   # test hook (injected masks)
         self._seed = None
         self._dist = None            # dist.DistContext: this module runs one rank of a multi-GPU job
+        self._nbt_flat: dict = {}
 
     def set_distributed(self, ctx):
         """Run as one rank of a destination-partitioned multi-GPU job (dist.DistContext):
@@ -175,6 +176,39 @@ class HeteroModule(nn.Module):
         st[1] += n4                  # advance the Philox counter (device side: graph-capturable)
         return m
 
+    def _masks(self, shapes, p, device, types):
+        """Dropout masks of all node types from ONE Philox launch (one flat buffer, per-type
+        views; every row is a multiple of 4 elements apart, so 128-bit accesses stay aligned)."""
+        if self.dropout_masks is not None:
+            return [self.dropout_masks[t] for t in types]
+        st = self._seed_state(device)
+        sizes = [((int(sh[0]) * int(sh[1]) + 3) // 4) * 4 for sh in shapes]
+        flat = ops.dropout_mask((sum(sizes),), p, st)
+        st[1] += sum(sizes) // 4     # advance the Philox counter (device side: graph-capturable)
+        out, off = [], 0
+        for sh, sz in zip(shapes, sizes):
+            out.append(flat[off:off + int(sh[0]) * int(sh[1])].view(int(sh[0]), int(sh[1])))
+            off += sz
+        return out
+
+    def _bump_batches_tracked(self, target, bns, types):
+        """``num_batches_tracked += 1`` of every BatchNorm of a layer as one add: the per-module
+        counters are re-pointed (once) at elements of one flat int64 tensor."""
+        live = [bns[t] for t in types if bns[t].training and bns[t].track_running_stats and
+                bns[t].num_batches_tracked is not None]
+        if not live:
+            return
+        key = (target, tuple(id(b) for b in live))
+        flat = self._nbt_flat.get(key)
+        ok = flat is not None and all(
+            b.num_batches_tracked.data_ptr() == flat[i].data_ptr() for i, b in enumerate(live))
+        if not ok:
+            flat = torch.stack([b.num_batches_tracked.detach().reshape(()) for b in live])
+            for i, b in enumerate(live):
+                b.num_batches_tracked = flat[i]
+            self._nbt_flat = {key: flat} if len(self._nbt_flat) > 16 else {**self._nbt_flat, key: flat}
+        flat += 1
+
     def _conv(self, node, x_dict, ei_dict, plan, is_input):
         convs = self.get_submodule(node.target)
         key = (node.target, id(plan))
@@ -222,11 +256,9 @@ class HeteroModule(nn.Module):
         if drop is not None:
             p = drop[1]
             if p > 0 or self.dropout_masks is not None:
-                dmasks = [self._mask(x_dict[t].shape, p, x_dict[t].device, t) for t in types]
-        for t in types:
-            bn = bns[t]
-            if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
-                bn.num_batches_tracked += 1
+                dmasks = self._masks([x_dict[t].shape for t in types], p,
+                                     x_dict[types[0]].device, types)
+        self._bump_batches_tracked(node.target, bns, types)
         spec = BNSpec(n=len(types), F=first.num_features, training=first.training or
                       not first.track_running_stats, momentum=first.momentum, eps=first.eps,
                       running=[(bns[t].running_mean, bns[t].running_var) for t in types],
@@ -308,7 +340,8 @@ class HeteroModule(nn.Module):
                         for k in keys)
             elif _is_log_softmax(node):
                 src = env[node.args[0].name]
-                env[node.name] = OrderedDict((k, AF.log_softmax(v, 1)) for k, v in src.items())
+                keys = list(src.keys())
+                env[node.name] = OrderedDict(zip(keys, AF.log_softmax_many([src[k] for k in keys])))
             elif _is_dropout_fn(node):
                 src = env[node.args[0].name]
                 p = node.kwargs.get('p', node.args[1] if len(node.args) > 1 else 0.5)
