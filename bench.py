@@ -28,6 +28,7 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_JSON_OUT = None
 METRIC = 'hetero_gnn_aggregated_edges_per_s'
 UNIT = 'edges/s'
 PASSES = 5                       # aggregation passes per training step
@@ -176,6 +177,16 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     dist = None
     if world > 1:
+        # the image exports NCCL_DEBUG=VERSION, which makes NCCL print a banner on stdout next to
+        # the one JSON line this script owes the driver
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'
+        # ... and whatever else native libraries write to fd 1 goes to stderr; the JSON line is
+        # written to the saved original stdout
+        global _JSON_OUT
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
 
@@ -337,7 +348,8 @@ def run_ours(args):
             'roofline': roofline,
             'cpu_baseline': cpu_base,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=_JSON_OUT or sys.stdout)
+        (_JSON_OUT or sys.stdout).flush()
     if dist is not None:
         # captured graphs hold NCCL work: finish everything, then leave without tearing the
         # communicator down under them

@@ -35,7 +35,7 @@ def _source_hash() -> str:
     files.append(os.path.join(os.path.dirname(PKG_DIR), 'include', 'agx.h'))
     for f in files:
         with open(f, 'rb') as fh:
-            h.update(f.encode())
+            h.update(os.path.basename(f).encode())     # not the absolute path: the tree moves
             h.update(fh.read())
     h.update(' '.join(NVCC_FLAGS).encode())
     return h.hexdigest()
@@ -52,6 +52,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every ``csrc/*.cu`` and link ``libagx.so``; returns its path."""
     if not force and is_current():
         return LIB_PATH
+    # one builder at a time (torchrun starts one process per GPU in the same tree); the others
+    # wait for the lock and then find the library current
+    import fcntl
+    lock = open(os.path.join(PKG_DIR, '.build.lock'), 'w')
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and is_current():
+            return LIB_PATH
+        return _build_locked(verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(verbose: bool) -> str:
     nvcc = _nvcc()
     objs = []
     procs = []
@@ -70,11 +85,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out.decode())
         if p.returncode != 0:
             raise RuntimeError(f'nvcc failed on {src}')
-    cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB_PATH, *objs]
+    tmp = LIB_PATH + f'.tmp{os.getpid()}'
+    cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', tmp, *objs]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if r.returncode != 0:
         sys.stderr.write(r.stdout.decode())
         raise RuntimeError('linking libagx.so failed')
+    os.replace(tmp, LIB_PATH)             # atomic: a concurrent dlopen never sees a partial file
     with open(STAMP, 'w') as fh:
         fh.write(_source_hash())
     return LIB_PATH
