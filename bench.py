@@ -153,6 +153,64 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def heads_throughput(dev, dist, world, batch: int = 4096, steps: int = 20):
+    """Secondary metric of north_star (artworks/s): one training step (forward + loss + backward +
+    Adam) of the new-multimodal multitask ViT heads (configs[3], reference batch loop
+    src/train_new_multimodal_multitask.py:62-90) and of the projector (configs[2],
+    src/train_projector.py:39-59) on precomputed synthetic features, batch-sharded over the ranks
+    with one gradient all-reduce per step.  Device-resident and end to end (pinned host -> device
+    copy of the batch, loss read-back)."""
+    import mmac_b200 as agx
+    from mmac_b200 import synth
+    from mmac_b200.trainer import HeadTrainer
+    group = dist.group.WORLD if dist is not None else None
+    feat, es, eg, ys, yg = synth.make_head_batch(batch, 'vit', seed=1 + int(os.environ.get('RANK', '0')))
+    host = [t.pin_memory() for t in (feat, es, eg, ys, yg)]
+    devt = [t.to(dev) for t in host]
+    ws = synth.class_weights(ys, 32).to(dev)
+    wg = synth.class_weights(yg, 18).to(dev)
+    torch.manual_seed(0)
+    out = {}
+    for kind in ('multitask', 'projector'):
+        if kind == 'multitask':
+            head = agx.NewMultiModalMultiTaskHead(128, {'style': 32, 'genre': 18}, 0.4, 768).to(dev)
+            tr = HeadTrainer(head, 'multitask', 3e-4, ws, wg, group=group, use_cuda_graph=True)
+            args_dev = devt
+            args_host = host
+        else:
+            head = agx.LabelProjectorHead(128, 768).to(dev)
+            tr = HeadTrainer(head, 'projector', 3e-4, group=group, use_cuda_graph=True)
+            args_dev = [devt[0], devt[1]]
+            args_host = [host[0], host[1]]
+        for _ in range(3):
+            tr.step(*args_dev)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            tr.step(*args_dev)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        t0 = time.perf_counter()
+        for _ in range(steps):          # pinned host batch -> static device buffers -> replay
+            float(tr.step(*args_host).item())
+        torch.cuda.synchronize()
+        ms_e2e = (time.perf_counter() - t0) * 1e3
+        if dist is not None:
+            t = torch.tensor([ms, ms_e2e], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, ms_e2e = float(t[0]), float(t[1])
+        out[kind] = {'artworks_per_s': world * batch * steps / (ms * 1e-3),
+                     'e2e_artworks_per_s': world * batch * steps / (ms_e2e * 1e-3),
+                     'ms_per_step': ms / steps}
+    out['batch_per_gpu'] = batch
+    out['features'] = 'synthetic ViT CLS features [B,768] + style/genre embeddings [B,128]'
+    return out
+
+
 def _workload_name(size):
     return (f"train_gnn_embeddings.py --label style: full-graph SAGEConv to_hetero training step on "
             f"synthetic ArtGraph '{size}' (one-hot node features as in artgraph.py:93-95)")
@@ -322,6 +380,9 @@ def run_ours(args):
             cpu_base = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
                         'sample': r['sample']}
 
+    heads = None
+    if not args.no_heads:
+        heads = heads_throughput(dev, dist, world)
     if rank == 0:
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -347,6 +408,7 @@ def run_ours(args):
             'clocks': clk,
             'roofline': roofline,
             'cpu_baseline': cpu_base,
+            'heads': heads,
         }
         print(json.dumps(line), file=_JSON_OUT or sys.stdout)
         (_JSON_OUT or sys.stdout).flush()
@@ -370,6 +432,8 @@ def main():
                     help="graph size of the bounded CPU sample (full: ~8 s per step on 8 cores)")
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA graph')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-heads', action='store_true',
+                    help='skip the secondary fusion-head / projector artworks/s measurement')
     ap.add_argument('--park-ms', type=float, default=60.0,
                     help='device-side delay in front of each per-kernel timing step (roofline leg)')
     ap.add_argument('--ncu', action='store_true',

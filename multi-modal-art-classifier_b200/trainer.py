@@ -24,6 +24,37 @@ from .heads import multitask_loss, projector_loss
 from .optim import FlatAdam
 
 
+class _StateSnapshot:
+    """Everything a training step mutates -- parameters and Adam state (flat arenas), module
+    buffers (BatchNorm running statistics), dropout Philox counters.  CUDA-graph capture needs
+    warm-up steps on the capture stream; they are real steps, so the state is put back afterwards
+    and N calls of ``train_step`` / ``step`` stay N optimizer steps."""
+
+    def __init__(self, model: torch.nn.Module, opt: FlatAdam):
+        self.model, self.opt = model, opt
+        self.opt_state = [t.clone() for t in (opt.flat, opt.exp_avg, opt.exp_avg_sq, opt.step_t)]
+        self.buffers = {k: v.clone() for k, v in model.named_buffers()}
+        self.seeds = {}
+        for name, m in model.named_modules():
+            if hasattr(m, '_seed'):
+                self.seeds[name] = None if m._seed is None else m._seed.clone()
+
+    @torch.no_grad()
+    def restore(self):
+        for t, saved in zip((self.opt.flat, self.opt.exp_avg, self.opt.exp_avg_sq, self.opt.step_t),
+                            self.opt_state):
+            t.copy_(saved)
+        for k, v in self.model.named_buffers():
+            if k in self.buffers:
+                v.copy_(self.buffers[k])
+        for name, m in self.model.named_modules():
+            if name in self.seeds and getattr(m, '_seed', None) is not None:
+                if self.seeds[name] is None:
+                    m._seed[1] = 0                      # the stream had not been started
+                else:
+                    m._seed.copy_(self.seeds[name])
+
+
 def _accuracy(logp: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
     """``predicted.argmax(dim=1).eq(labels).sum() / N`` (train_gnn_embeddings.py:20-21)."""
     return logp.argmax(dim=1).eq(labels).sum() / logp.shape[0]
@@ -93,7 +124,9 @@ class GNNTrainer:
             self._loss, self._emb, self._out = self._step_eager()
             return self._loss
         if self._graph is None:
+            snap = _StateSnapshot(self.model, self.opt)
             self._capture()
+            snap.restore()
         self._graph.replay()
         return self._loss
 
@@ -183,7 +216,7 @@ class HeadTrainer:
     """One fused step per mini-batch on device-resident (or freshly copied) features."""
 
     def __init__(self, head: torch.nn.Module, kind: str = 'multitask', lr: float = 3e-4,
-                 w_style=None, w_genre=None, group=None):
+                 w_style=None, w_genre=None, group=None, use_cuda_graph: bool = False):
         """``group``: batch-sharded data parallel -- ``step`` gets this rank's shard of the batch;
         weights are replicated (rank 0's), gradients all-reduced (one NCCL call on the arena)."""
         assert kind in ('multitask', 'projector')
@@ -198,8 +231,45 @@ class HeadTrainer:
             from .dist import broadcast_
             self.world = dist.get_world_size(group)
             broadcast_(self.opt.flat, group)
+        # CUDA graph: a head step is ~20 small launches, i.e. launch-bound from Python; the batch is
+        # copied into static buffers and the captured step replayed (one batch shape per trainer)
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+        self._static = None
+        self._loss = None
 
     def step(self, feat, *rest) -> torch.Tensor:
+        if not self.use_cuda_graph:
+            return self._step_eager(feat, *rest)
+        batch = (feat, *rest)
+        if self._static is not None and any(a.shape != b.shape or a.dtype != b.dtype
+                                            for a, b in zip(batch, self._static)):
+            self._graph = self._static = None           # new batch shape: capture again
+        if self._graph is None:
+            self._static = [torch.empty_like(t, device=self.opt.flat.device) for t in batch]
+            for st, t in zip(self._static, batch):
+                st.copy_(t, non_blocking=True)
+            snap = _StateSnapshot(self.head, self.opt)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):                      # warm-up steps are real steps
+                    self._step_eager(*self._static)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self._graph = torch.cuda.CUDAGraph()
+            mode = 'thread_local' if self.group is not None else 'global'
+            with torch.cuda.graph(self._graph, capture_error_mode=mode):
+                self._loss = self._step_eager(*self._static)
+            snap.restore()
+            self._graph.replay()
+            return self._loss
+        for st, t in zip(self._static, batch):
+            st.copy_(t, non_blocking=True)
+        self._graph.replay()
+        return self._loss
+
+    def _step_eager(self, feat, *rest) -> torch.Tensor:
         self.head.train()
         self.opt.zero_grad()
         if self.kind == 'multitask':

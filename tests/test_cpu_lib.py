@@ -139,3 +139,26 @@ def test_oracle_is_not_imported_by_the_product():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', txt, flags=re.M), f
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (the CPU oracle timed on the host cores) prints ONE JSON line
+    with the contract's keys; bounded here to the tiny graph."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(util.ROOT, 'bench.py'), '--impl', 'reference',
+                        '--cpu-size', 'tiny', '--size', 'tiny', '--steps', '1', '--warmup', '0'],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    lines = [ln for ln in r.stdout.decode().splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['metric'] == 'hetero_gnn_aggregated_edges_per_s'
+    assert d['unit'] == 'edges/s' and d['higher_is_better'] is True and d['value'] > 0
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['e2e'] == {'value': d['value'], 'unit': 'edges/s', 'h2d_bytes_per_step': 0,
+                        'd2h_bytes_per_step': 0}
+    for k in ('n_gpus', 'steps', 'warmup', 'ms_per_step', 'scaling', 'vs_baseline', 'dtype', 'data',
+              'config'):
+        assert k in d

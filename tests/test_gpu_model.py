@@ -384,3 +384,41 @@ def test_full_size_properties():
     ops.aggregate_rows([(o, [ops.RelArg(rev.csr, xs, mean_rows=True)], False)], 128)
     lab = data['artwork'].y_style.long().to(DEV)
     assert torch.equal(o, xs[lab])                     # exactly one style edge per artwork
+
+
+def test_trainers_cuda_graph_steps_equal_eager_steps():
+    """N calls of a CUDA-graph trainer are N optimizer steps with the values of N eager steps
+    (the capture warm-up is rolled back): GNN trainer and both head trainers."""
+    from mmac_b200.trainer import GNNTrainer, HeadTrainer
+    g, ei, orc, prod = _build_pair('SAGEConv', 32, 'tiny', dropout=0.0)
+    prod2 = copy.deepcopy(prod)
+    xd, ed, y = _to_dev(g.x_dict), _to_dev(ei), g['artwork'].y_style
+    t_e = GNNTrainer(prod, xd, ed, y, lr=0.01, use_cuda_graph=False)
+    t_g = GNNTrainer(prod2, xd, ed, y, lr=0.01, use_cuda_graph=True)
+    le = [float(t_e.train_step().item()) for _ in range(4)]
+    lg = [float(t_g.train_step().item()) for _ in range(4)]
+    assert abs(le[0] - lg[0]) <= RTOL_F32 * abs(le[0])
+    assert np.allclose(le, lg, rtol=2e-3)
+    sd_e, sd_g = prod.state_dict(), prod2.state_dict()
+    for k in sd_e:
+        if 'num_batches_tracked' in k:
+            assert int(sd_e[k]) == int(sd_g[k]) == 4 + 1, k      # + the lazy-init forward
+
+    feat, es, eg_, ys, yg = [t.to(DEV) for t in synth.make_head_batch(96, 'vit')]
+    for kind in ('multitask', 'projector'):
+        torch.manual_seed(3)
+        if kind == 'multitask':
+            h1 = agx.NewMultiModalMultiTaskHead(128, {'style': 32, 'genre': 18}, 0.0, 768).to(DEV)
+            batch = lambda i: (feat[32 * i:32 * i + 32], es[32 * i:32 * i + 32],      # noqa: E731
+                               eg_[32 * i:32 * i + 32], ys[32 * i:32 * i + 32], yg[32 * i:32 * i + 32])
+        else:
+            h1 = agx.LabelProjectorHead(128, 768).to(DEV)
+            batch = lambda i: (feat[32 * i:32 * i + 32], es[32 * i:32 * i + 32])      # noqa: E731
+        h2 = copy.deepcopy(h1)
+        a = HeadTrainer(h1, kind, 3e-4, use_cuda_graph=False)
+        b = HeadTrainer(h2, kind, 3e-4, use_cuda_graph=True)
+        la = [float(a.step(*batch(i % 3)).item()) for i in range(5)]
+        lb = [float(b.step(*batch(i % 3)).item()) for i in range(5)]
+        assert np.allclose(la, lb, rtol=1e-5), (kind, la, lb)
+        for (k, p), (_, q) in zip(h1.state_dict().items(), h2.state_dict().items()):
+            assert rel_err(q, p) <= 1e-5, (kind, k)
