@@ -227,9 +227,8 @@ int agx_bn_backward(const agx_bn_bwd_desc_t* h_descs, int n, int F, int training
 
 /* Multi-GPU BatchNorm (the node type's rows are spread over the ranks; statistics over ALL rows,
  * as on one GPU).  phases is a bit mask; between phases the caller all-reduces the float64 buffer:
- *   forward : 1 -> sums[n][F] = local column sums            (all-reduce sums)
- *             2 -> mean from sums/counts; sums = local centred second moments   (all-reduce sums)
- *             4 -> invstd + running stats from sums/counts; normalise (+ReLU, dropout)
+ *   forward : 1 -> sums[n][2F] = local column sums of x and of x*x            (all-reduce sums)
+ *             4 -> mean / invstd / running stats from sums and counts; normalise (+ReLU, dropout)
  *   backward: 1 -> totals[n][2F] = local (sum dy, sum dy*xhat); dweight/dbias += local sums
  *                                                                             (all-reduce totals)
  *             2 -> dx with the global totals / counts

@@ -41,80 +41,103 @@ struct BnParams {
     int32_t slab_start[AGX_MAX_GROUPS + 1];
     int32_t n;
     int32_t F;
-    double* ws;           // [total_slabs][F] float64 partials
+    double* ws;           // [total_slabs][2F] float64 partials: sum x, sum x^2
     int32_t training;
     float momentum, eps;
-    // multi-GPU (SyncBN): mode 1 = only reduce the slab partials into sums[n][F]; mode 2 = finalize
+    // multi-GPU (SyncBN): mode 1 = only reduce the slab partials into sums[n][2F]; mode 2 = finalize
     // from sums (already all-reduced across ranks) with the global row counts; mode 0 = fused
     int32_t mode;
     double* sums;
     const double* counts;
 };
 
-// pass: 0 -> sum x ; 1 -> sum (x - mean)^2
-__global__ void __launch_bounds__(kBnThreads) bn_stats(const __grid_constant__ BnParams P, int pass) {
+// One pass over x: per slab the float64 column sums of x and of x*x (a float32 square is exact in
+// float64, so var = E[x^2] - mean^2 loses nothing that matters: 53-bit sums of <= 2^24-bit terms).
+// part[slab][0..F) = sum x, part[slab][F..2F) = sum x^2.
+__global__ void __launch_bounds__(kBnThreads) bn_stats(const __grid_constant__ BnParams P) {
     int di = 0;
     while ((int)blockIdx.x >= P.slab_start[di + 1]) ++di;
     const agx_bn_desc_t& D = P.d[di];
     const int slab = blockIdx.x - P.slab_start[di];
     const int r0 = slab * kBnSlab, r1 = min(D.n_rows, r0 + kBnSlab);
     const int F = P.F;
-    double* part = P.ws + (size_t)blockIdx.x * F;
-    // thread t owns column (t % F) for F <= 256 lanes-of-columns; row groups stride over t / F.
-    // float64 accumulation: the reference's CPU BatchNorm accumulates its statistics in double
-    __shared__ double red[kBnThreads];
+    double* part = P.ws + (size_t)blockIdx.x * 2 * F;
     if ((F & 3) == 0 && F <= 4 * kBnThreads) {
-        // 128-bit path: thread owns 4 consecutive columns, row groups stride over t / (F/4);
-        // per column the same float64 sum order as below with `groups` row groups
-        __shared__ double red4[4][kBnThreads];
+        // 128-bit path: thread owns 4 consecutive columns, row groups stride over t / (F/4)
+        __shared__ double red1[4][kBnThreads], red2[4][kBnThreads];
         const int cols4 = F >> 2;
         const int groups = kBnThreads / cols4;
         const int c = (threadIdx.x % cols4) * 4, g = threadIdx.x / cols4;
-        double s[4] = {0.0, 0.0, 0.0, 0.0};
+        double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
         if (g < groups) {
-            float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (pass) m = *reinterpret_cast<const float4*>(D.save_mean + c);
-            for (int r = r0 + g; r < r1; r += groups) {
+            int r = r0 + g;
+            for (; r + 3 * groups < r1; r += 4 * groups) {          // four rows in flight
+                float4 x[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    x[u] = *reinterpret_cast<const float4*>(D.x + (int64_t)(r + u * groups) * F + c);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double v0 = x[u].x, v1 = x[u].y, v2 = x[u].z, v3 = x[u].w;
+                    s1[0] += v0; s2[0] += v0 * v0;
+                    s1[1] += v1; s2[1] += v1 * v1;
+                    s1[2] += v2; s2[2] += v2 * v2;
+                    s1[3] += v3; s2[3] += v3 * v3;
+                }
+            }
+            for (; r < r1; r += groups) {
                 const float4 x = *reinterpret_cast<const float4*>(D.x + (int64_t)r * F + c);
-                const double v0 = (double)x.x - (double)m.x, v1 = (double)x.y - (double)m.y;
-                const double v2 = (double)x.z - (double)m.z, v3 = (double)x.w - (double)m.w;
-                s[0] += pass ? v0 * v0 : v0;
-                s[1] += pass ? v1 * v1 : v1;
-                s[2] += pass ? v2 * v2 : v2;
-                s[3] += pass ? v3 * v3 : v3;
+                const double v0 = x.x, v1 = x.y, v2 = x.z, v3 = x.w;
+                s1[0] += v0; s2[0] += v0 * v0;
+                s1[1] += v1; s2[1] += v1 * v1;
+                s1[2] += v2; s2[2] += v2 * v2;
+                s1[3] += v3; s2[3] += v3 * v3;
             }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) red4[i][threadIdx.x] = s[i];
+        for (int i = 0; i < 4; ++i) {
+            red1[i][threadIdx.x] = s1[i];
+            red2[i][threadIdx.x] = s2[i];
+        }
         __syncthreads();
         if (threadIdx.x < cols4) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                double t = 0.0;
-                for (int gg = 0; gg < groups; ++gg) t += red4[i][gg * cols4 + threadIdx.x];
-                part[4 * threadIdx.x + i] = t;
+                double t1 = 0.0, t2 = 0.0;
+                for (int gg = 0; gg < groups; ++gg) {
+                    t1 += red1[i][gg * cols4 + threadIdx.x];
+                    t2 += red2[i][gg * cols4 + threadIdx.x];
+                }
+                part[4 * threadIdx.x + i] = t1;
+                part[F + 4 * threadIdx.x + i] = t2;
             }
         }
         return;
     }
+    __shared__ double red[2][kBnThreads];
     for (int c0 = 0; c0 < F; c0 += kBnThreads) {
         const int cols = min(kBnThreads, F - c0);
         const int groups = kBnThreads / cols > 0 ? kBnThreads / cols : 1;   // row groups
         const int c = threadIdx.x % cols, g = threadIdx.x / cols;
-        double s = 0.0;
+        double s1 = 0.0, s2 = 0.0;
         if (g < groups) {
-            const double m = pass ? (double)D.save_mean[c0 + c] : 0.0;
             for (int r = r0 + g; r < r1; r += groups) {
-                const double v = (double)D.x[(int64_t)r * F + c0 + c] - m;
-                s += pass ? v * v : v;
+                const double v = (double)D.x[(int64_t)r * F + c0 + c];
+                s1 += v;
+                s2 += v * v;
             }
         }
-        red[threadIdx.x] = s;
+        red[0][threadIdx.x] = s1;
+        red[1][threadIdx.x] = s2;
         __syncthreads();
         if (threadIdx.x < cols) {
-            double t = 0.0;
-            for (int gg = 0; gg < groups; ++gg) t += red[gg * cols + threadIdx.x];
-            part[c0 + threadIdx.x] = t;
+            double t1 = 0.0, t2 = 0.0;
+            for (int gg = 0; gg < groups; ++gg) {
+                t1 += red[0][gg * cols + threadIdx.x];
+                t2 += red[1][gg * cols + threadIdx.x];
+            }
+            part[c0 + threadIdx.x] = t1;
+            part[F + c0 + threadIdx.x] = t2;
         }
         __syncthreads();
     }
@@ -140,8 +163,10 @@ __device__ __forceinline__ double slab_total_32x32(const double* __restrict__ pa
     return t;
 }
 
-// grid (descriptor, 32-column block); float64 combination of slab partials
-__global__ void __launch_bounds__(1024) bn_finalize(const __grid_constant__ BnParams P, int pass) {
+// grid (descriptor, 32-column block); float64 combination of slab partials.
+// P.mode: 0 = finalize from the local partials; 1 = only write the local column sums to
+// sums[n][2F] (multi-GPU: all-reduced by the caller); 2 = finalize from sums with the global counts
+__global__ void __launch_bounds__(1024) bn_finalize(const __grid_constant__ BnParams P) {
     __shared__ double sm[32][33];
     const agx_bn_desc_t& D = P.d[blockIdx.x];
     const int s0 = P.slab_start[blockIdx.x], s1 = P.slab_start[blockIdx.x + 1];
@@ -149,36 +174,42 @@ __global__ void __launch_bounds__(1024) bn_finalize(const __grid_constant__ BnPa
     const int col0 = blockIdx.y * 32;
     const int c = col0 + (int)threadIdx.x;
     if (!P.training) {
-        if (pass == 0 && threadIdx.x < 32 && c < F) {
+        if (threadIdx.x < 32 && c < F) {
             D.save_mean[c] = D.running_mean[c];
             D.save_invstd[c] = (float)(1.0 / sqrt((double)D.running_var[c] + (double)P.eps));
         }
         return;
     }
-    double acc = 0.0;
+    double a1 = 0.0, a2 = 0.0;
     if (P.mode == 2) {
-        if (threadIdx.x < 32 && c < F) acc = P.sums[(size_t)blockIdx.x * F + c];
+        if (threadIdx.x < 32 && c < F) {
+            a1 = P.sums[(size_t)blockIdx.x * 2 * F + c];
+            a2 = P.sums[(size_t)blockIdx.x * 2 * F + F + c];
+        }
     } else {
-        acc = slab_total_32x32(P.ws + (size_t)s0 * F, s1 - s0, F, col0, F, sm);
+        const double* part = P.ws + (size_t)s0 * 2 * F;
+        a1 = slab_total_32x32(part, s1 - s0, (size_t)2 * F, col0, F, sm);
+        a2 = slab_total_32x32(part + F, s1 - s0, (size_t)2 * F, col0, F, sm);
     }
     if (P.mode == 1) {
-        if (threadIdx.x < 32 && c < F) P.sums[(size_t)blockIdx.x * F + c] = acc;
+        if (threadIdx.x < 32 && c < F) {
+            P.sums[(size_t)blockIdx.x * 2 * F + c] = a1;
+            P.sums[(size_t)blockIdx.x * 2 * F + F + c] = a2;
+        }
         return;
     }
     if (threadIdx.x < 32 && c < F) {
         const double n = P.counts ? P.counts[blockIdx.x] : (double)D.n_rows;
-        if (pass == 0) {
-            D.save_mean[c] = (float)(acc / n);
-        } else {
-            const double var = acc / n;
-            D.save_invstd[c] = (float)(1.0 / sqrt(var + (double)P.eps));
-            if (D.running_mean) {
-                const double unbiased = n > 1.0 ? acc / (n - 1.0) : var;
-                D.running_mean[c] = (float)((1.0 - P.momentum) * D.running_mean[c] +
-                                            P.momentum * (double)D.save_mean[c]);
-                D.running_var[c] = (float)((1.0 - P.momentum) * D.running_var[c] +
-                                           P.momentum * unbiased);
-            }
+        const double mean = a1 / n;
+        double var = a2 / n - mean * mean;               // biased (normalisation)
+        if (var < 0.0) var = 0.0;
+        D.save_mean[c] = (float)mean;
+        D.save_invstd[c] = (float)(1.0 / sqrt(var + (double)P.eps));
+        if (D.running_mean) {
+            const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+            D.running_mean[c] = (float)((1.0 - P.momentum) * D.running_mean[c] + P.momentum * mean);
+            D.running_var[c] = (float)((1.0 - P.momentum) * D.running_var[c] +
+                                       P.momentum * unbiased);
         }
     }
 }
@@ -867,36 +898,24 @@ static int bn_forward_impl(const agx_bn_desc_t* h_descs, int n, int F, int train
     const dim3 fgrid(n, (F + 31) / 32);
     if (!training) {
         if (phases & 4) {
-            bn_finalize<<<fgrid, 1024, 0, st>>>(P, 0);
+            bn_finalize<<<fgrid, 1024, 0, st>>>(P);
             AGX_LAUNCH_CHECK("bn_finalize");
         }
     } else {
         if (phases & 1) {
             if (slabs > 0) {
-                bn_stats<<<slabs, kBnThreads, 0, st>>>(P, 0);
+                bn_stats<<<slabs, kBnThreads, 0, st>>>(P);
                 AGX_LAUNCH_CHECK("bn_stats");
             }
-            P.mode = sums ? 1 : 0;
-            bn_finalize<<<fgrid, 1024, 0, st>>>(P, 0);
-            AGX_LAUNCH_CHECK("bn_finalize");
-        }
-        if (phases & 2) {
-            if (sums) {
-                P.mode = 2;
-                bn_finalize<<<fgrid, 1024, 0, st>>>(P, 0);
+            if (sums) {                      // hand the local sums to the caller's all-reduce
+                P.mode = 1;
+                bn_finalize<<<fgrid, 1024, 0, st>>>(P);
                 AGX_LAUNCH_CHECK("bn_finalize");
             }
-            if (slabs > 0) {
-                bn_stats<<<slabs, kBnThreads, 0, st>>>(P, 1);
-                AGX_LAUNCH_CHECK("bn_stats");
-            }
-            P.mode = sums ? 1 : 0;
-            bn_finalize<<<fgrid, 1024, 0, st>>>(P, 1);
-            AGX_LAUNCH_CHECK("bn_finalize");
         }
-        if ((phases & 4) && sums) {
-            P.mode = 2;
-            bn_finalize<<<fgrid, 1024, 0, st>>>(P, 1);
+        if (phases & 4) {
+            P.mode = sums ? 2 : 0;
+            bn_finalize<<<fgrid, 1024, 0, st>>>(P);
             AGX_LAUNCH_CHECK("bn_finalize");
         }
     }

@@ -505,14 +505,15 @@ class _BNActFn(torch.autograd.Function):
         n_ws = lib().agx_bn_workspace_floats(rows, n, F)
         wsb = torch.empty(n_ws, dtype=torch.float32, device=dev)
         if spec.group is not None and spec.training:
-            # SyncBN: statistics over the rows of ALL ranks (two float64 all-reduces of [n, F])
+            # SyncBN: statistics over the rows of ALL ranks (one float64 all-reduce of [n, 2F]:
+            # column sums of x and of x*x)
             import torch.distributed as dist
-            sums = torch.empty(n * F, dtype=torch.float64, device=dev)
-            for phase in (1, 2, 4):
+            sums = torch.empty(n * 2 * F, dtype=torch.float64, device=dev)
+            for phase in (1, 4):
                 check(lib().agx_bn_forward_phase(arr, n, F, 1, spec.momentum, spec.eps, ptr(wsb),
                                                  n_ws, phase, ptr(sums), ptr(spec.counts),
                                                  stream_ptr()), 'agx_bn_forward_phase')
-                if phase != 4:
+                if phase == 1:
                     dist.all_reduce(sums, group=spec.group)
         else:
             check(lib().agx_bn_forward(arr, n, F, int(spec.training), spec.momentum, spec.eps,
