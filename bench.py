@@ -341,10 +341,10 @@ def run_ours(args):
     # ---- roofline of the aggregation kernels: events around every launch, eager steps ----------
     roofline = None
     cpu_base = None
-    timer = ops.KernelTimer()
-    if rank == 0:
-        ops.TIMER = timer
-    for _ in range(3):                   # every rank steps (the step holds collectives)
+    timers = [ops.KernelTimer() for _ in range(3)]
+    for timer in timers:                 # every rank steps (the step holds collectives)
+        if rank == 0:
+            ops.TIMER = timer
         # an eager step is CPU-bound (~150 launches from Python): park the GPU behind a spin kernel
         # while the CPU enqueues the whole step, so that the CUDA events around each launch measure
         # kernel time, not the gaps in which the GPU waits for the next launch
@@ -355,7 +355,9 @@ def run_ours(args):
     barrier()
     if rank == 0:
         peak, peak_src = _peaks()
-        summ = timer.summary()
+        # every launch position is timed in three steps: keep its fastest time (a step whose
+        # enqueue outlasted the parking delay shows launch gaps, not kernel time)
+        summ = ops.KernelTimer.summary_min(timers)
         agg = {k: v for k, v in summ.items() if k.startswith('agg')}
         dom = max(agg, key=lambda k: agg[k]['ms'])
         d = agg[dom]
@@ -367,10 +369,10 @@ def run_ours(args):
                     'peak_source': peak_src, 'launches_timed': d['launches'],
                     'avg_launch_us': 1e3 * d['ms'] / d['launches'],
                     'all_aggregation': {'achieved': all_b / (all_ms * 1e-3) / 1e9,
-                                        'ms_per_step': all_ms / 3,
-                                        'bytes_per_step': all_b / 3},
+                                        'ms_per_step': all_ms,
+                                        'bytes_per_step': all_b},
                     'gemm': ({'tflops': summ['gemm']['flops'] / (summ['gemm']['ms'] * 1e-3) / 1e12,
-                              'ms_per_step': summ['gemm']['ms'] / 3} if 'gemm' in summ else None)}
+                              'ms_per_step': summ['gemm']['ms']} if 'gemm' in summ else None)}
         tr = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.exists(tr):
             with open(tr) as fh:
@@ -434,7 +436,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-heads', action='store_true',
                     help='skip the secondary fusion-head / projector artworks/s measurement')
-    ap.add_argument('--park-ms', type=float, default=60.0,
+    ap.add_argument('--park-ms', type=float, default=120.0,
                     help='device-side delay in front of each per-kernel timing step (roofline leg)')
     ap.add_argument('--ncu', action='store_true',
                     help='run one eager step between cudaProfilerStart/Stop and exit')

@@ -148,6 +148,30 @@ __device__ __forceinline__ void store_vec<__nv_bfloat16, 1>(__nv_bfloat16* p,
     *p = __float2bfloat16(a.v[0]);
 }
 
+template <typename T>
+__device__ __forceinline__ void store_elem(T* p, float v);
+template <>
+__device__ __forceinline__ void store_elem<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void store_elem<__nv_bfloat16>(__nv_bfloat16* p, float v) {
+    *p = __float2bfloat16(v);
+}
+// four consecutive output elements (16 B float / 8 B bfloat16, aligned)
+template <typename T>
+__device__ __forceinline__ void store_row4(T* p, const Vec<T, 4>& a);
+template <>
+__device__ __forceinline__ void store_row4<float>(float* p, const Vec<float, 4>& a) {
+    *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+}
+template <>
+__device__ __forceinline__ void store_row4<__nv_bfloat16>(__nv_bfloat16* p,
+                                                          const Vec<__nv_bfloat16, 4>& a) {
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.v[0], a.v[1]);
+    const __nv_bfloat162 h1 = __floats2bfloat162_rn(a.v[2], a.v[3]);
+    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0),
+                                             *reinterpret_cast<const uint32_t*>(&h1));
+}
+
 // ------------------------------------------------------------------------------------------------
 // agg_rows
 // ------------------------------------------------------------------------------------------------
@@ -449,32 +473,46 @@ __device__ __forceinline__ Vec<T, VEC> load_smem_vec(const uint8_t* p) {
     return r;
 }
 
+constexpr int kCtaEdges = kAggWarps * AGX_CHUNK_EDGES;      // 1024 edges per CTA
+constexpr int kMaxChunkF = 256;                              // columns per launch (host loops)
+
 template <typename T, int VEC, int LPR, bool TMA>
 __global__ void __launch_bounds__(kAggThreads, TMA ? 2 : 3)
 agg_chunks(const __grid_constant__ ChunkSegs P) {
     constexpr int SUB = 32 / LPR;
     constexpr int U = kGatherDepth;
-    __shared__ int s_col[kAggWarps][AGX_CHUNK_EDGES];
-    __shared__ float s_scl[kAggWarps][AGX_CHUNK_EDGES];
+    __shared__ int s_col[TMA ? kAggWarps : 1][AGX_CHUNK_EDGES];
+    __shared__ float s_scl[TMA ? kAggWarps : 1][AGX_CHUNK_EDGES];
     __shared__ uint64_t s_bar[kAggWarps][kRingGroups];
+    // row pieces a warp could not finish alone: [warp][0] = head (its first row began in an earlier
+    // warp's edges), [warp][1] = tail (its last row goes on); stitched by warp 0 after the barrier
+    __shared__ __align__(16) float s_part[kAggWarps][2][kMaxChunkF];
+    __shared__ int s_head_row[kAggWarps], s_head_open[kAggWarps], s_tail_row[kAggWarps];
+    __shared__ int s_row_beg[kAggWarps][2], s_row_end[kAggWarps][2];
     extern __shared__ __align__(128) uint8_t s_ring[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int sub = lane / LPR, l = lane % LPR;
-    const int64_t gchunk = (int64_t)blockIdx.x * kAggWarps + w;
-    if (gchunk >= P.chunk_start[P.n]) return;
+    // CTA -> (relation, 1024-edge block); warp w owns edges [128 w, 128 w + 128) of the block
     int si = 0;
-    while (gchunk >= P.chunk_start[si + 1]) ++si;
+    while ((int)blockIdx.x >= P.chunk_start[si + 1]) ++si;
     const agx_chunk_seg_t& S = P.s[si];
     const agx_rel_t& R = S.rel;
     const int F = P.F;
-    const int chunk = (int)(gchunk - P.chunk_start[si]);
-    const int nchunks = P.chunk_start[si + 1] - P.chunk_start[si];
-    const int start = chunk * AGX_CHUNK_EDGES;
+    const int cta = (int)blockIdx.x - P.chunk_start[si];          // block index inside the relation
+    const int nctas = P.chunk_start[si + 1] - P.chunk_start[si];
+    const int start = cta * kCtaEdges + w * AGX_CHUNK_EDGES;
     const int end = min(S.n_edges, start + AGX_CHUNK_EDGES);
     const int n_rows = S.n_rows;
-    float* lead = S.frag;
-    float* trail = S.frag + (size_t)nchunks * F;
+    float* lead = S.frag;                                         // [nctas][F]
+    float* trail = S.frag + (size_t)nctas * F;
+    const bool has_work = start < S.n_edges;
+    if (lane == 0) {
+        s_head_row[w] = -1;
+        s_head_open[w] = 0;
+        s_tail_row[w] = -1;
+    }
 
+    if (has_work) {
     // ---- stage neighbour ids / scales ----------------------------------------------------------
     // lane i of register k holds edge k*32 + i of the chunk (register path: read by shuffles);
     // the TMA path issues its copies from the shared-memory copy
@@ -521,7 +559,7 @@ agg_chunks(const __grid_constant__ ChunkSegs P) {
         if (lane < cnt)
             agg_bulk_row(ring + (size_t)(slot * kRingRows + lane) * RB,
                          reinterpret_cast<const uint8_t*>(R.x) +
-                             (int64_t)s_col[w][r0 + lane] * R.ldx * (int64_t)sizeof(T),
+                             (int64_t)s_col[TMA ? w : 0][r0 + lane] * R.ldx * (int64_t)sizeof(T),
                          RB, &s_bar[w][slot]);
     };
     if constexpr (TMA) {
@@ -533,7 +571,7 @@ agg_chunks(const __grid_constant__ ChunkSegs P) {
         __syncwarp();
         for (int g = 0; g < kRingGroups && g < ngroups; ++g) issue_group(g);
     }
-    if (chunk == 0) zero_rows<T, VEC>(S, F, 0, row, lane);
+    if (start == 0) zero_rows<T, VEC>(S, F, 0, row, lane);
 
     int wrow = row;                                // row-extent window: lane i holds rowptr[wrow+1+i]
     int rp = wrow + 1 + lane <= n_rows ? __ldg(R.rowptr + wrow + 1 + lane) : INT_MAX;
@@ -548,7 +586,7 @@ agg_chunks(const __grid_constant__ ChunkSegs P) {
         const int e1 = min(rend, end);
         const bool starts_here = rbeg >= start, ends_here = rend <= end;
         const int i0 = e - start, i1 = e1 - start;
-        // ---- the row segment [e, e1), one block of LPR*VEC columns at a time ---------------------
+        // ---- the row segment [e, e1) (F <= kMaxChunkF: at most LPR*VEC*? column blocks) ---------
         for (int cb = 0; cb < F; cb += LPR * VEC) {
             const int c0 = cb + l * VEC;
             const bool active = c0 < F;
@@ -579,7 +617,7 @@ agg_chunks(const __grid_constant__ ChunkSegs P) {
                     for (int u = 0; u < kRingRows / SUB; ++u) {
                         const int e_ = i + u * SUB + sub;
                         if (e_ < b && active) {
-                            const float sc = s_scl[w][e_];
+                            const float sc = s_scl[TMA ? w : 0][e_];
 #pragma unroll
                             for (int k = 0; k < VEC; ++k) acc.v[k] += v[u].v[k] * sc;
                         }
@@ -641,43 +679,20 @@ agg_chunks(const __grid_constant__ ChunkSegs P) {
                     }
                     store_vec<T, VEC>(reinterpret_cast<T*>(S.out) + (int64_t)row * S.ldo + c0, acc);
                 } else {
-                    store_frag<T, VEC>((starts_here ? trail : lead) + (size_t)chunk * F + c0, acc);
+                    store_frag<T, VEC>(&s_part[w][starts_here ? 1 : 0][c0], acc);
                 }
             }
         }
-        // ---- a fragment of a row that crosses chunks: the last one to arrive adds them up ----------
-        if (!(starts_here && ends_here)) {
-            const int c_first = rbeg / AGX_CHUNK_EDGES, c_last = (rend - 1) / AGX_CHUNK_EDGES;
-            __threadfence();
-            __syncwarp();
-            int old = 0;
-            if (lane == 0) old = atomicAdd(S.counters + c_first, 1);
-            old = __shfl_sync(0xffffffffu, old, 0);
-            if (old == c_last - c_first) {
-                __threadfence();
-                const float d = R.row_cnt ? __ldg(R.row_cnt + row) : 1.0f;
-                for (int c0 = lane * VEC; c0 < F; c0 += 32 * VEC) {
-                    Vec<T, VEC> tot = load_frag<T, VEC>(trail + (size_t)c_first * F + c0);
-                    constexpr int UC = 2 * U;          // fragments in flight (slots past the end
-                    for (int c = c_first + 1; c <= c_last; c += UC) {   // re-read the last one, unused)
-                        Vec<T, VEC> v[UC];
-#pragma unroll
-                        for (int u = 0; u < UC; ++u)
-                            v[u] = load_frag<T, VEC>(lead + (size_t)min(c + u, c_last) * F + c0);
-#pragma unroll
-                        for (int u = 0; u < UC; ++u)
-                            if (c + u <= c_last) {
-#pragma unroll
-                                for (int k = 0; k < VEC; ++k) tot.v[k] += v[u].v[k];
-                            }
-                    }
-                    if (R.row_cnt) {
-#pragma unroll
-                        for (int k = 0; k < VEC; ++k) tot.v[k] = tot.v[k] / d;
-                    }
-                    store_vec<T, VEC>(reinterpret_cast<T*>(S.out) + (int64_t)row * S.ldo + c0, tot);
-                }
-                if (lane == 0) S.counters[c_first] = 0;          // ready for the next launch
+        if (!(starts_here && ends_here) && lane == 0) {          // hand the piece to the stitcher
+            if (starts_here) {
+                s_tail_row[w] = row;
+                s_row_beg[w][1] = rbeg;
+                s_row_end[w][1] = rend;
+            } else {
+                s_head_row[w] = row;
+                s_head_open[w] = ends_here ? 0 : 1;
+                s_row_beg[w][0] = rbeg;
+                s_row_end[w][0] = rend;
             }
         }
         e = e1;
@@ -700,6 +715,125 @@ agg_chunks(const __grid_constant__ ChunkSegs P) {
         row = nr;
         rbeg = rend;
     }
+    }   // has_work
+
+    // ---- stitch the pieces of rows that cross warps (warp 0, warps in edge order) ---------------
+    __syncthreads();
+    if (w != 0) return;
+    Vec<float, 4> carry[kMaxChunkF / 128];          // lane owns columns 4*lane + 128*j
+    int carry_row = -1, carry_beg = 0, carry_end = 0;
+    bool carry_outside = false;
+    // finished row piece: a whole row -> out; the start / continuation of a row that crosses CTAs
+    // -> global fragment + arrival counter, the last CTA to arrive adds the fragments in CTA order
+    auto emit = [&](bool complete, bool is_lead) {
+        const float d = R.row_cnt ? __ldg(R.row_cnt + carry_row) : 1.0f;
+        if (complete) {
+#pragma unroll
+            for (int j = 0; j < kMaxChunkF / 128; ++j) {
+                const int c0 = j * 128 + lane * 4;
+                if (c0 < F) {
+                    Vec<T, 4> o;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) o.v[k] = R.row_cnt ? carry[j].v[k] / d : carry[j].v[k];
+                    if (c0 + 3 < F && VEC >= 4) {
+                        store_row4<T>(reinterpret_cast<T*>(S.out) + (int64_t)carry_row * S.ldo + c0, o);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (c0 + k < F)
+                                store_elem<T>(reinterpret_cast<T*>(S.out) + (int64_t)carry_row * S.ldo + c0 + k, o.v[k]);
+                    }
+                }
+            }
+            return;
+        }
+        float* f = (is_lead ? lead : trail) + (size_t)cta * F;
+#pragma unroll
+        for (int j = 0; j < kMaxChunkF / 128; ++j) {
+            const int c0 = j * 128 + lane * 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (c0 + k < F) f[c0 + k] = carry[j].v[k];
+        }
+        const int c_first = carry_beg / kCtaEdges, c_last = (carry_end - 1) / kCtaEdges;
+        __threadfence();
+        __syncwarp();
+        int old = 0;
+        if (lane == 0) old = atomicAdd(S.counters + c_first, 1);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old != c_last - c_first) return;
+        __threadfence();
+        constexpr int UC = U;
+        const bool v4ok = (F & 3) == 0;                          // fragment rows 16 B aligned
+        for (int c0 = lane * 4; c0 < F; c0 += 128) {
+            const int nc = min(4, F - c0);
+            float tot[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int k = 0; k < nc; ++k) tot[k] = __ldcg(trail + (size_t)c_first * F + c0 + k);
+            for (int c = c_first + 1; c <= c_last; c += UC) {
+                float v[UC][4];
+#pragma unroll
+                for (int u = 0; u < UC; ++u) {
+                    const float* q = lead + (size_t)min(c + u, c_last) * F + c0;
+                    if (v4ok) {
+                        asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(v[u][0]), "=f"(v[u][1]), "=f"(v[u][2]), "=f"(v[u][3]) : "l"(q));
+                    } else {
+                        for (int k = 0; k < 4; ++k) v[u][k] = k < nc ? __ldcg(q + k) : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UC; ++u)
+                    if (c + u <= c_last) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) tot[k] += v[u][k];
+                    }
+            }
+            for (int k = 0; k < nc; ++k)
+                store_elem<T>(reinterpret_cast<T*>(S.out) + (int64_t)carry_row * S.ldo + c0 + k,
+                              R.row_cnt ? tot[k] / d : tot[k]);
+        }
+        if (lane == 0) S.counters[c_first] = 0;                  // ready for the next launch
+    };
+    auto load_part = [&](int ww, int which, bool add) {
+#pragma unroll
+        for (int j = 0; j < kMaxChunkF / 128; ++j) {
+            const int c0 = j * 128 + lane * 4;
+            if (c0 < F) {
+                const float4 t = *reinterpret_cast<const float4*>(&s_part[ww][which][c0]);
+                if (add) {
+                    carry[j].v[0] += t.x; carry[j].v[1] += t.y; carry[j].v[2] += t.z; carry[j].v[3] += t.w;
+                } else {
+                    carry[j].v[0] = t.x; carry[j].v[1] = t.y; carry[j].v[2] = t.z; carry[j].v[3] = t.w;
+                }
+            }
+        }
+    };
+    for (int ww = 0; ww < kAggWarps; ++ww) {
+        const int hr = s_head_row[ww], tr = s_tail_row[ww];
+        if (hr >= 0) {
+            if (carry_row < 0) {                    // the row began before this CTA's edges
+                load_part(ww, 0, false);
+                carry_row = hr;
+                carry_beg = s_row_beg[ww][0];
+                carry_end = s_row_end[ww][0];
+                carry_outside = true;
+            } else {
+                load_part(ww, 0, true);
+            }
+            if (!s_head_open[ww]) {                 // the row ends inside warp ww's edges
+                emit(!carry_outside, true);
+                carry_row = -1;
+            }
+        }
+        if (tr >= 0) {
+            load_part(ww, 1, false);
+            carry_row = tr;
+            carry_beg = s_row_beg[ww][1];
+            carry_end = s_row_end[ww][1];
+            carry_outside = false;
+        }
+    }
+    if (carry_row >= 0) emit(false, carry_outside);   // goes on in the next CTA
 }
 
 static bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
@@ -777,11 +911,12 @@ extern "C" int agx_aggregate_rows(const agx_row_group_t* h_groups, int n_groups,
 }
 
 extern "C" size_t agx_chunk_frag_floats(int64_t n_edges, int F) {
-    return (size_t)2 * (size_t)ceil_div(n_edges > 0 ? n_edges : 1, AGX_CHUNK_EDGES) * (size_t)F;
+    const int fb = F < kMaxChunkF ? F : kMaxChunkF;             // one column block at a time
+    return (size_t)2 * (size_t)ceil_div(n_edges > 0 ? n_edges : 1, kCtaEdges) * (size_t)fb;
 }
 
 extern "C" size_t agx_chunk_counters(int64_t n_edges) {
-    return (size_t)ceil_div(n_edges > 0 ? n_edges : 1, AGX_CHUNK_EDGES);
+    return (size_t)ceil_div(n_edges > 0 ? n_edges : 1, kCtaEdges);
 }
 
 template <typename T, int VEC, int LPR>
@@ -822,11 +957,6 @@ extern "C" int agx_aggregate_chunks(const agx_chunk_seg_t* h_segs, int n_segs, i
     const size_t esz = dtype == AGX_F32 ? 4 : 2;
     const int wide = dtype == AGX_F32 ? 4 : 8;
     cudaStream_t st = (cudaStream_t)stream;
-    ChunkSegs P;
-    P.n = n_segs;
-    P.F = F;
-    P.chunk_start[0] = 0;
-    bool vec_ok = (F % wide) == 0;
     for (int s = 0; s < n_segs; ++s) {
         const agx_chunk_seg_t& S = h_segs[s];
         AGX_CHECK_ARG(S.n_rows >= 0 && S.n_edges >= 0, "agx_aggregate_chunks: seg %d sizes", s);
@@ -834,33 +964,49 @@ extern "C" int agx_aggregate_chunks(const agx_chunk_seg_t* h_segs, int n_segs, i
                       "agx_aggregate_chunks: seg %d: null pointer", s);
         AGX_CHECK_ARG(S.n_edges == 0 || (S.rel.col && S.frag && S.counters),
                       "agx_aggregate_chunks: seg %d: null col/frag/counters", s);
-        vec_ok = vec_ok && aligned_to(S.out, 16) && (S.ldo * esz) % 16 == 0 &&
-                 aligned_to(S.rel.x, 16) && (S.rel.ldx * esz) % 16 == 0 &&
-                 (S.n_edges == 0 || aligned_to(S.frag, 16));
-        P.s[s] = S;
-        P.chunk_start[s + 1] = P.chunk_start[s] + (int32_t)ceil_div(S.n_edges, AGX_CHUNK_EDGES);
         // a relation without edges is visited by no chunk: clear its output here
         if (S.n_edges == 0 && S.n_rows > 0)
             AGX_CUDA(cudaMemset2DAsync(S.out, (size_t)S.ldo * esz, 0, (size_t)F * esz,
                                        (size_t)S.n_rows, st));
     }
-    const int64_t chunks = P.chunk_start[n_segs];
-    if (chunks == 0) return AGX_OK;
-    const unsigned grid = (unsigned)ceil_div(chunks, kAggWarps);
-    // whole feature rows of <= 512 B go through the TMA row ring; wider / unaligned rows through
-    // register gathers
     // Measured on B200 (scratch/gather_probe.cu, 895k random 512 B rows of an L2-resident 60 MB
     // table): register gathers 15.7 TB/s, TMA row ring 11.7-13.7 TB/s, and the ring costs ~3x the
     // instructions per row (one UBLKCP per row is issued lane by lane): the ring is kept as an
     // option (AGX_TMA_GATHER=1), the default is the register path.
     static const bool want_tma = getenv("AGX_TMA_GATHER") != nullptr;
-    const bool tma = vec_ok && want_tma && (size_t)F * esz <= (size_t)kRingMaxRowBytes;
-    if (dtype == AGX_F32) {
-        if (vec_ok)
-            return launch_chunks<float, 4>(P, max(8, min(32, pow2_ceil(F / 4))), grid, tma, st);
-        return launch_chunks<float, 1>(P, max(8, min(32, pow2_ceil(F))), grid, false, st);
+    // the kernel covers up to kMaxChunkF columns (the row pieces are stitched in shared memory):
+    // wider features take one launch per column block
+    for (int cb = 0; cb < F; cb += kMaxChunkF) {
+        const int Fb = F - cb < kMaxChunkF ? F - cb : kMaxChunkF;
+        ChunkSegs P;
+        P.n = n_segs;
+        P.F = Fb;
+        P.chunk_start[0] = 0;
+        bool vec_ok = (Fb % wide) == 0;
+        for (int s = 0; s < n_segs; ++s) {
+            agx_chunk_seg_t S = h_segs[s];
+            S.rel.x = reinterpret_cast<const char*>(S.rel.x) + (size_t)cb * esz;
+            S.out = reinterpret_cast<char*>(S.out) + (size_t)cb * esz;
+            vec_ok = vec_ok && aligned_to(S.out, 16) && (S.ldo * esz) % 16 == 0 &&
+                     aligned_to(S.rel.x, 16) && (S.rel.ldx * esz) % 16 == 0 &&
+                     (S.n_edges == 0 || aligned_to(S.frag, 16));
+            P.s[s] = S;
+            P.chunk_start[s + 1] = P.chunk_start[s] + (int32_t)ceil_div(S.n_edges, kCtaEdges);
+        }
+        const unsigned grid = (unsigned)P.chunk_start[n_segs];
+        if (grid == 0) return AGX_OK;
+        const bool tma = vec_ok && want_tma && (size_t)Fb * esz <= (size_t)kRingMaxRowBytes;
+        int rc;
+        if (dtype == AGX_F32) {
+            rc = vec_ok ? launch_chunks<float, 4>(P, max(8, min(32, pow2_ceil(Fb / 4))), grid, tma, st)
+                        : launch_chunks<float, 1>(P, max(8, min(32, pow2_ceil(Fb))), grid, false, st);
+        } else {
+            rc = vec_ok ? launch_chunks<__nv_bfloat16, 8>(P, max(8, min(32, pow2_ceil(Fb / 8))), grid,
+                                                          tma, st)
+                        : launch_chunks<__nv_bfloat16, 1>(P, max(8, min(32, pow2_ceil(Fb))), grid,
+                                                          false, st);
+        }
+        if (rc) return rc;
     }
-    if (vec_ok)
-        return launch_chunks<__nv_bfloat16, 8>(P, max(8, min(32, pow2_ceil(F / 8))), grid, tma, st);
-    return launch_chunks<__nv_bfloat16, 1>(P, max(8, min(32, pow2_ceil(F))), grid, false, st);
+    return AGX_OK;
 }

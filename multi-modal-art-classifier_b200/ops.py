@@ -45,6 +45,25 @@ class KernelTimer:
         return out
 
 
+def _summary_min(timers):
+    """Per launch position the fastest of the repeated steps (same launch sequence in every
+    timer), summed per kernel class: {'kind': {'launches', 'ms', 'bytes', 'flops'}} of ONE step."""
+    torch.cuda.synchronize()
+    n = min(len(t.records) for t in timers)
+    out = {}
+    for i in range(n):
+        kind, nbytes, flops, _, _ = timers[0].records[i]
+        ms = min(t.records[i][3].elapsed_time(t.records[i][4]) for t in timers
+                 if t.records[i][0] == kind)
+        d = out.setdefault(kind, {'launches': 0, 'ms': 0.0, 'bytes': 0, 'flops': 0})
+        d['launches'] += 1
+        d['ms'] += ms
+        d['bytes'] += nbytes
+        d['flops'] += flops
+    return out
+
+
+KernelTimer.summary_min = staticmethod(_summary_min)
 TIMER: Optional[KernelTimer] = None
 _DEBUG = bool(int(__import__('os').environ.get('AGX_DEBUG', '0')))
 
