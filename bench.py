@@ -237,8 +237,9 @@ def run_ours(args):
     if world > 1:
         # the image exports NCCL_DEBUG=VERSION, which makes NCCL print a banner on stdout next to
         # the one JSON line this script owes the driver
-        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'
+        # (NCCL prints its version at the VERSION *and* WARN levels)
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() in ('VERSION', 'WARN'):
+            os.environ['NCCL_DEBUG'] = 'NONE'
         # ... and whatever else native libraries write to fd 1 goes to stderr; the JSON line is
         # written to the saved original stdout
         global _JSON_OUT
@@ -250,13 +251,32 @@ def run_ours(args):
 
     agx.lib()
     # ---- inputs: pinned host copies (e2e) + device residents ---------------------------------
-    g = synth.make_artgraph(args.size, features='one-hot', seed=None if world == 1 else 1234 + 2)
-    data = agx.ToUndirected()(g)
-    host_x = OrderedDict((k, v.pin_memory()) for k, v in data.x_dict.items())
-    host_ei = OrderedDict((k, v.pin_memory()) for k, v in data.edge_index_dict.items())
+    cut = args.partition == 'cut' and world > 1
+    part = None
+    if cut:
+        # ONE graph cut into `world` destination ranges per node type (strong scaling): edges cross
+        # ranks, so every conv layer all-gathers boundary source rows and the backward pass
+        # reduce-scatters their gradients.  128-d features for every node type (SURVEY.md 8d
+        # variant): boundary rows of one-hot inputs would be N_type floats wide.
+        from mmac_b200.dist import GraphPartition
+        g = synth.make_artgraph(args.size, features='dense')
+        data = agx.ToUndirected()(g)
+        part = GraphPartition(data.edge_index_dict, data.num_nodes_dict, world, rank)
+        host_x = OrderedDict((k, part.owned(k, v).contiguous().pin_memory())
+                             for k, v in data.x_dict.items())
+        host_ei = OrderedDict((k, v.pin_memory()) for k, v in part.edge_index.items())
+        y_all = part.owned('artwork', data['artwork'].y_style)
+        total_edges = sum(int(v.shape[1]) for v in data.edge_index_dict.values())
+    else:
+        g = synth.make_artgraph(args.size, features='one-hot', seed=None if world == 1 else 1234 + 2)
+        data = agx.ToUndirected()(g)
+        host_x = OrderedDict((k, v.pin_memory()) for k, v in data.x_dict.items())
+        host_ei = OrderedDict((k, v.pin_memory()) for k, v in data.edge_index_dict.items())
+        y_all = data['artwork'].y_style
+        total_edges = world * sum(int(v.shape[1]) for v in host_ei.values())
     x = OrderedDict((k, v.to(dev, non_blocking=True)) for k, v in host_x.items())
     ei = OrderedDict((k, v.to(dev, non_blocking=True)) for k, v in host_ei.items())
-    y = data['artwork'].y_style.to(dev)
+    y = y_all.to(dev)
     n_edges = sum(int(v.shape[1]) for v in ei.values())
     h2d = sum(v.numel() * v.element_size() for v in host_x.values()) + \
         sum(v.numel() * v.element_size() for v in host_ei.values())
@@ -269,8 +289,9 @@ def run_ours(args):
         # the world-times replicated block-diagonal graph (BASELINE config 5), one block per rank:
         # no edge is cut, so no feature rows move; BatchNorm statistics, the loss and the weight
         # gradients are those of the whole graph (NCCL all-reduces inside the captured step)
-        from mmac_b200.dist import block_context
-        ctx = block_context(dist.group.WORLD, {t: v.shape[0] for t, v in x.items()})
+        from mmac_b200.dist import block_context, partition_context
+        ctx = partition_context(part, dist.group.WORLD, dev) if cut else \
+            block_context(dist.group.WORLD, {t: v.shape[0] for t, v in x.items()})
     trainer = GNNTrainer(model, x, ei, y, lr=0.01, use_cuda_graph=not args.no_graph, dist_ctx=ctx)
 
     def barrier():
@@ -312,7 +333,7 @@ def run_ours(args):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = world * PASSES * n_edges * args.steps / (ms * 1e-3)
+    value = PASSES * total_edges * args.steps / (ms * 1e-3)
     final_loss = float(loss.item())
 
     # ---- end to end: host buffers in, loss out, every step ------------------------------------
@@ -336,7 +357,7 @@ def run_ours(args):
         t = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
-    e2e_value = world * PASSES * n_edges * args.steps / (e2e_ms * 1e-3)
+    e2e_value = PASSES * total_edges * args.steps / (e2e_ms * 1e-3)
 
     # ---- roofline of the aggregation kernels: events around every launch, eager steps ----------
     roofline = None
@@ -389,16 +410,25 @@ def run_ours(args):
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-            'data': 'synthetic',
-            'config': {'workload': _workload_name(args.size), 'operator': 'SAGEConv',
+            'higher_is_better': True, 'scaling': 'strong' if cut else 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': _workload_name(args.size) if not cut else
+                       _workload_name(args.size).replace('one-hot node features as in '
+                                                         'artgraph.py:93-95',
+                                                         '128-d features for every node type'),
+                       'operator': 'SAGEConv',
                        'label': 'style', 'hidden': 128, 'layers': 2,
                        'artworks_per_gpu': int(x['artwork'].shape[0]),
                        'directed_edges_per_gpu': n_edges,
                        'edges_per_step_per_gpu': PASSES * n_edges,
-                       'parallelism': 'single GPU' if world == 1 else
-                                      f'{world} graph blocks, one per GPU; weight-gradient + '
-                                      f'BatchNorm-statistic all-reduce (NCCL)',
+                       'parallelism': 'single GPU' if world == 1 else (
+                           f'one graph cut into {world} destination ranges per node type; per conv '
+                           f'layer an NCCL all-gather of boundary source rows '
+                           f'({part.halo_rows()} rows received per exchange on rank 0) and a '
+                           f'reduce-scatter of their gradients; weight-gradient, BatchNorm and loss '
+                           f'all-reduces' if cut else
+                           f'{world} graph blocks, one per GPU; weight-gradient + '
+                           f'BatchNorm-statistic all-reduce (NCCL)'),
                        'l2_policy': 'inputs larger than L2: features + activations of one step '
                                     '(~1 GB) exceed the 126 MB L2',
                        'cuda_graph': not args.no_graph, 'final_loss': final_loss},
@@ -432,6 +462,10 @@ def main():
     ap.add_argument('--size', default='full', help="synthetic graph size of the GPU arm")
     ap.add_argument('--cpu-size', default='full',
                     help="graph size of the bounded CPU sample (full: ~8 s per step on 8 cores)")
+    ap.add_argument('--partition', default='blocks', choices=['blocks', 'cut'],
+                    help="N > 1: 'blocks' = N-times replicated graph, one block per rank (weak "
+                         "scaling, the default the driver measures); 'cut' = one graph cut by "
+                         "destination node with boundary-row all-gather (strong scaling)")
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA graph')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-heads', action='store_true',
