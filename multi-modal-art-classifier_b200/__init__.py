@@ -14,7 +14,7 @@ from ._lib import AgxError, EXPORTED, lib  # noqa: F401
 from .graph import HeteroPlan, ToUndirected, get_plan, to_undirected_dict  # noqa: F401
 from .nn import GraphConv, Linear, MessagePassing, SAGEConv  # noqa: F401
 from .hetero import HeteroModule, to_hetero  # noqa: F401
-from .models import HeteroGNN, HeteroSGNN  # noqa: F401
+from .models import HeteroGNN, HeteroMGNN, HeteroSGNN  # noqa: F401
 from .heads import (LabelProjectorHead, NewMultiModalMultiTaskHead,  # noqa: F401
                     NewMultiModalSingleTaskHead, multitask_loss, projector_loss,
                     select_embeddings)

@@ -66,3 +66,24 @@ class HeteroSGNN(nn.Module):
     def forward(self, x, edge_index):
         emb, out_soft = self.gnn(x, edge_index)
         return emb, [out_soft]
+
+
+class HeteroMGNN(nn.Module):
+    """Three independent hetero towers with per-task output widths (artist / style / genre), as
+    /root/reference/src/models/models_graph.py:51-64; ``out_channels`` is a dict with those keys.
+    ``forward`` returns ``[tower(x, ei) for tower in (artist, style, genre)]``, each an
+    ``(embedding_dict, log_prob_dict)`` pair."""
+
+    def __init__(self, operator, activation, aggr, hidden_channels, out_channels, metadata,
+                 n_layers, dropout, bn, skip):
+        super().__init__()
+        def tower(c):
+            return to_hetero(HeteroGNN(operator, activation, hidden_channels, c, n_layers, dropout,
+                                       bn, skip), metadata, aggr=aggr)
+        self.gnn_artist = tower(out_channels['artist'])
+        self.gnn_style = tower(out_channels['style'])
+        self.gnn_genre = tower(out_channels['genre'])
+
+    def forward(self, x, edge_index):
+        return [self.gnn_artist(x, edge_index), self.gnn_style(x, edge_index),
+                self.gnn_genre(x, edge_index)]

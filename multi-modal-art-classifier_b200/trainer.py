@@ -92,6 +92,8 @@ class GNNTrainer:
         self._out = None
         self._emb = None
         self.launches_per_step = 0
+        self._stage = None
+        self._prefetched = False
 
     # -- one optimisation step, eager ------------------------------------------------------------
     def _step_eager(self):
@@ -154,11 +156,52 @@ class GNNTrainer:
         """Copy a new epoch's features and edge lists from (pinned) host memory into the static
         device tensors, re-sort the CSR/CSC in place and re-check the one-hot assumption on the
         device.  Nothing synchronises; ``verify_inputs()`` reads the flags back."""
-        from .hetero import _is_identity_input
         for k, v in host_x.items():
             self.x[k].copy_(v, non_blocking=True)
         for k, v in host_ei.items():
             self.ei[k].copy_(v, non_blocking=True)
+        self._inputs_changed()
+
+    # -- the same, one step ahead: host -> device copies overlap the previous step -----------------
+    def prefetch_inputs(self, host_x, host_ei):
+        """Start copying the NEXT step's inputs from pinned host memory into device staging
+        buffers on a copy stream (returns at once; the running step is not disturbed).
+        ``consume_prefetched()`` moves them into the static tensors of the captured step."""
+        dev = next(iter(self.x.values())).device
+        if self._stage is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage = (OrderedDict((k, torch.empty_like(v)) for k, v in self.x.items()),
+                           OrderedDict((k, torch.empty_like(v)) for k, v in self.ei.items()))
+            self._ev_staged = torch.cuda.Event()
+            self._ev_consumed = None
+        with torch.cuda.stream(self._copy_stream):
+            if self._ev_consumed is not None:           # the staging buffers were read out
+                self._copy_stream.wait_event(self._ev_consumed)
+            for k, v in host_x.items():
+                self._stage[0][k].copy_(v, non_blocking=True)
+            for k, v in host_ei.items():
+                self._stage[1][k].copy_(v, non_blocking=True)
+            self._ev_staged.record(self._copy_stream)
+        self._prefetched = True
+
+    def consume_prefetched(self):
+        """Device-to-device copy of the prefetched inputs into the static tensors (waits for the
+        host copy on the device, not on the host), then as ``update_inputs``."""
+        if not getattr(self, '_prefetched', False):
+            raise RuntimeError('consume_prefetched() without prefetch_inputs()')
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._ev_staged)
+        for k, v in self._stage[0].items():
+            self.x[k].copy_(v, non_blocking=True)
+        for k, v in self._stage[1].items():
+            self.ei[k].copy_(v, non_blocking=True)
+        self._ev_consumed = torch.cuda.Event()
+        self._ev_consumed.record(cur)
+        self._prefetched = False
+        self._inputs_changed()
+
+    def _inputs_changed(self):
+        from .hetero import _is_identity_input
         num_nodes = {t: v.shape[0] for t, v in self.x.items()}
         num_dst = None
         if self.ctx is not None and self.ctx.halo is not None:

@@ -422,3 +422,69 @@ def test_trainers_cuda_graph_steps_equal_eager_steps():
         assert np.allclose(la, lb, rtol=1e-5), (kind, la, lb)
         for (k, p), (_, q) in zip(h1.state_dict().items(), h2.state_dict().items()):
             assert rel_err(q, p) <= 1e-5, (kind, k)
+
+
+def test_prefetched_inputs_equal_inline_update():
+    """The input pipeline (host -> staging on a copy stream, staging -> static tensors on the step's
+    stream) feeds the captured step exactly what update_inputs() feeds it: different graphs per
+    step, same losses."""
+    from mmac_b200.trainer import GNNTrainer
+    g, ei, orc, prod = _build_pair('SAGEConv', 32, 'tiny', dropout=0.0)
+    prod2 = copy.deepcopy(prod)
+    y = g['artwork'].y_style
+    xd, ed = _to_dev(g.x_dict), _to_dev(ei)
+    xd2 = OrderedDict((k, v.clone()) for k, v in xd.items())
+    ed2 = OrderedDict((k, v.clone()) for k, v in ed.items())
+    a = GNNTrainer(prod, xd, ed, y, lr=0.01, use_cuda_graph=True)
+    b = GNNTrainer(prod2, xd2, ed2, y, lr=0.01, use_cuda_graph=True)
+    gen = torch.Generator().manual_seed(9)
+    hosts = []
+    for _ in range(3):                       # three "epochs": permuted edge lists, perturbed features
+        hx = OrderedDict((k, (v + (0.01 * torch.randn(v.shape, generator=gen) if k == 'artwork' else 0))
+                          .pin_memory()) for k, v in g.x_dict.items())
+        he = OrderedDict((k, v[:, torch.randperm(v.shape[1], generator=gen)].contiguous().pin_memory())
+                         for k, v in ei.items())
+        hosts.append((hx, he))
+    la, lb = [], []
+    b.prefetch_inputs(*hosts[0])
+    for i in range(3):
+        a.update_inputs(*hosts[i])
+        la.append(float(a.train_step().item()))
+        a.verify_inputs()
+        b.consume_prefetched()
+        if i + 1 < 3:
+            b.prefetch_inputs(*hosts[i + 1])
+        lb.append(float(b.train_step().item()))
+        b.verify_inputs()
+    assert la == lb, (la, lb)
+    assert len(set(la)) == 3
+
+
+def test_hetero_mgnn_three_towers_vs_oracle():
+    """HeteroMGNN (models_graph.py:51-64): three to_hetero towers with their own output widths;
+    each tower equals the single-tower oracle with the same weights."""
+    g, ei, md = util.undirected_graph('tiny', features='one-hot')
+    widths = {'artist': 24, 'style': 32, 'genre': 18}
+    model = agx.HeteroMGNN(agx.SAGEConv, torch.nn.ReLU(), 'sum', 128, widths, md, 2, 0.0, True, False)
+    xd, ed = _to_dev(g.x_dict), _to_dev(ei)
+    towers = {'artist': model.gnn_artist, 'style': model.gnn_style, 'genre': model.gnn_genre}
+    orcs = {}
+    for name, c in widths.items():
+        orc = go.HeteroSGNNOracle(go.SAGEConv, torch.nn.ReLU(), 'sum', 128, c, md, 2, 0.0, True, False)
+        with torch.no_grad():
+            orc(g.x_dict, ei)
+        util.fill_params_deterministic(orc)
+        util.reset_bn(orc)
+        orcs[name] = orc.train()
+        missing, unexpected = towers[name].load_state_dict(
+            {k[len('gnn.'):]: v for k, v in orc.state_dict().items()
+             if not isinstance(v, torch.nn.parameter.UninitializedParameter)}, strict=False)
+        assert not unexpected
+    model = model.to(DEV).train()
+    outs = model(xd, ed)
+    assert len(outs) == 3
+    for (name, orc), (emb, logp) in zip(orcs.items(), outs):
+        emb_o, out_o = orc(g.x_dict, ei)
+        assert logp['artwork'].shape[1] == widths[name]
+        assert rel_err(emb['artwork'], emb_o['artwork']) <= RTOL_F32, name
+        assert rel_err(logp['artwork'], out_o[0]['artwork']) <= RTOL_F32, name
