@@ -295,6 +295,22 @@ size_t agx_smooth_l1_workspace_floats(void);
 int agx_smooth_l1(const float* out, const float* target, int64_t numel, float* loss,
                   float* dout /*nullable*/, float* workspace, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * ContextNet / Castellano encoder heads
+ *   replaces: nn.Tanh of the encoder (src/models/models_kg.py:80-85,120-125), MSELoss and
+ *   SGD(momentum=0.9) of src/train_baseline_context.py:47-54.
+ * ------------------------------------------------------------------------------------------ */
+/* MSE (mean): loss[0] = mean((out - target)^2); dout = 2*(out - target)/numel; workspace as
+ * agx_smooth_l1 */
+int agx_mse(const float* out, const float* target, int64_t numel, float* loss,
+            float* dout /*nullable*/, float* workspace, void* stream);
+int agx_tanh(const float* x, float* y, int64_t numel, void* stream);
+/* dx = dy * (1 - y^2) */
+int agx_tanh_bwd(const float* y, const float* dy, float* dx, int64_t numel, void* stream);
+/* torch.optim.SGD with momentum (dampening 0, no nesterov): buf = momentum*buf + g; p -= lr*buf */
+int agx_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t numel, float lr,
+                 float momentum, float weight_decay, void* stream);
+
 /* misc elementwise */
 int agx_fill_f32(float* p, int64_t numel, float v, void* stream);
 int agx_scale_mask(const float* x, const float* mask, float* y, int64_t numel, void* stream);

@@ -15,8 +15,9 @@ from .graph import HeteroPlan, ToUndirected, get_plan, to_undirected_dict  # noq
 from .nn import GraphConv, Linear, MessagePassing, SAGEConv  # noqa: F401
 from .hetero import HeteroModule, to_hetero  # noqa: F401
 from .models import HeteroGNN, HeteroMGNN, HeteroSGNN  # noqa: F401
-from .heads import (LabelProjectorHead, NewMultiModalMultiTaskHead,  # noqa: F401
-                    NewMultiModalSingleTaskHead, multitask_loss, projector_loss,
-                    select_embeddings)
-from .optim import FlatAdam  # noqa: F401
+from .heads import (ContextNetMultiTaskHead, ContextNetSingleTaskHead,  # noqa: F401
+                    LabelProjectorHead, MultiModalMultiTaskHead, MultiModalSingleTaskHead,
+                    NewMultiModalMultiTaskHead, NewMultiModalSingleTaskHead, context_loss,
+                    generate_projections, multitask_loss, projector_loss, select_embeddings)
+from .optim import FlatAdam, FlatSGD  # noqa: F401
 from . import functional  # noqa: F401

@@ -122,6 +122,10 @@ _SIGS = {
     'agx_dropout_mask': (C.c_int, [vp, c_i64, c_f32, vp, vp]),
     'agx_smooth_l1_workspace_floats': (C.c_size_t, []),
     'agx_smooth_l1': (C.c_int, [vp, vp, c_i64, vp, vp, vp, vp]),
+    'agx_mse': (C.c_int, [vp, vp, c_i64, vp, vp, vp, vp]),
+    'agx_tanh': (C.c_int, [vp, vp, c_i64, vp]),
+    'agx_tanh_bwd': (C.c_int, [vp, vp, vp, c_i64, vp]),
+    'agx_sgd_step': (C.c_int, [vp, vp, vp, c_i64, c_f32, c_f32, c_f32, vp]),
     'agx_fill_f32': (C.c_int, [vp, c_i64, c_f32, vp]),
     'agx_scale_mask': (C.c_int, [vp, vp, vp, c_i64, vp]),
     'agx_gather_rows': (C.c_int, [vp, c_i64, vp, c_i64, c_i32, vp, c_i64, vp]),

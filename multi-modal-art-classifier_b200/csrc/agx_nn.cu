@@ -702,9 +702,10 @@ dropout_mask(float* __restrict__ mask, int64_t n, float p, const uint64_t* __res
 // ------------------------------------------------------------------------------------------------
 // SmoothL1 (beta = 1), mean
 // ------------------------------------------------------------------------------------------------
+// squared = 0: SmoothL1 (Huber, beta 1); squared = 1: MSE
 __global__ void __launch_bounds__(256)
 smooth_l1_partial(const float* __restrict__ out, const float* __restrict__ target, int64_t n,
-                  float* __restrict__ dout, float* __restrict__ part) {
+                  float* __restrict__ dout, float* __restrict__ part, int squared) {
     __shared__ float red[256];
     float s = 0.f;
     const float inv_n = 1.0f / (float)n;
@@ -712,8 +713,13 @@ smooth_l1_partial(const float* __restrict__ out, const float* __restrict__ targe
          i += (int64_t)gridDim.x * blockDim.x) {
         const float d = out[i] - target[i];
         const float a = fabsf(d);
-        s += a < 1.0f ? 0.5f * d * d : a - 0.5f;
-        if (dout) dout[i] = (a < 1.0f ? d : (d > 0.f ? 1.0f : -1.0f)) * inv_n;
+        if (squared) {
+            s += d * d;
+            if (dout) dout[i] = 2.0f * d * inv_n;
+        } else {
+            s += a < 1.0f ? 0.5f * d * d : a - 0.5f;
+            if (dout) dout[i] = (a < 1.0f ? d : (d > 0.f ? 1.0f : -1.0f)) * inv_n;
+        }
     }
     red[threadIdx.x] = s;
     __syncthreads();
@@ -1133,10 +1139,78 @@ extern "C" int agx_smooth_l1(const float* out, const float* target, int64_t nume
     cudaStream_t st = (cudaStream_t)stream;
     int grid = grid_for(numel, 256);
     if (grid > 1024) grid = 1024;
-    smooth_l1_partial<<<grid, 256, 0, st>>>(out, target, numel, dout, workspace);
+    smooth_l1_partial<<<grid, 256, 0, st>>>(out, target, numel, dout, workspace, 0);
     AGX_LAUNCH_CHECK("smooth_l1_partial");
     smooth_l1_final<<<1, 256, 0, st>>>(workspace, grid, numel, loss);
     AGX_LAUNCH_CHECK("smooth_l1_final");
+    return AGX_OK;
+}
+
+extern "C" int agx_mse(const float* out, const float* target, int64_t numel, float* loss,
+                       float* dout, float* workspace, void* stream) {
+    AGX_CHECK_ARG(out && target && loss && workspace && numel > 0, "agx_mse: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    int grid = grid_for(numel, 256);
+    if (grid > 1024) grid = 1024;
+    smooth_l1_partial<<<grid, 256, 0, st>>>(out, target, numel, dout, workspace, 1);
+    AGX_LAUNCH_CHECK("mse_partial");
+    smooth_l1_final<<<1, 256, 0, st>>>(workspace, grid, numel, loss);
+    AGX_LAUNCH_CHECK("mse_final");
+    return AGX_OK;
+}
+
+__global__ void __launch_bounds__(256)
+tanh_fwd(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = tanhf(x[i]);
+}
+
+__global__ void __launch_bounds__(256)
+tanh_bwd(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        dx[i] = dy[i] * (1.0f - y[i] * y[i]);
+}
+
+extern "C" int agx_tanh(const float* x, float* y, int64_t numel, void* stream) {
+    AGX_CHECK_ARG((x && y) || numel == 0, "agx_tanh: null pointer");
+    if (numel <= 0) return AGX_OK;
+    tanh_fwd<<<grid_for(numel, 256), 256, 0, (cudaStream_t)stream>>>(x, y, numel);
+    AGX_LAUNCH_CHECK("tanh_fwd");
+    return AGX_OK;
+}
+
+extern "C" int agx_tanh_bwd(const float* y, const float* dy, float* dx, int64_t numel, void* stream) {
+    AGX_CHECK_ARG((y && dy && dx) || numel == 0, "agx_tanh_bwd: null pointer");
+    if (numel <= 0) return AGX_OK;
+    tanh_bwd<<<grid_for(numel, 256), 256, 0, (cudaStream_t)stream>>>(y, dy, dx, numel);
+    AGX_LAUNCH_CHECK("tanh_bwd");
+    return AGX_OK;
+}
+
+// torch.optim.SGD(momentum, dampening 0, no nesterov): buf = momentum*buf + g ; p -= lr*buf
+// (buf starts at zero, so the first step uses buf = g exactly like torch's lazy initialisation)
+__global__ void __launch_bounds__(256)
+sgd_step(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, int64_t n,
+         float lr, float momentum, float weight_decay) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float gi = g[i];
+        if (weight_decay != 0.f) gi = fmaf(weight_decay, p[i], gi);
+        const float b = momentum * buf[i] + gi;
+        buf[i] = b;
+        p[i] -= lr * b;
+    }
+}
+
+extern "C" int agx_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t numel,
+                            float lr, float momentum, float weight_decay, void* stream) {
+    AGX_CHECK_ARG((param && grad && momentum_buf) || numel == 0, "agx_sgd_step: null pointer");
+    if (numel <= 0) return AGX_OK;
+    sgd_step<<<grid_for(numel, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, momentum_buf, numel,
+                                                                    lr, momentum, weight_decay);
+    AGX_LAUNCH_CHECK("sgd_step");
     return AGX_OK;
 }
 

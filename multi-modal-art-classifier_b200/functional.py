@@ -889,3 +889,53 @@ class _SmoothL1Fn(torch.autograd.Function):
 def smooth_l1_loss(out, target):
     """``torch.nn.SmoothL1Loss()`` (beta=1, mean), src/train_projector.py:33,52."""
     return _SmoothL1Fn.apply(out, target)
+
+
+class _MSEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, out, target):
+        L.require_cuda(out, 'mse input')
+        out = out.contiguous()
+        target = target.to(out.device).contiguous()
+        loss = torch.empty(1, dtype=torch.float32, device=out.device)
+        dout = torch.empty_like(out)
+        ws = torch.empty(lib().agx_smooth_l1_workspace_floats(), dtype=torch.float32,
+                         device=out.device)
+        check(lib().agx_mse(ptr(out), ptr(target), out.numel(), ptr(loss), ptr(dout), ptr(ws),
+                            stream_ptr()), 'agx_mse')
+        ctx.save_for_backward(dout)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (dout,) = ctx.saved_tensors
+        return dout * g, None
+
+
+def mse_loss(out, target):
+    """``torch.nn.MSELoss()`` (mean), the Castellano encoder criterion
+    (src/train_baseline_context.py:51-53)."""
+    return _MSEFn.apply(out, target)
+
+
+class _TanhFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        L.require_cuda(x, 'tanh input')
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        check(lib().agx_tanh(ptr(x), ptr(y), x.numel(), stream_ptr()), 'agx_tanh')
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        g = g.contiguous()
+        dx = torch.empty_like(y)
+        check(lib().agx_tanh_bwd(ptr(y), ptr(g), ptr(dx), y.numel(), stream_ptr()), 'agx_tanh_bwd')
+        return dx
+
+
+def tanh(x):
+    return _TanhFn.apply(x)

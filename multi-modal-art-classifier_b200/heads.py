@@ -96,6 +96,112 @@ class LabelProjectorHead(nn.Module):
         return AF.fused_linear([visual_features], self.encoder.weight, self.encoder.bias)
 
 
+class ContextNetSingleTaskHead(nn.Module):
+    """Garcia et al. ContextNet after the backbone (models_kg.py:7-33): ``classifier`` and
+    ``encoder`` both read the visual features; returns ``(out, graph_proj)``."""
+
+    def __init__(self, emb_size: int, num_class: int, feat_size: int = 2048):
+        super().__init__()
+        self.classifier = nn.Linear(feat_size, num_class)
+        self.encoder = nn.Linear(feat_size, emb_size)
+
+    def forward(self, visual_features):
+        out = AF.fused_linear([visual_features], self.classifier.weight, self.classifier.bias)
+        proj = AF.fused_linear([visual_features], self.encoder.weight, self.encoder.bias)
+        return out, proj
+
+
+class ContextNetMultiTaskHead(nn.Module):
+    """models_kg.py:35-62: ``class_style`` / ``class_genre`` / ``encoder`` on the visual features;
+    returns ``([out_style, out_genre], graph_proj)``."""
+
+    def __init__(self, emb_size: int, num_classes: Dict[str, int], feat_size: int = 2048):
+        super().__init__()
+        self.class_style = nn.Linear(feat_size, num_classes['style'])
+        self.class_genre = nn.Linear(feat_size, num_classes['genre'])
+        self.encoder = nn.Linear(feat_size, emb_size)
+
+    def forward(self, visual_features):
+        f = [visual_features]
+        proj = AF.fused_linear(f, self.encoder.weight, self.encoder.bias)
+        return [AF.fused_linear(f, self.class_style.weight, self.class_style.bias),
+                AF.fused_linear(f, self.class_genre.weight, self.class_genre.bias)], proj
+
+
+class _CastellanoBase(_HeadBase):
+    """Castellano et al. (models_kg.py:64-137): ``encoder = Linear -> Tanh -> Linear -> Tanh``
+    produces the graph projection, the classifiers read ``cat(features, projection)`` through
+    ``Dropout(0.2)`` -- concat-free like the new-multimodal heads."""
+
+    def _encode(self, feat):
+        e = self.encoder
+        h = AF.tanh(AF.fused_linear([feat], e[0].weight, e[0].bias))
+        return AF.tanh(AF.fused_linear([h], e[2].weight, e[2].bias))
+
+    @staticmethod
+    def _make_encoder(feat_size, emb_size):
+        return nn.Sequential(nn.Linear(feat_size, emb_size), nn.Tanh(),
+                             nn.Linear(emb_size, emb_size), nn.Tanh())
+
+
+class MultiModalSingleTaskHead(_CastellanoBase):
+    def __init__(self, emb_size: int, num_class: int, feat_size: int = 2048, dropout: float = 0.2):
+        super().__init__()
+        self.classifier = nn.Sequential(nn.Dropout(dropout),
+                                        nn.Linear(feat_size + emb_size, num_class))
+        self.encoder = self._make_encoder(feat_size, emb_size)
+
+    def forward(self, visual_features):
+        proj = self._encode(visual_features)
+        return self._head('classifier', self.classifier, visual_features, proj), proj
+
+
+class MultiModalMultiTaskHead(_CastellanoBase):
+    def __init__(self, emb_size: int, num_classes: Dict[str, int], feat_size: int = 2048,
+                 dropout: float = 0.2):
+        super().__init__()
+        self.class_style = nn.Sequential(nn.Dropout(dropout),
+                                         nn.Linear(feat_size + emb_size, num_classes['style']))
+        self.class_genre = nn.Sequential(nn.Dropout(dropout),
+                                         nn.Linear(feat_size + emb_size, num_classes['genre']))
+        self.encoder = self._make_encoder(feat_size, emb_size)
+
+    def forward(self, visual_features):
+        proj = self._encode(visual_features)
+        return [self._head('style', self.class_style, visual_features, proj),
+                self._head('genre', self.class_genre, visual_features, proj)], proj
+
+
+def context_loss(out, graph_proj, labels, embedding, lamb: float, encoder: str = 'smooth_l1',
+                 weight=None, w_genre=None):
+    """``lamb * class_loss + (1 - lamb) * encoder_loss`` (src/train_baseline_context.py:47-54,
+    75-77; multitask: src/train_baseline_context_multitask.py:76-79 with
+    ``class_loss = 0.5*CE_style + 0.5*CE_genre``).  ContextNet: SmoothL1, lamb 0.9 (SGD);
+    Castellano: MSE, lamb 0.6 (Adam).  ``out`` / ``labels``: tensors, or [style, genre] pairs."""
+    if isinstance(out, (list, tuple)):
+        class_loss = AF.cross_entropy(out[0], labels[0], weight, coef=0.5 * lamb) + \
+            AF.cross_entropy(out[1], labels[1], w_genre, coef=0.5 * lamb)
+    else:
+        class_loss = AF.cross_entropy(out, labels, weight, coef=lamb)
+    enc = AF.smooth_l1_loss(graph_proj, embedding) if encoder == 'smooth_l1' else \
+        AF.mse_loss(graph_proj, embedding)
+    return class_loss + (1.0 - lamb) * enc
+
+
+@torch.no_grad()
+def generate_projections(projector: nn.Module, features: torch.Tensor, batch_size: int = 4096):
+    """src/generate_projections.py:27-84 after the backbone: run the (trained) projector over all
+    validation / test features in batches and return the ``[N, emb]`` tensor the fusion heads index
+    (``data_kg.py:169-178``) -- on the device, no file round trip."""
+    projector.eval()
+    out = torch.empty(features.shape[0], projector.encoder.out_features, dtype=torch.float32,
+                      device=projector.encoder.weight.device)
+    for i in range(0, features.shape[0], batch_size):
+        f = features[i:i + batch_size].to(out.device, non_blocking=True)
+        out[i:i + batch_size] = projector(f)
+    return out
+
+
 def multitask_loss(out, style_labels, genre_labels, w_style=None, w_genre=None, group=None):
     """``0.5*CE(out[0], y_style; w) + 0.5*CE(out[1], y_genre; w)``
     (src/train_new_multimodal_multitask.py:48-55,79-81), fused softmax+nll per head.  With

@@ -19,6 +19,7 @@ import torch
 from torch import nn
 
 from . import ops
+from ._lib import check, lib, ptr, stream_ptr
 
 
 class FlatAdam:
@@ -103,3 +104,24 @@ class FlatAdam:
     def state_dict(self):
         return {'step': self.step_t, 'exp_avg': self.exp_avg, 'exp_avg_sq': self.exp_avg_sq,
                 'lr': self.lr, 'betas': self.betas, 'eps': self.eps}
+
+
+class FlatSGD(FlatAdam):
+    """``torch.optim.SGD(lr, momentum)`` (the ContextNet optimizer,
+    /root/reference/src/train_baseline_context.py:49) over the same flat arena as ``FlatAdam``."""
+
+    def __init__(self, params, lr: float = 1e-3, momentum: float = 0.0, weight_decay: float = 0.0):
+        super().__init__(params, lr=lr, weight_decay=weight_decay)
+        self.momentum = float(momentum)
+
+    @torch.no_grad()
+    def step(self):
+        self._ensure()
+        self.step_t += 1
+        check(lib().agx_sgd_step(ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), self.flat.numel(),
+                                 self.lr, self.momentum, self.weight_decay, stream_ptr()),
+              'agx_sgd_step')
+
+    def state_dict(self):
+        return {'step': self.step_t, 'momentum_buffer': self.exp_avg, 'lr': self.lr,
+                'momentum': self.momentum}

@@ -165,6 +165,64 @@ def heads_fixture(arch):
     return res
 
 
+def context_fixture():
+    """ContextNet / Castellano heads from the reference's classes with the
+    ResNet stubbed by the identity: outputs, the combined loss of train_baseline_context*.py and
+    gradients."""
+    from models import models_kg
+    n = 64
+    feat, emb_s, _, y_s, y_g = synth.make_head_batch(n, arch='resnet', seed=11)
+    img = feat.view(n, -1, 1, 1)
+    res = {}
+    # ContextNet single task: SmoothL1, lamb 0.9
+    m = models_kg.ContextNetSingleTask(emb_size=128, num_class=32)
+    util.fill_params_deterministic(m, only=('classifier', 'encoder'))
+    out, proj = m(img)
+    loss = 0.9 * torch.nn.CrossEntropyLoss()(out, y_s) + 0.1 * torch.nn.SmoothL1Loss()(proj, emb_s * 3.0)
+    loss.backward()
+    res.update({'cn1_out': out.detach().numpy(), 'cn1_proj': proj.detach().numpy(),
+                'cn1_loss': np.float32(loss.item()),
+                'cn1_grad_cls_w': m.classifier.weight.grad.numpy(),
+                'cn1_grad_enc_w': m.encoder.weight.grad.numpy()[:8]})
+    # ContextNet multitask
+    m = models_kg.ContextNetlMultiTask(emb_size=128, num_classes={'style': 32, 'genre': 18})
+    util.fill_params_deterministic(m, only=('class_style', 'class_genre', 'encoder'))
+    outs, proj = m(img)
+    loss = 0.9 * (0.5 * torch.nn.CrossEntropyLoss()(outs[0], y_s) +
+                  0.5 * torch.nn.CrossEntropyLoss()(outs[1], y_g)) + \
+        0.1 * torch.nn.SmoothL1Loss()(proj, emb_s * 3.0)
+    loss.backward()
+    res.update({'cn2_out_style': outs[0].detach().numpy(), 'cn2_out_genre': outs[1].detach().numpy(),
+                'cn2_loss': np.float32(loss.item()),
+                'cn2_grad_enc_b': m.encoder.bias.grad.numpy()})
+    # Castellano single / multi: MSE, lamb 0.6, Dropout(0.2) switched off by eval-free p=0 copy
+    for tag, cls, kw in (('mm1', models_kg.MultiModalSingleTask, dict(num_class=32)),
+                         ('mm2', models_kg.MultiModalMultiTask,
+                          dict(num_classes={'style': 32, 'genre': 18}))):
+        m = cls(emb_size=128, **kw)
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        util.fill_params_deterministic(m, only=('classifier', 'class_style', 'class_genre', 'encoder'))
+        f_in = feat.clone().requires_grad_(True)
+        out, proj = m(f_in)
+        if tag == 'mm1':
+            cl = torch.nn.CrossEntropyLoss()(out, y_s)
+            res['mm1_out'] = out.detach().numpy()
+        else:
+            cl = 0.5 * torch.nn.CrossEntropyLoss()(out[0], y_s) + \
+                0.5 * torch.nn.CrossEntropyLoss()(out[1], y_g)
+            res['mm2_out_style'] = out[0].detach().numpy()
+            res['mm2_out_genre'] = out[1].detach().numpy()
+        loss = 0.6 * cl + 0.4 * torch.nn.MSELoss()(proj, emb_s)
+        loss.backward()
+        res.update({f'{tag}_proj': proj.detach().numpy(), f'{tag}_loss': np.float32(loss.item()),
+                    f'{tag}_grad_enc0_w': m.encoder[0].weight.grad.numpy()[:8],
+                    f'{tag}_grad_enc2_b': m.encoder[2].bias.grad.numpy(),
+                    f'{tag}_grad_feat': f_in.grad.numpy()[:8]})
+    return res
+
+
 def main():
     if not os.path.isdir(REF_SRC):
         raise SystemExit('the reference is not mounted; fixtures can only be regenerated in the '
@@ -177,6 +235,7 @@ def main():
                             **gnn_fixture(op, label, size))
     for arch in ('vit', 'resnet'):
         np.savez_compressed(os.path.join(HERE, f'heads_{arch}.npz'), **heads_fixture(arch))
+    np.savez_compressed(os.path.join(HERE, 'heads_context.npz'), **context_fixture())
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -207,3 +207,46 @@ def test_synth_graph_schema():
                                                  g2.edge_index_dict.values()))
     r = synth.replicate(synth.make_artgraph('tiny'), 3)
     assert r['artwork'].x.shape[0] == 900 and r.num_edges() == 3 * synth.make_artgraph('tiny').num_edges()
+
+
+def test_context_heads_oracle_matches_reference_golden():
+    """ContextNet / Castellano heads: the oracle classes reproduce the
+    outputs, combined losses and gradients of the reference's own classes (heads_context.npz)."""
+    gold = util.load_golden('heads_context.npz')
+    n = 64
+    feat, emb_s, _, y_s, y_g = synth.make_head_batch(n, arch='resnet', seed=11)
+
+    m = ho.ContextNetSingleOracle(2048, 128, 32)
+    util.fill_params_deterministic(m)
+    out, proj = m(feat)
+    loss = ho.context_loss(out, proj, y_s, emb_s * 3.0, 0.9, 'smooth_l1')
+    loss.backward()
+    assert np.array_equal(out.detach().numpy(), gold['cn1_out'])
+    assert np.array_equal(proj.detach().numpy(), gold['cn1_proj'])
+    assert abs(loss.item() - float(gold['cn1_loss'])) <= 1e-6 * abs(float(gold['cn1_loss']))
+    assert np.allclose(m.classifier.weight.grad.numpy(), gold['cn1_grad_cls_w'], rtol=1e-5, atol=1e-9)
+    assert np.allclose(m.encoder.weight.grad.numpy()[:8], gold['cn1_grad_enc_w'], rtol=1e-5, atol=1e-9)
+
+    m = ho.ContextNetMultiOracle(2048, 128, {'style': 32, 'genre': 18})
+    util.fill_params_deterministic(m)
+    outs, proj = m(feat)
+    loss = ho.context_loss(outs, proj, (y_s, y_g), emb_s * 3.0, 0.9, 'smooth_l1')
+    loss.backward()
+    assert np.array_equal(outs[0].detach().numpy(), gold['cn2_out_style'])
+    assert np.array_equal(outs[1].detach().numpy(), gold['cn2_out_genre'])
+    assert abs(loss.item() - float(gold['cn2_loss'])) <= 1e-6 * abs(float(gold['cn2_loss']))
+    assert np.allclose(m.encoder.bias.grad.numpy(), gold['cn2_grad_enc_b'], rtol=1e-5, atol=1e-9)
+
+    for tag, m in (('mm1', ho.CastellanoSingleOracle(2048, 128, 32, 0.0)),
+                   ('mm2', ho.CastellanoMultiOracle(2048, 128, {'style': 32, 'genre': 18}, 0.0))):
+        util.fill_params_deterministic(m)
+        f_in = feat.clone().requires_grad_(True)
+        out, proj = m(f_in)
+        labels = y_s if tag == 'mm1' else (y_s, y_g)
+        loss = ho.context_loss(out, proj, labels, emb_s, 0.6, 'mse')
+        loss.backward()
+        assert np.array_equal(proj.detach().numpy(), gold[f'{tag}_proj'])
+        assert abs(loss.item() - float(gold[f'{tag}_loss'])) <= 1e-6 * abs(float(gold[f'{tag}_loss']))
+        assert np.allclose(m.encoder[0].weight.grad.numpy()[:8], gold[f'{tag}_grad_enc0_w'],
+                           rtol=1e-5, atol=1e-9)
+        assert np.allclose(f_in.grad.numpy()[:8], gold[f'{tag}_grad_feat'], rtol=1e-5, atol=1e-9)

@@ -488,3 +488,84 @@ def test_hetero_mgnn_three_towers_vs_oracle():
         assert logp['artwork'].shape[1] == widths[name]
         assert rel_err(emb['artwork'], emb_o['artwork']) <= RTOL_F32, name
         assert rel_err(logp['artwork'], out_o[0]['artwork']) <= RTOL_F32, name
+
+
+def test_context_and_castellano_heads_match_reference_golden():
+    """SURVEY.md 8f rank 4 on the GPU: ContextNet (SmoothL1, lamb 0.9) and Castellano (tanh encoder,
+    MSE, lamb 0.6) heads against the fixtures generated from the reference's own classes."""
+    gold = util.load_golden('heads_context.npz')
+    n = 64
+    feat, emb_s, _, y_s, y_g = synth.make_head_batch(n, arch='resnet', seed=11)
+    fd, ed, ys, yg = feat.to(DEV), emb_s.to(DEV), y_s.to(DEV), y_g.to(DEV)
+
+    m = agx.ContextNetSingleTaskHead(128, 32, 2048)
+    util.fill_params_deterministic(m)
+    m = m.to(DEV)
+    out, proj = m(fd)
+    loss = agx.context_loss(out, proj, ys, ed * 3.0, 0.9, 'smooth_l1')
+    loss.backward()
+    assert rel_err(out, gold['cn1_out']) <= RTOL_F32 and rel_err(proj, gold['cn1_proj']) <= RTOL_F32
+    assert abs(loss.item() - float(gold['cn1_loss'])) <= RTOL_F32 * abs(float(gold['cn1_loss']))
+    assert rel_err(m.classifier.weight.grad, gold['cn1_grad_cls_w']) <= GRAD_RTOL
+    assert rel_err(m.encoder.weight.grad[:8], gold['cn1_grad_enc_w']) <= GRAD_RTOL
+
+    m = agx.ContextNetMultiTaskHead(128, {'style': 32, 'genre': 18}, 2048)
+    util.fill_params_deterministic(m)
+    m = m.to(DEV)
+    outs, proj = m(fd)
+    loss = agx.context_loss(outs, proj, (ys, yg), ed * 3.0, 0.9, 'smooth_l1')
+    loss.backward()
+    assert rel_err(outs[0], gold['cn2_out_style']) <= RTOL_F32
+    assert rel_err(outs[1], gold['cn2_out_genre']) <= RTOL_F32
+    assert abs(loss.item() - float(gold['cn2_loss'])) <= RTOL_F32 * abs(float(gold['cn2_loss']))
+    assert rel_err(m.encoder.bias.grad, gold['cn2_grad_enc_b']) <= GRAD_RTOL
+
+    for tag, m in (('mm1', agx.MultiModalSingleTaskHead(128, 32, 2048, 0.0)),
+                   ('mm2', agx.MultiModalMultiTaskHead(128, {'style': 32, 'genre': 18}, 2048, 0.0))):
+        util.fill_params_deterministic(m)
+        m = m.to(DEV).train()
+        f_in = fd.clone().requires_grad_(True)
+        out, proj = m(f_in)
+        labels = ys if tag == 'mm1' else (ys, yg)
+        loss = agx.context_loss(out, proj, labels, ed, 0.6, 'mse')
+        loss.backward()
+        assert rel_err(proj, gold[f'{tag}_proj']) <= RTOL_F32, tag
+        if tag == 'mm1':
+            assert rel_err(out, gold['mm1_out']) <= RTOL_F32
+        else:
+            assert rel_err(out[0], gold['mm2_out_style']) <= RTOL_F32
+            assert rel_err(out[1], gold['mm2_out_genre']) <= RTOL_F32
+        assert abs(loss.item() - float(gold[f'{tag}_loss'])) <= RTOL_F32 * abs(float(gold[f'{tag}_loss']))
+        assert rel_err(m.encoder[0].weight.grad[:8], gold[f'{tag}_grad_enc0_w']) <= GRAD_RTOL, tag
+        assert rel_err(m.encoder[2].bias.grad, gold[f'{tag}_grad_enc2_b']) <= GRAD_RTOL, tag
+        assert rel_err(f_in.grad[:8], gold[f'{tag}_grad_feat']) <= GRAD_RTOL, tag
+
+
+def test_flat_sgd_matches_torch_and_projection_generation():
+    torch.manual_seed(4)
+    ref = torch.nn.Linear(40, 16)
+    mod = copy.deepcopy(ref).to(DEV)
+    o_ref = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.9)
+    o_mod = agx.FlatSGD(mod.parameters(), lr=0.05, momentum=0.9)
+    gen = torch.Generator().manual_seed(1)
+    for _ in range(5):
+        x = torch.randn(32, 40, generator=gen)
+        t = torch.randn(32, 16, generator=gen)
+        o_ref.zero_grad()
+        torch.nn.functional.mse_loss(ref(x), t).backward()
+        o_ref.step()
+        o_mod.zero_grad()
+        agx.functional.mse_loss(agx.functional.fused_linear([x.to(DEV)], mod.weight, mod.bias),
+                                t.to(DEV)).backward()
+        o_mod.step()
+    assert rel_err(mod.weight, ref.weight) <= 1e-5 and rel_err(mod.bias, ref.bias) <= 1e-5
+
+    # generate_projections.py after the backbone: batched inference == one big forward
+    proj = agx.LabelProjectorHead(128, 768)
+    util.fill_params_deterministic(proj)
+    proj = proj.to(DEV)
+    feats = torch.randn(1000, 768, generator=gen)
+    out = agx.generate_projections(proj, feats, batch_size=256)
+    want = feats.double() @ proj.encoder.weight.detach().cpu().double().t() + \
+        proj.encoder.bias.detach().cpu().double()
+    assert out.shape == (1000, 128) and rel_err(out, want) <= RTOL_F32
