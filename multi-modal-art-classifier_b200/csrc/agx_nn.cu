@@ -152,8 +152,19 @@ __device__ __forceinline__ double slab_total_32x32(const double* __restrict__ pa
                                                    double (*sm)[33]) {
     const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
     double a = 0.0;
-    if (col0 + c < ncols)
-        for (int s = g; s < slabs; s += 32) a += part[(size_t)s * stride + col0 + c];
+    if (col0 + c < ncols) {
+        // four independent partial sums keep four loads in flight (fixed order: still reproducible)
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int s = g;
+        for (; s + 96 < slabs; s += 128) {
+            a0 += part[(size_t)s * stride + col0 + c];
+            a1 += part[(size_t)(s + 32) * stride + col0 + c];
+            a2 += part[(size_t)(s + 64) * stride + col0 + c];
+            a3 += part[(size_t)(s + 96) * stride + col0 + c];
+        }
+        for (; s < slabs; s += 32) a0 += part[(size_t)s * stride + col0 + c];
+        a = (a0 + a1) + (a2 + a3);
+    }
     sm[g][c] = a;
     __syncthreads();
     double t = 0.0;
@@ -484,6 +495,45 @@ __global__ void __launch_bounds__(256) colsum_partial(const __grid_constant__ Co
     const int F = D.F;
     double* part = P.ws + P.part_start[di] + (size_t)slab * F;
     __shared__ double red[256];
+    if ((F & 3) == 0 && F <= 1024 && (D.ldx & 3) == 0 &&
+        (reinterpret_cast<uintptr_t>(D.x) & 15) == 0) {
+        // 128-bit path: thread owns 4 consecutive columns, four rows in flight
+        __shared__ double red4[4][256];
+        const int cols4 = F >> 2;
+        const int groups = 256 / cols4;
+        const int c = (threadIdx.x % cols4) * 4, g = threadIdx.x / cols4;
+        double s[4] = {0.0, 0.0, 0.0, 0.0};
+        if (g < groups) {
+            int r = r0 + g;
+            for (; r + 3 * groups < r1; r += 4 * groups) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    v[u] = *reinterpret_cast<const float4*>(D.x + (int64_t)(r + u * groups) * D.ldx + c);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    s[0] += (double)v[u].x; s[1] += (double)v[u].y;
+                    s[2] += (double)v[u].z; s[3] += (double)v[u].w;
+                }
+            }
+            for (; r < r1; r += groups) {
+                const float4 v = *reinterpret_cast<const float4*>(D.x + (int64_t)r * D.ldx + c);
+                s[0] += (double)v.x; s[1] += (double)v.y; s[2] += (double)v.z; s[3] += (double)v.w;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) red4[i][threadIdx.x] = s[i];
+        __syncthreads();
+        if (threadIdx.x < cols4) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double t = 0.0;
+                for (int gg = 0; gg < groups; ++gg) t += red4[i][gg * cols4 + threadIdx.x];
+                part[4 * threadIdx.x + i] = t;
+            }
+        }
+        return;
+    }
     for (int c0 = 0; c0 < F; c0 += 256) {
         const int cols = min(256, F - c0);
         const int groups = 256 / cols > 0 ? 256 / cols : 1;

@@ -314,6 +314,7 @@ def aggregate(out: torch.Tensor, rel: RelArg, F: int):
 # K4: grouped GEMM
 # ------------------------------------------------------------------------------------------------
 TC_MIN_ROWS = 512        # agx_gemm_tc.cu takes problems with at least this many output rows
+TC_MAX_K = 256           # ... and at most this much reduction per launch (accumulator error)
 
 
 class GemmBatch:
@@ -325,12 +326,36 @@ class GemmBatch:
         self.segs: List[L.GemmSeg] = []
         self._keep = []
         self._transposes: list = []
+        self._later: list = []        # follow-up batches (K-split tall problems), run in order
+        self._wave = None
 
     def add(self, C_out: torch.Tensor, segs: Sequence[tuple], bias: Optional[torch.Tensor] = None,
             accumulate: bool = False, row_scale: Optional[torch.Tensor] = None,
             split_k: int = 1, skip_flag: Optional[torch.Tensor] = None):
         """``segs``: (opA [M,K], opB [K,N]) or (opA, opB, A_mask, B_mask)."""
         M, N = C_out.shape
+        # a tall problem whose segments add up to more than the tensor-core kernel's K budget
+        # (256: accumulator error, agx_gemm_tc.cu) is cut into consecutive launches of <= 256 each,
+        # the later ones accumulating onto the first
+        if (M >= TC_MIN_ROWS and split_k <= 1 and row_scale is None and len(segs) > 1 and
+                sum(sg[0].shape[1] for sg in segs) > TC_MAX_K and
+                all(sg[0].shape[1] <= TC_MAX_K for sg in segs) and self._wave is None):
+            groups, cur, k = [], [], 0
+            for sg in segs:
+                if cur and k + sg[0].shape[1] > TC_MAX_K:
+                    groups.append(cur)
+                    cur, k = [], 0
+                cur.append(sg)
+                k += sg[0].shape[1]
+            groups.append(cur)
+            self.add(C_out, groups[0], bias=bias, accumulate=accumulate, skip_flag=skip_flag)
+            for gi, grp in enumerate(groups[1:]):
+                while len(self._later) <= gi:
+                    self._later.append(GemmBatch())
+                self._later[gi]._wave = gi + 1
+                self._later[gi].add(C_out, grp, accumulate=True, skip_flag=skip_flag)
+                self._later[gi]._wave = None
+            return
         if C_out.stride(1) != 1:
             raise ValueError('C must be row-major')
         p = L.GemmProblem()
@@ -417,6 +442,9 @@ class GemmBatch:
                 TIMER.end('gemm', nb, fl, t0)
             i = j
         self.problems, self.segs, self._keep = [], [], []
+        later, self._later = self._later, []
+        for gb in later:
+            gb.run()
 
 
 def split_k_for(k_rows: int, slab: int = 384, max_split: int = 512) -> int:
