@@ -296,6 +296,31 @@ int agx_smooth_l1(const float* out, const float* target, int64_t numel, float* l
                   float* dout /*nullable*/, float* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * GATConv attention aggregation
+ *   replaces: GATConv.propagate / message / torch_geometric.utils.softmax (PyG 2.0.2, one head),
+ *   selected by the reference's default --operator (src/train_gnn_embeddings.py:15,99).
+ *   CSR / CSC of the relation's edge list WITH the self loops GATConv adds (agx_csr_build);
+ *   a_l [n_src], a_r [n_dst] attention logits, x_l [n_src, F] transformed sources, F <= 256.
+ *   alpha_e / de_e: per edge, indexed by the ORIGINAL edge position (the CSR / CSC `eid`).
+ * ------------------------------------------------------------------------------------------ */
+/* out[i] = sum_j softmax_i(leaky_relu(a_l[j] + a_r[i])) x_l[j] (+ bias); alpha_e receives alpha */
+int agx_gat_forward(const int32_t* rowptr, const int32_t* col, const int32_t* eid, const float* a_l,
+                    const float* a_r, const float* x_l, int64_t ldx, int32_t F, float slope,
+                    const float* bias /*nullable*/, float* out, int64_t ldo, float* alpha_e,
+                    int32_t n_rows, void* stream);
+/* de_e[e] = d loss / d (a_l[j] + a_r[i]) ; da_r[i] = sum_j de_ij   (rows = destinations) */
+int agx_gat_backward_dst(const int32_t* rowptr, const int32_t* col, const int32_t* eid,
+                         const float* a_l, const float* a_r, const float* x_l, int64_t ldx,
+                         int32_t F, float slope, const float* dout, int64_t ldd,
+                         const float* alpha_e, float* de_e, float* da_r, int32_t n_rows,
+                         void* stream);
+/* dx_l[j] = sum_i alpha_ij dout[i] ; da_l[j] = sum_i de_ij            (rows = sources, CSC) */
+int agx_gat_backward_src(const int32_t* cscptr, const int32_t* dstid, const int32_t* eid,
+                         const float* alpha_e, const float* de_e, const float* dout, int64_t ldd,
+                         int32_t F, float* dx_l, int64_t ldx, float* da_l, int32_t n_src,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * ContextNet / Castellano encoder heads
  *   replaces: nn.Tanh of the encoder (src/models/models_kg.py:80-85,120-125), MSELoss and
  *   SGD(momentum=0.9) of src/train_baseline_context.py:47-54.

@@ -122,6 +122,12 @@ _SIGS = {
     'agx_dropout_mask': (C.c_int, [vp, c_i64, c_f32, vp, vp]),
     'agx_smooth_l1_workspace_floats': (C.c_size_t, []),
     'agx_smooth_l1': (C.c_int, [vp, vp, c_i64, vp, vp, vp, vp]),
+    'agx_gat_forward': (C.c_int, [vp, vp, vp, vp, vp, vp, c_i64, c_i32, c_f32, vp, vp, c_i64, vp,
+                                  c_i32, vp]),
+    'agx_gat_backward_dst': (C.c_int, [vp, vp, vp, vp, vp, vp, c_i64, c_i32, c_f32, vp, c_i64, vp,
+                                       vp, vp, c_i32, vp]),
+    'agx_gat_backward_src': (C.c_int, [vp, vp, vp, vp, vp, vp, c_i64, c_i32, vp, c_i64, vp, c_i32,
+                                       vp]),
     'agx_mse': (C.c_int, [vp, vp, c_i64, vp, vp, vp, vp]),
     'agx_tanh': (C.c_int, [vp, vp, c_i64, vp]),
     'agx_tanh_bwd': (C.c_int, [vp, vp, vp, c_i64, vp]),

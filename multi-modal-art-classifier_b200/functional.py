@@ -939,3 +939,105 @@ class _TanhFn(torch.autograd.Function):
 
 def tanh(x):
     return _TanhFn.apply(x)
+
+
+# ------------------------------------------------------------------------------------------------
+# GATConv: attention aggregation over the self-loop augmented relation
+# ------------------------------------------------------------------------------------------------
+class GATPlan:
+    """CSR (by destination) and CSC (by source) of one relation's edge list as GATConv sees it:
+    self loops removed, then (i, i) for i < min(N_src, N_dst) appended (PyG 2.0.2, also for
+    bipartite edge types).  Index preparation only; cached per edge_index tensor."""
+
+    _cache: "dict" = {}
+
+    def __init__(self, edge_index: torch.Tensor, n_src: int, n_dst: int, add_self_loops: bool):
+        L.require_cuda(edge_index, 'edge_index')
+        ei = edge_index
+        if add_self_loops:
+            keep = ei[0] != ei[1]
+            loops = torch.arange(min(n_src, n_dst), dtype=ei.dtype, device=ei.device)
+            ei = torch.cat([ei[:, keep], torch.stack([loops, loops])], dim=1)
+        self.n_src, self.n_dst, self.n_edges = int(n_src), int(n_dst), int(ei.shape[1])
+        self.edge_index = ei.contiguous()
+        self.csr, self.csc = ops.csr_build([(self.edge_index[1], self.edge_index[0], n_dst, n_src),
+                                            (self.edge_index[0], self.edge_index[1], n_src, n_dst)])
+
+    @classmethod
+    def get(cls, edge_index, n_src, n_dst, add_self_loops=True):
+        key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(n_src),
+               int(n_dst), bool(add_self_loops))
+        plan = cls._cache.get(key)
+        if plan is None:
+            if len(cls._cache) > 64:
+                cls._cache.clear()
+            plan = cls._cache[key] = cls(edge_index, n_src, n_dst, add_self_loops)
+            plan._keepalive = edge_index
+        return plan
+
+
+class _GATAggFn(torch.autograd.Function):
+    """out_i = sum_j softmax_i(leaky_relu(a_l[j] + a_r[i])) x_l[j] + bias."""
+
+    @staticmethod
+    def forward(ctx, plan: GATPlan, slope: float, x_l, a_l, a_r, bias):
+        x_l, a_l, a_r = x_l.contiguous(), a_l.contiguous(), a_r.contiguous()
+        F_ = x_l.shape[1]
+        dev = x_l.device
+        out = torch.empty(plan.n_dst, F_, dtype=torch.float32, device=dev)
+        alpha = torch.empty(max(plan.n_edges, 1), dtype=torch.float32, device=dev)
+        c = plan.csr
+        check(lib().agx_gat_forward(ptr(c.rowptr), ptr(c.col), ptr(c.eid), ptr(a_l), ptr(a_r),
+                                    ptr(x_l), x_l.stride(0), F_, float(slope), ptr(bias), ptr(out),
+                                    out.stride(0), ptr(alpha), plan.n_dst, stream_ptr()),
+              'agx_gat_forward')
+        ctx.plan, ctx.slope, ctx.has_bias = plan, float(slope), bias is not None
+        ctx.save_for_backward(x_l, a_l, a_r, alpha)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x_l, a_l, a_r, alpha = ctx.saved_tensors
+        plan: GATPlan = ctx.plan
+        g = g.contiguous()
+        F_ = x_l.shape[1]
+        dev = g.device
+        de = torch.empty_like(alpha)
+        da_r = torch.empty(plan.n_dst, dtype=torch.float32, device=dev)
+        c, t = plan.csr, plan.csc
+        check(lib().agx_gat_backward_dst(ptr(c.rowptr), ptr(c.col), ptr(c.eid), ptr(a_l), ptr(a_r),
+                                         ptr(x_l), x_l.stride(0), F_, ctx.slope, ptr(g), g.stride(0),
+                                         ptr(alpha), ptr(de), ptr(da_r), plan.n_dst, stream_ptr()),
+              'agx_gat_backward_dst')
+        dx_l = torch.empty_like(x_l)
+        da_l = torch.empty(plan.n_src, dtype=torch.float32, device=dev)
+        check(lib().agx_gat_backward_src(ptr(t.rowptr), ptr(t.col), ptr(t.eid), ptr(alpha), ptr(de),
+                                         ptr(g), g.stride(0), F_, ptr(dx_l), dx_l.stride(0),
+                                         ptr(da_l), plan.n_src, stream_ptr()),
+              'agx_gat_backward_src')
+        db = None
+        if ctx.has_bias:
+            db = torch.empty(F_, dtype=torch.float32, device=dev)
+            ops.colsum([(g, db, False)])
+        return None, None, dx_l, da_l, da_r, db
+
+
+def gat_aggregate(plan: GATPlan, x_l, a_l, a_r, bias=None, negative_slope: float = 0.2):
+    return _GATAggFn.apply(plan, negative_slope, x_l, a_l, a_r, bias)
+
+
+class _AddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        out = torch.empty_like(a)
+        ops.sum_arrays([(out, [a.contiguous(), b.contiguous()])])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def add(a, b):
+    """a + b on the agx elementwise kernel (the relation sum of to_hetero)."""
+    return _AddFn.apply(a, b)

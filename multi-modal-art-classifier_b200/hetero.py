@@ -209,8 +209,25 @@ class HeteroModule(nn.Module):
             self._nbt_flat = {key: flat} if len(self._nbt_flat) > 16 else {**self._nbt_flat, key: flat}
         flat += 1
 
+    def _conv_generic(self, node, x_dict, ei_dict):
+        """Operators without a fused hetero layer (GATConv): one call per edge type, relation
+        outputs of a destination type added in metadata order (PyG's pairwise torch.add queue
+        differs only in summation order)."""
+        convs = self.get_submodule(node.target)
+        if self._dist is not None:
+            raise NotImplementedError('multi-GPU execution is implemented for SAGEConv / GraphConv')
+        outs: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+        for et in self.edge_types:
+            s, _, d = et
+            o = convs[key2str(et)]((x_dict[s], x_dict[d]), ei_dict[et])
+            outs[d] = o if d not in outs else AF.add(outs[d], o)
+        return outs
+
     def _conv(self, node, x_dict, ei_dict, plan, is_input):
         convs = self.get_submodule(node.target)
+        if not hasattr(next(iter(convs.values())), 'rel_params') or \
+                type(next(iter(convs.values()))).__name__ == 'GATConv':
+            return self._conv_generic(node, x_dict, ei_dict)
         key = (node.target, id(plan))
         if self._dist is not None and self._dist.halo is not None:
             # boundary rows of the other ranks behind the owned rows (static inputs: once)

@@ -193,3 +193,61 @@ class GraphConv(MessagePassing):
 
     def _lins(self):
         return self.lin_rel, self.lin_root
+
+
+class GATConv(MessagePassing):
+    """PyG 2.0.2 ``GATConv`` with the reference's settings (one head, ``negative_slope=0.2``, no
+    attention dropout, self loops added): the default ``--operator`` of
+    /root/reference/src/train_gnn_embeddings.py:15,99.  Parameters ``lin_l.weight``,
+    ``lin_r.weight`` (no bias), ``att_l``, ``att_r`` ``[1, 1, C]``, ``bias [C]``.
+
+        x_l = lin_l(x_src); a_l = <x_l, att_l>; a_r = <lin_r(x_dst), att_r>
+        out_i = sum_j softmax_i(leaky_relu(a_l[j] + a_r[i])) x_l[j] + bias
+    """
+
+    aggr = 'add'
+
+    def __init__(self, in_channels, out_channels: int, heads: int = 1, concat: bool = True,
+                 negative_slope: float = 0.2, dropout: float = 0.0, add_self_loops: bool = True,
+                 bias: bool = True):
+        super().__init__()
+        if heads != 1 or not concat or dropout != 0.0:
+            raise NotImplementedError('GATConv: only heads=1, concat=True, dropout=0 (the '
+                                      'reference constructs operator((-1, -1), C) with defaults)')
+        if isinstance(in_channels, int):
+            in_channels = (in_channels, in_channels)
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.heads, self.negative_slope, self.add_self_loops = 1, negative_slope, add_self_loops
+        self.lin_l = Linear(in_channels[0], out_channels, bias=False)
+        self.lin_r = Linear(in_channels[1], out_channels, bias=False)
+        self.att_l = nn.Parameter(torch.empty(1, 1, out_channels))
+        self.att_r = nn.Parameter(torch.empty(1, 1, out_channels))
+        if bias:
+            self.bias = nn.Parameter(torch.empty(out_channels))
+        else:
+            self.register_parameter('bias', None)
+        self.reset_parameters()
+
+    def _lins(self):
+        return self.lin_l, self.lin_r
+
+    def reset_parameters(self):
+        super().reset_parameters()
+        nn.init.xavier_uniform_(self.att_l)
+        nn.init.xavier_uniform_(self.att_r)
+        if self.bias is not None:
+            nn.init.zeros_(self.bias)
+
+    def forward(self, x, edge_index: torch.Tensor, size=None) -> torch.Tensor:
+        if torch.is_tensor(x):
+            x = (x, x)
+        x_src, x_dst = x
+        self.lin_l.materialize(x_src.shape[1], x_src.device)
+        self.lin_r.materialize(x_dst.shape[1], x_dst.device)
+        C_ = self.out_channels
+        plan = AF.GATPlan.get(edge_index, x_src.shape[0], x_dst.shape[0], self.add_self_loops)
+        x_l = AF.fused_linear([x_src], self.lin_l.weight)
+        x_r = AF.fused_linear([x_dst], self.lin_r.weight)
+        a_l = AF.fused_linear([x_l], self.att_l.view(1, C_)).view(-1)
+        a_r = AF.fused_linear([x_r], self.att_r.view(1, C_)).view(-1)
+        return AF.gat_aggregate(plan, x_l, a_l, a_r, self.bias, self.negative_slope)

@@ -206,6 +206,72 @@ class GraphConv(MessagePassing):
         return out + self.lin_root(x[1])
 
 
+# 8f rank 3  GATConv -- the DEFAULT --operator of src/train_gnn_embeddings.py:15, registry :99.
+# [PyG-recall] PyG 2.0.2 GATConv(in=(-1,-1), out, heads=1, concat=True, negative_slope=0.2,
+# dropout=0.0, add_self_loops=True, bias=True):
+#   x_l = lin_l(x_src), x_r = lin_r(x_dst)        (Linear, no bias; separate for tuple in_channels)
+#   a_l = (x_l * att_l).sum(-1), a_r = (x_r * att_r).sum(-1)
+#   edge_index: self loops removed, then (i, i) for i < min(N_src, N_dst) appended -- also for
+#   bipartite edge types under to_hetero (the index pairs a source and a destination node of
+#   different types; kept as the reference library does it)
+#   e_ij = leaky_relu(a_l[j] + a_r[i]);  alpha = softmax over the incoming edges of i
+#   (torch_geometric.utils.softmax: exp(e - max) / (sum + 1e-16));  out_i = sum_j alpha_ij x_l[j] + bias
+def gat_edges(edge_index: torch.Tensor, n_src: int, n_dst: int) -> torch.Tensor:
+    keep = edge_index[0] != edge_index[1]
+    n = min(int(n_src), int(n_dst))
+    loops = torch.arange(n, dtype=edge_index.dtype, device=edge_index.device)
+    return torch.cat([edge_index[:, keep], torch.stack([loops, loops])], dim=1)
+
+
+class GATConv(MessagePassing):
+    def __init__(self, in_channels, out_channels, heads=1, concat=True, negative_slope=0.2,
+                 dropout=0.0, add_self_loops=True, bias=True):
+        super().__init__()
+        assert heads == 1 and concat and dropout == 0.0, 'oracle restates the reference defaults'
+        if isinstance(in_channels, int):
+            in_channels = (in_channels, in_channels)
+        self.negative_slope, self.add_self_loops = negative_slope, add_self_loops
+        self.out_channels = out_channels
+        self.lin_l = Linear(in_channels[0], out_channels, bias=False)
+        self.lin_r = Linear(in_channels[1], out_channels, bias=False)
+        self.att_l = nn.Parameter(torch.empty(1, 1, out_channels))
+        self.att_r = nn.Parameter(torch.empty(1, 1, out_channels))
+        self.bias = nn.Parameter(torch.empty(out_channels)) if bias else None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.lin_l.reset_parameters()
+        self.lin_r.reset_parameters()
+        nn.init.xavier_uniform_(self.att_l)          # PyG glorot
+        nn.init.xavier_uniform_(self.att_r)
+        if self.bias is not None:
+            nn.init.zeros_(self.bias)
+
+    def forward(self, x, edge_index):
+        if torch.is_tensor(x):
+            x = (x, x)
+        x_src, x_dst = x
+        n_src, n_dst = x_src.shape[0], x_dst.shape[0]
+        x_l = self.lin_l(x_src)
+        x_r = self.lin_r(x_dst)
+        a_l = (x_l * self.att_l.view(1, -1)).sum(-1)
+        a_r = (x_r * self.att_r.view(1, -1)).sum(-1)
+        ei = gat_edges(edge_index, n_src, n_dst) if self.add_self_loops else edge_index
+        src, dst = ei[0], ei[1]
+        e = F.leaky_relu(a_l[src] + a_r[dst], self.negative_slope)
+        m = torch.full((n_dst,), float('-inf'), dtype=e.dtype).scatter_reduce(
+            0, dst, e, reduce='amax', include_self=True)
+        ex = torch.exp(e - m[dst])
+        den = torch.zeros(n_dst, dtype=e.dtype).scatter_add_(0, dst, ex)
+        alpha = ex / (den[dst] + 1e-16)
+        msg = x_l.index_select(0, src) * alpha.view(-1, 1)
+        out = torch.zeros(n_dst, self.out_channels, dtype=x_l.dtype).scatter_add_(
+            0, dst.view(-1, 1).expand_as(msg), msg)
+        if self.bias is not None:
+            out = out + self.bias
+        return out
+
+
 # --------------------------------------------------------------------------------------------
 # a-3  to_hetero group aggregation: pairwise torch.add through a FIFO queue, metadata edge order
 # --------------------------------------------------------------------------------------------

@@ -40,6 +40,7 @@ def _stub_pyg():
     tg = types.ModuleType('torch_geometric')
     tgn = types.ModuleType('torch_geometric.nn')
     tgn.SAGEConv, tgn.GraphConv, tgn.GCNConv = go.SAGEConv, go.GraphConv, go.GraphConv
+    tgn.GATConv = go.GATConv
     tgn.Linear, tgn.to_hetero = go.Linear, go.to_hetero
     tg.nn = tgn
     sys.modules['torch_geometric'] = tg
@@ -80,7 +81,7 @@ def gnn_fixture(operator_name, label, size):
     g = synth.make_artgraph(size)
     ei = go.to_undirected(g.edge_index_dict)
     md = (g.node_types, list(ei.keys()))
-    op = {'SAGEConv': go.SAGEConv, 'GraphConv': go.GraphConv}[operator_name]
+    op = {'SAGEConv': go.SAGEConv, 'GraphConv': go.GraphConv, 'GATConv': go.GATConv}[operator_name]
     C = {'style': 32, 'genre': 18}[label]
     torch.manual_seed(0)
     model = HeteroSGNN(op, torch.nn.ReLU(), 'sum', 128, C, md, 2, 0.0, True, False)
@@ -230,7 +231,8 @@ def main():
     _stub_pyg()
     _stub_backbones()
     sys.path.insert(0, REF_SRC)
-    for op, label, size in (('SAGEConv', 'style', 'tiny'), ('GraphConv', 'genre', 'tiny')):
+    for op, label, size in (('SAGEConv', 'style', 'tiny'), ('GraphConv', 'genre', 'tiny'),
+                            ('GATConv', 'style', 'tiny')):
         np.savez_compressed(os.path.join(HERE, f'gnn_{size}_{op.lower()}_{label}.npz'),
                             **gnn_fixture(op, label, size))
     for arch in ('vit', 'resnet'):

@@ -24,7 +24,8 @@ def _oracle_gnn(op, label, size='tiny', dtype=torch.float32):
     return g, ei, m
 
 
-@pytest.mark.parametrize('opname,label', [('SAGEConv', 'style'), ('GraphConv', 'genre')])
+@pytest.mark.parametrize('opname,label', [('SAGEConv', 'style'), ('GraphConv', 'genre'),
+                                          ('GATConv', 'style')])
 def test_oracle_matches_reference_wiring_golden(opname, label):
     gold = util.load_golden(f'gnn_tiny_{opname.lower()}_{label}.npz')
     op = getattr(go, opname)

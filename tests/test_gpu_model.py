@@ -111,7 +111,8 @@ def _compare_grads(orc, prod, g64=None):
     return worst
 
 
-@pytest.mark.parametrize('opname,label,C', [('SAGEConv', 'style', 32), ('GraphConv', 'genre', 18)])
+@pytest.mark.parametrize('opname,label,C', [('SAGEConv', 'style', 32), ('GraphConv', 'genre', 18),
+                                            ('GATConv', 'style', 32)])
 def test_product_matches_reference_golden(opname, label, C):
     """The fixtures were produced by the reference's own models_graph.py (make_golden.py)."""
     gold = util.load_golden(f'gnn_tiny_{opname.lower()}_{label}.npz')
@@ -131,12 +132,16 @@ def test_product_matches_reference_golden(opname, label, C):
     assert rel_err(sd['gnn.bns.1.artwork.running_mean'], gold['running_mean_bn1_artwork']) <= RTOL_F32
     assert rel_err(sd['gnn.bns.1.artwork.running_var'], gold['running_var_bn1_artwork']) <= RTOL_F32
     named = dict(prod.named_parameters())
+    gmax = max(float(np.abs(v).max()) for k, v in gold.items() if k.startswith('grad::'))
     for k, v in gold.items():
         if k.startswith('grad::'):
             name = k[6:]
             if opname == 'GraphConv':
                 name = name.replace('.lin_l.', '.lin_rel.').replace('.lin_r.', '.lin_root.')
-            assert rel_err(named[name].grad, v) <= GRAD_RTOL, k
+            # tensors whose true gradient is rounding noise (GATConv's lin_r only shifts the
+            # logits of a softmax row: ~1e-12) are compared on the scale of the model's gradients
+            err = float(np.abs(named[name].grad.cpu().numpy() - v).max())
+            assert err <= GRAD_RTOL * float(np.abs(v).max()) or err <= 1e-7 * gmax, (k, err)
 
 
 @pytest.mark.parametrize('opname', ['SAGEConv', 'GraphConv'])
@@ -569,3 +574,59 @@ def test_flat_sgd_matches_torch_and_projection_generation():
     want = feats.double() @ proj.encoder.weight.detach().cpu().double().t() + \
         proj.encoder.bias.detach().cpu().double()
     assert out.shape == (1000, 128) and rel_err(out, want) <= RTOL_F32
+
+
+def test_gatconv_standalone_and_gradients_vs_oracle():
+    """GATConv (the reference's default --operator): bipartite and homogeneous calls, duplicate
+    edges, explicit self loops (dropped and re-added), rows whose only edge is the added self loop;
+    outputs and every gradient (inputs, lin_l / lin_r, att_l / att_r, bias) against the CPU oracle."""
+    gen = torch.Generator().manual_seed(21)
+    for (n_src, n_dst, e, fs, fd, C, same) in ((70, 50, 400, 24, 40, 32, False),
+                                              (60, 60, 300, 16, 16, 128, True),
+                                              (9, 300, 500, 8, 12, 18, False)):
+        src = torch.randint(0, n_src, (e,), generator=gen)
+        dst = torch.randint(0, n_dst, (e,), generator=gen)
+        dst[:5] = src[:5] % n_dst                                  # some explicit self loops
+        ei = torch.stack([src, dst])
+        xs = torch.randn(n_src, fs, generator=gen)
+        xd = xs if same else torch.randn(n_dst, fd, generator=gen)
+        orc = go.GATConv((-1, -1), C)
+        with torch.no_grad():
+            orc(xs if same else (xs, xd), ei)
+        util.fill_params_deterministic(orc)
+        prod = agx.GATConv((-1, -1), C)
+        util.copy_state(orc, prod)
+        prod = prod.to(DEV)
+        # float64 oracle: the attention gradients hold a cancellation (d alpha - sum alpha d alpha)
+        # that costs the float32 CPU reference itself ~1e-5; the product is held to 5e-5 of exact
+        orc = orc.double()
+        xs_o = xs.double().requires_grad_(True)
+        xd_o = xs_o if same else xd.double().requires_grad_(True)
+        xs_p = xs.to(DEV).requires_grad_(True)
+        xd_p = xs_p if same else xd.to(DEV).requires_grad_(True)
+        w = torch.randn(n_dst, C, generator=gen)
+        out_o = orc(xs_o if same else (xs_o, xd_o), ei)
+        (out_o * w.double()).sum().backward()
+        out_p = prod(xs_p if same else (xs_p, xd_p), ei.to(DEV))
+        (out_p * w.to(DEV)).sum().backward()
+        assert rel_err(out_p, out_o) <= RTOL_F32
+        assert rel_err(xs_p.grad, xs_o.grad) <= 5e-5
+        if not same:
+            assert rel_err(xd_p.grad, xd_o.grad) <= 5e-5
+        po, pp = dict(orc.named_parameters()), dict(prod.named_parameters())
+        for k in po:
+            assert rel_err(pp[k].grad, po[k].grad) <= 5e-5, k
+
+
+def test_gatconv_trainer_cuda_graph():
+    """The reference script's default operator through the captured trainer: graph steps equal
+    eager steps."""
+    from mmac_b200.trainer import GNNTrainer
+    g, ei, orc, prod = _build_pair('GATConv', 32, 'tiny', dropout=0.0)
+    prod2 = copy.deepcopy(prod)
+    xd, ed, y = _to_dev(g.x_dict), _to_dev(ei), g['artwork'].y_style
+    le = [float(GNNTrainer(prod, xd, ed, y, lr=0.01, use_cuda_graph=False).train_step().item())]
+    t_g = GNNTrainer(prod2, xd, ed, y, lr=0.01, use_cuda_graph=True)
+    lg = [float(t_g.train_step().item()) for _ in range(3)]
+    assert abs(le[0] - lg[0]) <= RTOL_F32 * abs(le[0])
+    assert lg[2] < lg[0]
