@@ -969,7 +969,7 @@ extern "C" int agx_aggregate_chunks(const agx_chunk_seg_t* h_segs, int n_segs, i
             AGX_CUDA(cudaMemset2DAsync(S.out, (size_t)S.ldo * esz, 0, (size_t)F * esz,
                                        (size_t)S.n_rows, st));
     }
-    // Measured on B200 (scratch/gather_probe.cu, 895k random 512 B rows of an L2-resident 60 MB
+    // Measured on B200 (profiles/probes/gather_probe.cu, 895k random 512 B rows of an L2-resident 60 MB
     // table): register gathers 15.7 TB/s, TMA row ring 11.7-13.7 TB/s, and the ring costs ~3x the
     // instructions per row (one UBLKCP per row is issued lane by lane): the ring is kept as an
     // option (AGX_TMA_GATHER=1), the default is the register path.

@@ -686,7 +686,7 @@ static bool tc_seg_ok(const agx_gemm_seg_t& S) {
 bool gemm_tc_eligible(const agx_gemm_problem_t& Q, const agx_gemm_seg_t* segs) {
     if (Q.split_k > 1 || Q.row_scale || Q.skip_flag || Q.seg_count < 1 || Q.seg_count > kTcMaxSegs)
         return false;
-    // Measured on B200 (scratch/tc_err_probe.py): the tensor core's float32 accumulator truncates,
+    // Measured on B200 (profiles/probes/tc_err_probe.py): the tensor core's float32 accumulator truncates,
     // the error grows ~1.2e-8 per accumulated K element (1.5e-6 at K=128, 1.2e-5 at K=1024).
     // Only reductions up to 256 stay an order of magnitude inside the 1e-5 parity bound; longer
     // ones (the heads' K = 896 / 2176) and the tiny node types (whose 18-row BatchNorm amplifies
