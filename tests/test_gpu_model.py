@@ -103,7 +103,7 @@ def _compare_grads(orc, prod, g64=None):
         # the exact value independently: allow a small multiple of the reference's own distance
         # (observed: BatchNorm over the 18 / 30 rows of the genre / media types amplifies rounding
         # ~100x; the CPU reference is itself 1e-5 off there.)  Hard ceiling 1e-4 of the tensor scale.
-        # Measured on the 'small' graph (scratch/grad_probe.py): the float32 CPU reference is
+        # Measured on the 'small' graph (profiles/probes/grad_probe.py): the float32 CPU reference is
         # 2e-6 .. 3e-5 away from float64 on these tensors, the product 3e-6 .. 4e-5.
         floor = max(scale, 1e-2 * gmax)
         assert prod_err <= max(8 * ref_err + 2e-6 * scale, 5e-5 * floor) and \
