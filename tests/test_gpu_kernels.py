@@ -220,6 +220,27 @@ def test_aggregate_bf16():
     assert rel_err(out.float(), ref) <= util.RTOL_BF16
 
 
+@pytest.mark.parametrize('F', [128, 64, 200])
+def test_aggregate_chunks_bf16(F):
+    """bfloat16 feature storage through the edge-balanced kernel (float32 accumulation, rel 2e-2):
+    long rows crossing CTAs, rows inside a chunk, empty rows."""
+    gen = torch.Generator().manual_seed(500 + F)
+    n_src, n_dst, e = 4000, 50, 60000
+    p = torch.zeros(n_dst, dtype=torch.float64)
+    p[2:n_dst - 3] = 1.0 / torch.arange(1, n_dst - 4, dtype=torch.float64)
+    dst = torch.multinomial(p / p.sum(), e, replacement=True, generator=gen)
+    ei = torch.stack([torch.randint(0, n_src, (e,), generator=gen), dst])
+    x = torch.randn(n_src, F, generator=gen).bfloat16()
+    for reduce in ('mean', 'add'):
+        ref = go.propagate(x.float(), ei, n_dst, reduce)
+        (csr,) = ops.csr_build([(ei[1].to(DEV), ei[0].to(DEV), n_dst, n_src)])
+        out = torch.full((n_dst, F), float('nan'), device=DEV, dtype=torch.bfloat16)
+        ops.aggregate_chunks([(out, ops.RelArg(csr, x.to(DEV), mean_rows=reduce == 'mean'))], F)
+        assert not torch.isnan(out.float()).any()
+        assert rel_err(out.float(), ref) <= util.RTOL_BF16
+        assert torch.all(out[:2].float() == 0) and torch.all(out[-3:].float() == 0)
+
+
 # ---------------------------------------------------------------- K4
 @pytest.mark.parametrize('M,K,N', [(300, 128, 128), (1000, 200, 32), (77, 5, 18), (513, 129, 130),
                                    (4, 768, 50)])
