@@ -258,10 +258,11 @@ def run_ours(args):
         # ranks, so every conv layer all-gathers boundary source rows and the backward pass
         # reduce-scatters their gradients.  128-d features for every node type (SURVEY.md 8d
         # variant): boundary rows of one-hot inputs would be N_type floats wide.
-        from mmac_b200.dist import GraphPartition
+        from mmac_b200.dist import GraphPartition, balanced_bounds
         g = synth.make_artgraph(args.size, features='dense')
         data = agx.ToUndirected()(g)
-        part = GraphPartition(data.edge_index_dict, data.num_nodes_dict, world, rank)
+        part = GraphPartition(data.edge_index_dict, data.num_nodes_dict, world, rank,
+                              balanced_bounds(data.edge_index_dict, data.num_nodes_dict, world))
         host_x = OrderedDict((k, part.owned(k, v).contiguous().pin_memory())
                              for k, v in data.x_dict.items())
         host_ei = OrderedDict((k, v.pin_memory()) for k, v in part.edge_index.items())

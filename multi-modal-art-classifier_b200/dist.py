@@ -45,6 +45,33 @@ def split_bounds(n: int, world: int) -> List[int]:
     return out
 
 
+def balanced_bounds(edge_index_dict, num_nodes: Dict[str, int], world: int) -> Dict[str, List[int]]:
+    """Contiguous destination ranges per node type that carry about the same number of INCOMING
+    edges each (the aggregation work of a rank is its edges, not its rows: with Zipf-distributed
+    tags or artists an equal-rows split leaves one rank with most of the edges).  Types without
+    incoming edges are split by rows."""
+    deg = {t: None for t in num_nodes}
+    for (s, r, d), ei in edge_index_dict.items():
+        c = torch.bincount(ei[1], minlength=int(num_nodes[d])).to(torch.int64)
+        deg[d] = c if deg[d] is None else deg[d] + c
+    out = {}
+    for t, n in num_nodes.items():
+        if deg[t] is None or int(deg[t].sum()) == 0 or n < world:
+            out[t] = split_bounds(n, world)
+            continue
+        # weight = edges + 1 per row so that empty rows are spread too
+        cum = torch.cumsum(deg[t] + 1, 0)
+        total = int(cum[-1])
+        b = [0]
+        for q in range(1, world):
+            target = total * q // world
+            idx = int(torch.searchsorted(cum, torch.tensor(target, device=cum.device)))
+            b.append(min(max(idx, b[-1]), n))
+        b.append(n)
+        out[t] = b
+    return out
+
+
 class GraphPartition:
     """Destination-node partition of one heterograph, from the point of view of ``rank``.
 

@@ -166,3 +166,24 @@ def test_partition_single_rank_is_identity():
     assert not part.has_halo
     for k, v in ei.items():
         assert torch.equal(part.edge_index[k], v)
+
+
+def test_balanced_bounds_equalise_edges():
+    import mmac_b200  # noqa: F401
+    from mmac_b200 import synth
+    from mmac_b200.dist import GraphPartition, balanced_bounds
+    g = synth.make_artgraph('small', features='dense')
+    ei = go.to_undirected(g.edge_index_dict)
+    n = g.num_nodes_dict
+    for world in (2, 4):
+        b = balanced_bounds(ei, n, world)
+        for t in n:
+            assert len(b[t]) == world + 1 and b[t][0] == 0 and b[t][-1] == n[t]
+            assert all(b[t][i] <= b[t][i + 1] for i in range(world))
+        even = [sum(v.shape[1] for v in GraphPartition(ei, n, world, r).edge_index.values())
+                for r in range(world)]
+        bal = [sum(v.shape[1] for v in GraphPartition(ei, n, world, r, b).edge_index.values())
+               for r in range(world)]
+        assert sum(even) == sum(bal) == sum(v.shape[1] for v in ei.values())
+        assert max(bal) / min(bal) < max(even) / min(even)
+        assert max(bal) <= 1.25 * sum(bal) / world
