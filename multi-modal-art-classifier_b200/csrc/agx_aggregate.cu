@@ -237,7 +237,7 @@ __device__ __noinline__ void agg_row_direct(const agx_row_group_t& G, int row, i
     }
 }
 
-// agg_rows: a warp owns 32 consecutive output rows.
+// agg_rows: a warp owns kRowsPerWarp (16) consecutive output rows.
 //   index phase   lane i walks the row extents and neighbour ids of ITS row for every relation of
 //                 the group (coalesced rowptr reads across the warp, all relations issued before
 //                 the first use) and stages up to kRowCap (id, relation, scale) triples in shared
@@ -250,6 +250,9 @@ __device__ __noinline__ void agg_row_direct(const agx_row_group_t& G, int row, i
 constexpr int kRowCap = 16;
 constexpr int kRowsWarps = 4;
 constexpr int kRowsThreads = kRowsWarps * 32;
+// output rows per warp.  16, not 32: the big groups are ~1.25 "waves" of resident warps, and the
+// work left after the first wave runs on a quarter-full machine; half-size units halve that tail.
+constexpr int kRowsPerWarp = 16;
 
 template <typename T, int VEC, int LPR>
 __global__ void __launch_bounds__(kRowsThreads)
@@ -257,14 +260,14 @@ agg_rows(const __grid_constant__ RowGroups P) {
     constexpr int RPW = 32 / LPR;                  // rows gathered concurrently by one warp
     // per staged edge: address of the source row, multiplier, and "closes its relation" marker
     // (0 = more edges of the relation follow; d >= 1 = last edge, divide the relation sum by d)
-    __shared__ const T* s_ptr[kRowsWarps][32][kRowCap];
-    __shared__ float s_scl[kRowsWarps][32][kRowCap];
-    __shared__ float s_div[kRowsWarps][32][kRowCap];
+    __shared__ const T* s_ptr[kRowsWarps][kRowsPerWarp][kRowCap];
+    __shared__ float s_scl[kRowsWarps][kRowsPerWarp][kRowCap];
+    __shared__ float s_div[kRowsWarps][kRowsPerWarp][kRowCap];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int sub = lane / LPR, l = lane % LPR;
     const int F = P.F;
-    const int64_t slot = ((int64_t)blockIdx.x * kRowsWarps + w) * 32 + lane;
-    const bool valid = slot < P.slot_start[P.n];
+    const int64_t slot = ((int64_t)blockIdx.x * kRowsWarps + w) * kRowsPerWarp + lane;
+    const bool valid = lane < kRowsPerWarp && slot < P.slot_start[P.n];
     int gi = 0, row = 0, tot = 0;
     bool overflow = false;
     if (valid) {
@@ -302,7 +305,7 @@ agg_rows(const __grid_constant__ RowGroups P) {
     }
     __syncwarp();
 
-    for (int j0 = 0; j0 < 32; j0 += RPW) {
+    for (int j0 = 0; j0 < kRowsPerWarp; j0 += RPW) {
         const int j = j0 + sub;
         const bool vj = __shfl_sync(0xffffffffu, valid ? 1 : 0, j) != 0;
         const bool oj = __shfl_sync(0xffffffffu, overflow ? 1 : 0, j) != 0;
@@ -842,7 +845,7 @@ template <typename T, int VEC>
 static int launch_rows(const RowGroups& P, int lpr, int64_t slots, cudaStream_t st) {
 #define AGX_ROWS_CASE(L)                                                                  \
     case L: {                                                                             \
-        const int64_t per_block = (int64_t)kRowsWarps * 32;   /* 32 row slots per warp */   \
+        const int64_t per_block = (int64_t)kRowsWarps * kRowsPerWarp;                      \
         agg_rows<T, VEC, L><<<(unsigned)ceil_div(slots, per_block), kRowsThreads, 0, st>>>(P); \
         break;                                                                            \
     }
