@@ -375,7 +375,7 @@ agg_rows(const __grid_constant__ RowGroups P) {
 //     results are reproducible; no float atomics, no second kernel;
 //   * rows without edges are zero-filled by the chunk that holds the preceding edge (no memset).
 // ------------------------------------------------------------------------------------------------
-constexpr int kGatherDepth = 8;                    // feature-row loads in flight per lane
+constexpr int kGatherDepth = 4;                    // feature-row loads in flight per lane
 
 // fragment loads: from L2 (other SMs wrote them), volatile so that a batch stays in flight together
 template <typename T, int VEC>
@@ -480,7 +480,7 @@ constexpr int kCtaEdges = kAggWarps * AGX_CHUNK_EDGES;      // 1024 edges per CT
 constexpr int kMaxChunkF = 256;                              // columns per launch (host loops)
 
 template <typename T, int VEC, int LPR, bool TMA>
-__global__ void __launch_bounds__(kAggThreads, TMA ? 2 : 3)
+__global__ void __launch_bounds__(kAggThreads, TMA ? 2 : 4)
 agg_chunks(const __grid_constant__ ChunkSegs P) {
     constexpr int SUB = 32 / LPR;
     constexpr int U = kGatherDepth;
