@@ -1041,3 +1041,22 @@ class _AddFn(torch.autograd.Function):
 def add(a, b):
     """a + b on the agx elementwise kernel (the relation sum of to_hetero)."""
     return _AddFn.apply(a, b)
+
+
+class _TransposeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, w):
+        out = torch.empty(w.shape[1], w.shape[0], dtype=torch.float32, device=w.device)
+        ops.transpose_many([(out, w.contiguous())])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        out = torch.empty(g.shape[1], g.shape[0], dtype=torch.float32, device=g.device)
+        ops.transpose_many([(out, g.contiguous())])
+        return out
+
+
+def transposed(w):
+    """``w.t()`` materialised by the agx transpose kernel (x = I: x @ w.T = w.T exactly)."""
+    return _TransposeFn.apply(w)

@@ -246,8 +246,14 @@ class GATConv(MessagePassing):
         self.lin_r.materialize(x_dst.shape[1], x_dst.device)
         C_ = self.out_channels
         plan = AF.GATPlan.get(edge_index, x_src.shape[0], x_dst.shape[0], self.add_self_loops)
-        x_l = AF.fused_linear([x_src], self.lin_l.weight)
-        x_r = AF.fused_linear([x_dst], self.lin_r.weight)
+        from .hetero import _is_identity_input          # one-hot node features: I W^T = W^T
+
+        def lin(x_in, w):
+            if not x_in.requires_grad and _is_identity_input(x_in):
+                return AF.transposed(w)
+            return AF.fused_linear([x_in], w)
+        x_l = lin(x_src, self.lin_l.weight)
+        x_r = lin(x_dst, self.lin_r.weight)
         a_l = AF.fused_linear([x_l], self.att_l.view(1, C_)).view(-1)
         a_r = AF.fused_linear([x_r], self.att_r.view(1, C_)).view(-1)
         return AF.gat_aggregate(plan, x_l, a_l, a_r, self.bias, self.negative_slope)
