@@ -107,6 +107,10 @@ typedef struct {
     const float* row_cnt;     /* nullable: divide the row sum by row_cnt[row]   (scatter-mean)   */
     const float* nbr_scale;   /* nullable: multiply neighbour j's row by 1/nbr_scale[j]
                                  (transpose of scatter-mean)                                      */
+    const float* edge_w;      /* nullable: multiply the row gathered for slot e (position in `col`)
+                                 by edge_w[e] (GATConv attention coefficients)                    */
+    const int32_t* edge_w_idx;/* nullable: the weight of slot e is edge_w[edge_w_idx[e]] (the CSC
+                                 reads the coefficients stored in CSR order)                      */
 } agx_rel_t;
 
 /* One output row = sum over up to 8 relations of that relation's (scaled) neighbour sum:
@@ -119,6 +123,7 @@ typedef struct {
     int32_t accumulate;       /* 1: out += result                                                 */
     int32_t relu_dmask;       /* reserved                                                         */
     agx_rel_t rel[AGX_MAX_REL_PER_GROUP];
+    const float* bias;        /* nullable: [F] float32 added to every output row                  */
 } agx_row_group_t;
 
 /* warp (or sub-warp) per destination row; deterministic edge-order accumulation */
@@ -188,7 +193,11 @@ int agx_gemm_grouped(const agx_gemm_problem_t* h_problems, int n_problems,
 
 /* out = sum of up to 8 equally-sized float arrays (sum of lin_r weights / lin_l biases that share
  * a destination type; exact restatement of adding the per-relation outputs, a-3) */
-typedef struct { float* out; const float* in[8]; int32_t n_in; int64_t numel; } agx_sum_desc_t;
+typedef struct {
+    float* out; const float* in[8]; int32_t n_in; int64_t numel;
+    const float* bias;        /* nullable: + bias[i % bias_F] (row-broadcast bias of [rows, bias_F]) */
+    int64_t bias_F;
+} agx_sum_desc_t;
 int agx_sum_arrays(const agx_sum_desc_t* h_descs, int n, void* stream);
 
 /* a-7  BatchNorm1d per node type (src/models/models_graph.py:19,32-33), batched over types, with
@@ -300,25 +309,51 @@ int agx_smooth_l1(const float* out, const float* target, int64_t numel, float* l
  *   replaces: GATConv.propagate / message / torch_geometric.utils.softmax (PyG 2.0.2, one head),
  *   selected by the reference's default --operator (src/train_gnn_embeddings.py:15,99).
  *   CSR / CSC of the relation's edge list WITH the self loops GATConv adds (agx_csr_build);
- *   a_l [n_src], a_r [n_dst] attention logits, x_l [n_src, F] transformed sources, F <= 256.
- *   alpha_e / de_e: per edge, indexed by the ORIGINAL edge position (the CSR / CSC `eid`).
+ *   a_l [n_src], a_r [n_dst] attention logits, x_l [n_src, F] transformed sources.
+ *   The layer is split into per-edge SCALAR passes (softmax and its backward, below) and WIDE
+ *   passes that run on the edge-balanced aggregation kernels with per-edge weights
+ *   (agx_rel_t.edge_w): out = sum_j alpha_ij x_l[j] over the CSR, dx_l = sum_i alpha_ij dout[i]
+ *   and da_l[j] = sum_i de_ij (F = 1) over the CSC, d alpha by agx_sddmm.  No row of any
+ *   degree is ever walked by a single warp.
  * ------------------------------------------------------------------------------------------ */
-/* out[i] = sum_j softmax_i(leaky_relu(a_l[j] + a_r[i])) x_l[j] (+ bias); alpha_e receives alpha */
-int agx_gat_forward(const int32_t* rowptr, const int32_t* col, const int32_t* eid, const float* a_l,
-                    const float* a_r, const float* x_l, int64_t ldx, int32_t F, float slope,
-                    const float* bias /*nullable*/, float* out, int64_t ldo, float* alpha_e,
-                    int32_t n_rows, void* stream);
-/* de_e[e] = d loss / d (a_l[j] + a_r[i]) ; da_r[i] = sum_j de_ij   (rows = destinations) */
-int agx_gat_backward_dst(const int32_t* rowptr, const int32_t* col, const int32_t* eid,
-                         const float* a_l, const float* a_r, const float* x_l, int64_t ldx,
-                         int32_t F, float slope, const float* dout, int64_t ldd,
-                         const float* alpha_e, float* de_e, float* da_r, int32_t n_rows,
-                         void* stream);
-/* dx_l[j] = sum_i alpha_ij dout[i] ; da_l[j] = sum_i de_ij            (rows = sources, CSC) */
-int agx_gat_backward_src(const int32_t* cscptr, const int32_t* dstid, const int32_t* eid,
-                         const float* alpha_e, const float* de_e, const float* dout, int64_t ldd,
-                         int32_t F, float* dx_l, int64_t ldx, float* da_l, int32_t n_src,
-                         void* stream);
+#define AGX_MAX_GAT_RELS 24
+#define AGX_GAT_LONG_ROW 1024    /* rows with more edges are reduced by a whole CTA, not a warp */
+
+/* One relation of an attention layer.  All per-edge arrays are in CSR order (slot e of `col`). */
+typedef struct {
+    const int32_t* rowptr;    /* [n_rows+1] CSR by destination                                    */
+    const int32_t* col;       /* [n_edges] source ids                                             */
+    const float* a_l;         /* [n_src]  <x_l[j], att_l>                                         */
+    const float* a_r;         /* [n_rows] <x_r[i], att_r>                                         */
+    float* alpha;             /* [n_edges] softmax: written;  backward: read                      */
+    const float* dalpha;      /* backward: [n_edges] d loss / d alpha (agx_sddmm of dout and x_l) */
+    float* de;                /* backward: [n_edges] d loss / d (a_l[j] + a_r[i])                 */
+    float* da_r;              /* backward: [n_rows]  sum_j de_ij                                  */
+    int32_t n_rows;
+    int32_t pad_;
+} agx_gat_rel_t;
+
+/* alpha_ij = softmax_i(leaky_relu(a_l[j] + a_r[i])) per destination row, for up to 24 relations in
+ * ONE launch.  A warp per row; rows with more than AGX_GAT_LONG_ROW edges (artwork -> style /
+ * genre / tag hubs) by the whole CTA.  Fixed reduction order: reproducible. */
+int agx_gat_edge_softmax(const agx_gat_rel_t* h_rels, int n_rels, float slope, void* stream);
+/* de_ij = alpha_ij (dalpha_ij - sum_j alpha_ij dalpha_ij) leaky_relu'(a_l[j] + a_r[i]);
+ * da_r[i] = sum_j de_ij */
+int agx_gat_edge_softmax_bwd(const agx_gat_rel_t* h_rels, int n_rels, float slope, void* stream);
+
+/* Sampled dense-dense product: out[e] = <a[row[e]], b[col[e]]> over F columns, edge-balanced (a warp
+ * per 32 slots) -- d loss / d alpha_ij = <dout[i], x_l[j]> of the attention layer. */
+#define AGX_MAX_SDDMM_SEGS 24
+typedef struct {
+    const int32_t* row;       /* [n_edges] row of `a` per slot (the destination of CSR slot e)    */
+    const int32_t* col;       /* [n_edges] row of `b` per slot                                    */
+    const float* a; int64_t lda;
+    const float* b; int64_t ldb;
+    float* out;               /* [n_edges]                                                        */
+    int32_t n_edges;
+    int32_t pad_;
+} agx_sddmm_seg_t;
+int agx_sddmm(const agx_sddmm_seg_t* h_segs, int n_segs, int32_t F, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * ContextNet / Castellano encoder heads

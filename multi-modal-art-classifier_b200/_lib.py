@@ -24,6 +24,9 @@ CHUNK_EDGES = 128
 MAX_GEMM_PROBLEMS = 24
 MAX_GEMM_SEGS = 64
 MAX_TENSORS = 48
+MAX_GAT_RELS = 24
+MAX_SDDMM_SEGS = 24
+GAT_LONG_ROW = 1024
 F32, BF16 = 0, 1
 
 
@@ -34,12 +37,13 @@ class EdgeList(C.Structure):
 
 class Rel(C.Structure):
     _fields_ = [('rowptr', vp), ('col', vp), ('x', vp), ('ldx', c_i64), ('row_cnt', vp),
-                ('nbr_scale', vp)]
+                ('nbr_scale', vp), ('edge_w', vp), ('edge_w_idx', vp)]
 
 
 class RowGroup(C.Structure):
     _fields_ = [('out', vp), ('ldo', c_i64), ('n_rows', c_i32), ('n_rel', c_i32),
-                ('accumulate', c_i32), ('relu_dmask', c_i32), ('rel', Rel * MAX_REL_PER_GROUP)]
+                ('accumulate', c_i32), ('relu_dmask', c_i32), ('rel', Rel * MAX_REL_PER_GROUP),
+                ('bias', vp)]
 
 
 class ChunkSeg(C.Structure):
@@ -64,7 +68,18 @@ class TransposeDesc(C.Structure):
 
 
 class SumDesc(C.Structure):
-    _fields_ = [('out', vp), ('inp', vp * 8), ('n_in', c_i32), ('numel', c_i64)]
+    _fields_ = [('out', vp), ('inp', vp * 8), ('n_in', c_i32), ('numel', c_i64), ('bias', vp),
+                ('bias_F', c_i64)]
+
+
+class GatRel(C.Structure):
+    _fields_ = [('rowptr', vp), ('col', vp), ('a_l', vp), ('a_r', vp), ('alpha', vp),
+                ('dalpha', vp), ('de', vp), ('da_r', vp), ('n_rows', c_i32), ('pad_', c_i32)]
+
+
+class SddmmSeg(C.Structure):
+    _fields_ = [('row', vp), ('col', vp), ('a', vp), ('lda', c_i64), ('b', vp), ('ldb', c_i64),
+                ('out', vp), ('n_edges', c_i32), ('pad_', c_i32)]
 
 
 class BnDesc(C.Structure):
@@ -122,12 +137,9 @@ _SIGS = {
     'agx_dropout_mask': (C.c_int, [vp, c_i64, c_f32, vp, vp]),
     'agx_smooth_l1_workspace_floats': (C.c_size_t, []),
     'agx_smooth_l1': (C.c_int, [vp, vp, c_i64, vp, vp, vp, vp]),
-    'agx_gat_forward': (C.c_int, [vp, vp, vp, vp, vp, vp, c_i64, c_i32, c_f32, vp, vp, c_i64, vp,
-                                  c_i32, vp]),
-    'agx_gat_backward_dst': (C.c_int, [vp, vp, vp, vp, vp, vp, c_i64, c_i32, c_f32, vp, c_i64, vp,
-                                       vp, vp, c_i32, vp]),
-    'agx_gat_backward_src': (C.c_int, [vp, vp, vp, vp, vp, vp, c_i64, c_i32, vp, c_i64, vp, c_i32,
-                                       vp]),
+    'agx_gat_edge_softmax': (C.c_int, [C.POINTER(GatRel), C.c_int, c_f32, vp]),
+    'agx_gat_edge_softmax_bwd': (C.c_int, [C.POINTER(GatRel), C.c_int, c_f32, vp]),
+    'agx_sddmm': (C.c_int, [C.POINTER(SddmmSeg), C.c_int, c_i32, vp]),
     'agx_mse': (C.c_int, [vp, vp, c_i64, vp, vp, vp, vp]),
     'agx_tanh': (C.c_int, [vp, vp, c_i64, vp]),
     'agx_tanh_bwd': (C.c_int, [vp, vp, vp, c_i64, vp]),

@@ -172,6 +172,14 @@ __device__ __forceinline__ void store_row4<__nv_bfloat16>(__nv_bfloat16* p,
                                              *reinterpret_cast<const uint32_t*>(&h1));
 }
 
+// multiplier of the row gathered for CSR slot e from neighbour c: 1/nbr_scale[c] (transpose of
+// scatter-mean) and / or the per-edge weight (GATConv attention).  Exactly 1.0f when neither is set.
+__device__ __forceinline__ float edge_scale(const agx_rel_t& R, int e, int c) {
+    float s = R.nbr_scale ? 1.0f / __ldg(R.nbr_scale + c) : 1.0f;
+    if (R.edge_w) s *= __ldg(R.edge_w + (R.edge_w_idx ? __ldg(R.edge_w_idx + e) : e));
+    return s;
+}
+
 // ------------------------------------------------------------------------------------------------
 // agg_rows
 // ------------------------------------------------------------------------------------------------
@@ -198,9 +206,9 @@ __device__ __noinline__ void agg_row_direct(const agx_row_group_t& G, int row, i
                 for (int u = 0; u < U; ++u) c[u] = __ldg(R.col + e + u);
 #pragma unroll
                 for (int u = 0; u < U; ++u) v[u] = load_vec<T, VEC>(x + (int64_t)c[u] * R.ldx);
-                if (R.nbr_scale) {
+                if (R.nbr_scale || R.edge_w) {
 #pragma unroll
-                    for (int u = 0; u < U; ++u) s[u] = 1.0f / __ldg(R.nbr_scale + c[u]);
+                    for (int u = 0; u < U; ++u) s[u] = edge_scale(R, e + u, c[u]);
 #pragma unroll
                     for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -215,7 +223,7 @@ __device__ __noinline__ void agg_row_direct(const agx_row_group_t& G, int row, i
             for (; e < end_r; ++e) {
                 const int c = __ldg(R.col + e);
                 const Vec<T, VEC> v = load_vec<T, VEC>(x + (int64_t)c * R.ldx);
-                const float s = R.nbr_scale ? 1.0f / __ldg(R.nbr_scale + c) : 1.0f;
+                const float s = edge_scale(R, e, c);
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) racc.v[i] += v.v[i] * s;
             }
@@ -232,6 +240,10 @@ __device__ __noinline__ void agg_row_direct(const agx_row_group_t& G, int row, i
             const Vec<T, VEC> old = load_vec<T, VEC>(o);
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc.v[i] += old.v[i];
+        }
+        if (G.bias) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc.v[i] += __ldg(G.bias + c0 + i);
         }
         store_vec<T, VEC>(o, acc);
     }
@@ -293,7 +305,7 @@ agg_rows(const __grid_constant__ RowGroups P) {
                     if (tot < kRowCap) {
                         const int c = __ldg(R.col + e);
                         s_ptr[w][lane][tot] = xb + (int64_t)c * R.ldx;
-                        s_scl[w][lane][tot] = R.nbr_scale ? 1.0f / __ldg(R.nbr_scale + c) : 1.0f;
+                        s_scl[w][lane][tot] = edge_scale(R, e, c);
                         s_div[w][lane][tot] = (e + 1 == end[r]) ? d : 0.f;
                         ++tot;
                     } else {
@@ -353,6 +365,10 @@ agg_rows(const __grid_constant__ RowGroups P) {
                 const Vec<T, VEC> old = load_vec<T, VEC>(o);
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) acc.v[i] += old.v[i];
+            }
+            if (G.bias) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc.v[i] += __ldg(G.bias + c0 + i);
             }
             store_vec<T, VEC>(o, acc);
         }
@@ -529,7 +545,7 @@ agg_chunks(const __grid_constant__ ChunkSegs P) {
 #pragma unroll
     for (int k = 0; k < AGX_CHUNK_EDGES / 32; ++k) {
         const int i = k * 32 + lane;
-        sr[k] = (R.nbr_scale && start + i < end) ? 1.0f / __ldg(R.nbr_scale + cr[k]) : 1.0f;
+        sr[k] = start + i < end ? edge_scale(R, start + i, cr[k]) : 1.0f;
         if constexpr (TMA) {
             s_col[w][i] = cr[k];
             s_scl[w][i] = sr[k];

@@ -42,7 +42,7 @@ extern "C" int agx_kernel_inventory(char* h_buf, size_t h_buf_bytes) {
         "sum_arrays,bn_stats,bn_apply,bn_bwd_reduce,bn_bwd_apply,colsum,"
         "log_softmax_nll,log_softmax_nll_bwd,adam_step,head_forward,ce_forward,ce_finish,"
         "smooth_l1,fill_f32,scale_mask,gather_rows,is_identity,transpose,pack_rows,"
-        "unpack_rows_add";
+        "unpack_rows_add,gat_edge_softmax,sddmm";
     if (!h_buf || h_buf_bytes == 0) {
         agx::set_error("agx_kernel_inventory: null buffer");
         return AGX_ERR_INVALID;

@@ -1,205 +1,278 @@
-// GATConv attention aggregation (the reference script's default --operator,
+// GATConv attention (the reference script's default --operator,
 // /root/reference/src/train_gnn_embeddings.py:15,99; PyG 2.0.2 GATConv, one head):
 //
 //   e_ij = leaky_relu(a_l[j] + a_r[i]),  alpha_ij = exp(e_ij - max_i) / (sum_i + 1e-16),
 //   out_i = sum_j alpha_ij x_l[j] (+ bias)
 //
-// over the CSR (by destination) of the relation's edge list with self loops added.  One warp per
-// row, neighbours in edge order, float32, no atomics: reproducible.  The backward pass is the
-// softmax / leaky-relu chain per destination row plus the transpose (CSC, by source) of the
-// weighted sum; per-edge quantities are exchanged between the two in ORIGINAL edge order
-// (alpha_e[eid], de_e[eid]) so no inverse permutation is needed.
+// over the CSR (by destination) of the relation's edge list with self loops added.  ArtGraph's
+// relations into style / genre / tag / media have a few rows of 10^3..10^4 edges, so nothing here
+// lets one warp walk a row of feature vectors:
+//
+//   scalar passes (this file, 4-12 B per edge)
+//     gat_edge_softmax      alpha per CSR slot; a warp per row, rows longer than AGX_GAT_LONG_ROW by
+//                           the whole CTA (three strided passes over the row, values parked in alpha)
+//     gat_edge_softmax_bwd  de_ij = alpha_ij (dalpha_ij - sum_j alpha_ij dalpha_ij) leaky'(.),
+//                           da_r[i] = sum_j de_ij, same row mapping
+//     sddmm                 dalpha_ij = <dout[i], x_l[j]>, a warp per 32 CSR slots (edge-balanced)
+//   wide passes (agx_aggregate.cu, 4 F B per edge)
+//     out  = weighted neighbour sum over the CSR   (agx_rel_t.edge_w = alpha)
+//     dx_l = weighted neighbour sum over the CSC   (edge_w = alpha through edge_w_idx)
+//     da_l = sum over the CSC of de (F = 1)
+//
+// All reductions run in a fixed order (lane-strided partial sums, shuffle tree, warp order): results
+// are reproducible run to run; float32 throughout.
 #include "agx_common.cuh"
 
 namespace agx {
 
-constexpr int kGatMaxF = 256;                 // feature width handled in registers (8 per lane)
-constexpr int kGatCols = kGatMaxF / 32;
+constexpr int kGatThreads = 256;
+constexpr int kGatWarps = kGatThreads / 32;
+
+struct GatRels {
+    agx_gat_rel_t r[AGX_MAX_GAT_RELS];
+    int32_t blk_start[AGX_MAX_GAT_RELS + 1];       // CTA -> relation (8 rows per CTA)
+    int32_t n;
+    float slope;
+};
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 __device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? v : slope * v; }
 
-__global__ void __launch_bounds__(256)
-gat_fwd(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-        const int32_t* __restrict__ eid, const float* __restrict__ a_l,
-        const float* __restrict__ a_r, const float* __restrict__ x_l, int64_t ldx, int F,
-        float slope, const float* __restrict__ bias, float* __restrict__ out, int64_t ldo,
-        float* __restrict__ alpha_e, int n_rows) {
-    const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= n_rows) return;
-    const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
-    const float ar = __ldg(a_r + row);
+// reduction over the NT threads that share a row: NT = 32 one warp, NT = kGatThreads the CTA
+// (warp results combined in warp order by every thread; s_red is reused, hence the leading barrier)
+template <int NT, bool MAX>
+__device__ __forceinline__ float group_reduce(float v, float* s_red) {
+    v = MAX ? warp_max(v) : warp_sum(v);
+    if constexpr (NT > 32) {
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        v = s_red[0];
+#pragma unroll
+        for (int w = 1; w < kGatWarps; ++w) v = MAX ? fmaxf(v, s_red[w]) : v + s_red[w];
+    }
+    return v;
+}
+
+// softmax of one destination row by NT threads (t = this thread's index among them)
+template <int NT>
+__device__ __forceinline__ void softmax_row(const agx_gat_rel_t& R, int row, int beg, int end, int t,
+                                            float slope, float* s_red) {
+    const float ar = __ldg(R.a_r + row);
     float m = -INFINITY;
-    for (int e = beg + lane; e < end; e += 32)
-        m = fmaxf(m, leaky(__ldg(a_l + __ldg(col + e)) + ar, slope));
-    m = warp_max(m);
+#pragma unroll 4
+    for (int e = beg + t; e < end; e += NT) {
+        const float l = leaky(__ldg(R.a_l + __ldg(R.col + e)) + ar, slope);
+        R.alpha[e] = l;                            // parked: the same thread reads it back
+        m = fmaxf(m, l);
+    }
+    m = group_reduce<NT, true>(m, s_red);
     float s = 0.f;
-    for (int e = beg + lane; e < end; e += 32)
-        s += expf(leaky(__ldg(a_l + __ldg(col + e)) + ar, slope) - m);
-    s = warp_sum(s);
+#pragma unroll 4
+    for (int e = beg + t; e < end; e += NT) {
+        const float p = expf(R.alpha[e] - m);
+        R.alpha[e] = p;
+        s += p;
+    }
+    s = group_reduce<NT, false>(s, s_red);
     const float inv = 1.0f / (s + 1e-16f);
-    float acc[kGatCols];
+#pragma unroll 4
+    for (int e = beg + t; e < end; e += NT) R.alpha[e] *= inv;
+}
+
+template <int NT>
+__device__ __forceinline__ void softmax_bwd_row(const agx_gat_rel_t& R, int row, int beg, int end,
+                                                int t, float slope, float* s_red) {
+    const float ar = __ldg(R.a_r + row);
+    float s = 0.f;
+#pragma unroll 4
+    for (int e = beg + t; e < end; e += NT) s = fmaf(R.alpha[e], __ldg(R.dalpha + e), s);
+    s = group_reduce<NT, false>(s, s_red);
+    float d = 0.f;
+#pragma unroll 4
+    for (int e = beg + t; e < end; e += NT) {
+        const float raw = __ldg(R.a_l + __ldg(R.col + e)) + ar;
+        const float de = R.alpha[e] * (__ldg(R.dalpha + e) - s) * (raw > 0.f ? 1.0f : slope);
+        R.de[e] = de;
+        d += de;
+    }
+    d = group_reduce<NT, false>(d, s_red);
+    if (t == 0) R.da_r[row] = d;
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(kGatThreads) gat_edge_softmax(const __grid_constant__ GatRels P) {
+    __shared__ float s_red[kGatWarps];
+    __shared__ int s_long[kGatWarps];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int ri = 0;
+    while ((int)blockIdx.x >= P.blk_start[ri + 1]) ++ri;
+    const agx_gat_rel_t& R = P.r[ri];
+    const int row = ((int)blockIdx.x - P.blk_start[ri]) * kGatWarps + w;
+    int beg = 0, end = 0;
+    if (row < R.n_rows) {
+        beg = __ldg(R.rowptr + row);
+        end = __ldg(R.rowptr + row + 1);
+    }
+    const bool is_long = end - beg > AGX_GAT_LONG_ROW;
+    if (lane == 0) s_long[w] = is_long ? 1 : 0;
+    if (row < R.n_rows && !is_long) {
+        if constexpr (BWD)
+            softmax_bwd_row<32>(R, row, beg, end, lane, P.slope, s_red);
+        else
+            softmax_row<32>(R, row, beg, end, lane, P.slope, s_red);
+    }
+    __syncthreads();
+    // hub rows of this CTA, one after the other, by all of its threads (CTA-uniform control flow)
+    for (int ww = 0; ww < kGatWarps; ++ww) {
+        if (!s_long[ww]) continue;
+        const int lrow = ((int)blockIdx.x - P.blk_start[ri]) * kGatWarps + ww;
+        const int lbeg = __ldg(R.rowptr + lrow), lend = __ldg(R.rowptr + lrow + 1);
+        if constexpr (BWD)
+            softmax_bwd_row<kGatThreads>(R, lrow, lbeg, lend, threadIdx.x, P.slope, s_red);
+        else
+            softmax_row<kGatThreads>(R, lrow, lbeg, lend, threadIdx.x, P.slope, s_red);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sddmm: out[e] = <a[row[e]], b[col[e]]>.  A warp owns 32 consecutive slots; LPR lanes cover one
+// pair of feature rows (VEC columns per lane and step), the 32 / LPR sub-warps take different
+// slots, kSddmmDepth slots per sub-warp are loaded before the first is reduced.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSddmmDepth = 4;
+
+struct SddmmSegs {
+    agx_sddmm_seg_t s[AGX_MAX_SDDMM_SEGS];
+    int32_t blk_start[AGX_MAX_SDDMM_SEGS + 1];     // CTA -> segment (256 slots per CTA)
+    int32_t n;
+    int32_t F;
+};
+
+template <int VEC, int LPR>
+__global__ void __launch_bounds__(kGatThreads) sddmm(const __grid_constant__ SddmmSegs P) {
+    constexpr int SUB = 32 / LPR;
+    constexpr int U = kSddmmDepth;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int sub = lane / LPR, l = lane % LPR;
+    int si = 0;
+    while ((int)blockIdx.x >= P.blk_start[si + 1]) ++si;
+    const agx_sddmm_seg_t& S = P.s[si];
+    const int e0 = (((int)blockIdx.x - P.blk_start[si]) * kGatWarps + w) * 32;
+    const int n = min(32, S.n_edges - e0);
+    if (n <= 0) return;
+    const int F = P.F;
+    const int my_r = lane < n ? __ldg(S.row + e0 + lane) : 0;
+    const int my_c = lane < n ? __ldg(S.col + e0 + lane) : 0;
+    for (int j0 = 0; j0 < n; j0 += SUB * U) {
+        float part[U];
 #pragma unroll
-    for (int k = 0; k < kGatCols; ++k) acc[k] = 0.f;
-    for (int e0 = beg; e0 < end; e0 += 32) {
-        const int n = min(32, end - e0);
-        int c = 0;
-        float al = 0.f;
-        if (lane < n) {
-            c = __ldg(col + e0 + lane);
-            al = expf(leaky(__ldg(a_l + c) + ar, slope) - m) * inv;
-            alpha_e[__ldg(eid + e0 + lane)] = al;
-        }
-        for (int j = 0; j < n; ++j) {
-            const int cj = __shfl_sync(0xffffffffu, c, j);
-            const float aj = __shfl_sync(0xffffffffu, al, j);
-            const float* xr = x_l + (int64_t)cj * ldx;
-#pragma unroll
-            for (int k = 0; k < kGatCols; ++k) {
-                const int cc = lane + 32 * k;
-                if (cc < F) acc[k] = fmaf(aj, __ldg(xr + cc), acc[k]);
+        for (int u = 0; u < U; ++u) {
+            const int j = min(j0 + u * SUB + sub, n - 1);          // clamped: valid rows, not stored
+            const int rj = __shfl_sync(0xffffffffu, my_r, j);
+            const int cj = __shfl_sync(0xffffffffu, my_c, j);
+            const float* pa = S.a + (int64_t)rj * S.lda;
+            const float* pb = S.b + (int64_t)cj * S.ldb;
+            float acc = 0.f;
+            for (int c0 = l * VEC; c0 < F; c0 += LPR * VEC) {
+                if constexpr (VEC == 4) {
+                    const float4 x = ldg_f4(pa + c0), y = ldg_f4(pb + c0);
+                    acc = fmaf(x.x, y.x, acc);
+                    acc = fmaf(x.y, y.y, acc);
+                    acc = fmaf(x.z, y.z, acc);
+                    acc = fmaf(x.w, y.w, acc);
+                } else {
+                    acc = fmaf(__ldg(pa + c0), __ldg(pb + c0), acc);
+                }
             }
+            part[u] = acc;
         }
-    }
 #pragma unroll
-    for (int k = 0; k < kGatCols; ++k) {
-        const int cc = lane + 32 * k;
-        if (cc < F) out[(int64_t)row * ldo + cc] = acc[k] + (bias ? __ldg(bias + cc) : 0.f);
+        for (int u = 0; u < U; ++u) {
+            float v = part[u];
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            const int j = j0 + u * SUB + sub;
+            if (l == 0 && j < n) S.out[e0 + j] = v;
+        }
     }
 }
 
-// per destination row: d alpha_ij = dout_i . x_l[j];  s_i = sum_j alpha_ij d alpha_ij;
-// de_ij = alpha_ij (d alpha_ij - s_i) * leaky'(a_l[j] + a_r[i]);  da_r[i] = sum_j de_ij
-__global__ void __launch_bounds__(256)
-gat_bwd_dst(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-            const int32_t* __restrict__ eid, const float* __restrict__ a_l,
-            const float* __restrict__ a_r, const float* __restrict__ x_l, int64_t ldx, int F,
-            float slope, const float* __restrict__ dout, int64_t ldd,
-            const float* __restrict__ alpha_e, float* __restrict__ de_e, float* __restrict__ da_r,
-            int n_rows) {
-    const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= n_rows) return;
-    const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
-    const float ar = __ldg(a_r + row);
-    float g[kGatCols];
-#pragma unroll
-    for (int k = 0; k < kGatCols; ++k) {
-        const int cc = lane + 32 * k;
-        g[k] = cc < F ? __ldg(dout + (int64_t)row * ldd + cc) : 0.f;
-    }
-    float s = 0.f;                                   // same value in every lane
-    for (int e = beg; e < end; ++e) {
-        const int c = __ldg(col + e);
-        const float* xr = x_l + (int64_t)c * ldx;
-        float d = 0.f;
-#pragma unroll
-        for (int k = 0; k < kGatCols; ++k) {
-            const int cc = lane + 32 * k;
-            if (cc < F) d = fmaf(g[k], __ldg(xr + cc), d);
-        }
-        d = warp_sum(d);
-        const int id = __ldg(eid + e);
-        s = fmaf(alpha_e[id], d, s);
-        if (lane == 0) de_e[id] = d;                 // d alpha for now
-    }
-    __syncwarp();
-    float t = 0.f;
-    for (int e = beg + lane; e < end; e += 32) {
-        const int id = __ldg(eid + e);
-        const float raw = __ldg(a_l + __ldg(col + e)) + ar;
-        const float de = alpha_e[id] * (de_e[id] - s) * (raw > 0.f ? 1.0f : slope);
-        de_e[id] = de;
-        t += de;
-    }
-    t = warp_sum(t);
-    if (lane == 0) da_r[row] = t;
-}
+static bool gat_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// per source row (CSC): dx_l[j] = sum_i alpha_ij dout_i ;  da_l[j] = sum_i de_ij
-__global__ void __launch_bounds__(256)
-gat_bwd_src(const int32_t* __restrict__ cscptr, const int32_t* __restrict__ dstid,
-            const int32_t* __restrict__ eid, const float* __restrict__ alpha_e,
-            const float* __restrict__ de_e, const float* __restrict__ dout, int64_t ldd, int F,
-            float* __restrict__ dx_l, int64_t ldx, float* __restrict__ da_l, int n_src) {
-    const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= n_src) return;
-    const int beg = __ldg(cscptr + row), end = __ldg(cscptr + row + 1);
-    float acc[kGatCols];
-#pragma unroll
-    for (int k = 0; k < kGatCols; ++k) acc[k] = 0.f;
-    float sde = 0.f;
-    for (int q = beg; q < end; ++q) {
-        const int i = __ldg(dstid + q), id = __ldg(eid + q);
-        const float a = alpha_e[id];
-        sde += de_e[id];
-        const float* gr = dout + (int64_t)i * ldd;
-#pragma unroll
-        for (int k = 0; k < kGatCols; ++k) {
-            const int cc = lane + 32 * k;
-            if (cc < F) acc[k] = fmaf(a, __ldg(gr + cc), acc[k]);
-        }
+template <bool BWD>
+static int launch_edge_softmax(const agx_gat_rel_t* h_rels, int n_rels, float slope, void* stream,
+                               const char* what) {
+    AGX_CHECK_ARG(h_rels && n_rels >= 1 && n_rels <= AGX_MAX_GAT_RELS, "%s: n_rels=%d out of [1,%d]",
+                  what, n_rels, AGX_MAX_GAT_RELS);
+    GatRels P;
+    P.n = n_rels;
+    P.slope = slope;
+    P.blk_start[0] = 0;
+    for (int i = 0; i < n_rels; ++i) {
+        const agx_gat_rel_t& R = h_rels[i];
+        AGX_CHECK_ARG(R.n_rows >= 0, "%s: relation %d: n_rows=%d", what, i, R.n_rows);
+        AGX_CHECK_ARG(R.n_rows == 0 || (R.rowptr && R.col && R.a_l && R.a_r && R.alpha),
+                      "%s: relation %d: null pointer", what, i);
+        AGX_CHECK_ARG(!BWD || R.n_rows == 0 || (R.dalpha && R.de && R.da_r),
+                      "%s: relation %d: null backward pointer", what, i);
+        P.r[i] = R;
+        P.blk_start[i + 1] = P.blk_start[i] + (int32_t)ceil_div(R.n_rows, kGatWarps);
     }
-#pragma unroll
-    for (int k = 0; k < kGatCols; ++k) {
-        const int cc = lane + 32 * k;
-        if (cc < F) dx_l[(int64_t)row * ldx + cc] = acc[k];
-    }
-    if (lane == 0) da_l[row] = sde;
+    if (P.blk_start[n_rels] == 0) return AGX_OK;
+    gat_edge_softmax<BWD><<<(unsigned)P.blk_start[n_rels], kGatThreads, 0, (cudaStream_t)stream>>>(P);
+    AGX_LAUNCH_CHECK(what);
+    return AGX_OK;
 }
 
 }  // namespace agx
 
 using namespace agx;
 
-extern "C" int agx_gat_forward(const int32_t* rowptr, const int32_t* col, const int32_t* eid,
-                               const float* a_l, const float* a_r, const float* x_l, int64_t ldx,
-                               int32_t F, float slope, const float* bias, float* out, int64_t ldo,
-                               float* alpha_e, int32_t n_rows, void* stream) {
-    AGX_CHECK_ARG(F >= 1 && F <= kGatMaxF, "agx_gat_forward: F=%d out of [1,%d]", F, kGatMaxF);
-    AGX_CHECK_ARG(n_rows >= 0, "agx_gat_forward: n_rows=%d", n_rows);
-    if (n_rows == 0) return AGX_OK;
-    AGX_CHECK_ARG(rowptr && a_l && a_r && x_l && out, "agx_gat_forward: null pointer");
-    gat_fwd<<<(unsigned)ceil_div(n_rows, 8), 256, 0, (cudaStream_t)stream>>>(
-        rowptr, col, eid, a_l, a_r, x_l, ldx, F, slope, bias, out, ldo, alpha_e, n_rows);
-    AGX_LAUNCH_CHECK("gat_fwd");
-    return AGX_OK;
+extern "C" int agx_gat_edge_softmax(const agx_gat_rel_t* h_rels, int n_rels, float slope,
+                                    void* stream) {
+    return launch_edge_softmax<false>(h_rels, n_rels, slope, stream, "agx_gat_edge_softmax");
 }
 
-extern "C" int agx_gat_backward_dst(const int32_t* rowptr, const int32_t* col, const int32_t* eid,
-                                    const float* a_l, const float* a_r, const float* x_l,
-                                    int64_t ldx, int32_t F, float slope, const float* dout,
-                                    int64_t ldd, const float* alpha_e, float* de_e, float* da_r,
-                                    int32_t n_rows, void* stream) {
-    AGX_CHECK_ARG(F >= 1 && F <= kGatMaxF, "agx_gat_backward_dst: F=%d out of [1,%d]", F, kGatMaxF);
-    if (n_rows <= 0) return AGX_OK;
-    AGX_CHECK_ARG(rowptr && a_l && a_r && x_l && dout && da_r, "agx_gat_backward_dst: null pointer");
-    gat_bwd_dst<<<(unsigned)ceil_div(n_rows, 8), 256, 0, (cudaStream_t)stream>>>(
-        rowptr, col, eid, a_l, a_r, x_l, ldx, F, slope, dout, ldd, alpha_e, de_e, da_r, n_rows);
-    AGX_LAUNCH_CHECK("gat_bwd_dst");
-    return AGX_OK;
+extern "C" int agx_gat_edge_softmax_bwd(const agx_gat_rel_t* h_rels, int n_rels, float slope,
+                                        void* stream) {
+    return launch_edge_softmax<true>(h_rels, n_rels, slope, stream, "agx_gat_edge_softmax_bwd");
 }
 
-extern "C" int agx_gat_backward_src(const int32_t* cscptr, const int32_t* dstid, const int32_t* eid,
-                                    const float* alpha_e, const float* de_e, const float* dout,
-                                    int64_t ldd, int32_t F, float* dx_l, int64_t ldx, float* da_l,
-                                    int32_t n_src, void* stream) {
-    AGX_CHECK_ARG(F >= 1 && F <= kGatMaxF, "agx_gat_backward_src: F=%d out of [1,%d]", F, kGatMaxF);
-    if (n_src <= 0) return AGX_OK;
-    AGX_CHECK_ARG(cscptr && dout && dx_l && da_l, "agx_gat_backward_src: null pointer");
-    gat_bwd_src<<<(unsigned)ceil_div(n_src, 8), 256, 0, (cudaStream_t)stream>>>(
-        cscptr, dstid, eid, alpha_e, de_e, dout, ldd, F, dx_l, ldx, da_l, n_src);
-    AGX_LAUNCH_CHECK("gat_bwd_src");
+extern "C" int agx_sddmm(const agx_sddmm_seg_t* h_segs, int n_segs, int32_t F, void* stream) {
+    AGX_CHECK_ARG(h_segs && n_segs >= 1 && n_segs <= AGX_MAX_SDDMM_SEGS,
+                  "agx_sddmm: n_segs=%d out of [1,%d]", n_segs, AGX_MAX_SDDMM_SEGS);
+    AGX_CHECK_ARG(F >= 1, "agx_sddmm: F=%d", F);
+    SddmmSegs P;
+    P.n = n_segs;
+    P.F = F;
+    P.blk_start[0] = 0;
+    bool vec_ok = (F & 3) == 0;
+    for (int i = 0; i < n_segs; ++i) {
+        const agx_sddmm_seg_t& S = h_segs[i];
+        AGX_CHECK_ARG(S.n_edges >= 0, "agx_sddmm: segment %d: n_edges=%d", i, S.n_edges);
+        AGX_CHECK_ARG(S.n_edges == 0 || (S.row && S.col && S.a && S.b && S.out),
+                      "agx_sddmm: segment %d: null pointer", i);
+        vec_ok = vec_ok && gat_aligned16(S.a) && gat_aligned16(S.b) && (S.lda & 3) == 0 &&
+                 (S.ldb & 3) == 0;
+        P.s[i] = S;
+        P.blk_start[i + 1] = P.blk_start[i] + (int32_t)ceil_div(S.n_edges, kGatThreads);
+    }
+    const unsigned grid = (unsigned)P.blk_start[n_segs];
+    if (grid == 0) return AGX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!vec_ok)
+        sddmm<1, 32><<<grid, kGatThreads, 0, st>>>(P);
+    else if (F > 64)
+        sddmm<4, 32><<<grid, kGatThreads, 0, st>>>(P);
+    else if (F > 32)
+        sddmm<4, 16><<<grid, kGatThreads, 0, st>>>(P);
+    else
+        sddmm<4, 8><<<grid, kGatThreads, 0, st>>>(P);
+    AGX_LAUNCH_CHECK("sddmm");
     return AGX_OK;
 }

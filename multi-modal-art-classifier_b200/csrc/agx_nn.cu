@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(256) sum_arrays(const __grid_constant__ SumPar
         const int64_t e = i - P.start[di];
         float v = D.in[0][e];
         for (int k = 1; k < D.n_in; ++k) v += D.in[k][e];
+        if (D.bias) v += __ldg(D.bias + e % D.bias_F);
         D.out[e] = v;
     }
 }
@@ -897,6 +898,8 @@ extern "C" int agx_sum_arrays(const agx_sum_desc_t* h_descs, int n, void* stream
                       "agx_sum_arrays: desc %d invalid", i);
         for (int k = 0; k < D.n_in; ++k)
             AGX_CHECK_ARG(D.numel == 0 || D.in[k], "agx_sum_arrays: desc %d input %d null", i, k);
+        AGX_CHECK_ARG(!D.bias || D.bias_F >= 1, "agx_sum_arrays: desc %d: bias_F=%lld", i,
+                      (long long)D.bias_F);
         P.d[i] = D;
         P.start[i + 1] = P.start[i] + D.numel;
     }

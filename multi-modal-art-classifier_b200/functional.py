@@ -942,12 +942,16 @@ def tanh(x):
 
 
 # ------------------------------------------------------------------------------------------------
-# GATConv: attention aggregation over the self-loop augmented relation
+# GATConv: attention layer over the self-loop augmented relations
 # ------------------------------------------------------------------------------------------------
 class GATPlan:
     """CSR (by destination) and CSC (by source) of one relation's edge list as GATConv sees it:
     self loops removed, then (i, i) for i < min(N_src, N_dst) appended (PyG 2.0.2, also for
-    bipartite edge types).  Index preparation only; cached per edge_index tensor."""
+    bipartite edge types).  Index preparation only; cached per edge_index tensor.
+
+    ``csr_row[e]``  destination of CSR slot e (the row index agx_sddmm needs per slot);
+    ``csc2csr[q]``  CSR slot of the edge in CSC slot q (per-edge arrays live in CSR order);
+    ``csc_pos``     the CSC with ``col = csc2csr``: gathers per-edge scalars by source row."""
 
     _cache: "dict" = {}
 
@@ -962,6 +966,17 @@ class GATPlan:
         self.edge_index = ei.contiguous()
         self.csr, self.csc = ops.csr_build([(self.edge_index[1], self.edge_index[0], n_dst, n_src),
                                             (self.edge_index[0], self.edge_index[1], n_src, n_dst)])
+        E = self.n_edges
+        dev = ei.device
+        for c in (self.csr, self.csc):
+            c.max_degree = int((c.rowptr[1:] - c.rowptr[:-1]).max()) if c.n_rows > 0 and E > 0 else 0
+        csr_eid = self.csr.eid[:E].long()
+        self.csr_row = self.edge_index[1][csr_eid].to(torch.int32).contiguous()
+        inv = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+        inv[csr_eid] = torch.arange(E, dtype=torch.int32, device=dev)
+        self.csc2csr = inv[self.csc.eid[:E].long()].contiguous()
+        import dataclasses
+        self.csc_pos = dataclasses.replace(self.csc, col=self.csc2csr, n_cols=max(E, 1))
 
     @classmethod
     def get(cls, edge_index, n_src, n_dst, add_self_loops=True):
@@ -976,87 +991,276 @@ class GATPlan:
         return plan
 
 
-class _GATAggFn(torch.autograd.Function):
-    """out_i = sum_j softmax_i(leaky_relu(a_l[j] + a_r[i])) x_l[j] + bias."""
-
-    @staticmethod
-    def forward(ctx, plan: GATPlan, slope: float, x_l, a_l, a_r, bias):
-        x_l, a_l, a_r = x_l.contiguous(), a_l.contiguous(), a_r.contiguous()
-        F_ = x_l.shape[1]
-        dev = x_l.device
-        out = torch.empty(plan.n_dst, F_, dtype=torch.float32, device=dev)
-        alpha = torch.empty(max(plan.n_edges, 1), dtype=torch.float32, device=dev)
-        c = plan.csr
-        check(lib().agx_gat_forward(ptr(c.rowptr), ptr(c.col), ptr(c.eid), ptr(a_l), ptr(a_r),
-                                    ptr(x_l), x_l.stride(0), F_, float(slope), ptr(bias), ptr(out),
-                                    out.stride(0), ptr(alpha), plan.n_dst, stream_ptr()),
-              'agx_gat_forward')
-        ctx.plan, ctx.slope, ctx.has_bias = plan, float(slope), bias is not None
-        ctx.save_for_backward(x_l, a_l, a_r, alpha)
-        return out
-
-    @staticmethod
-    def backward(ctx, g):
-        x_l, a_l, a_r, alpha = ctx.saved_tensors
-        plan: GATPlan = ctx.plan
-        g = g.contiguous()
-        F_ = x_l.shape[1]
-        dev = g.device
-        de = torch.empty_like(alpha)
-        da_r = torch.empty(plan.n_dst, dtype=torch.float32, device=dev)
-        c, t = plan.csr, plan.csc
-        check(lib().agx_gat_backward_dst(ptr(c.rowptr), ptr(c.col), ptr(c.eid), ptr(a_l), ptr(a_r),
-                                         ptr(x_l), x_l.stride(0), F_, ctx.slope, ptr(g), g.stride(0),
-                                         ptr(alpha), ptr(de), ptr(da_r), plan.n_dst, stream_ptr()),
-              'agx_gat_backward_dst')
-        dx_l = torch.empty_like(x_l)
-        da_l = torch.empty(plan.n_src, dtype=torch.float32, device=dev)
-        check(lib().agx_gat_backward_src(ptr(t.rowptr), ptr(t.col), ptr(t.eid), ptr(alpha), ptr(de),
-                                         ptr(g), g.stride(0), F_, ptr(dx_l), dx_l.stride(0),
-                                         ptr(da_l), plan.n_src, stream_ptr()),
-              'agx_gat_backward_src')
-        db = None
-        if ctx.has_bias:
-            db = torch.empty(F_, dtype=torch.float32, device=dev)
-            ops.colsum([(g, db, False)])
-        return None, None, dx_l, da_l, da_r, db
+@dataclass
+class GATRelSpec:
+    plan: GATPlan
+    src: str                      # node-type keys (into GATSpec.node_types)
+    dst: str
+    i_wl: int                     # indices into the flat parameter list
+    i_wr: int
+    i_al: int
+    i_ar: int
+    i_b: int                      # -1: no bias
 
 
-def gat_aggregate(plan: GATPlan, x_l, a_l, a_r, bias=None, negative_slope: float = 0.2):
-    return _GATAggFn.apply(plan, negative_slope, x_l, a_l, a_r, bias)
+@dataclass
+class GATSpec:
+    """Static description of one attention layer (all relations) for _HeteroGATFn."""
+    node_types: List[str]
+    rels: List[GATRelSpec]
+    out_channels: int
+    slope: float
+    identity: Dict[str, bool] = field(default_factory=dict)   # type -> x[type] is eye(N)
+    param_refs: Optional[list] = None
 
-
-class _AddFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, a, b):
-        out = torch.empty_like(a)
-        ops.sum_arrays([(out, [a.contiguous(), b.contiguous()])])
-        return out
-
-    @staticmethod
-    def backward(ctx, g):
-        return g, g
-
-
-def add(a, b):
-    """a + b on the agx elementwise kernel (the relation sum of to_hetero)."""
-    return _AddFn.apply(a, b)
-
-
-class _TransposeFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, w):
-        out = torch.empty(w.shape[1], w.shape[0], dtype=torch.float32, device=w.device)
-        ops.transpose_many([(out, w.contiguous())])
-        return out
-
-    @staticmethod
-    def backward(ctx, g):
-        out = torch.empty(g.shape[1], g.shape[0], dtype=torch.float32, device=g.device)
-        ops.transpose_many([(out, g.contiguous())])
+    @property
+    def dst_types(self) -> List[str]:
+        out: List[str] = []
+        for rs in self.rels:
+            if rs.dst not in out:
+                out.append(rs.dst)
         return out
 
 
-def transposed(w):
-    """``w.t()`` materialised by the agx transpose kernel (x = I: x @ w.T = w.T exactly)."""
-    return _TransposeFn.apply(w)
+def _chain_sum(out: torch.Tensor, ins: list, bias: Optional[torch.Tensor] = None):
+    """out = sum(ins) (+ bias rows), at most 8 inputs per descriptor (chained in place)."""
+    while len(ins) > 8:
+        ops.sum_arrays([(out, ins[:8])])
+        ins = [out] + ins[8:]
+    ops.sum_arrays([(out, ins, bias)])
+
+
+class _HeteroGATFn(torch.autograd.Function):
+    """All GATConv relations of one hetero layer (PyG 2.0.2 GATConv inside to_hetero, aggr='sum'):
+
+        x_l = x_src W_l^T;  a_l = x_l att_l;  a_r = x_dst (W_r^T att_r)
+        alpha_ij = softmax_i(leaky_relu(a_l[j] + a_r[i]));  out[t] = sum_{r: dst(r)=t} (sum_j alpha_ij x_l[j] + b_r)
+
+    The dense parts run as two grouped-GEMM waves (``lin_r`` only ever meets ``att_r``, so
+    x_dst W_r^T [N_dst, C] is never formed: a_r is a matrix-vector product with v = W_r^T att_r);
+    the attention softmax of every relation is ONE scalar launch, the weighted neighbour sums of
+    every relation run on the edge-balanced aggregation kernels with per-edge weights."""
+
+    @staticmethod
+    def forward(ctx, spec: GATSpec, *tensors):
+        ctx.set_materialize_grads(False)
+        nt = len(spec.node_types)
+        xs = {t: tensors[i] for i, t in enumerate(spec.node_types)}
+        params = tensors[nt:]
+        for t, x in xs.items():
+            L.require_cuda(x, f'x[{t}]')
+            if x.dtype != torch.float32 or not x.is_contiguous():
+                raise TypeError(f'x[{t}] must be contiguous float32')
+        C_ = spec.out_channels
+        dev = tensors[0].device
+        R = len(spec.rels)
+        f32 = dict(dtype=torch.float32, device=dev)
+
+        # f1: x_l = x_src W_l^T (one-hot sources: W_l^T) and v = att_r W_r
+        gb = ops.GemmBatch()
+        tr: list = []
+        x_l, v = [], []
+        for rs in spec.rels:
+            p = rs.plan
+            y = torch.empty(p.n_src, C_, **f32)
+            x_l.append(y)
+            if spec.identity.get(rs.src, False):
+                tr.append((y, params[rs.i_wl]))
+            else:
+                gb.add(y, [(xs[rs.src], _t(params[rs.i_wl]))])
+            vv = torch.empty(1, params[rs.i_wr].shape[1], **f32)
+            v.append(vv)
+            gb.add(vv, [(params[rs.i_ar].view(1, C_), params[rs.i_wr])])
+        if tr:
+            ops.transpose_many(tr)
+        gb.run()
+        # f2: a_l = x_l att_l, a_r = x_dst v^T (one-hot destinations: v itself)
+        gb = ops.GemmBatch()
+        a_l, a_r = [], []
+        for k, rs in enumerate(spec.rels):
+            p = rs.plan
+            al = torch.empty(p.n_src, 1, **f32)
+            a_l.append(al)
+            gb.add(al, [(x_l[k], params[rs.i_al].view(C_, 1))])
+            if spec.identity.get(rs.dst, False):
+                a_r.append(v[k].view(-1, 1))
+            else:
+                ar = torch.empty(p.n_dst, 1, **f32)
+                a_r.append(ar)
+                gb.add(ar, [(xs[rs.dst], v[k].view(-1, 1))])
+        gb.run()
+        # f3: attention coefficients of every relation, CSR order
+        alpha = [torch.empty(max(rs.plan.n_edges, 1), **f32) for rs in spec.rels]
+        ops.gat_edge_softmax([ops.GatArg(rs.plan.csr, a_l[k].view(-1), a_r[k].view(-1), alpha[k])
+                              for k, rs in enumerate(spec.rels)], spec.slope)
+        # f4: weighted neighbour sums, relation sum and biases per destination type
+        outs: Dict[str, torch.Tensor] = {}
+        rows_waves: Dict[int, list] = {}
+        chunks: list = []
+        finals: list = []
+        bias_sums: list = []
+        for t in spec.dst_types:
+            lst = [(k, rs) for k, rs in enumerate(spec.rels) if rs.dst == t]
+            n_t = lst[0][1].plan.n_dst
+            biases = [params[rs.i_b] for _, rs in lst if rs.i_b >= 0]
+            if not biases:
+                bias = None
+            elif len(biases) == 1:
+                bias = biases[0]
+            else:
+                bias = torch.empty(C_, **f32)
+                bias_sums.append((bias, biases))
+            short = [(k, rs) for k, rs in lst if not rs.plan.csr.long_rows]
+            long_ = [(k, rs) for k, rs in lst if rs.plan.csr.long_rows]
+            out = torch.empty(n_t, C_, **f32)
+            for base in range(0, len(short), L.MAX_REL_PER_GROUP):
+                part = short[base:base + L.MAX_REL_PER_GROUP]
+                rows_waves.setdefault(base // L.MAX_REL_PER_GROUP, []).append(
+                    (out, [ops.RelArg(rs.plan.csr, x_l[k], edge_w=alpha[k]) for k, rs in part],
+                     base > 0, bias if base == 0 else None))
+            temps = []
+            for k, rs in long_:
+                tmp = out if (not short and len(long_) == 1 and bias is None) else \
+                    torch.empty(n_t, C_, **f32)
+                temps.append(tmp)
+                chunks.append((tmp, ops.RelArg(rs.plan.csr, x_l[k], edge_w=alpha[k])))
+            if temps and temps[0] is not out:
+                finals.append((out, ([out] if short else []) + temps, None if short else bias))
+            outs[t] = out
+        for b, items in bias_sums:
+            _chain_sum(b, list(items))
+        for wave in sorted(rows_waves):
+            ops.aggregate_rows(rows_waves[wave], C_)
+        ops.aggregate_chunks(chunks, C_)
+        for out, ins, bias in finals:
+            _chain_sum(out, ins, bias)
+
+        ctx.spec, ctx.nt = spec, nt
+        ctx.save_for_backward(*tensors, *x_l, *v, *a_l, *a_r, *alpha)
+        return tuple(outs[t] for t in spec.dst_types)
+
+    @staticmethod
+    def backward(ctx, *douts):
+        spec: GATSpec = ctx.spec
+        nt = ctx.nt
+        saved = ctx.saved_tensors
+        R = len(spec.rels)
+        n_in = len(saved) - 5 * R
+        tensors = saved[:n_in]
+        x_l, v, a_l, a_r, alpha = (saved[n_in + q * R:n_in + (q + 1) * R] for q in range(5))
+        xs = {t: tensors[i] for i, t in enumerate(spec.node_types)}
+        params = tensors[nt:]
+        C_ = spec.out_channels
+        dev = tensors[0].device
+        f32 = dict(dtype=torch.float32, device=dev)
+        dout: Dict[str, Optional[torch.Tensor]] = {}
+        for t, g in zip(spec.dst_types, douts):
+            dout[t] = None if g is None else g.contiguous()
+        need_x = {t: ctx.needs_input_grad[1 + i] for i, t in enumerate(spec.node_types)}
+        grads: List[Optional[torch.Tensor]] = [None] * len(tensors)
+        pidx = lambda i: nt + i                                            # noqa: E731
+        live = [(k, rs) for k, rs in enumerate(spec.rels) if dout[rs.dst] is not None]
+        if not live:
+            return (None, *grads)
+
+        # b1: bias gradients = column sums of dout, shared by the relations of a type
+        dbias: Dict[str, torch.Tensor] = {}
+        cs_items = []
+        for t in spec.dst_types:
+            if dout[t] is not None and any(rs.i_b >= 0 for _, rs in live if rs.dst == t):
+                dbias[t] = torch.empty(C_, **f32)
+                cs_items.append((dout[t], dbias[t], False))
+        ops.colsum(cs_items)
+        for k, rs in live:
+            if rs.i_b >= 0:
+                grads[pidx(rs.i_b)] = dbias[rs.dst]
+
+        # b2: d alpha_ij = <dout[i], x_l[j]> per CSR slot;  b3: softmax / leaky-relu chain
+        dalpha = {k: torch.empty(max(rs.plan.n_edges, 1), **f32) for k, rs in live}
+        ops.sddmm([(rs.plan.csr_row, rs.plan.csr.col, dout[rs.dst], x_l[k], dalpha[k])
+                   for k, rs in live if rs.plan.n_edges > 0], C_)
+        de = {k: torch.empty(max(rs.plan.n_edges, 1), **f32) for k, rs in live}
+        da_r = {k: torch.empty(rs.plan.n_dst, 1, **f32) for k, rs in live}
+        ops.gat_edge_softmax([ops.GatArg(rs.plan.csr, a_l[k].view(-1), a_r[k].view(-1), alpha[k],
+                                         dalpha=dalpha[k], de=de[k], da_r=da_r[k].view(-1))
+                              for k, rs in live], spec.slope, backward=True)
+
+        # b4: transposes over the CSC: dX_l = sum_i alpha_ij dout[i], da_l[j] = sum_i de_ij
+        dxl = {k: torch.empty(rs.plan.n_src, C_, **f32) for k, rs in live}
+        da_l = {k: torch.empty(rs.plan.n_src, 1, **f32) for k, rs in live}
+        rows_w, chunks_w, rows_1, chunks_1 = [], [], [], []
+        for k, rs in live:
+            p = rs.plan
+            wide = ops.RelArg(p.csc, dout[rs.dst], edge_w=alpha[k], edge_w_idx=p.csc2csr)
+            one = ops.RelArg(p.csc_pos, de[k].view(-1, 1))
+            if p.csc.long_rows:
+                chunks_w.append((dxl[k], wide))
+                chunks_1.append((da_l[k], one))
+            else:
+                rows_w.append((dxl[k], [wide], False))
+                rows_1.append((da_l[k], [one], False))
+        ops.aggregate_rows(rows_w, C_)
+        ops.aggregate_chunks(chunks_w, C_)
+        ops.aggregate_rows(rows_1, 1)
+        ops.aggregate_chunks(chunks_1, 1)
+
+        # b5 (wave A): dX_l += da_l att_l^T;  d att_l = x_l^T da_l;  dv = da_r^T x_dst
+        gb = ops.GemmBatch()
+        dv = {}
+        for k, rs in live:
+            p = rs.plan
+            gb.add(dxl[k], [(da_l[k], params[rs.i_al].view(1, C_))], accumulate=True)
+            datt_l = torch.empty(C_, 1, **f32)
+            gb.add(datt_l, [(_t(x_l[k]), da_l[k])], split_k=ops.split_k_for(p.n_src))
+            grads[pidx(rs.i_al)] = datt_l
+            if spec.identity.get(rs.dst, False):
+                dv[k] = da_r[k].view(1, -1)
+            else:
+                dv[k] = torch.empty(1, xs[rs.dst].shape[1], **f32)
+                gb.add(dv[k], [(_t(da_r[k]), xs[rs.dst])], split_k=ops.split_k_for(p.n_dst))
+        gb.run()
+        # b6 (wave B): weight gradients and input gradients
+        gb = ops.GemmBatch()
+        trb: list = []
+        for k, rs in live:
+            p = rs.plan
+            x = xs[rs.src]
+            dwl = torch.empty(C_, x.shape[1], **f32)
+            grads[pidx(rs.i_wl)] = dwl
+            if spec.identity.get(rs.src, False):
+                trb.append((dwl, dxl[k]))                        # dX_l^T I
+            else:
+                gb.add(dwl, [(_t(dxl[k]), x)], split_k=ops.split_k_for(p.n_src))
+            fd = params[rs.i_wr].shape[1]
+            datt_r = torch.empty(C_, 1, **f32)
+            gb.add(datt_r, [(params[rs.i_wr], dv[k].view(fd, 1))])          # W_r dv^T
+            grads[pidx(rs.i_ar)] = datt_r
+            dwr = torch.empty(C_, fd, **f32)
+            gb.add(dwr, [(params[rs.i_ar].view(C_, 1), dv[k].view(1, fd))])  # att_r dv
+            grads[pidx(rs.i_wr)] = dwr
+        for i, t in enumerate(spec.node_types):
+            if not need_x[t]:
+                continue
+            segs = []
+            for k, rs in live:
+                if rs.src == t:
+                    segs.append((dxl[k], params[rs.i_wl]))                  # dX_l W_l
+                if rs.dst == t:
+                    segs.append((da_r[k], v[k]))                            # da_r v
+            if segs:
+                dx = torch.empty_like(xs[t])
+                grads[i] = dx
+                gb.add(dx, segs)
+        if trb:
+            ops.transpose_many(trb)
+        gb.run()
+        # gradients in the parameters' own shapes (att_l / att_r are [1, 1, C])
+        for i in range(nt, len(tensors)):
+            if grads[i] is not None and grads[i].shape != tensors[i].shape:
+                grads[i] = grads[i].view(tensors[i].shape)
+        _deliver_param_grads(spec.param_refs, grads, nt)
+        return (None, *grads)
+
+
+def hetero_gat(spec: GATSpec, x_list: Sequence[torch.Tensor], params: Sequence[torch.Tensor]):
+    return _HeteroGATFn.apply(spec, *x_list, *params)

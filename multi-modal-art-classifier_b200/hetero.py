@@ -209,25 +209,47 @@ class HeteroModule(nn.Module):
             self._nbt_flat = {key: flat} if len(self._nbt_flat) > 16 else {**self._nbt_flat, key: flat}
         flat += 1
 
-    def _conv_generic(self, node, x_dict, ei_dict):
-        """Operators without a fused hetero layer (GATConv): one call per edge type, relation
-        outputs of a destination type added in metadata order (PyG's pairwise torch.add queue
-        differs only in summation order)."""
+    def _conv_gat(self, node, x_dict, ei_dict, is_input):
+        """GATConv (the reference script's default --operator): every edge type of the layer in ONE
+        fused call (functional._HeteroGATFn); relation outputs of a destination type are added in
+        metadata order (PyG's pairwise torch.add queue differs only in summation order)."""
         convs = self.get_submodule(node.target)
         if self._dist is not None:
             raise NotImplementedError('multi-GPU execution is implemented for SAGEConv / GraphConv')
-        outs: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+        types = [t for t in self.node_types if t in x_dict]
+        dev = x_dict[types[0]].device
+        params: List[torch.Tensor] = []
+        rels = []
+        slope = None
         for et in self.edge_types:
             s, _, d = et
-            o = convs[key2str(et)]((x_dict[s], x_dict[d]), ei_dict[et])
-            outs[d] = o if d not in outs else AF.add(outs[d], o)
-        return outs
+            conv = convs[key2str(et)]
+            wl, wr, al, ar, b = conv.gat_params(x_dict[s].shape[1], x_dict[d].shape[1], dev)
+            plan = AF.GATPlan.get(ei_dict[et], x_dict[s].shape[0], x_dict[d].shape[0],
+                                  conv.add_self_loops)
+            base = len(params)
+            params += [wl, wr, al, ar]
+            i_b = -1
+            if b is not None:
+                i_b = len(params)
+                params.append(b)
+            rels.append(AF.GATRelSpec(plan, s, d, base, base + 1, base + 2, base + 3, i_b))
+            if slope is None:
+                slope = float(conv.negative_slope)
+            elif slope != float(conv.negative_slope):
+                raise NotImplementedError('GATConv: one negative_slope per layer')
+        spec = AF.GATSpec(node_types=types, rels=rels, out_channels=params[0].shape[0], slope=slope,
+                          identity=({t: _is_identity_input(x_dict[t]) for t in types}
+                                    if (is_input and self.detect_identity) else {}),
+                          param_refs=params)
+        outs = AF.hetero_gat(spec, [x_dict[t].contiguous() for t in types], params)
+        return OrderedDict(zip(spec.dst_types, outs))
 
     def _conv(self, node, x_dict, ei_dict, plan, is_input):
         convs = self.get_submodule(node.target)
-        if not hasattr(next(iter(convs.values())), 'rel_params') or \
-                type(next(iter(convs.values()))).__name__ == 'GATConv':
-            return self._conv_generic(node, x_dict, ei_dict)
+        if type(next(iter(convs.values()))).__name__ == 'GATConv':
+            return self._conv_gat(node, x_dict, ei_dict, is_input)
+        plan = plan()
         key = (node.target, id(plan))
         if self._dist is not None and self._dist.halo is not None:
             # boundary rows of the other ranks behind the owned rows (static inputs: once)
@@ -307,8 +329,15 @@ class HeteroModule(nn.Module):
         if self._dist is not None and self._dist.halo is not None:
             num_dst, num_nodes = num_nodes, {t: self._dist.halo.n_ext.get(t, n)
                                              for t, n in num_nodes.items()}
-        plan = get_plan(OrderedDict((et, ei_dict[et]) for et in self.edge_types), num_nodes,
-                        num_dst=num_dst)
+        plan_box: list = []
+
+        def plan():
+            # CSR / CSC of the plain edge lists (SAGEConv / GraphConv); GATConv layers sort their
+            # own self-loop augmented lists (functional.GATPlan) and never ask for this one
+            if not plan_box:
+                plan_box.append(get_plan(OrderedDict((et, ei_dict[et]) for et in self.edge_types),
+                                         num_nodes, num_dst=num_dst))
+            return plan_box[0]
         env = {self._placeholders[0]: x_dict, self._placeholders[1]: ei_dict}
         provided = {}
 

@@ -238,22 +238,29 @@ class GATConv(MessagePassing):
         if self.bias is not None:
             nn.init.zeros_(self.bias)
 
+    def gat_params(self, f_src: int, f_dst: int, device):
+        """(W_l, W_r, att_l, att_r, bias or None) with lazy sizes resolved."""
+        self.lin_l.materialize(f_src, device)
+        self.lin_r.materialize(f_dst, device)
+        return self.lin_l.weight, self.lin_r.weight, self.att_l, self.att_r, self.bias
+
     def forward(self, x, edge_index: torch.Tensor, size=None) -> torch.Tensor:
         if torch.is_tensor(x):
             x = (x, x)
         x_src, x_dst = x
-        self.lin_l.materialize(x_src.shape[1], x_src.device)
-        self.lin_r.materialize(x_dst.shape[1], x_dst.device)
-        C_ = self.out_channels
+        same = x_src is x_dst
         plan = AF.GATPlan.get(edge_index, x_src.shape[0], x_dst.shape[0], self.add_self_loops)
+        params = [p for p in self.gat_params(x_src.shape[1], x_dst.shape[1], x_src.device)
+                  if p is not None]
         from .hetero import _is_identity_input          # one-hot node features: I W^T = W^T
-
-        def lin(x_in, w):
-            if not x_in.requires_grad and _is_identity_input(x_in):
-                return AF.transposed(w)
-            return AF.fused_linear([x_in], w)
-        x_l = lin(x_src, self.lin_l.weight)
-        x_r = lin(x_dst, self.lin_r.weight)
-        a_l = AF.fused_linear([x_l], self.att_l.view(1, C_)).view(-1)
-        a_r = AF.fused_linear([x_r], self.att_r.view(1, C_)).view(-1)
-        return AF.gat_aggregate(plan, x_l, a_l, a_r, self.bias, self.negative_slope)
+        types = ['s'] if same else ['s', 'd']
+        xs = [x_src.contiguous()] if same else [x_src.contiguous(), x_dst.contiguous()]
+        spec = AF.GATSpec(
+            node_types=types,
+            rels=[AF.GATRelSpec(plan, 's', 's' if same else 'd', 0, 1, 2, 3,
+                                4 if self.bias is not None else -1)],
+            out_channels=self.out_channels, slope=float(self.negative_slope),
+            identity={t: (not xt.requires_grad) and _is_identity_input(xt)
+                      for t, xt in zip(types, xs)})
+        (out,) = AF.hetero_gat(spec, xs, params)
+        return out

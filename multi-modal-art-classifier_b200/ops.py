@@ -199,6 +199,8 @@ class RelArg:
     x: torch.Tensor
     mean_rows: bool = False          # divide by the row's own count (forward scatter-mean)
     nbr_scale: Optional[torch.Tensor] = None   # per-neighbour counts (transpose of scatter-mean)
+    edge_w: Optional[torch.Tensor] = None      # per-slot weights (GATConv attention coefficients)
+    edge_w_idx: Optional[torch.Tensor] = None  # int32: slot e uses edge_w[edge_w_idx[e]]
 
 
 def _dtype_code(t: torch.Tensor) -> int:
@@ -212,18 +214,24 @@ def _dtype_code(t: torch.Tensor) -> int:
 def _rel_struct(a: RelArg) -> L.Rel:
     if a.x.stride(-1) != 1:
         raise ValueError('feature rows must be contiguous')
+    if a.edge_w is not None and (a.edge_w.dtype != torch.float32 or not a.edge_w.is_contiguous()):
+        raise TypeError('edge_w must be contiguous float32')
+    if a.edge_w_idx is not None and (a.edge_w_idx.dtype != torch.int32 or
+                                     not a.edge_w_idx.is_contiguous()):
+        raise TypeError('edge_w_idx must be contiguous int32')
     return L.Rel(ptr(a.csr.rowptr), ptr(a.csr.col), ptr(a.x), a.x.stride(0),
-                 ptr(a.csr.cnt) if a.mean_rows else None, ptr(a.nbr_scale))
+                 ptr(a.csr.cnt) if a.mean_rows else None, ptr(a.nbr_scale), ptr(a.edge_w),
+                 ptr(a.edge_w_idx))
 
 
-def aggregate_rows(groups: Sequence[Tuple[torch.Tensor, Sequence[RelArg], bool]], F: int):
-    """``groups``: (out [n_rows, F], relations, accumulate).  One launch per <=24 groups; each output
-    row is the sum over the group's relations of the (scaled) neighbour sums."""
+def aggregate_rows(groups: Sequence[tuple], F: int):
+    """``groups``: (out [n_rows, F], relations, accumulate[, bias [F]]).  One launch per <=24 groups;
+    each output row is the sum over the group's relations of the (scaled) neighbour sums."""
     if not groups:
         return
     dt = _dtype_code(groups[0][0])
     if _DEBUG:
-        for out, rels, acc in groups:
+        for out, rels, acc, *_ in groups:
             print(f'[agx] agg_rows F={F} rows={out.shape[0]} acc={acc} rels=' + ', '.join(
                 f'(E={a.csr.n_edges} avg={a.csr.avg_degree:.1f} max={a.csr.max_degree} '
                 f'mean={a.mean_rows} scale={a.nbr_scale is not None} x={tuple(a.x.shape)})'
@@ -231,21 +239,26 @@ def aggregate_rows(groups: Sequence[Tuple[torch.Tensor, Sequence[RelArg], bool]]
     for base in range(0, len(groups), L.MAX_GROUPS):
         part = groups[base:base + L.MAX_GROUPS]
         arr = (L.RowGroup * len(part))()
-        for i, (out, rels, acc) in enumerate(part):
+        for i, (out, rels, acc, *rest) in enumerate(part):
             if len(rels) > L.MAX_REL_PER_GROUP:
                 raise ValueError('more than 8 relations in one aggregation group')
             g = arr[i]
             g.out, g.ldo, g.n_rows, g.n_rel, g.accumulate = ptr(out), out.stride(0), out.shape[0], \
                 len(rels), int(acc)
+            if rest and rest[0] is not None:
+                if rest[0].dtype != torch.float32 or rest[0].numel() != F or \
+                        not rest[0].is_contiguous():
+                    raise ValueError('row-group bias must be contiguous float32 [F]')
+                g.bias = ptr(rest[0])
             for j, a in enumerate(rels):
                 g.rel[j] = _rel_struct(a)
         t0 = TIMER.begin() if TIMER is not None else None
         check(lib().agx_aggregate_rows(arr, len(part), F, dt, stream_ptr()), 'agx_aggregate_rows')
         if TIMER is not None:
             esz = 4 if dt == L.F32 else 2
-            nb = sum(aggregation_bytes(a.csr.n_edges, 0, F, esz) + (out.shape[0] + 1) * 4
-                     for out, rels, _ in part for a in rels)
-            nb += sum(out.shape[0] * F * esz for out, _, _ in part)
+            nb = sum(aggregation_bytes(a.csr.n_edges, 0, F, esz) + (g_[0].shape[0] + 1) * 4
+                     for g_ in part for a in g_[1])
+            nb += sum(g_[0].shape[0] * F * esz for g_ in part)
             TIMER.end('agg_rows', nb, 0, t0)
 
 
@@ -308,6 +321,59 @@ def aggregate(out: torch.Tensor, rel: RelArg, F: int):
         aggregate_chunks([(out, rel)], F)
     else:
         aggregate_rows([(out, [rel], False)], F)
+
+
+# ------------------------------------------------------------------------------------------------
+# GATConv scalar passes (agx_gat.cu)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class GatArg:
+    """One relation of an attention layer; per-edge arrays in CSR order."""
+    csr: CSR
+    a_l: torch.Tensor                # [n_src]
+    a_r: torch.Tensor                # [n_dst]
+    alpha: torch.Tensor              # [n_edges]
+    dalpha: Optional[torch.Tensor] = None
+    de: Optional[torch.Tensor] = None
+    da_r: Optional[torch.Tensor] = None
+
+
+def gat_edge_softmax(rels: Sequence[GatArg], slope: float, backward: bool = False):
+    """alpha = softmax over each destination row of leaky_relu(a_l[src] + a_r[dst]) (forward), or
+    de / da_r from alpha and dalpha (backward); <= 24 relations per launch."""
+    fn = lib().agx_gat_edge_softmax_bwd if backward else lib().agx_gat_edge_softmax
+    what = 'agx_gat_edge_softmax_bwd' if backward else 'agx_gat_edge_softmax'
+    for base in range(0, len(rels), L.MAX_GAT_RELS):
+        part = rels[base:base + L.MAX_GAT_RELS]
+        arr = (L.GatRel * len(part))()
+        for i, a in enumerate(part):
+            for t in (a.a_l, a.a_r, a.alpha, a.dalpha, a.de, a.da_r):
+                if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+                    raise TypeError('attention arrays must be contiguous float32')
+            if a.a_r.numel() != a.csr.n_rows or a.a_l.numel() != a.csr.n_cols or \
+                    a.alpha.numel() < a.csr.n_edges:
+                raise ValueError('attention array sizes do not match the CSR')
+            arr[i] = L.GatRel(ptr(a.csr.rowptr), ptr(a.csr.col), ptr(a.a_l), ptr(a.a_r),
+                              ptr(a.alpha), ptr(a.dalpha), ptr(a.de), ptr(a.da_r), a.csr.n_rows, 0)
+        check(fn(arr, len(part), float(slope), stream_ptr()), what)
+
+
+def sddmm(segs: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]],
+          F: int):
+    """``segs``: (row int32 [E], col int32 [E], a [*, F], b [*, F], out [E]):
+    out[e] = <a[row[e]], b[col[e]]>; <= 24 segments per launch."""
+    for base in range(0, len(segs), L.MAX_SDDMM_SEGS):
+        part = segs[base:base + L.MAX_SDDMM_SEGS]
+        arr = (L.SddmmSeg * len(part))()
+        for i, (row, col, a, b, out) in enumerate(part):
+            if a.stride(-1) != 1 or b.stride(-1) != 1 or a.shape[1] != F or b.shape[1] != F:
+                raise ValueError('sddmm operands must be [*, F] with contiguous rows')
+            if row.dtype != torch.int32 or col.dtype != torch.int32 or row.numel() != col.numel() \
+                    or out.numel() < row.numel():
+                raise ValueError('sddmm index arrays must be int32 of equal length')
+            arr[i] = L.SddmmSeg(ptr(row), ptr(col), ptr(a), a.stride(0), ptr(b), b.stride(0),
+                                ptr(out), row.numel(), 0)
+        check(lib().agx_sddmm(arr, len(part), F, stream_ptr()), 'agx_sddmm')
 
 
 # ------------------------------------------------------------------------------------------------
@@ -454,14 +520,21 @@ def split_k_for(k_rows: int, slab: int = 384, max_split: int = 512) -> int:
 # ------------------------------------------------------------------------------------------------
 # small batched ops
 # ------------------------------------------------------------------------------------------------
-def sum_arrays(items: Sequence[Tuple[torch.Tensor, Sequence[torch.Tensor]]]):
-    """``items``: (out, [in_0..in_k]) -- out = sum of inputs (same numel, contiguous)."""
+def sum_arrays(items: Sequence[tuple]):
+    """``items``: (out, [in_0..in_k][, bias]) -- out = sum of inputs (same numel, contiguous)
+    (+ bias [F] broadcast over the rows of out [*, F])."""
     for base in range(0, len(items), L.MAX_TENSORS):
         part = items[base:base + L.MAX_TENSORS]
         arr = (L.SumDesc * len(part))()
-        for i, (out, ins) in enumerate(part):
+        for i, (out, ins, *rest) in enumerate(part):
             d = arr[i]
             d.out, d.n_in, d.numel = ptr(out), len(ins), out.numel()
+            if rest and rest[0] is not None:
+                b = rest[0]
+                if b.dtype != torch.float32 or not b.is_contiguous() or out.dim() != 2 or \
+                        b.numel() != out.shape[1] or not out.is_contiguous():
+                    raise ValueError('sum_arrays bias must be contiguous float32 [out.shape[1]]')
+                d.bias, d.bias_F = ptr(b), b.numel()
             for k, t in enumerate(ins):
                 if not t.is_contiguous() or t.numel() != out.numel():
                     raise ValueError('sum_arrays needs contiguous equally sized tensors')

@@ -122,7 +122,7 @@ class GNNTrainer:
         """``hetero_training()``: returns the (device) loss of this step."""
         self._lazy_init()
         self.model.train()
-        if not self.use_cuda_graph:
+        if not self.use_cuda_graph or getattr(self, '_eager_only', False):
             self._loss, self._emb, self._out = self._step_eager()
             return self._loss
         if self._graph is None:
@@ -207,7 +207,15 @@ class GNNTrainer:
         if self.ctx is not None and self.ctx.halo is not None:
             num_dst, num_nodes = num_nodes, {t: self.ctx.halo.n_ext.get(t, n)
                                              for t, n in num_nodes.items()}
-        self._plan = get_plan(self.ei, num_nodes, num_dst=num_dst)   # version bump -> re-sort
+        if any(type(m).__name__ == 'GATConv' for m in self.model.modules()):
+            # GATConv sorts self-loop augmented edge lists whose LENGTH depends on the data
+            # (functional.GATPlan): no in-place re-sort under a captured step; steps that follow an
+            # input update re-plan and run eagerly
+            self._graph = None
+            self._plan = None
+            self._eager_only = True
+        else:
+            self._plan = get_plan(self.ei, num_nodes, num_dst=num_dst)   # version bump -> re-sort
         if self.ctx is not None and self.ctx.halo is not None:
             self.ctx.halo.refresh(self.x)
         self._id_flags = {}

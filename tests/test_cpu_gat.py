@@ -1,0 +1,149 @@
+"""CPU suite, part 4: host-side logic of the fused GATConv layer (functional._HeteroGATFn): which
+buffers meet which index arrays, the gradient formulas and the GEMM wave order, checked against
+the oracle with the ``ops`` entry points restated in torch (tests/cpu_shim.py).  The kernels
+themselves are compared with the oracle on the GPU (tests/test_gpu_model.py, test_gpu_kernels.py)."""
+from collections import OrderedDict
+
+import pytest
+import torch
+
+import util
+import mmac_b200 as agx
+from cpu_shim import cpu_ops
+from oracle import graph_oracle as go
+from util import rel_err
+
+
+def _pair(C, xs, xd, ei, same):
+    orc = go.GATConv((-1, -1), C)
+    with torch.no_grad():
+        orc(xs if same else (xs, xd), ei)
+    util.fill_params_deterministic(orc)
+    with torch.no_grad():
+        orc.bias.copy_(torch.linspace(-0.3, 0.4, C))
+    prod = agx.GATConv((-1, -1), C)
+    util.copy_state(orc, prod)
+    return orc.double(), prod
+
+
+CASES = [  # n_src, n_dst, edges, F_src, F_dst, C, same tensor, hub
+    (70, 50, 400, 24, 40, 32, False, False),
+    (60, 60, 300, 16, 16, 128, True, False),
+    (9, 300, 500, 8, 12, 18, False, False),
+    (400, 6, 5000, 12, 10, 32, False, True),       # rows of ~800 edges, one of > 1024
+]
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_gatconv_host_logic_vs_oracle(case):
+    n_src, n_dst, e, fs, fd, C, same, hub = case
+    gen = torch.Generator().manual_seed(21)
+    src = torch.randint(0, n_src, (e,), generator=gen)
+    dst = torch.randint(0, n_dst, (e,), generator=gen)
+    if hub:
+        dst[: e // 2] = 2
+    dst[:5] = src[:5] % n_dst
+    ei = torch.stack([src, dst])
+    xs = torch.randn(n_src, fs, generator=gen)
+    xd = xs if same else torch.randn(n_dst, fd, generator=gen)
+    orc, prod = _pair(C, xs, xd, ei, same)
+    xs_o = xs.double().requires_grad_(True)
+    xd_o = xs_o if same else xd.double().requires_grad_(True)
+    xs_p = xs.clone().requires_grad_(True)
+    xd_p = xs_p if same else xd.clone().requires_grad_(True)
+    w = torch.randn(n_dst, C, generator=gen)
+    out_o = orc(xs_o if same else (xs_o, xd_o), ei)
+    (out_o * w.double()).sum().backward()
+    with cpu_ops():
+        agx.functional.GATPlan._cache.clear()
+        out_p = prod(xs_p if same else (xs_p, xd_p), ei)
+        (out_p * w).sum().backward()
+    assert rel_err(out_p, out_o) <= 1e-5
+    assert rel_err(xs_p.grad, xs_o.grad) <= 5e-5
+    if not same:
+        assert rel_err(xd_p.grad, xd_o.grad) <= 5e-5
+    po, pp = dict(orc.named_parameters()), dict(prod.named_parameters())
+    for k in po:
+        assert pp[k].grad.shape == pp[k].shape
+        assert rel_err(pp[k].grad, po[k].grad) <= 5e-5, k
+
+
+class _OneConv(torch.nn.Module):
+    def __init__(self, op, C):
+        super().__init__()
+        self.conv = op((-1, -1), C)
+
+    def forward(self, x, edge_index):
+        return self.conv(x, edge_index)
+
+
+def test_hetero_gat_layer_host_logic_vs_oracle():
+    """Three node types (one with one-hot features), five relations: two destinations with several
+    incoming relations (short rows, hub rows, both), a homogeneous relation, a type that is only a
+    source.  Outputs and all gradients against the oracle's per-relation GATConv + relation sum."""
+    gen = torch.Generator().manual_seed(5)
+    n = {'a': 300, 'b': 7, 'c': 40}
+    feats = {'a': torch.randn(300, 20, generator=gen), 'b': torch.eye(7),
+             'c': torch.randn(40, 12, generator=gen)}
+    C = 16
+
+    def edges(ns, nd, e, hub=None):
+        s = torch.randint(0, ns, (e,), generator=gen)
+        d = torch.randint(0, nd, (e,), generator=gen)
+        if hub is not None:
+            d[: e // 2] = hub
+        return torch.stack([s, d])
+    ei = OrderedDict([
+        (('a', 'r1', 'b'), edges(300, 7, 3000, hub=3)),     # hub rows (avg 430, one > 1024)
+        (('c', 'r2', 'b'), edges(40, 7, 30)),               # short rows into the same type
+        (('b', 'r3', 'a'), edges(7, 300, 500)),             # hub SOURCES (transpose is long)
+        (('c', 'r4', 'a'), edges(40, 300, 600)),
+        (('a', 'r5', 'a'), edges(300, 300, 900)),           # homogeneous
+    ])
+    md = (list(n.keys()), list(ei.keys()))
+    convs_o = torch.nn.ModuleDict()
+    for (s, r, d) in ei:
+        cv = go.GATConv((-1, -1), C)
+        with torch.no_grad():
+            cv((feats[s], feats[d]), ei[(s, r, d)])
+        convs_o['__'.join((s, r, d))] = cv
+    util.fill_params_deterministic(convs_o)
+    with torch.no_grad():
+        for i, cv in enumerate(convs_o.values()):
+            cv.bias.copy_(torch.linspace(-0.2, 0.3, C) * (i + 1))
+    prod = agx.to_hetero(_OneConv(agx.GATConv, C), md, aggr='sum')
+    util.copy_state(convs_o, prod.conv)
+    convs_o = convs_o.double()
+    x_o = {t: v.double().requires_grad_(t != 'b') for t, v in feats.items()}
+    x_p = {t: v.clone().requires_grad_(t != 'b') for t, v in feats.items()}
+    outs_o = {}
+    for (s, r, d), e in ei.items():
+        o = convs_o['__'.join((s, r, d))]((x_o[s], x_o[d]), e)
+        outs_o[d] = o if d not in outs_o else outs_o[d] + o
+    w = {t: torch.randn(n[t], C, generator=gen) for t in outs_o}
+    sum((outs_o[t] * w[t].double()).sum() for t in outs_o).backward()
+    with cpu_ops():
+        agx.functional.GATPlan._cache.clear()
+        outs_p = prod(x_p, ei)
+        assert list(outs_p.keys()) == list(outs_o.keys())
+        sum((outs_p[t] * w[t]).sum() for t in outs_p).backward()
+    for t in outs_o:
+        assert rel_err(outs_p[t], outs_o[t]) <= 1e-5, t
+    for t in ('a', 'c'):
+        assert rel_err(x_p[t].grad, x_o[t].grad) <= 5e-5, t
+    po, pp = dict(convs_o.named_parameters()), dict(prod.conv.named_parameters())
+    assert set(po) == set(pp)
+    gmax = max(float(p.grad.abs().max()) for p in po.values())
+    for k in po:
+        err = float((pp[k].grad.double() - po[k].grad).abs().max())
+        assert err <= 5e-5 * float(po[k].grad.abs().max()) or err <= 1e-7 * gmax, k
+
+    # only some destination types receive a gradient (conv_out: only 'artwork' feeds the loss)
+    for p in pp.values():
+        p.grad = None
+    with cpu_ops():
+        outs_p = prod(x_p, ei)
+        (outs_p['b'] * w['b']).sum().backward()
+    for k, p in pp.items():
+        live = k.split('.')[0].endswith('__b')
+        assert (p.grad is not None) == live, k

@@ -45,10 +45,12 @@ def test_ctypes_structs_match_c_layout():
              'agx_chunk_seg_t': L.ChunkSeg, 'agx_gemm_seg_t': L.GemmSeg,
              'agx_gemm_problem_t': L.GemmProblem, 'agx_sum_desc_t': L.SumDesc,
              'agx_bn_desc_t': L.BnDesc, 'agx_bn_bwd_desc_t': L.BnBwdDesc,
-             'agx_colsum_desc_t': L.ColsumDesc}
+             'agx_colsum_desc_t': L.ColsumDesc, 'agx_gat_rel_t': L.GatRel,
+             'agx_sddmm_seg_t': L.SddmmSeg}
     body = '\n'.join(f'printf("{n} %zu\\n", sizeof({n}));' for n in names)
     consts = ['AGX_MAX_CSR_RELS', 'AGX_MAX_REL_PER_GROUP', 'AGX_MAX_GROUPS', 'AGX_MAX_CHUNK_SEGS',
-              'AGX_CHUNK_EDGES', 'AGX_MAX_GEMM_PROBLEMS', 'AGX_MAX_GEMM_SEGS', 'AGX_MAX_TENSORS']
+              'AGX_CHUNK_EDGES', 'AGX_MAX_GEMM_PROBLEMS', 'AGX_MAX_GEMM_SEGS', 'AGX_MAX_TENSORS',
+              'AGX_MAX_GAT_RELS', 'AGX_MAX_SDDMM_SEGS', 'AGX_GAT_LONG_ROW']
     body += '\n' + '\n'.join(f'printf("{c} %d\\n", (int){c});' for c in consts)
     with tempfile.TemporaryDirectory() as d:
         src = os.path.join(d, 't.c')
@@ -67,6 +69,9 @@ def test_ctypes_structs_match_c_layout():
     assert int(out['AGX_MAX_GEMM_PROBLEMS']) == L.MAX_GEMM_PROBLEMS
     assert int(out['AGX_MAX_GEMM_SEGS']) == L.MAX_GEMM_SEGS
     assert int(out['AGX_MAX_TENSORS']) == L.MAX_TENSORS
+    assert int(out['AGX_MAX_GAT_RELS']) == L.MAX_GAT_RELS
+    assert int(out['AGX_MAX_SDDMM_SEGS']) == L.MAX_SDDMM_SEGS
+    assert int(out['AGX_GAT_LONG_ROW']) == L.GAT_LONG_ROW
 
 
 def test_invalid_arguments_return_error_codes_not_crashes():
@@ -77,6 +82,9 @@ def test_invalid_arguments_return_error_codes_not_crashes():
     assert lib.agx_csr_build(None, 0, None, None, None, None, None, None, 0, None) == -1
     assert lib.agx_adam_step(None, None, None, None, 10, 0.1, 0.9, 0.999, 1e-8, 0.0, None, None) == -1
     assert lib.agx_csr_workspace_bytes(1000, 10) > 4 * 4 * 1000
+    assert lib.agx_gat_edge_softmax(None, 0, 0.2, None) == -1
+    assert lib.agx_gat_edge_softmax_bwd(None, 1, 0.2, None) == -1
+    assert lib.agx_sddmm(None, 1, 128, None) == -1
 
 
 def test_product_model_has_reference_state_dict_layout():

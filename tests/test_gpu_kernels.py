@@ -503,3 +503,118 @@ def test_gather_pack_unpack():
     ref = table.clone()
     ref[uniq.long()] *= 2
     assert torch.equal(acc.cpu(), ref)
+
+
+# ---------------------------------------------------------------- GATConv kernels (agx_gat.cu)
+def _cpu_csr(c):
+    """Host copy of a device CSR (the torch restatements in cpu_shim.py work on CPU tensors)."""
+    return ops.CSR(c.rowptr.cpu(), c.col.cpu(), c.eid.cpu(), c.cnt.cpu(), c.n_rows, c.n_cols,
+                   c.n_edges, c.max_degree)
+
+
+def _skewed_rel(gen, n_src, n_dst, e, hubs):
+    """Random edges; ``hubs``: {row: edges} rows that receive that many extra edges; the last two
+    rows stay empty."""
+    src = [torch.randint(0, n_src, (e,), generator=gen)]
+    dst = [torch.randint(0, max(n_dst - 2, 1), (e,), generator=gen)]
+    for row, k in hubs.items():
+        src.append(torch.randint(0, n_src, (k,), generator=gen))
+        dst.append(torch.full((k,), row, dtype=torch.int64))
+    ei = torch.stack([torch.cat(src), torch.cat(dst)])
+    return ei[:, torch.randperm(ei.shape[1], generator=gen)]
+
+
+def test_gat_edge_softmax_and_backward_hub_rows():
+    """Rows of 0, a few, ~1000 and > AGX_GAT_LONG_ROW edges (warp and whole-CTA paths), two
+    relations in one launch; forward and backward against the torch restatement."""
+    import cpu_shim
+    gen = torch.Generator().manual_seed(3)
+    rels = [_skewed_rel(gen, 500, 40, 600, {1: 1000, 7: 1500, 8: 5000, 30: 1025}),
+            _skewed_rel(gen, 64, 9, 50, {0: 3000})]
+    sizes = [(500, 40), (64, 9)]
+    csrs = ops.csr_build([(ei[1].to(DEV), ei[0].to(DEV), nd, ns) for ei, (ns, nd) in zip(rels, sizes)])
+    dev_args, cpu_args = [], []
+    for c, (ns, nd) in zip(csrs, sizes):
+        a_l, a_r = torch.randn(ns, generator=gen) * 2, torch.randn(nd, generator=gen) * 2
+        dal = torch.randn(c.n_edges, generator=gen)
+        mk = lambda n: torch.empty(n, dtype=torch.float32, device=DEV)            # noqa: E731
+        dev_args.append(ops.GatArg(c, a_l.to(DEV), a_r.to(DEV), mk(c.n_edges), dal.to(DEV),
+                                   mk(c.n_edges), mk(nd)))
+        z = lambda n: torch.zeros(n)                                              # noqa: E731
+        cpu_args.append(ops.GatArg(_cpu_csr(c), a_l, a_r, z(c.n_edges), dal, z(c.n_edges), z(nd)))
+    ops.gat_edge_softmax(dev_args, 0.2)
+    cpu_shim._gat_edge_softmax(cpu_args, 0.2)
+    for d, h in zip(dev_args, cpu_args):
+        assert rel_err(d.alpha, h.alpha) <= RTOL_F32
+        rows = cpu_shim._rows_of(h.csr)
+        sums = torch.zeros(h.csr.n_rows, dtype=torch.float64).index_add_(0, rows, d.alpha.cpu().double())
+        deg = (h.csr.rowptr[1:] - h.csr.rowptr[:-1])
+        assert float((sums[deg > 0] - 1).abs().max()) <= 1e-5         # every row sums to one
+        h.alpha.copy_(d.alpha.cpu())                 # same coefficients into the backward check
+    ops.gat_edge_softmax(dev_args, 0.2, backward=True)
+    cpu_shim._gat_edge_softmax(cpu_args, 0.2, backward=True)
+    for d, h in zip(dev_args, cpu_args):
+        assert rel_err(d.de, h.de) <= 2e-5
+        assert float((d.da_r.cpu() - h.da_r).abs().max()) <= 2e-5 * float(h.de.abs().max()) * 10
+    # reproducible: a second launch gives the same bits
+    a0 = dev_args[0].alpha.clone()
+    ops.gat_edge_softmax(dev_args, 0.2)
+    assert torch.equal(a0, dev_args[0].alpha)
+
+
+@pytest.mark.parametrize('F', [128, 32, 18, 64, 200])
+def test_sddmm_matches_torch(F):
+    gen = torch.Generator().manual_seed(F)
+    segs_d, refs = [], []
+    for (na, nb, e) in ((30, 500, 4000), (7, 9, 33), (5, 5, 0)):
+        row = torch.randint(0, na, (e,), generator=gen).to(torch.int32)
+        col = torch.randint(0, nb, (e,), generator=gen).to(torch.int32)
+        a, b = torch.randn(na, F, generator=gen), torch.randn(nb, F, generator=gen)
+        out = torch.full((max(e, 1),), 7.0, device=DEV)
+        segs_d.append((row.to(DEV), col.to(DEV), a.to(DEV), b.to(DEV), out))
+        refs.append((a.double()[row.long()] * b.double()[col.long()]).sum(1))
+    ops.sddmm([s for s in segs_d if s[0].numel() > 0], F)
+    for s, ref in zip(segs_d, refs):
+        if ref.numel():
+            assert rel_err(s[4][:ref.numel()], ref) <= RTOL_F32
+
+
+@pytest.mark.parametrize('F', [128, 32, 18, 1])
+def test_weighted_aggregation_rows_and_chunks(F):
+    """Per-edge weights (directly and through an index array), the row-group bias, and the
+    one-column aggregation used for the attention logit gradients."""
+    import cpu_shim
+    gen = torch.Generator().manual_seed(40 + F)
+    n_src, n_dst = 300, 50
+    ei = _skewed_rel(gen, n_src, n_dst, 400, {3: 700, 9: 2000})
+    (csr,) = ops.csr_build([(ei[1].to(DEV), ei[0].to(DEV), n_dst, n_src)])
+    E = csr.n_edges
+    x = torch.randn(n_src, F, generator=gen)
+    w = torch.rand(E, generator=gen)
+    perm = torch.randperm(E, generator=gen).to(torch.int32)
+    bias = torch.randn(F, generator=gen)
+    h = _cpu_csr(csr)
+    for idx in (None, perm):
+        ref = cpu_shim._rel_sum(ops.RelArg(h, x, edge_w=w, edge_w_idx=idx), n_dst, F)
+        arg = ops.RelArg(csr, x.to(DEV), edge_w=w.to(DEV),
+                         edge_w_idx=None if idx is None else idx.to(DEV))
+        out = torch.full((n_dst, F), 5.0, device=DEV)
+        ops.aggregate_chunks([(out, arg)], F)
+        assert rel_err(out, ref) <= RTOL_F32
+        out2 = torch.full((n_dst, F), 5.0, device=DEV)
+        ops.aggregate_rows([(out2, [arg], False, bias.to(DEV))], F)
+        assert rel_err(out2, ref + bias.double()) <= RTOL_F32
+        out3 = torch.ones(n_dst, F, device=DEV)
+        ops.aggregate_rows([(out3, [arg, arg], True)], F)
+        assert rel_err(out3, 2 * ref + 1) <= RTOL_F32
+
+
+def test_sum_arrays_with_row_bias():
+    a, b = torch.randn(37, 24), torch.randn(37, 24)
+    bias = torch.randn(24)
+    out = torch.empty(37, 24, device=DEV)
+    ops.sum_arrays([(out, [a.to(DEV), b.to(DEV)], bias.to(DEV)), ])
+    assert torch.equal(out.cpu(), (a + b) + bias)
+    out2 = torch.empty(37, 24, device=DEV)
+    ops.sum_arrays([(out2, [a.to(DEV)], bias.to(DEV)), (out, [a.to(DEV), b.to(DEV)])])
+    assert torch.equal(out2.cpu(), a + bias) and torch.equal(out.cpu(), a + b)
