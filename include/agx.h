@@ -334,8 +334,9 @@ typedef struct {
 } agx_gat_rel_t;
 
 /* alpha_ij = softmax_i(leaky_relu(a_l[j] + a_r[i])) per destination row, for up to 24 relations in
- * ONE launch.  A warp per row; rows with more than AGX_GAT_LONG_ROW edges (artwork -> style /
- * genre / tag hubs) by the whole CTA.  Fixed reduction order: reproducible. */
+ * ONE launch.  Eight lanes per row of up to 8 edges, a warp per row up to AGX_GAT_LONG_ROW edges,
+ * longer rows (artwork -> style / genre / tag hubs) by the whole CTA.  Fixed reduction order:
+ * reproducible. */
 int agx_gat_edge_softmax(const agx_gat_rel_t* h_rels, int n_rels, float slope, void* stream);
 /* de_ij = alpha_ij (dalpha_ij - sum_j alpha_ij dalpha_ij) leaky_relu'(a_l[j] + a_r[i]);
  * da_r[i] = sum_j de_ij */

@@ -9,8 +9,9 @@
 // lets one warp walk a row of feature vectors:
 //
 //   scalar passes (this file, 4-12 B per edge)
-//     gat_edge_softmax      alpha per CSR slot; a warp per row, rows longer than AGX_GAT_LONG_ROW by
-//                           the whole CTA (three strided passes over the row, values parked in alpha)
+//     gat_edge_softmax      alpha per CSR slot; 8 lanes per row up to 8 edges, a warp per row up to
+//                           AGX_GAT_LONG_ROW, longer rows by the whole CTA (three strided passes
+//                           over the row, values parked in alpha)
 //     gat_edge_softmax_bwd  de_ij = alpha_ij (dalpha_ij - sum_j alpha_ij dalpha_ij) leaky'(.),
 //                           da_r[i] = sum_j de_ij, same row mapping
 //     sddmm                 dalpha_ij = <dout[i], x_l[j]>, a warp per 32 CSR slots (edge-balanced)
@@ -30,7 +31,7 @@ constexpr int kGatWarps = kGatThreads / 32;
 
 struct GatRels {
     agx_gat_rel_t r[AGX_MAX_GAT_RELS];
-    int32_t blk_start[AGX_MAX_GAT_RELS + 1];       // CTA -> relation (8 rows per CTA)
+    int32_t blk_start[AGX_MAX_GAT_RELS + 1];       // CTA -> relation (32 rows per CTA)
     int32_t n;
     float slope;
 };
@@ -104,33 +105,91 @@ __device__ __forceinline__ void softmax_bwd_row(const agx_gat_rel_t& R, int row,
     if (t == 0) R.da_r[row] = d;
 }
 
+// A row of at most NL (8 or 32) edges by NL lanes, one edge per lane, everything in registers:
+// three dependent memory round trips (row extent, source id, logit) instead of the nine of the
+// strided three-pass walk -- rows of 1..8 edges are >95% of ArtGraph's destination rows and their
+// cost is latency, not bandwidth.  Every lane of the warp calls this (shuffles); `row_ok` = the
+// lane's row exists and has <= NL edges, `sl` = lane index inside its group of NL.
+template <int NL, bool BWD>
+__device__ __forceinline__ void softmax_small(const agx_gat_rel_t& R, int row, int beg, int deg,
+                                              bool row_ok, int sl, float slope) {
+    const bool act = row_ok && sl < deg;
+    const int e = beg + sl;
+    const float ar = row_ok ? __ldg(R.a_r + row) : 0.f;
+    const int c = act ? __ldg(R.col + e) : 0;
+    const float raw = act ? __ldg(R.a_l + c) + ar : 0.f;
+    if constexpr (!BWD) {
+        const float l = act ? leaky(raw, slope) : -INFINITY;
+        float m = l;
+#pragma unroll
+        for (int o = NL / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const float p = act ? expf(l - m) : 0.f;
+        float s = p;
+#pragma unroll
+        for (int o = NL / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (act) R.alpha[e] = p * (1.0f / (s + 1e-16f));
+    } else {
+        const float al = act ? R.alpha[e] : 0.f;
+        const float dal = act ? __ldg(R.dalpha + e) : 0.f;
+        float s = al * dal;
+#pragma unroll
+        for (int o = NL / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float de = al * (dal - s) * (raw > 0.f ? 1.0f : slope);      // 0 for idle lanes
+        if (act) R.de[e] = de;
+        float d = de;
+#pragma unroll
+        for (int o = NL / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (row_ok && sl == 0) R.da_r[row] = d;
+    }
+}
+
+constexpr int kGatGroup = 8;                              // lanes per short row
+constexpr int kGatRowsPerWarp = 32 / kGatGroup;           // 4
+constexpr int kGatRowsPerCta = kGatWarps * kGatRowsPerWarp;   // 32
+
+// A CTA owns 32 consecutive destination rows of one relation, a warp 4 of them:
+//   deg <= 8             8 lanes per row, four rows of the warp at once (registers)
+//   8 < deg <= 32        the whole warp, one edge per lane (registers)
+//   32 < deg <= LONG     the whole warp, strided three-pass walk
+//   deg > LONG           the whole CTA after a barrier (style / genre / tag hubs)
 template <bool BWD>
 __global__ void __launch_bounds__(kGatThreads) gat_edge_softmax(const __grid_constant__ GatRels P) {
     __shared__ float s_red[kGatWarps];
-    __shared__ int s_long[kGatWarps];
+    __shared__ int s_long[kGatRowsPerCta];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int g = lane / kGatGroup, gl = lane % kGatGroup;
     int ri = 0;
     while ((int)blockIdx.x >= P.blk_start[ri + 1]) ++ri;
     const agx_gat_rel_t& R = P.r[ri];
-    const int row = ((int)blockIdx.x - P.blk_start[ri]) * kGatWarps + w;
-    int beg = 0, end = 0;
+    const int cta_row0 = ((int)blockIdx.x - P.blk_start[ri]) * kGatRowsPerCta;
+    const int row0 = cta_row0 + w * kGatRowsPerWarp;
+    const int row = row0 + g;
+    int beg = 0, deg = 0;
     if (row < R.n_rows) {
         beg = __ldg(R.rowptr + row);
-        end = __ldg(R.rowptr + row + 1);
+        deg = __ldg(R.rowptr + row + 1) - beg;
     }
-    const bool is_long = end - beg > AGX_GAT_LONG_ROW;
-    if (lane == 0) s_long[w] = is_long ? 1 : 0;
-    if (row < R.n_rows && !is_long) {
-        if constexpr (BWD)
-            softmax_bwd_row<32>(R, row, beg, end, lane, P.slope, s_red);
-        else
-            softmax_row<32>(R, row, beg, end, lane, P.slope, s_red);
+    if (gl == 0) s_long[w * kGatRowsPerWarp + g] = deg > AGX_GAT_LONG_ROW ? 1 : 0;
+    softmax_small<kGatGroup, BWD>(R, row, beg, deg, row < R.n_rows && deg <= kGatGroup, gl, P.slope);
+#pragma unroll
+    for (int gg = 0; gg < kGatRowsPerWarp; ++gg) {       // warp-uniform: values of group gg's row
+        const int rdeg = __shfl_sync(0xffffffffu, deg, gg * kGatGroup);
+        const int rbeg = __shfl_sync(0xffffffffu, beg, gg * kGatGroup);
+        const int rrow = row0 + gg;
+        if (rdeg <= kGatGroup || rdeg > AGX_GAT_LONG_ROW) continue;
+        if (rdeg <= 32) {
+            softmax_small<32, BWD>(R, rrow, rbeg, rdeg, true, lane, P.slope);
+        } else if constexpr (BWD) {
+            softmax_bwd_row<32>(R, rrow, rbeg, rbeg + rdeg, lane, P.slope, s_red);
+        } else {
+            softmax_row<32>(R, rrow, rbeg, rbeg + rdeg, lane, P.slope, s_red);
+        }
     }
     __syncthreads();
     // hub rows of this CTA, one after the other, by all of its threads (CTA-uniform control flow)
-    for (int ww = 0; ww < kGatWarps; ++ww) {
-        if (!s_long[ww]) continue;
-        const int lrow = ((int)blockIdx.x - P.blk_start[ri]) * kGatWarps + ww;
+    for (int q = 0; q < kGatRowsPerCta; ++q) {
+        if (!s_long[q]) continue;
+        const int lrow = cta_row0 + q;
         const int lbeg = __ldg(R.rowptr + lrow), lend = __ldg(R.rowptr + lrow + 1);
         if constexpr (BWD)
             softmax_bwd_row<kGatThreads>(R, lrow, lbeg, lend, threadIdx.x, P.slope, s_red);
@@ -221,7 +280,7 @@ static int launch_edge_softmax(const agx_gat_rel_t* h_rels, int n_rels, float sl
         AGX_CHECK_ARG(!BWD || R.n_rows == 0 || (R.dalpha && R.de && R.da_r),
                       "%s: relation %d: null backward pointer", what, i);
         P.r[i] = R;
-        P.blk_start[i + 1] = P.blk_start[i] + (int32_t)ceil_div(R.n_rows, kGatWarps);
+        P.blk_start[i + 1] = P.blk_start[i] + (int32_t)ceil_div(R.n_rows, kGatRowsPerCta);
     }
     if (P.blk_start[n_rels] == 0) return AGX_OK;
     gat_edge_softmax<BWD><<<(unsigned)P.blk_start[n_rels], kGatThreads, 0, (cudaStream_t)stream>>>(P);

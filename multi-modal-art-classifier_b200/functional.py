@@ -1022,6 +1022,16 @@ class GATSpec:
         return out
 
 
+def _gat_logit_rows(spec: "GATSpec") -> "Dict[str, list]":
+    """Per node type the (relation index, role) pairs whose attention logits are computed from that
+    type's features: role 'l' = the type is the relation's source, 'r' = its destination."""
+    slots: Dict[str, list] = {}
+    for k, rs in enumerate(spec.rels):
+        slots.setdefault(rs.src, []).append((k, 'l'))
+        slots.setdefault(rs.dst, []).append((k, 'r'))
+    return slots
+
+
 def _chain_sum(out: torch.Tensor, ins: list, bias: Optional[torch.Tensor] = None):
     """out = sum(ins) (+ bias rows), at most 8 inputs per descriptor (chained in place)."""
     while len(ins) > 8:
@@ -1056,11 +1066,15 @@ class _HeteroGATFn(torch.autograd.Function):
         R = len(spec.rels)
         f32 = dict(dtype=torch.float32, device=dev)
 
-        # f1: x_l = x_src W_l^T (one-hot sources: W_l^T) and v = att_r W_r
+        # f1: x_l = x_src W_l^T (one-hot sources: W_l^T) and, per node type, the stacked logit
+        # projections UV[t]: row (k, 'l') = att_l_k W_l_k for the relations t feeds, row (k, 'r') =
+        # att_r_k W_r_k for the relations it receives -- a_l = x_src (W_l^T att_l), a_r likewise
+        slots = _gat_logit_rows(spec)
+        UV = {t: torch.empty(len(rows), xs[t].shape[1], **f32) for t, rows in slots.items()}
         gb = ops.GemmBatch()
         tr: list = []
-        x_l, v = [], []
-        for rs in spec.rels:
+        x_l = []
+        for k, rs in enumerate(spec.rels):
             p = rs.plan
             y = torch.empty(p.n_src, C_, **f32)
             x_l.append(y)
@@ -1068,30 +1082,30 @@ class _HeteroGATFn(torch.autograd.Function):
                 tr.append((y, params[rs.i_wl]))
             else:
                 gb.add(y, [(xs[rs.src], _t(params[rs.i_wl]))])
-            vv = torch.empty(1, params[rs.i_wr].shape[1], **f32)
-            v.append(vv)
-            gb.add(vv, [(params[rs.i_ar].view(1, C_), params[rs.i_wr])])
+        for t, rows in slots.items():
+            for i, (k, role) in enumerate(rows):
+                rs = spec.rels[k]
+                att, w = (rs.i_al, rs.i_wl) if role == 'l' else (rs.i_ar, rs.i_wr)
+                gb.add(UV[t][i:i + 1], [(params[att].view(1, C_), params[w])])
         if tr:
             ops.transpose_many(tr)
         gb.run()
-        # f2: a_l = x_l att_l, a_r = x_dst v^T (one-hot destinations: v itself)
+        # f2: all logits of a node type in ONE product A[t] = UV[t] x[t]^T (x[t] is read once, not
+        # once per relation); one-hot features: A[t] = UV[t]
         gb = ops.GemmBatch()
-        a_l, a_r = [], []
-        for k, rs in enumerate(spec.rels):
-            p = rs.plan
-            al = torch.empty(p.n_src, 1, **f32)
-            a_l.append(al)
-            gb.add(al, [(x_l[k], params[rs.i_al].view(C_, 1))])
-            if spec.identity.get(rs.dst, False):
-                a_r.append(v[k].view(-1, 1))
+        A = {}
+        for t, rows in slots.items():
+            if spec.identity.get(t, False):
+                A[t] = UV[t]
             else:
-                ar = torch.empty(p.n_dst, 1, **f32)
-                a_r.append(ar)
-                gb.add(ar, [(xs[rs.dst], v[k].view(-1, 1))])
+                A[t] = torch.empty(len(rows), xs[t].shape[0], **f32)
+                gb.add(A[t], [(UV[t], _t(xs[t]))])
         gb.run()
+        a_l = [A[rs.src][slots[rs.src].index((k, 'l'))] for k, rs in enumerate(spec.rels)]
+        a_r = [A[rs.dst][slots[rs.dst].index((k, 'r'))] for k, rs in enumerate(spec.rels)]
         # f3: attention coefficients of every relation, CSR order
         alpha = [torch.empty(max(rs.plan.n_edges, 1), **f32) for rs in spec.rels]
-        ops.gat_edge_softmax([ops.GatArg(rs.plan.csr, a_l[k].view(-1), a_r[k].view(-1), alpha[k])
+        ops.gat_edge_softmax([ops.GatArg(rs.plan.csr, a_l[k], a_r[k], alpha[k])
                               for k, rs in enumerate(spec.rels)], spec.slope)
         # f4: weighted neighbour sums, relation sum and biases per destination type
         outs: Dict[str, torch.Tensor] = {}
@@ -1136,7 +1150,9 @@ class _HeteroGATFn(torch.autograd.Function):
             _chain_sum(out, ins, bias)
 
         ctx.spec, ctx.nt = spec, nt
-        ctx.save_for_backward(*tensors, *x_l, *v, *a_l, *a_r, *alpha)
+        ctx.slot_types = list(slots.keys())
+        ctx.save_for_backward(*tensors, *x_l, *alpha, *[UV[t] for t in ctx.slot_types],
+                              *[A[t] for t in ctx.slot_types])
         return tuple(outs[t] for t in spec.dst_types)
 
     @staticmethod
@@ -1145,9 +1161,15 @@ class _HeteroGATFn(torch.autograd.Function):
         nt = ctx.nt
         saved = ctx.saved_tensors
         R = len(spec.rels)
-        n_in = len(saved) - 5 * R
+        T = len(ctx.slot_types)
+        n_in = len(saved) - 2 * R - 2 * T
         tensors = saved[:n_in]
-        x_l, v, a_l, a_r, alpha = (saved[n_in + q * R:n_in + (q + 1) * R] for q in range(5))
+        x_l, alpha = saved[n_in:n_in + R], saved[n_in + R:n_in + 2 * R]
+        UV = dict(zip(ctx.slot_types, saved[n_in + 2 * R:n_in + 2 * R + T]))
+        A = dict(zip(ctx.slot_types, saved[n_in + 2 * R + T:]))
+        slots = _gat_logit_rows(spec)
+        a_l = [A[rs.src][slots[rs.src].index((k, 'l'))] for k, rs in enumerate(spec.rels)]
+        a_r = [A[rs.dst][slots[rs.dst].index((k, 'r'))] for k, rs in enumerate(spec.rels)]
         xs = {t: tensors[i] for i, t in enumerate(spec.node_types)}
         params = tensors[nt:]
         C_ = spec.out_channels
@@ -1180,14 +1202,27 @@ class _HeteroGATFn(torch.autograd.Function):
         ops.sddmm([(rs.plan.csr_row, rs.plan.csr.col, dout[rs.dst], x_l[k], dalpha[k])
                    for k, rs in live if rs.plan.n_edges > 0], C_)
         de = {k: torch.empty(max(rs.plan.n_edges, 1), **f32) for k, rs in live}
-        da_r = {k: torch.empty(rs.plan.n_dst, 1, **f32) for k, rs in live}
-        ops.gat_edge_softmax([ops.GatArg(rs.plan.csr, a_l[k].view(-1), a_r[k].view(-1), alpha[k],
-                                         dalpha=dalpha[k], de=de[k], da_r=da_r[k].view(-1))
-                              for k, rs in live], spec.slope, backward=True)
+        # logit gradients land in the rows of dA[t] (the layout of A[t]); rows of relations whose
+        # output received no gradient are cleared
+        live_k = {k for k, _ in live}
+        dA = {}
+        shapes = {t: (len(rows), xs[t].shape[0]) for t, rows in slots.items()
+                  if any(k in live_k for k, _ in rows)}
+        flat = torch.empty(sum(a * b for a, b in shapes.values()), **f32)
+        if any(k not in live_k for t in shapes for k, _ in slots[t]):
+            ops.fill_(flat, 0.0)
+        off = 0
+        for t, (a, b) in shapes.items():
+            dA[t] = flat[off:off + a * b].view(a, b)
+            off += a * b
+        da_l = {k: dA[rs.src][slots[rs.src].index((k, 'l'))] for k, rs in live}
+        da_r = {k: dA[rs.dst][slots[rs.dst].index((k, 'r'))] for k, rs in live}
+        ops.gat_edge_softmax([ops.GatArg(rs.plan.csr, a_l[k], a_r[k], alpha[k], dalpha=dalpha[k],
+                                         de=de[k], da_r=da_r[k]) for k, rs in live], spec.slope,
+                             backward=True)
 
         # b4: transposes over the CSC: dX_l = sum_i alpha_ij dout[i], da_l[j] = sum_i de_ij
         dxl = {k: torch.empty(rs.plan.n_src, C_, **f32) for k, rs in live}
-        da_l = {k: torch.empty(rs.plan.n_src, 1, **f32) for k, rs in live}
         rows_w, chunks_w, rows_1, chunks_1 = [], [], [], []
         for k, rs in live:
             p = rs.plan
@@ -1195,64 +1230,64 @@ class _HeteroGATFn(torch.autograd.Function):
             one = ops.RelArg(p.csc_pos, de[k].view(-1, 1))
             if p.csc.long_rows:
                 chunks_w.append((dxl[k], wide))
-                chunks_1.append((da_l[k], one))
+                chunks_1.append((da_l[k].view(-1, 1), one))
             else:
                 rows_w.append((dxl[k], [wide], False))
-                rows_1.append((da_l[k], [one], False))
+                rows_1.append((da_l[k].view(-1, 1), [one], False))
         ops.aggregate_rows(rows_w, C_)
         ops.aggregate_chunks(chunks_w, C_)
         ops.aggregate_rows(rows_1, 1)
         ops.aggregate_chunks(chunks_1, 1)
 
-        # b5 (wave A): dX_l += da_l att_l^T;  d att_l = x_l^T da_l;  dv = da_r^T x_dst
-        gb = ops.GemmBatch()
-        dv = {}
-        for k, rs in live:
-            p = rs.plan
-            gb.add(dxl[k], [(da_l[k], params[rs.i_al].view(1, C_))], accumulate=True)
-            datt_l = torch.empty(C_, 1, **f32)
-            gb.add(datt_l, [(_t(x_l[k]), da_l[k])], split_k=ops.split_k_for(p.n_src))
-            grads[pidx(rs.i_al)] = datt_l
-            if spec.identity.get(rs.dst, False):
-                dv[k] = da_r[k].view(1, -1)
-            else:
-                dv[k] = torch.empty(1, xs[rs.dst].shape[1], **f32)
-                gb.add(dv[k], [(_t(da_r[k]), xs[rs.dst])], split_k=ops.split_k_for(p.n_dst))
-        gb.run()
-        # b6 (wave B): weight gradients and input gradients
+        # b5 (wave A): dUV[t] = dA[t] x[t] (one-hot: dA[t]);  dW_l = dX_l^T x_src (one-hot: dX_l^T)
         gb = ops.GemmBatch()
         trb: list = []
+        dUV = {}
+        for t in dA:
+            if spec.identity.get(t, False):
+                dUV[t] = dA[t]
+            else:
+                dUV[t] = torch.empty_like(UV[t])
+                gb.add(dUV[t], [(dA[t], xs[t])], split_k=ops.split_k_for(xs[t].shape[0]))
         for k, rs in live:
-            p = rs.plan
             x = xs[rs.src]
             dwl = torch.empty(C_, x.shape[1], **f32)
             grads[pidx(rs.i_wl)] = dwl
             if spec.identity.get(rs.src, False):
                 trb.append((dwl, dxl[k]))                        # dX_l^T I
             else:
-                gb.add(dwl, [(_t(dxl[k]), x)], split_k=ops.split_k_for(p.n_src))
-            fd = params[rs.i_wr].shape[1]
-            datt_r = torch.empty(C_, 1, **f32)
-            gb.add(datt_r, [(params[rs.i_wr], dv[k].view(fd, 1))])          # W_r dv^T
-            grads[pidx(rs.i_ar)] = datt_r
+                gb.add(dwl, [(_t(dxl[k]), x)], split_k=ops.split_k_for(rs.plan.n_src))
+        if trb:
+            ops.transpose_many(trb)
+        gb.run()
+        # b6 (wave B): u = W_l^T att_l, v = W_r^T att_r  =>  dW += att du^T, d att = W du;
+        # dx[t] = sum_{src(k)=t} dX_l W_l + dA[t]^T UV[t]
+        gb = ops.GemmBatch()
+        for k, rs in live:
+            du = dUV[rs.src][slots[rs.src].index((k, 'l'))]
+            dv = dUV[rs.dst][slots[rs.dst].index((k, 'r'))]
+            fs, fd = du.numel(), dv.numel()
+            gb.add(grads[pidx(rs.i_wl)], [(params[rs.i_al].view(C_, 1), du.view(1, fs))],
+                   accumulate=True)
             dwr = torch.empty(C_, fd, **f32)
-            gb.add(dwr, [(params[rs.i_ar].view(C_, 1), dv[k].view(1, fd))])  # att_r dv
+            gb.add(dwr, [(params[rs.i_ar].view(C_, 1), dv.view(1, fd))])
             grads[pidx(rs.i_wr)] = dwr
+            datt_l = torch.empty(C_, 1, **f32)
+            gb.add(datt_l, [(params[rs.i_wl], du.view(fs, 1))], split_k=ops.split_k_for(fs))
+            grads[pidx(rs.i_al)] = datt_l
+            datt_r = torch.empty(C_, 1, **f32)
+            gb.add(datt_r, [(params[rs.i_wr], dv.view(fd, 1))], split_k=ops.split_k_for(fd))
+            grads[pidx(rs.i_ar)] = datt_r
         for i, t in enumerate(spec.node_types):
             if not need_x[t]:
                 continue
-            segs = []
-            for k, rs in live:
-                if rs.src == t:
-                    segs.append((dxl[k], params[rs.i_wl]))                  # dX_l W_l
-                if rs.dst == t:
-                    segs.append((da_r[k], v[k]))                            # da_r v
+            segs = [(dxl[k], params[rs.i_wl]) for k, rs in live if rs.src == t]
+            if t in dA:
+                segs.append((_t(dA[t]), UV[t]))
             if segs:
                 dx = torch.empty_like(xs[t])
                 grads[i] = dx
                 gb.add(dx, segs)
-        if trb:
-            ops.transpose_many(trb)
         gb.run()
         # gradients in the parameters' own shapes (att_l / att_r are [1, 1, C])
         for i in range(nt, len(tensors)):

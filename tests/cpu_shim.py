@@ -158,6 +158,10 @@ def _transpose_many(pairs):
         out.copy_(inp.t())
 
 
+def _fill_(t, v):
+    return t.fill_(v)
+
+
 def _is_identity(x):
     n = x.shape[0]
     return torch.tensor(int(x.shape[0] == x.shape[1] and bool(torch.equal(x, torch.eye(n)))))
@@ -168,6 +172,7 @@ _PATCHES = {
     'aggregate_chunks': _aggregate_chunks, 'GemmBatch': _GemmBatch,
     'gat_edge_softmax': _gat_edge_softmax, 'sddmm': _sddmm, 'sum_arrays': _sum_arrays,
     'colsum': _colsum, 'transpose_many': _transpose_many, 'is_identity': _is_identity,
+    'fill_': _fill_,
 }
 
 

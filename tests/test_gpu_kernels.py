@@ -530,8 +530,10 @@ def test_gat_edge_softmax_and_backward_hub_rows():
     import cpu_shim
     gen = torch.Generator().manual_seed(3)
     rels = [_skewed_rel(gen, 500, 40, 600, {1: 1000, 7: 1500, 8: 5000, 30: 1025}),
-            _skewed_rel(gen, 64, 9, 50, {0: 3000})]
-    sizes = [(500, 40), (64, 9)]
+            _skewed_rel(gen, 64, 9, 50, {0: 3000}),
+            # mostly rows of 0..8 edges (8 lanes per row), some of 9..32 and 33..100 (one warp)
+            _skewed_rel(gen, 300, 1003, 2500, {5: 9, 6: 31, 7: 32, 8: 33, 500: 100, 1000: 8})]
+    sizes = [(500, 40), (64, 9), (300, 1003)]
     csrs = ops.csr_build([(ei[1].to(DEV), ei[0].to(DEV), nd, ns) for ei, (ns, nd) in zip(rels, sizes)])
     dev_args, cpu_args = [], []
     for c, (ns, nd) in zip(csrs, sizes):
