@@ -329,14 +329,17 @@ typedef struct {
     const float* dalpha;      /* backward: [n_edges] d loss / d alpha (agx_sddmm of dout and x_l) */
     float* de;                /* backward: [n_edges] d loss / d (a_l[j] + a_r[i])                 */
     float* da_r;              /* backward: [n_rows]  sum_j de_ij                                  */
+    const int32_t* long_rows; /* [n_long] the rows with more than AGX_GAT_LONG_ROW edges, found once
+                                 per graph by the caller: each gets a CTA of its own                */
     int32_t n_rows;
-    int32_t pad_;
+    int32_t n_long;
 } agx_gat_rel_t;
 
 /* alpha_ij = softmax_i(leaky_relu(a_l[j] + a_r[i])) per destination row, for up to 24 relations in
- * ONE launch.  Eight lanes per row of up to 8 edges, a warp per row up to AGX_GAT_LONG_ROW edges,
- * longer rows (artwork -> style / genre / tag hubs) by the whole CTA.  Fixed reduction order:
- * reproducible. */
+ * ONE launch.  Eight lanes per row of up to 8 edges, a warp per row up to AGX_GAT_LONG_ROW edges;
+ * every longer row (artwork -> style / genre / tag hubs, listed in `long_rows`) is reduced by a
+ * 1024-thread CTA of its own, so hub rows neither queue behind one another nor behind short rows.
+ * Fixed reduction order: reproducible. */
 int agx_gat_edge_softmax(const agx_gat_rel_t* h_rels, int n_rels, float slope, void* stream);
 /* de_ij = alpha_ij (dalpha_ij - sum_j alpha_ij dalpha_ij) leaky_relu'(a_l[j] + a_r[i]);
  * da_r[i] = sum_j de_ij */

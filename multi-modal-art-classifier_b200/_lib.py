@@ -74,7 +74,8 @@ class SumDesc(C.Structure):
 
 class GatRel(C.Structure):
     _fields_ = [('rowptr', vp), ('col', vp), ('a_l', vp), ('a_r', vp), ('alpha', vp),
-                ('dalpha', vp), ('de', vp), ('da_r', vp), ('n_rows', c_i32), ('pad_', c_i32)]
+                ('dalpha', vp), ('de', vp), ('da_r', vp), ('long_rows', vp), ('n_rows', c_i32),
+                ('n_long', c_i32)]
 
 
 class SddmmSeg(C.Structure):

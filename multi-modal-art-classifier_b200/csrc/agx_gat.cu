@@ -10,8 +10,8 @@
 //
 //   scalar passes (this file, 4-12 B per edge)
 //     gat_edge_softmax      alpha per CSR slot; 8 lanes per row up to 8 edges, a warp per row up to
-//                           AGX_GAT_LONG_ROW, longer rows by the whole CTA (three strided passes
-//                           over the row, values parked in alpha)
+//                           AGX_GAT_LONG_ROW, every longer row by a 1024-thread CTA of its own
+//                           (three strided passes over the row, values parked in alpha)
 //     gat_edge_softmax_bwd  de_ij = alpha_ij (dalpha_ij - sum_j alpha_ij dalpha_ij) leaky'(.),
 //                           da_r[i] = sum_j de_ij, same row mapping
 //     sddmm                 dalpha_ij = <dout[i], x_l[j]>, a warp per 32 CSR slots (edge-balanced)
@@ -26,12 +26,15 @@
 
 namespace agx {
 
-constexpr int kGatThreads = 256;
+constexpr int kGatThreads = 1024;                  // softmax kernels: a hub row gets all of them
 constexpr int kGatWarps = kGatThreads / 32;
+constexpr int kSddmmThreads = 256;
+constexpr int kSddmmWarps = kSddmmThreads / 32;
 
 struct GatRels {
     agx_gat_rel_t r[AGX_MAX_GAT_RELS];
-    int32_t blk_start[AGX_MAX_GAT_RELS + 1];       // CTA -> relation (32 rows per CTA)
+    int32_t blk_start[AGX_MAX_GAT_RELS + 1];       // CTA -> relation (128 rows per CTA) ...
+    int32_t hub_start[AGX_MAX_GAT_RELS + 1];       // ... then one CTA per long row, per relation
     int32_t n;
     float slope;
 };
@@ -145,38 +148,48 @@ __device__ __forceinline__ void softmax_small(const agx_gat_rel_t& R, int row, i
 
 constexpr int kGatGroup = 8;                              // lanes per short row
 constexpr int kGatRowsPerWarp = 32 / kGatGroup;           // 4
-constexpr int kGatRowsPerCta = kGatWarps * kGatRowsPerWarp;   // 32
 
-// A CTA owns 32 consecutive destination rows of one relation, a warp 4 of them:
+// The first blk_start[n] CTAs own 128 consecutive destination rows of one relation each, a warp 4:
 //   deg <= 8             8 lanes per row, four rows of the warp at once (registers)
 //   8 < deg <= 32        the whole warp, one edge per lane (registers)
 //   32 < deg <= LONG     the whole warp, strided three-pass walk
-//   deg > LONG           the whole CTA after a barrier (style / genre / tag hubs)
+//   deg > LONG           skipped: row long_rows[b] belongs to hub CTA hub_start[rel] + b (all 1024
+//                        threads on one row; style / genre / tag hubs of 10^3..10^4 edges)
 template <bool BWD>
 __global__ void __launch_bounds__(kGatThreads) gat_edge_softmax(const __grid_constant__ GatRels P) {
     __shared__ float s_red[kGatWarps];
-    __shared__ int s_long[kGatRowsPerCta];
+    if ((int)blockIdx.x >= P.blk_start[P.n]) {                   // hub CTA (CTA-uniform branch)
+        int ri = 0;
+        while ((int)blockIdx.x >= P.hub_start[ri + 1]) ++ri;
+        const agx_gat_rel_t& R = P.r[ri];
+        const int lrow = __ldg(R.long_rows + ((int)blockIdx.x - P.hub_start[ri]));
+        const int lbeg = __ldg(R.rowptr + lrow), lend = __ldg(R.rowptr + lrow + 1);
+        if constexpr (BWD)
+            softmax_bwd_row<kGatThreads>(R, lrow, lbeg, lend, threadIdx.x, P.slope, s_red);
+        else
+            softmax_row<kGatThreads>(R, lrow, lbeg, lend, threadIdx.x, P.slope, s_red);
+        return;
+    }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int g = lane / kGatGroup, gl = lane % kGatGroup;
     int ri = 0;
     while ((int)blockIdx.x >= P.blk_start[ri + 1]) ++ri;
     const agx_gat_rel_t& R = P.r[ri];
-    const int cta_row0 = ((int)blockIdx.x - P.blk_start[ri]) * kGatRowsPerCta;
-    const int row0 = cta_row0 + w * kGatRowsPerWarp;
+    const int row0 = (((int)blockIdx.x - P.blk_start[ri]) * kGatWarps + w) * kGatRowsPerWarp;
     const int row = row0 + g;
     int beg = 0, deg = 0;
     if (row < R.n_rows) {
         beg = __ldg(R.rowptr + row);
         deg = __ldg(R.rowptr + row + 1) - beg;
     }
-    if (gl == 0) s_long[w * kGatRowsPerWarp + g] = deg > AGX_GAT_LONG_ROW ? 1 : 0;
     softmax_small<kGatGroup, BWD>(R, row, beg, deg, row < R.n_rows && deg <= kGatGroup, gl, P.slope);
 #pragma unroll
     for (int gg = 0; gg < kGatRowsPerWarp; ++gg) {       // warp-uniform: values of group gg's row
         const int rdeg = __shfl_sync(0xffffffffu, deg, gg * kGatGroup);
         const int rbeg = __shfl_sync(0xffffffffu, beg, gg * kGatGroup);
         const int rrow = row0 + gg;
-        if (rdeg <= kGatGroup || rdeg > AGX_GAT_LONG_ROW) continue;
+        // (without a long_rows list the warp walks a hub row itself: slow, still correct)
+        if (rdeg <= kGatGroup || (rdeg > AGX_GAT_LONG_ROW && R.n_long > 0)) continue;
         if (rdeg <= 32) {
             softmax_small<32, BWD>(R, rrow, rbeg, rdeg, true, lane, P.slope);
         } else if constexpr (BWD) {
@@ -184,17 +197,6 @@ __global__ void __launch_bounds__(kGatThreads) gat_edge_softmax(const __grid_con
         } else {
             softmax_row<32>(R, rrow, rbeg, rbeg + rdeg, lane, P.slope, s_red);
         }
-    }
-    __syncthreads();
-    // hub rows of this CTA, one after the other, by all of its threads (CTA-uniform control flow)
-    for (int q = 0; q < kGatRowsPerCta; ++q) {
-        if (!s_long[q]) continue;
-        const int lrow = cta_row0 + q;
-        const int lbeg = __ldg(R.rowptr + lrow), lend = __ldg(R.rowptr + lrow + 1);
-        if constexpr (BWD)
-            softmax_bwd_row<kGatThreads>(R, lrow, lbeg, lend, threadIdx.x, P.slope, s_red);
-        else
-            softmax_row<kGatThreads>(R, lrow, lbeg, lend, threadIdx.x, P.slope, s_red);
     }
 }
 
@@ -213,7 +215,7 @@ struct SddmmSegs {
 };
 
 template <int VEC, int LPR>
-__global__ void __launch_bounds__(kGatThreads) sddmm(const __grid_constant__ SddmmSegs P) {
+__global__ void __launch_bounds__(kSddmmThreads) sddmm(const __grid_constant__ SddmmSegs P) {
     constexpr int SUB = 32 / LPR;
     constexpr int U = kSddmmDepth;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(kGatThreads) sddmm(const __grid_constant__ Sdd
     int si = 0;
     while ((int)blockIdx.x >= P.blk_start[si + 1]) ++si;
     const agx_sddmm_seg_t& S = P.s[si];
-    const int e0 = (((int)blockIdx.x - P.blk_start[si]) * kGatWarps + w) * 32;
+    const int e0 = (((int)blockIdx.x - P.blk_start[si]) * kSddmmWarps + w) * 32;
     const int n = min(32, S.n_edges - e0);
     if (n <= 0) return;
     const int F = P.F;
@@ -274,16 +276,21 @@ static int launch_edge_softmax(const agx_gat_rel_t* h_rels, int n_rels, float sl
     P.blk_start[0] = 0;
     for (int i = 0; i < n_rels; ++i) {
         const agx_gat_rel_t& R = h_rels[i];
-        AGX_CHECK_ARG(R.n_rows >= 0, "%s: relation %d: n_rows=%d", what, i, R.n_rows);
+        AGX_CHECK_ARG(R.n_rows >= 0 && R.n_long >= 0 && R.n_long <= R.n_rows,
+                      "%s: relation %d: n_rows=%d n_long=%d", what, i, R.n_rows, R.n_long);
         AGX_CHECK_ARG(R.n_rows == 0 || (R.rowptr && R.col && R.a_l && R.a_r && R.alpha),
                       "%s: relation %d: null pointer", what, i);
+        AGX_CHECK_ARG(R.n_long == 0 || R.long_rows, "%s: relation %d: null long_rows", what, i);
         AGX_CHECK_ARG(!BWD || R.n_rows == 0 || (R.dalpha && R.de && R.da_r),
                       "%s: relation %d: null backward pointer", what, i);
         P.r[i] = R;
-        P.blk_start[i + 1] = P.blk_start[i] + (int32_t)ceil_div(R.n_rows, kGatRowsPerCta);
+        P.blk_start[i + 1] =
+            P.blk_start[i] + (int32_t)ceil_div(R.n_rows, kGatWarps * kGatRowsPerWarp);
     }
-    if (P.blk_start[n_rels] == 0) return AGX_OK;
-    gat_edge_softmax<BWD><<<(unsigned)P.blk_start[n_rels], kGatThreads, 0, (cudaStream_t)stream>>>(P);
+    P.hub_start[0] = P.blk_start[n_rels];
+    for (int i = 0; i < n_rels; ++i) P.hub_start[i + 1] = P.hub_start[i] + h_rels[i].n_long;
+    if (P.hub_start[n_rels] == 0) return AGX_OK;
+    gat_edge_softmax<BWD><<<(unsigned)P.hub_start[n_rels], kGatThreads, 0, (cudaStream_t)stream>>>(P);
     AGX_LAUNCH_CHECK(what);
     return AGX_OK;
 }
@@ -319,19 +326,19 @@ extern "C" int agx_sddmm(const agx_sddmm_seg_t* h_segs, int n_segs, int32_t F, v
         vec_ok = vec_ok && gat_aligned16(S.a) && gat_aligned16(S.b) && (S.lda & 3) == 0 &&
                  (S.ldb & 3) == 0;
         P.s[i] = S;
-        P.blk_start[i + 1] = P.blk_start[i] + (int32_t)ceil_div(S.n_edges, kGatThreads);
+        P.blk_start[i + 1] = P.blk_start[i] + (int32_t)ceil_div(S.n_edges, kSddmmThreads);
     }
     const unsigned grid = (unsigned)P.blk_start[n_segs];
     if (grid == 0) return AGX_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (!vec_ok)
-        sddmm<1, 32><<<grid, kGatThreads, 0, st>>>(P);
+        sddmm<1, 32><<<grid, kSddmmThreads, 0, st>>>(P);
     else if (F > 64)
-        sddmm<4, 32><<<grid, kGatThreads, 0, st>>>(P);
+        sddmm<4, 32><<<grid, kSddmmThreads, 0, st>>>(P);
     else if (F > 32)
-        sddmm<4, 16><<<grid, kGatThreads, 0, st>>>(P);
+        sddmm<4, 16><<<grid, kSddmmThreads, 0, st>>>(P);
     else
-        sddmm<4, 8><<<grid, kGatThreads, 0, st>>>(P);
+        sddmm<4, 8><<<grid, kSddmmThreads, 0, st>>>(P);
     AGX_LAUNCH_CHECK("sddmm");
     return AGX_OK;
 }

@@ -977,6 +977,7 @@ class GATPlan:
         self.csc2csr = inv[self.csc.eid[:E].long()].contiguous()
         import dataclasses
         self.csc_pos = dataclasses.replace(self.csc, col=self.csc2csr, n_cols=max(E, 1))
+        self.long_rows = ops.gat_long_rows(self.csr)       # hub destinations: a CTA each
 
     @classmethod
     def get(cls, edge_index, n_src, n_dst, add_self_loops=True):
@@ -1105,7 +1106,8 @@ class _HeteroGATFn(torch.autograd.Function):
         a_r = [A[rs.dst][slots[rs.dst].index((k, 'r'))] for k, rs in enumerate(spec.rels)]
         # f3: attention coefficients of every relation, CSR order
         alpha = [torch.empty(max(rs.plan.n_edges, 1), **f32) for rs in spec.rels]
-        ops.gat_edge_softmax([ops.GatArg(rs.plan.csr, a_l[k], a_r[k], alpha[k])
+        ops.gat_edge_softmax([ops.GatArg(rs.plan.csr, a_l[k], a_r[k], alpha[k],
+                                         long_rows=rs.plan.long_rows)
                               for k, rs in enumerate(spec.rels)], spec.slope)
         # f4: weighted neighbour sums, relation sum and biases per destination type
         outs: Dict[str, torch.Tensor] = {}
@@ -1218,8 +1220,8 @@ class _HeteroGATFn(torch.autograd.Function):
         da_l = {k: dA[rs.src][slots[rs.src].index((k, 'l'))] for k, rs in live}
         da_r = {k: dA[rs.dst][slots[rs.dst].index((k, 'r'))] for k, rs in live}
         ops.gat_edge_softmax([ops.GatArg(rs.plan.csr, a_l[k], a_r[k], alpha[k], dalpha=dalpha[k],
-                                         de=de[k], da_r=da_r[k]) for k, rs in live], spec.slope,
-                             backward=True)
+                                         de=de[k], da_r=da_r[k], long_rows=rs.plan.long_rows)
+                              for k, rs in live], spec.slope, backward=True)
 
         # b4: transposes over the CSC: dX_l = sum_i alpha_ij dout[i], da_l[j] = sum_i de_ij
         dxl = {k: torch.empty(rs.plan.n_src, C_, **f32) for k, rs in live}

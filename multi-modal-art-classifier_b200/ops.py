@@ -336,6 +336,17 @@ class GatArg:
     dalpha: Optional[torch.Tensor] = None
     de: Optional[torch.Tensor] = None
     da_r: Optional[torch.Tensor] = None
+    long_rows: Optional[torch.Tensor] = None   # int32: ALL rows with > GAT_LONG_ROW edges
+
+
+def gat_long_rows(csr: CSR) -> Optional[torch.Tensor]:
+    """The rows of ``csr`` that agx_gat_edge_softmax must be told about (one read-back: call once
+    per graph, not per step)."""
+    if csr.n_rows == 0 or csr.n_edges <= L.GAT_LONG_ROW:
+        return None
+    deg = csr.rowptr[1:] - csr.rowptr[:-1]
+    rows = torch.nonzero(deg > L.GAT_LONG_ROW).view(-1).to(torch.int32)
+    return rows.contiguous() if rows.numel() else None
 
 
 def gat_edge_softmax(rels: Sequence[GatArg], slope: float, backward: bool = False):
@@ -353,8 +364,12 @@ def gat_edge_softmax(rels: Sequence[GatArg], slope: float, backward: bool = Fals
             if a.a_r.numel() != a.csr.n_rows or a.a_l.numel() != a.csr.n_cols or \
                     a.alpha.numel() < a.csr.n_edges:
                 raise ValueError('attention array sizes do not match the CSR')
+            if a.long_rows is not None and a.long_rows.dtype != torch.int32:
+                raise TypeError('long_rows must be int32')
             arr[i] = L.GatRel(ptr(a.csr.rowptr), ptr(a.csr.col), ptr(a.a_l), ptr(a.a_r),
-                              ptr(a.alpha), ptr(a.dalpha), ptr(a.de), ptr(a.da_r), a.csr.n_rows, 0)
+                              ptr(a.alpha), ptr(a.dalpha), ptr(a.de), ptr(a.da_r),
+                              ptr(a.long_rows), a.csr.n_rows,
+                              0 if a.long_rows is None else a.long_rows.numel())
         check(fn(arr, len(part), float(slope), stream_ptr()), what)
 
 

@@ -540,10 +540,14 @@ def test_gat_edge_softmax_and_backward_hub_rows():
         a_l, a_r = torch.randn(ns, generator=gen) * 2, torch.randn(nd, generator=gen) * 2
         dal = torch.randn(c.n_edges, generator=gen)
         mk = lambda n: torch.empty(n, dtype=torch.float32, device=DEV)            # noqa: E731
+        # relation 1 is launched WITHOUT its hub list (a warp then walks the hub row itself)
         dev_args.append(ops.GatArg(c, a_l.to(DEV), a_r.to(DEV), mk(c.n_edges), dal.to(DEV),
-                                   mk(c.n_edges), mk(nd)))
+                                   mk(c.n_edges), mk(nd),
+                                   long_rows=ops.gat_long_rows(c) if len(dev_args) != 1 else None))
         z = lambda n: torch.zeros(n)                                              # noqa: E731
         cpu_args.append(ops.GatArg(_cpu_csr(c), a_l, a_r, z(c.n_edges), dal, z(c.n_edges), z(nd)))
+    assert sorted(dev_args[0].long_rows.cpu().tolist()) == [7, 8, 30]     # > 1024 edges
+    assert dev_args[2].long_rows is None
     ops.gat_edge_softmax(dev_args, 0.2)
     cpu_shim._gat_edge_softmax(cpu_args, 0.2)
     for d, h in zip(dev_args, cpu_args):
