@@ -211,6 +211,30 @@ def heads_throughput(dev, dist, world, batch: int = 4096, steps: int = 20):
     return out
 
 
+def operator_throughput(opname, metadata, x, ei, y, dev, n_edges, steps: int = 10):
+    """Secondary line: the same training step with another operator of the reference's
+    ``operator_registry`` (train_gnn_embeddings.py:96-102; GATConv is the script's default
+    ``--operator``), inputs resident, CUDA-graph replay, timed with CUDA events."""
+    import mmac_b200 as agx
+    from mmac_b200.trainer import GNNTrainer
+    torch.manual_seed(0)
+    model = agx.HeteroSGNN(getattr(agx, opname), torch.nn.ReLU(), 'sum', 128, 32, metadata, 2, 0.4,
+                           True, False).to(dev)
+    tr = GNNTrainer(model, x, ei, y, lr=0.01, use_cuda_graph=True)
+    for _ in range(3):
+        tr.train_step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = tr.train_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {'ms_per_step': ms, 'edges_per_s': PASSES * n_edges / (ms * 1e-3),
+            'launches_per_step': int(tr.launches_per_step), 'loss': float(loss.item())}
+
+
 def _workload_name(size, operator='SAGEConv'):
     return (f"train_gnn_embeddings.py --label style: full-graph {operator} to_hetero training step on "
             f"synthetic ArtGraph '{size}' (one-hot node features as in artgraph.py:93-95)")
@@ -426,6 +450,15 @@ def run_ours(args):
     heads = None
     if not args.no_heads:
         heads = heads_throughput(dev, dist, world)
+    operators = None
+    if world == 1 and not args.no_operators and args.operator == 'SAGEConv':
+        operators = {}
+        for opname in ('GraphConv', 'GATConv'):
+            try:
+                operators[opname] = operator_throughput(opname, data.metadata(), x, ei, y, dev,
+                                                        n_edges)
+            except Exception as e:  # noqa: BLE001  (a secondary line must not cost the headline)
+                operators[opname] = {'error': f'{type(e).__name__}: {e}'[:300]}
     if rank == 0:
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -465,6 +498,7 @@ def run_ours(args):
             'roofline': roofline,
             'cpu_baseline': cpu_base,
             'heads': heads,
+            'operators': operators,
         }
         print(json.dumps(line), file=_JSON_OUT or sys.stdout)
         (_JSON_OUT or sys.stdout).flush()
@@ -500,6 +534,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-heads', action='store_true',
                     help='skip the secondary fusion-head / projector artworks/s measurement')
+    ap.add_argument('--no-operators', action='store_true',
+                    help='skip the secondary GraphConv / GATConv training-step measurement')
     ap.add_argument('--park-ms', type=float, default=120.0,
                     help='device-side delay in front of each per-kernel timing step (roofline leg)')
     ap.add_argument('--ncu', action='store_true',

@@ -214,8 +214,11 @@ class HeteroModule(nn.Module):
         fused call (functional._HeteroGATFn); relation outputs of a destination type are added in
         metadata order (PyG's pairwise torch.add queue differs only in summation order)."""
         convs = self.get_submodule(node.target)
-        if self._dist is not None:
-            raise NotImplementedError('multi-GPU execution is implemented for SAGEConv / GraphConv')
+        if self._dist is not None and self._dist.halo is not None:
+            # (a graph block per rank needs no exchange inside the layer; a destination partition
+            # that cuts edges would need GATConv's self loops in global node ids)
+            raise NotImplementedError('GATConv on a partition that cuts edges is not implemented '
+                                      '(SAGEConv / GraphConv are)')
         types = [t for t in self.node_types if t in x_dict]
         dev = x_dict[types[0]].device
         params: List[torch.Tensor] = []
