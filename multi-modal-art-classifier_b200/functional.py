@@ -1033,6 +1033,17 @@ def _gat_logit_rows(spec: "GATSpec") -> "Dict[str, list]":
     return slots
 
 
+def _sum_many(items: list):
+    """(out, inputs, bias) sums that do not depend on one another: ONE launch for those with at
+    most 8 inputs, the (rare) longer ones chained."""
+    if not items:
+        return
+    ops.sum_arrays([it for it in items if len(it[1]) <= 8])
+    for out, ins, bias in items:
+        if len(ins) > 8:
+            _chain_sum(out, ins, bias)
+
+
 def _chain_sum(out: torch.Tensor, ins: list, bias: Optional[torch.Tensor] = None):
     """out = sum(ins) (+ bias rows), at most 8 inputs per descriptor (chained in place)."""
     while len(ins) > 8:
@@ -1115,9 +1126,14 @@ class _HeteroGATFn(torch.autograd.Function):
         chunks: list = []
         finals: list = []
         bias_sums: list = []
+        # all destination types' outputs are row blocks of ONE buffer (consumers that run the same
+        # row-wise op on every type -- log_softmax -- then need a single launch)
+        n_of = {t: next(rs.plan.n_dst for rs in spec.rels if rs.dst == t) for t in spec.dst_types}
+        out_all = torch.empty(sum(n_of.values()), C_, **f32)
+        row0 = 0
         for t in spec.dst_types:
             lst = [(k, rs) for k, rs in enumerate(spec.rels) if rs.dst == t]
-            n_t = lst[0][1].plan.n_dst
+            n_t = n_of[t]
             biases = [params[rs.i_b] for _, rs in lst if rs.i_b >= 0]
             if not biases:
                 bias = None
@@ -1128,7 +1144,8 @@ class _HeteroGATFn(torch.autograd.Function):
                 bias_sums.append((bias, biases))
             short = [(k, rs) for k, rs in lst if not rs.plan.csr.long_rows]
             long_ = [(k, rs) for k, rs in lst if rs.plan.csr.long_rows]
-            out = torch.empty(n_t, C_, **f32)
+            out = out_all[row0:row0 + n_t]
+            row0 += n_t
             for base in range(0, len(short), L.MAX_REL_PER_GROUP):
                 part = short[base:base + L.MAX_REL_PER_GROUP]
                 rows_waves.setdefault(base // L.MAX_REL_PER_GROUP, []).append(
@@ -1143,13 +1160,11 @@ class _HeteroGATFn(torch.autograd.Function):
             if temps and temps[0] is not out:
                 finals.append((out, ([out] if short else []) + temps, None if short else bias))
             outs[t] = out
-        for b, items in bias_sums:
-            _chain_sum(b, list(items))
+        _sum_many([(b, list(items), None) for b, items in bias_sums])
         for wave in sorted(rows_waves):
             ops.aggregate_rows(rows_waves[wave], C_)
         ops.aggregate_chunks(chunks, C_)
-        for out, ins, bias in finals:
-            _chain_sum(out, ins, bias)
+        _sum_many(finals)
 
         ctx.spec, ctx.nt = spec, nt
         ctx.slot_types = list(slots.keys())
@@ -1250,7 +1265,8 @@ class _HeteroGATFn(torch.autograd.Function):
                 dUV[t] = dA[t]
             else:
                 dUV[t] = torch.empty_like(UV[t])
-                gb.add(dUV[t], [(dA[t], xs[t])], split_k=ops.split_k_for(xs[t].shape[0]))
+                # few output rows, a very long reduction: short slabs (more CTAs in flight)
+                gb.add(dUV[t], [(dA[t], xs[t])], split_k=ops.split_k_for(xs[t].shape[0], slab=128))
         for k, rs in live:
             x = xs[rs.src]
             dwl = torch.empty(C_, x.shape[1], **f32)
@@ -1275,10 +1291,12 @@ class _HeteroGATFn(torch.autograd.Function):
             gb.add(dwr, [(params[rs.i_ar].view(C_, 1), dv.view(1, fd))])
             grads[pidx(rs.i_wr)] = dwr
             datt_l = torch.empty(C_, 1, **f32)
-            gb.add(datt_l, [(params[rs.i_wl], du.view(fs, 1))], split_k=ops.split_k_for(fs))
+            gb.add(datt_l, [(params[rs.i_wl], du.view(fs, 1))],
+                   split_k=ops.split_k_for(fs, slab=64))
             grads[pidx(rs.i_al)] = datt_l
             datt_r = torch.empty(C_, 1, **f32)
-            gb.add(datt_r, [(params[rs.i_wr], dv.view(fd, 1))], split_k=ops.split_k_for(fd))
+            gb.add(datt_r, [(params[rs.i_wr], dv.view(fd, 1))],
+                   split_k=ops.split_k_for(fd, slab=64))
             grads[pidx(rs.i_ar)] = datt_r
         for i, t in enumerate(spec.node_types):
             if not need_x[t]:
