@@ -1260,13 +1260,8 @@ class _HeteroGATFn(torch.autograd.Function):
         gb = ops.GemmBatch()
         trb: list = []
         dUV = {}
-        for t in dA:
-            if spec.identity.get(t, False):
-                dUV[t] = dA[t]
-            else:
-                dUV[t] = torch.empty_like(UV[t])
-                # few output rows, a very long reduction: short slabs (more CTAs in flight)
-                gb.add(dUV[t], [(dA[t], xs[t])], split_k=ops.split_k_for(xs[t].shape[0], slab=128))
+        # (the weight gradients first: a grouped call takes 24 problems, and the tensor-core
+        # split-K problems among them should share one launch)
         for k, rs in live:
             x = xs[rs.src]
             dwl = torch.empty(C_, x.shape[1], **f32)
@@ -1275,6 +1270,13 @@ class _HeteroGATFn(torch.autograd.Function):
                 trb.append((dwl, dxl[k]))                        # dX_l^T I
             else:
                 gb.add(dwl, [(_t(dxl[k]), x)], split_k=ops.split_k_for(rs.plan.n_src))
+        for t in dA:
+            if spec.identity.get(t, False):
+                dUV[t] = dA[t]
+            else:
+                dUV[t] = torch.empty_like(UV[t])
+                # few output rows, a very long reduction: short slabs (more CTAs in flight)
+                gb.add(dUV[t], [(dA[t], xs[t])], split_k=ops.split_k_for(xs[t].shape[0], slab=128))
         if trb:
             ops.transpose_many(trb)
         gb.run()
