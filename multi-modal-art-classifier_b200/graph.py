@@ -12,8 +12,8 @@ from typing import Dict, Optional, Tuple
 
 import torch
 
+from . import _lib as L
 from . import ops
-from ._lib import AgxError
 
 EdgeType = Tuple[str, str, str]
 
@@ -47,8 +47,7 @@ class HeteroPlan:
         keys = list(edge_index_dict.keys())
         for (s, r, d) in keys:
             ei = edge_index_dict[(s, r, d)]
-            if not ei.is_cuda:
-                raise AgxError('edge_index must be a CUDA tensor: this package has no CPU path')
+            L.require_cuda(ei, 'edge_index')
             if ei.dim() != 2 or ei.shape[0] != 2 or ei.dtype != torch.int64:
                 raise ValueError(f'edge_index of {(s, r, d)} must be int64 [2, E]')
             lists.append((ei[1], ei[0], num_dst[d], num_nodes[s]))       # CSR: key = dst

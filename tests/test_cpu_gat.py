@@ -147,3 +147,61 @@ def test_hetero_gat_layer_host_logic_vs_oracle():
     for k, p in pp.items():
         live = k.split('.')[0].endswith('__b')
         assert (p.grad is not None) == live, k
+
+
+@pytest.mark.parametrize('opname', ['SAGEConv', 'GraphConv'])
+def test_hetero_sage_graphconv_layer_host_logic_vs_oracle(opname):
+    """The same check for the fused SAGEConv / GraphConv layer (functional._HeteroConvFn):
+    transform-first and aggregate-first relations, one-hot inputs, hub rows in both directions."""
+    gen = torch.Generator().manual_seed(9)
+    n = {'a': 300, 'b': 7, 'c': 40}
+    feats = {'a': torch.randn(300, 20, generator=gen), 'b': torch.eye(7),
+             'c': torch.randn(40, 12, generator=gen)}
+    C = 16
+
+    def edges(ns, nd, e, hub=None):
+        s = torch.randint(0, ns, (e,), generator=gen)
+        d = torch.randint(0, nd, (e,), generator=gen)
+        if hub is not None:
+            d[: e // 2] = hub
+        return torch.stack([s, d])
+    ei = OrderedDict([
+        (('a', 'r1', 'b'), edges(300, 7, 3000, hub=3)),
+        (('c', 'r2', 'b'), edges(40, 7, 30)),
+        (('b', 'r3', 'a'), edges(7, 300, 500)),
+        (('c', 'r4', 'a'), edges(40, 300, 600)),
+        (('a', 'r5', 'a'), edges(300, 300, 900)),
+    ])
+    md = (list(n.keys()), list(ei.keys()))
+    convs_o = torch.nn.ModuleDict()
+    for (s, r, d) in ei:
+        cv = getattr(go, opname)((-1, -1), C)
+        with torch.no_grad():
+            cv((feats[s], feats[d]), ei[(s, r, d)])
+        convs_o['__'.join((s, r, d))] = cv
+    util.fill_params_deterministic(convs_o)
+    prod = agx.to_hetero(_OneConv(getattr(agx, opname), C), md, aggr='sum')
+    util.copy_state(convs_o, prod.conv)
+    convs_o = convs_o.double()
+    x_o = {t: v.double().requires_grad_(t != 'b') for t, v in feats.items()}
+    x_p = {t: v.clone().requires_grad_(t != 'b') for t, v in feats.items()}
+    outs_o = {}
+    for (s, r, d), e in ei.items():
+        o = convs_o['__'.join((s, r, d))]((x_o[s], x_o[d]), e)
+        outs_o[d] = o if d not in outs_o else outs_o[d] + o
+    w = {t: torch.randn(n[t], C, generator=gen) for t in outs_o}
+    sum((outs_o[t] * w[t].double()).sum() for t in outs_o).backward()
+    with cpu_ops():
+        agx.graph.clear_plan_cache()
+        outs_p = prod(x_p, ei)
+        assert list(outs_p.keys()) == list(outs_o.keys())
+        sum((outs_p[t] * w[t]).sum() for t in outs_p).backward()
+        agx.graph.clear_plan_cache()
+    for t in outs_o:
+        assert rel_err(outs_p[t], outs_o[t]) <= 1e-5, t
+    for t in ('a', 'c'):
+        assert rel_err(x_p[t].grad, x_o[t].grad) <= 5e-5, t
+    po, pp = dict(convs_o.named_parameters()), dict(prod.conv.named_parameters())
+    assert set(po) == set(pp)
+    for k in po:
+        assert rel_err(pp[k].grad, po[k].grad) <= 5e-5, k
