@@ -251,3 +251,41 @@ def test_context_heads_oracle_matches_reference_golden():
         assert np.allclose(m.encoder[0].weight.grad.numpy()[:8], gold[f'{tag}_grad_enc0_w'],
                            rtol=1e-5, atol=1e-9)
         assert np.allclose(f_in.grad.numpy()[:8], gold[f'{tag}_grad_feat'], rtol=1e-5, atol=1e-9)
+
+
+def test_gatconv_oracle_vs_dense_attention():
+    """Independent second opinion for the GATConv restatement: the same layer written as dense
+    masked attention (an [N_dst, N_src] multiplicity matrix, torch.softmax over the rows) in
+    float64 -- duplicate edges count twice, existing self loops are dropped and (i, i) added for
+    i < min(N_src, N_dst), rows without any edge give the bias."""
+    gen = torch.Generator().manual_seed(17)
+    n_src, n_dst, C = 23, 31, 8
+    ei = torch.stack([torch.randint(0, n_src, (90,), generator=gen),
+                      torch.randint(0, n_dst - 3, (90,), generator=gen)])
+    ei[:, :4] = torch.tensor([[1, 1, 5, 5], [1, 1, 7, 7]])       # a repeated self loop, a duplicate
+    xs, xd = torch.randn(n_src, 6, generator=gen), torch.randn(n_dst, 9, generator=gen)
+    conv = go.GATConv((-1, -1), C)
+    with torch.no_grad():
+        conv((xs, xd), ei)
+    util.fill_params_deterministic(conv)
+    with torch.no_grad():
+        conv.bias.copy_(torch.linspace(-1, 1, C))
+    conv = conv.double()
+    out = conv((xs.double(), xd.double()), ei)
+
+    x_l = xs.double() @ conv.lin_l.weight.t()
+    a_l = x_l @ conv.att_l.view(-1)
+    a_r = (xd.double() @ conv.lin_r.weight.t()) @ conv.att_r.view(-1)
+    mult = torch.zeros(n_dst, n_src, dtype=torch.float64)
+    for s, d in ei.t().tolist():
+        if s != d:
+            mult[d, s] += 1
+    for i in range(min(n_src, n_dst)):
+        mult[i, i] += 1
+    logits = torch.nn.functional.leaky_relu(a_r[:, None] + a_l[None, :], 0.2)
+    w = mult * torch.exp(logits - logits.max())
+    alpha = w / w.sum(1, keepdim=True).clamp(min=1e-300)
+    want = alpha @ x_l + conv.bias
+    assert mult[n_dst - 1].sum() == 0                            # a row with no edge at all
+    assert rel_err(out, want) <= 1e-12
+    assert torch.allclose(out[n_dst - 1], conv.bias)
