@@ -167,26 +167,188 @@ def _is_identity(x):
     return torch.tensor(int(x.shape[0] == x.shape[1] and bool(torch.equal(x, torch.eye(n)))))
 
 
+def _scale_mask(x, mask):
+    return x * mask
+
+
+def _zeros(shape, device):
+    return torch.zeros(shape, dtype=torch.float32, device=device)
+
+
+# ------------------------------------------------------------------------------------------------
+# pointer-level restatement of the entry points functional.py calls on ``lib()`` directly
+# (BatchNorm, log_softmax / nll): host addresses of CPU tensors viewed through numpy
+# ------------------------------------------------------------------------------------------------
+def _view(addr, rows, cols, ld=None, dtype=torch.float32):
+    """torch view of ``rows x cols`` elements at host address ``addr`` (row stride ``ld``)."""
+    import ctypes
+    import numpy as np
+    if not addr:
+        return None
+    ld = cols if ld is None else int(ld)
+    ct = {torch.float32: ctypes.c_float, torch.int64: ctypes.c_int64}[dtype]
+    n = (rows - 1) * ld + cols if rows > 0 else 0
+    if n == 0:
+        return torch.empty(rows, cols, dtype=dtype)
+    flat = torch.from_numpy(np.ctypeslib.as_array((ct * n).from_address(int(addr))))
+    return torch.as_strided(flat, (rows, cols), (ld, 1))
+
+
+class _FakeLib:
+    """The agx_* functions with device pointers replaced by host addresses (include/agx.h
+    semantics, float64 arithmetic, results rounded to float32 once)."""
+
+    def agx_last_error(self):
+        return b'cpu shim'
+
+    def agx_bn_workspace_floats(self, rows, n, F):
+        return 16
+
+    def agx_bn_forward(self, arr, n, F, training, momentum, eps, ws, n_ws, stream):
+        for i in range(n):
+            d = arr[i]
+            N = d.n_rows
+            x = _view(d.x, N, F).double()
+            w, b = _view(d.weight, 1, F).double(), _view(d.bias, 1, F).double()
+            rm, rv = _view(d.running_mean, 1, F), _view(d.running_var, 1, F)
+            if training:
+                mean = x.mean(0, keepdim=True)
+                var = x.var(0, unbiased=False, keepdim=True)
+                if rm is not None:
+                    rm.copy_(((1 - momentum) * rm.double() + momentum * mean).float())
+                    rv.copy_(((1 - momentum) * rv.double() + momentum * var * N / (N - 1)).float())
+            else:
+                mean, var = rm.double(), rv.double()
+            invstd = 1.0 / torch.sqrt(var + eps)
+            y = (x - mean) * invstd * w + b
+            _view(d.y, N, F).copy_(y.float())
+            _view(d.save_mean, 1, F).copy_(mean.float())
+            _view(d.save_invstd, 1, F).copy_(invstd.float())
+            if d.y_act:
+                a = torch.relu(_view(d.y, N, F).double())
+                if d.dmask:
+                    a = a * _view(d.dmask, N, F).double()
+                _view(d.y_act, N, F).copy_(a.float())
+        return 0
+
+    def agx_bn_backward(self, arr, n, F, training, ws, n_ws, stream):
+        for i in range(n):
+            d = arr[i]
+            N = d.n_rows
+            x = _view(d.x, N, F).double()
+            g = torch.zeros(N, F, dtype=torch.float64)
+            if d.dy:
+                g = g + _view(d.dy, N, F).double()
+            if d.dy_act:
+                ga = _view(d.dy_act, N, F).double() * (_view(d.y, N, F) > 0).double()
+                if d.dmask:
+                    ga = ga * _view(d.dmask, N, F).double()
+                g = g + ga
+            w = _view(d.weight, 1, F).double()
+            mean, invstd = _view(d.save_mean, 1, F).double(), _view(d.save_invstd, 1, F).double()
+            xhat = (x - mean) * invstd
+            if d.dweight:
+                dw = _view(d.dweight, 1, F)
+                dw.copy_((dw.double() + (g * xhat).sum(0, keepdim=True)).float())
+            if d.dbias:
+                db = _view(d.dbias, 1, F)
+                db.copy_((db.double() + g.sum(0, keepdim=True)).float())
+            if d.dx:
+                if training:
+                    dx = w * invstd * (g - g.mean(0, keepdim=True) -
+                                       xhat * (g * xhat).mean(0, keepdim=True))
+                else:
+                    dx = g * w * invstd
+                _view(d.dx, N, F).copy_(dx.float())
+        return 0
+
+    @staticmethod
+    def _weights(labels, class_w, n, C):
+        y = _view(labels, 1, n, dtype=torch.int64).view(-1)
+        ok = (y >= 0) & (y < C)
+        wy = ok.double()
+        if class_w:
+            wy = wy * _view(class_w, 1, C).double().view(-1)[y.clamp(0, C - 1)]
+        return y.clamp(0, C - 1), wy
+
+    def agx_log_softmax_nll(self, logits, ld, n, C, labels, class_w, logp, ldp, loss_sum, row_ws,
+                            stream):
+        lp = torch.log_softmax(_view(logits, n, C, ld).double(), dim=1)
+        if logp:
+            _view(logp, n, C, ldp).copy_(lp.float())
+        if labels:
+            y, wy = self._weights(labels, class_w, n, C)
+            nll = -lp[torch.arange(n), y]
+            _view(loss_sum, 1, 2).copy_(torch.stack([(wy * nll).sum(), wy.sum()]).float().view(1, 2))
+        return 0
+
+    def agx_nll_forward(self, logp, ld, n, C, labels, class_w, loss_sum, row_ws, stream):
+        lp = _view(logp, n, C, ld).double()
+        y, wy = self._weights(labels, class_w, n, C)
+        nll = -lp[torch.arange(n), y]
+        _view(loss_sum, 1, 2).copy_(torch.stack([(wy * nll).sum(), wy.sum()]).float().view(1, 2))
+        return 0
+
+    def agx_nll_backward(self, n, C, labels, class_w, loss_sum, gscale, coef, dlogp, ld, stream):
+        y, wy = self._weights(labels, class_w, n, C)
+        ls = _view(loss_sum, 1, 2).double().view(-1)
+        gs = _view(gscale, 1, 1).double().view(-1)[0]
+        out = torch.zeros(n, C, dtype=torch.float64)
+        out[torch.arange(n), y] = -coef * gs * wy / ls[1]
+        _view(dlogp, n, C, ld).copy_(out.float())
+        return 0
+
+    def agx_loss_finish(self, loss_sum, coef, loss, accumulate, stream):
+        ls = _view(loss_sum, 1, 2).double().view(-1)
+        out = _view(loss, 1, 1)
+        v = coef * ls[0] / ls[1]
+        out.copy_((out.double() + v if accumulate else v).float().view(1, 1))
+        return 0
+
+    def agx_log_softmax_nll_bwd(self, logp, ldp, n, C, labels, class_w, loss_sum, gscale, coef,
+                                dlogp, lddp, dlogits, ld, stream):
+        lp = _view(logp, n, C, ldp).double()
+        sm = torch.exp(lp)
+        out = torch.zeros(n, C, dtype=torch.float64)
+        if labels:
+            y, wy = self._weights(labels, class_w, n, C)
+            ls = _view(loss_sum, 1, 2).double().view(-1)
+            gs = _view(gscale, 1, 1).double().view(-1)[0]
+            onehot = torch.zeros(n, C, dtype=torch.float64)
+            onehot[torch.arange(n), y] = 1.0
+            out = coef * gs * wy[:, None] * (sm - onehot) / ls[1]
+        if dlogp:
+            g = _view(dlogp, n, C, lddp).double()
+            out = out + g - sm * g.sum(1, keepdim=True)
+        _view(dlogits, n, C, ld).copy_(out.float())
+        return 0
+
+
 _PATCHES = {
     'csr_build': _csr_build, 'aggregate_rows': _aggregate_rows,
     'aggregate_chunks': _aggregate_chunks, 'GemmBatch': _GemmBatch,
     'gat_edge_softmax': _gat_edge_softmax, 'sddmm': _sddmm, 'sum_arrays': _sum_arrays,
     'colsum': _colsum, 'transpose_many': _transpose_many, 'is_identity': _is_identity,
-    'fill_': _fill_,
+    'fill_': _fill_, 'scale_mask': _scale_mask, 'zeros': _zeros,
 }
 
 
 @contextlib.contextmanager
 def cpu_ops():
     """Inside the block ``mmac_b200.ops`` computes with torch on CPU (see the module docstring)."""
+    from mmac_b200 import functional as AF
     saved = {k: getattr(ops, k) for k in _PATCHES}
-    saved_req = L.require_cuda
+    saved_req, saved_lib, saved_stream = L.require_cuda, AF.lib, AF.stream_ptr
+    fake = _FakeLib()
     try:
         for k, v in _PATCHES.items():
             setattr(ops, k, v)
         L.require_cuda = lambda t, name: None
+        AF.lib = lambda: fake
+        AF.stream_ptr = lambda: 0
         yield
     finally:
         for k, v in saved.items():
             setattr(ops, k, v)
         L.require_cuda = saved_req
+        AF.lib, AF.stream_ptr = saved_lib, saved_stream

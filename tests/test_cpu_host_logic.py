@@ -1,7 +1,8 @@
-"""CPU suite, part 4: host-side logic of the fused GATConv layer (functional._HeteroGATFn): which
-buffers meet which index arrays, the gradient formulas and the GEMM wave order, checked against
-the oracle with the ``ops`` entry points restated in torch (tests/cpu_shim.py).  The kernels
-themselves are compared with the oracle on the GPU (tests/test_gpu_model.py, test_gpu_kernels.py)."""
+"""CPU suite, part 4: HOST-SIDE logic of the fused layers and of the whole hetero model (functional.
+_HeteroGATFn / _HeteroConvFn / _BNActFn / losses, hetero.HeteroModule): which buffers meet which index
+arrays, the gradient formulas, the GEMM wave order, descriptor wiring -- checked against the oracle with
+every agx entry point restated in torch (tests/cpu_shim.py).  The kernels themselves are compared with
+the oracle on the GPU (tests/test_gpu_model.py, test_gpu_kernels.py)."""
 from collections import OrderedDict
 
 import pytest
@@ -205,3 +206,62 @@ def test_hetero_sage_graphconv_layer_host_logic_vs_oracle(opname):
     assert set(po) == set(pp)
     for k in po:
         assert rel_err(pp[k].grad, po[k].grad) <= 5e-5, k
+
+
+@pytest.mark.parametrize('opname', ['SAGEConv', 'GraphConv', 'GATConv'])
+def test_whole_model_host_logic_vs_oracle(opname):
+    """HeteroSGNN through to_hetero on the tiny ArtGraph (one-hot inputs, 17 relations, BatchNorm,
+    fused ReLU + dropout with injected masks, log_softmax, nll_loss): the product's host logic
+    (tracing, fusion plan, descriptor wiring, gradient delivery) against the oracle, every agx
+    entry point restated in torch (tests/cpu_shim.py)."""
+    import copy
+    g, ei, md = util.undirected_graph('tiny')
+    C = 32
+    orc = go.HeteroSGNNOracle(getattr(go, opname), torch.nn.ReLU(), 'sum', 128, C, md, 2, 0.4,
+                              True, False)
+    with torch.no_grad():
+        orc(g.x_dict, ei)
+    util.fill_params_deterministic(orc)
+    util.reset_bn(orc)
+    prod = agx.HeteroSGNN(getattr(agx, opname), torch.nn.ReLU(), 'sum', 128, C, md, 2, 0.4, True,
+                          False)
+    util.copy_state(orc, prod)
+    gen = torch.Generator().manual_seed(77)
+    masks = {t: (torch.rand(n, 128, generator=gen) >= 0.4).float() / 0.6
+             for t, n in g.num_nodes_dict.items()}
+    o64 = copy.deepcopy(orc).double()
+    o64.gnn.dropout_masks = {t: m.double() for t, m in masks.items()}
+    prod.gnn.dropout_masks = masks
+    o64.train(); prod.train()
+    y = g['artwork'].y_style
+    e_o, o_o = o64({k: v.double() for k, v in g.x_dict.items()}, ei)
+    l_o = go.nll_loss_artwork(o_o[0], y)
+    l_o.backward()
+    with cpu_ops():
+        agx.graph.clear_plan_cache()
+        agx.functional.GATPlan._cache.clear()
+        e_p, o_p = prod(g.x_dict, ei)
+        l_p = agx.functional.nll_loss(o_p[0]['artwork'], y)
+        l_p.backward()
+        agx.graph.clear_plan_cache()
+        agx.functional.GATPlan._cache.clear()
+    assert list(e_p.keys()) == list(e_o.keys())
+    for t in e_o:
+        assert rel_err(e_p[t], e_o[t]) <= 2e-5, ('emb', t)
+        assert rel_err(o_p[0][t], o_o[0][t]) <= 2e-5, ('logp', t)
+    assert rel_err(l_p, l_o) <= 1e-5
+    og = {n: p.grad for n, p in o64.named_parameters() if p.grad is not None}
+    pg = {n: p.grad for n, p in prod.named_parameters() if p.grad is not None}
+    if opname == 'GraphConv':
+        og = {n.replace('.lin_l.', '.lin_rel.').replace('.lin_r.', '.lin_root.'): v
+              for n, v in og.items()}
+    gmax = max(float(v.abs().max()) for v in og.values())
+    for n, v in og.items():
+        if float(v.abs().max()) == 0.0 and n not in pg:
+            continue
+        err = float((pg[n].double() - v).abs().max())
+        # (noise-level tensors -- biases in front of a training-mode BatchNorm have a zero true
+        # gradient -- are compared on the scale of the model's gradients, as in the GPU suite)
+        assert err <= 1e-4 * max(float(v.abs().max()), 1e-2 * gmax), (n, err)
+    for (n, b_o), (_, b_p) in zip(o64.named_buffers(), prod.named_buffers()):
+        assert rel_err(b_p, b_o) <= 1e-5, n
