@@ -186,7 +186,8 @@ def _view(addr, rows, cols, ld=None, dtype=torch.float32):
     if not addr:
         return None
     ld = cols if ld is None else int(ld)
-    ct = {torch.float32: ctypes.c_float, torch.int64: ctypes.c_int64}[dtype]
+    ct = {torch.float32: ctypes.c_float, torch.int64: ctypes.c_int64, torch.int32: ctypes.c_int32,
+          torch.float64: ctypes.c_double}[dtype]
     n = (rows - 1) * ld + cols if rows > 0 else 0
     if n == 0:
         return torch.empty(rows, cols, dtype=dtype)
@@ -260,6 +261,86 @@ class _FakeLib:
                 else:
                     dx = g * w * invstd
                 _view(d.dx, N, F).copy_(dx.float())
+        return 0
+
+    # -- multi-GPU BatchNorm: statistics over the rows of all ranks (phases, see agx.h) ----------
+    def agx_bn_forward_phase(self, arr, n, F, training, momentum, eps, ws, n_ws, phases, sums,
+                             counts, stream):
+        S = _view(sums, n, 2 * F, dtype=torch.float64)
+        cnt = _view(counts, 1, n, dtype=torch.float64).view(-1)
+        for i in range(n):
+            d = arr[i]
+            N = d.n_rows
+            x = _view(d.x, N, F).double()
+            if phases & 1:
+                S[i, :F] = x.sum(0)
+                S[i, F:] = (x * x).sum(0)
+            if phases & 4:
+                c = float(cnt[i])
+                mean = (S[i, :F] / c).view(1, F)
+                var = (S[i, F:] / c).view(1, F) - mean * mean
+                rm, rv = _view(d.running_mean, 1, F), _view(d.running_var, 1, F)
+                if rm is not None:
+                    rm.copy_(((1 - momentum) * rm.double() + momentum * mean).float())
+                    rv.copy_(((1 - momentum) * rv.double() + momentum * var * c / (c - 1)).float())
+                invstd = 1.0 / torch.sqrt(var + eps)
+                w, b = _view(d.weight, 1, F).double(), _view(d.bias, 1, F).double()
+                _view(d.y, N, F).copy_(((x - mean) * invstd * w + b).float())
+                _view(d.save_mean, 1, F).copy_(mean.float())
+                _view(d.save_invstd, 1, F).copy_(invstd.float())
+                if d.y_act:
+                    a = torch.relu(_view(d.y, N, F).double())
+                    if d.dmask:
+                        a = a * _view(d.dmask, N, F).double()
+                    _view(d.y_act, N, F).copy_(a.float())
+        return 0
+
+    def agx_bn_backward_phase(self, arr, n, F, training, ws, n_ws, phases, totals, counts, stream):
+        T = _view(totals, n, 2 * F, dtype=torch.float64)
+        cnt = _view(counts, 1, n, dtype=torch.float64).view(-1)
+        for i in range(n):
+            d = arr[i]
+            N = d.n_rows
+            x = _view(d.x, N, F).double()
+            g = torch.zeros(N, F, dtype=torch.float64)
+            if d.dy:
+                g = g + _view(d.dy, N, F).double()
+            if d.dy_act:
+                ga = _view(d.dy_act, N, F).double() * (_view(d.y, N, F) > 0).double()
+                if d.dmask:
+                    ga = ga * _view(d.dmask, N, F).double()
+                g = g + ga
+            mean, invstd = _view(d.save_mean, 1, F).double(), _view(d.save_invstd, 1, F).double()
+            xhat = (x - mean) * invstd
+            if phases & 1:
+                T[i, :F] = g.sum(0)
+                T[i, F:] = (g * xhat).sum(0)
+                if d.dweight:
+                    dw = _view(d.dweight, 1, F)
+                    dw.copy_((dw.double() + (g * xhat).sum(0, keepdim=True)).float())
+                if d.dbias:
+                    db = _view(d.dbias, 1, F)
+                    db.copy_((db.double() + g.sum(0, keepdim=True)).float())
+            if phases & 2 and d.dx:
+                c = float(cnt[i])
+                w = _view(d.weight, 1, F).double()
+                dx = w * invstd * (g - T[i, :F].view(1, F) / c - xhat * T[i, F:].view(1, F) / c)
+                _view(d.dx, N, F).copy_(dx.float())
+        return 0
+
+    # -- boundary rows of a destination partition ----------------------------------------------
+    def agx_pack_rows(self, x, ld, idx, n_idx, F, out, stream):
+        if n_idx:
+            rows = _view(idx, 1, n_idx, dtype=torch.int32).view(-1).long()
+            xv = _view(x, int(rows.max()) + 1, F, ld)
+            _view(out, n_idx, F).copy_(xv[rows])
+        return 0
+
+    def agx_unpack_rows_add(self, x, ld, idx, n_idx, F, src, stream):
+        if n_idx:
+            rows = _view(idx, 1, n_idx, dtype=torch.int32).view(-1).long()
+            xv = _view(x, int(rows.max()) + 1, F, ld)
+            xv.index_add_(0, rows, _view(src, n_idx, F))
         return 0
 
     @staticmethod
@@ -336,19 +417,23 @@ _PATCHES = {
 @contextlib.contextmanager
 def cpu_ops():
     """Inside the block ``mmac_b200.ops`` computes with torch on CPU (see the module docstring)."""
+    from mmac_b200 import dist as AD
     from mmac_b200 import functional as AF
     saved = {k: getattr(ops, k) for k in _PATCHES}
-    saved_req, saved_lib, saved_stream = L.require_cuda, AF.lib, AF.stream_ptr
+    saved_req = L.require_cuda
+    saved_mod = [(m, m.lib, m.stream_ptr) for m in (AF, AD)]
     fake = _FakeLib()
     try:
         for k, v in _PATCHES.items():
             setattr(ops, k, v)
         L.require_cuda = lambda t, name: None
-        AF.lib = lambda: fake
-        AF.stream_ptr = lambda: 0
+        for m, _, _ in saved_mod:
+            m.lib = lambda: fake
+            m.stream_ptr = lambda: 0
         yield
     finally:
         for k, v in saved.items():
             setattr(ops, k, v)
         L.require_cuda = saved_req
-        AF.lib, AF.stream_ptr = saved_lib, saved_stream
+        for m, lib_, sp_ in saved_mod:
+            m.lib, m.stream_ptr = lib_, sp_

@@ -187,3 +187,104 @@ def test_balanced_bounds_equalise_edges():
         assert sum(even) == sum(bal) == sum(v.shape[1] for v in ei.values())
         assert max(bal) / min(bal) < max(even) / min(even)
         assert max(bal) <= 1.25 * sum(bal) / world
+
+
+# ------------------------------------------------------------------------------------------------
+# the PRODUCT's multi-GPU path itself (hetero module + dist.HaloExchange + cross-rank BatchNorm /
+# loss) on two gloo ranks, every agx entry point restated in torch (tests/cpu_shim.py)
+# ------------------------------------------------------------------------------------------------
+def _product_worker(rank, world, port, opname, errq):
+    try:
+        os.environ['MASTER_ADDR'] = '127.0.0.1'
+        os.environ['MASTER_PORT'] = str(port)
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+        torch.set_num_threads(2)
+        import mmac_b200 as agx
+        from cpu_shim import cpu_ops
+        from mmac_b200 import synth
+        from mmac_b200.dist import GraphPartition, partition_context
+        from mmac_b200.hetero import HeteroModule
+        from util import rel_err
+        g = synth.make_artgraph('tiny', features='dense')
+        ei = go.to_undirected(g.edge_index_dict)
+        md = (g.node_types, list(ei.keys()))
+        n = g.num_nodes_dict
+        y = g['artwork'].y_style
+        orc = go.HeteroSGNNOracle(getattr(go, opname), torch.nn.ReLU(), 'sum', 128, 32, md, 2, 0.0,
+                                  True, False)
+        with torch.no_grad():
+            orc(g.x_dict, ei)
+        util.fill_params_deterministic(orc)
+        util.reset_bn(orc)
+        prod = agx.HeteroSGNN(getattr(agx, opname), torch.nn.ReLU(), 'sum', 128, 32, md, 2, 0.0,
+                              True, False)
+        util.copy_state(orc, prod)
+        o64 = orc.double().train()
+        e_o, o_o = o64({k: v.double() for k, v in g.x_dict.items()}, ei)
+        l_o = go.nll_loss_artwork(o_o[0], y)
+        l_o.backward()
+
+        part = GraphPartition(ei, n, world, rank)
+        assert part.has_halo
+        ctx = partition_context(part, dist.group.WORLD, 'cpu')
+        for m in prod.modules():
+            if isinstance(m, HeteroModule):
+                m.set_distributed(ctx)
+        prod.train()
+        x_own = {t: part.owned(t, v).contiguous() for t, v in g.x_dict.items()}
+        with cpu_ops():
+            e_p, o_p = prod(x_own, part.edge_index)
+            l_p = agx.functional.nll_loss(o_p[0]['artwork'], part.owned('artwork', y),
+                                          dist.group.WORLD)
+            l_p.backward()
+        assert rel_err(l_p, l_o) <= 1e-5                      # the GLOBAL loss on every rank
+        for t in e_o:
+            lo, hi = part.bounds[t][rank], part.bounds[t][rank + 1]
+            if hi > lo:
+                assert rel_err(e_p[t], e_o[t][lo:hi]) <= 2e-5, ('emb', t)
+                assert rel_err(o_p[0][t], o_o[0][t][lo:hi]) <= 2e-5, ('logp', t)
+        og = {k: p.grad for k, p in o64.named_parameters() if p.grad is not None}
+        if opname == 'GraphConv':
+            og = {k.replace('.lin_l.', '.lin_rel.').replace('.lin_r.', '.lin_root.'): v
+                  for k, v in og.items()}
+        pp = dict(prod.named_parameters())
+        gmax = max(float(v.abs().max()) for v in og.values())
+        for k in sorted(og):
+            p = pp[k]
+            gk = p.grad.clone() if p.grad is not None else torch.zeros_like(p)
+            dist.all_reduce(gk)                               # weight gradients: sum over ranks
+            err = float((gk.double() - og[k]).abs().max())
+            scale = float(og[k].abs().max())
+            # small tensors (biases in front of a training-mode BatchNorm have a zero true gradient,
+            # BatchNorm biases are sums of thousands of cancelling terms) carry float32 noise on
+            # the scale of the model's gradients, as in tests/test_gpu_model.py
+            assert err <= max(1e-4 * scale, 2e-6 * gmax), (k, err, scale)
+        for (k, b_o), (_, b_p) in zip(o64.named_buffers(), prod.named_buffers()):
+            assert rel_err(b_p, b_o) <= 1e-5, k                # running statistics of ALL rows
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        errq.put(f'rank {rank}:\\n{traceback.format_exc()}')
+        raise
+
+
+@pytest.mark.parametrize('opname', ['SAGEConv', 'GraphConv'])
+def test_product_cut_partition_world2_gloo(opname):
+    """Two ranks, one graph cut by destination node: embeddings / log-probabilities of the owned
+    rows, the global loss, the all-reduced weight gradients and the BatchNorm running statistics
+    equal the single-process oracle on the whole graph."""
+    world = 2
+    ctx = mp.get_context('spawn')
+    errq = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_product_worker, args=(r, world, port, opname, errq))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+    msgs = []
+    while not errq.empty():
+        msgs.append(errq.get())
+    assert not msgs, '\\n'.join(msgs)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
