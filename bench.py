@@ -290,7 +290,11 @@ def run_ours(args):
         # relations dominate either way)
         bounds = balanced_bounds(data.edge_index_dict, data.num_nodes_dict, world) \
             if args.balanced_cut else None
-        part = GraphPartition(data.edge_index_dict, data.num_nodes_dict, world, rank, bounds)
+        # --replicate-small: every node type but artwork lives on all ranks: no
+        # boundary rows, the artwork -> X neighbour sums are all-reduced inside the conv layer
+        part = GraphPartition(data.edge_index_dict, data.num_nodes_dict, world, rank, bounds,
+                              replicated=[t for t in data.num_nodes_dict if t != 'artwork']
+                              if args.replicate_small else ())
         host_x = OrderedDict((k, part.owned(k, v).contiguous().pin_memory())
                              for k, v in data.x_dict.items())
         host_ei = OrderedDict((k, v.pin_memory()) for k, v in part.edge_index.items())
@@ -475,6 +479,11 @@ def run_ours(args):
                        'directed_edges_per_gpu': n_edges,
                        'edges_per_step_per_gpu': PASSES * n_edges,
                        'parallelism': 'single GPU' if world == 1 else (
+                           f'artwork rows cut into {world} ranges, every other node type replicated '
+                           f'on all ranks; per conv layer one all-reduce of the partial neighbour '
+                           f'sums of the artwork -> X relations (and one of their gradients); '
+                           f'weight-gradient, BatchNorm and loss all-reduces'
+                           if cut and args.replicate_small else
                            f'one graph cut into {world} destination ranges per node type; per conv '
                            f'layer an NCCL all-gather of boundary source rows '
                            f'({part.halo_rows()} rows received per exchange on rank 0) and a '
@@ -526,6 +535,9 @@ def main():
                     help="N > 1: 'blocks' = N-times replicated graph, one block per rank (weak "
                          "scaling, the default the driver measures); 'cut' = one graph cut by "
                          "destination node with boundary-row all-gather (strong scaling)")
+    ap.add_argument('--replicate-small', action='store_true',
+                    help="--partition cut: replicate every node type but artwork on all ranks "
+                         "(partial neighbour sums all-reduced; no boundary-row exchange)")
     ap.add_argument('--balanced-cut', action='store_true',
                     help="--partition cut: destination ranges with equal incoming edges, not rows")
     ap.add_argument('--e2e-serial', action='store_true',

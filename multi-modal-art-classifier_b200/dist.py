@@ -86,9 +86,20 @@ class GraphPartition:
     """
 
     def __init__(self, edge_index_dict, num_nodes: Dict[str, int], world: int, rank: int,
-                 bounds: Optional[Dict[str, List[int]]] = None):
+                 bounds: Optional[Dict[str, List[int]]] = None, replicated=()):
         self.world, self.rank = int(world), int(rank)
         self.num_nodes = OrderedDict((t, int(n)) for t, n in num_nodes.items())
+        # ``replicated`` node types (the tiny ones -- style, genre, field, media,
+        # movement, gallery, ...) live on EVERY rank with all their rows:
+        #   replicated -> partitioned relation : every source row is local, nothing is exchanged
+        #   partitioned -> replicated relation : a rank owns the edges whose SOURCE it owns and
+        #       produces PARTIAL neighbour sums for all destination rows (``partial`` relations: the
+        #       conv layer all-reduces them, [N_t, F] floats instead of the source rows)
+        #   replicated -> replicated relation  : computed by every rank, redundantly
+        self.replicated = set(replicated)
+        for t in self.replicated:
+            if t not in self.num_nodes:
+                raise ValueError(f'replicated type {t} is not a node type')
         self.bounds = {t: list(bounds[t]) if bounds and t in bounds else split_bounds(n, world)
                        for t, n in self.num_nodes.items()}
         for t, b in self.bounds.items():
@@ -104,13 +115,25 @@ class GraphPartition:
         # 1. boundary rows: sources of edges whose destination lives on another rank
         is_b = {t: torch.zeros(n, dtype=torch.bool, device=dev) for t, n in self.num_nodes.items()}
         own_dst = {}
+        rep = self.replicated
+        self.partial: "OrderedDict[tuple, torch.Tensor]" = OrderedDict()
         for (s, r, d), ei in edge_index_dict.items():
             if ei.numel() and (int(ei[0].max()) >= self.num_nodes[s] or int(ei[0].min()) < 0 or
                                int(ei[1].max()) >= self.num_nodes[d] or int(ei[1].min()) < 0):
                 raise IndexError('edge_index contains node ids outside [0, num_nodes)')
+            if d in rep:
+                if s in rep:                      # every rank computes the whole relation
+                    own_dst[(s, r, d)] = torch.full_like(ei[1], rank)
+                else:                             # edges follow their SOURCE; sums are partial
+                    own_dst[(s, r, d)] = owner(s, ei[0])
+                    # max(in-degree over ALL ranks' edges, 1): the divisor of scatter-mean
+                    self.partial[(s, r, d)] = torch.bincount(
+                        ei[1], minlength=self.num_nodes[d]).clamp(min=1).to(torch.float32)
+                continue
             od = owner(d, ei[1])
             own_dst[(s, r, d)] = od
-            is_b[s][ei[0][owner(s, ei[0]) != od]] = True
+            if s not in rep:
+                is_b[s][ei[0][owner(s, ei[0]) != od]] = True
 
         # 2. slots of the boundary rows inside their owner's packed send buffer
         self.n_owned: Dict[str, int] = {}
@@ -121,6 +144,14 @@ class GraphPartition:
         self.ext_global: Dict[str, torch.Tensor] = {}
         ext_of_global = {}
         for t, n in self.num_nodes.items():
+            if t in rep:                          # all rows, in global order, no boundary region
+                self.n_boundary[t] = [0] * world
+                self.max_boundary[t] = 0
+                self.n_owned[t] = self.n_ext[t] = n
+                self.boundary_idx[t] = torch.zeros(0, dtype=torch.int32, device=dev)
+                ext_of_global[t] = torch.arange(n, dtype=torch.int64, device=dev)
+                self.ext_global[t] = ext_of_global[t]
+                continue
             lo, hi = self.bounds[t][rank], self.bounds[t][rank + 1]
             csum0 = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev),
                                torch.cumsum(is_b[t].to(torch.int64), 0)])
@@ -147,15 +178,19 @@ class GraphPartition:
         self.edge_index = OrderedDict()
         for (s, r, d), ei in edge_index_dict.items():
             m = own_dst[(s, r, d)] == rank
+            dst0 = 0 if d in rep else self.bounds[d][rank]
             self.edge_index[(s, r, d)] = torch.stack(
-                [ext_of_global[s][ei[0][m]], ei[1][m] - self.bounds[d][rank]], dim=0).contiguous()
+                [ext_of_global[s][ei[0][m]], ei[1][m] - dst0], dim=0).contiguous()
 
     @property
     def has_halo(self) -> bool:
         return any(b > 0 for b in self.max_boundary.values())
 
     def owned(self, t: str, x_global: torch.Tensor) -> torch.Tensor:
-        """This rank's rows of a per-node tensor of type t (features, labels)."""
+        """This rank's rows of a per-node tensor of type t (features, labels): all rows of a
+        replicated type."""
+        if t in self.replicated:
+            return x_global
         return x_global[self.bounds[t][self.rank]:self.bounds[t][self.rank + 1]]
 
     def halo_rows(self) -> int:
@@ -259,6 +294,8 @@ class DistContext:
     num_nodes_global: Dict[str, int]            # rows of every node type over all ranks
     halo: Optional[HaloExchange] = None
     _counts: Optional[dict] = None
+    replicated: frozenset = frozenset()         # node types every rank holds completely
+    partial: Optional[dict] = None              # edge type -> global max(in-degree, 1) [N_dst]
 
     def __deepcopy__(self, memo):           # process groups are not copyable; share the context
         return self
@@ -286,7 +323,9 @@ def block_context(group, num_nodes_block: Dict[str, int]) -> DistContext:
 
 def partition_context(part: GraphPartition, group, device) -> DistContext:
     halo = HaloExchange(part, group, device) if part.has_halo else None
-    return DistContext(group, part.rank, part.world, dict(part.num_nodes), halo)
+    return DistContext(group, part.rank, part.world, dict(part.num_nodes), halo,
+                       replicated=frozenset(part.replicated),
+                       partial={k: v.to(device) for k, v in part.partial.items()})
 
 
 def all_reduce_(t: torch.Tensor, group) -> torch.Tensor:

@@ -35,6 +35,9 @@ class RelSpec:
     i_bl: int                     # -1: no bias
     i_wr: int                     # -1: no root weight
     transform_first: bool = False
+    partial: bool = False         # multi-GPU: this rank holds SOME of each destination's edges
+                                  # (partitioned source -> replicated destination type); the
+                                  # neighbour sums of all ranks are all-reduced inside the layer
 
 
 @dataclass
@@ -47,6 +50,7 @@ class ConvSpec:
     identity: Dict[str, bool] = field(default_factory=dict)   # type -> x[type] is eye(N)
     planned: bool = False
     param_refs: Optional[list] = None    # the nn.Parameters behind the flat parameter list
+    group: object = None                 # process group of the partial relations' all-reduce
 
     def plan_modes(self, feat_dims: Dict[str, int]):
         """Per relation: transform-first (Y = X_src W_l^T, gather at width O) or aggregate-first
@@ -69,6 +73,10 @@ class ConvSpec:
             tf += r.n_edges * O * 4.0 / _BYTE_RATE
             af = r.n_edges * fs * 4.0 / _BYTE_RATE + gemm_cost(r.n_dst)
             rs.transform_first = tf < af or (tf <= af * 1.05 and r.n_src <= r.n_dst)
+            if rs.partial:
+                # aggregate first: the [N_dst, F_src] partial sums are what is all-reduced, before
+                # any term that every rank computes in full (root weight, bias) is added
+                rs.transform_first = False
         self.dst_types = []
         for rs in self.rels:
             if rs.rel.dst not in self.dst_types:
@@ -188,12 +196,21 @@ class _HeteroConvFn(torch.autograd.Function):
                 rows_by_F.setdefault((base // L.MAX_REL_PER_GROUP, O), []).append(
                     (outs[t], [ops.RelArg(rs.rel.csr, Y[k], mean_rows=rs.mean) for k, rs in part],
                      base > 0 or id_root[t]))
+        part_k = [k for k, rs in enumerate(spec.rels) if rs.partial]
+        part_flat = None
+        if part_k:
+            sizes = [spec.rels[k].rel.n_dst * xs[spec.rels[k].rel.src].shape[1] for k in part_k]
+            part_flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+            off = 0
+            for k, sz in zip(part_k, sizes):
+                G[k] = part_flat[off:off + sz].view(spec.rels[k].rel.n_dst, -1)
+                off += sz
         for k, rs in enumerate(spec.rels):
             if rs.transform_first:
                 continue
             r = rs.rel
             fs = xs[r.src].shape[1]
-            g = torch.empty(r.n_dst, fs, dtype=torch.float32, device=dev)
+            g = G[k] if rs.partial else torch.empty(r.n_dst, fs, dtype=torch.float32, device=dev)
             G[k] = g
             arg = ops.RelArg(r.csr, xs[r.src], mean_rows=rs.mean)
             if r.csr.long_rows:
@@ -208,6 +225,11 @@ class _HeteroConvFn(torch.autograd.Function):
             ops.aggregate_rows(rows_by_F[(wave, F)], F)
         for F, segs in chunks_by_F.items():
             ops.aggregate_chunks(segs, F)
+        if part_flat is not None:
+            # partial neighbour sums of all ranks -> the full sums, on every rank (one all-reduce
+            # per layer; the mean relations were divided by the GLOBAL in-degree above)
+            import torch.distributed as dist
+            dist.all_reduce(part_flat, group=spec.group)
         if tf_long:
             items = []
             for t, temps in tf_long.items():
@@ -316,6 +338,18 @@ class _HeteroConvFn(torch.autograd.Function):
             else:
                 gb.add(dw, [(_t(dout[t]), x)], split_k=ops.split_k_for(x.shape[0]))
         dG: Dict[int, torch.Tensor] = {}
+        # d(full neighbour sum) of the partial relations: every rank holds a PART of that gradient
+        # (its own consumers of the replicated rows); the transpose over a rank's edges needs the
+        # sum over the ranks -> one flat buffer, one all-reduce
+        part_k = [k for k, rs in live if rs.partial and need_x[rs.rel.src]]
+        dpart_flat = None
+        if part_k:
+            sizes = [spec.rels[k].rel.n_dst * xs[spec.rels[k].rel.src].shape[1] for k in part_k]
+            dpart_flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+            off = 0
+            for k, sz in zip(part_k, sizes):
+                dG[k] = dpart_flat[off:off + sz].view(spec.rels[k].rel.n_dst, -1)
+                off += sz
         for k, rs in live:
             r = rs.rel
             x = xs[r.src]
@@ -328,13 +362,17 @@ class _HeteroConvFn(torch.autograd.Function):
             else:
                 gb.add(dw, [(_t(dout[r.dst]), G[k])], split_k=ops.split_k_for(r.n_dst))
                 if need_x[r.src]:
-                    dg = torch.empty(r.n_dst, x.shape[1], dtype=torch.float32, device=dev)
+                    dg = dG[k] if k in dG else \
+                        torch.empty(r.n_dst, x.shape[1], dtype=torch.float32, device=dev)
                     dG[k] = dg
                     gb.add(dg, [(dout[r.dst], params[rs.i_wl])])
         if trb:
             ops.transpose_many(trb)
         if gb.problems:
             gb.run()
+        if dpart_flat is not None:
+            import torch.distributed as dist
+            dist.all_reduce(dpart_flat, group=spec.group)
         for k, rs in live:
             if rs.i_wr >= 0:
                 grads[pidx(rs.i_wr)] = dwroot[rs.rel.dst]

@@ -116,6 +116,7 @@ class HeteroModule(nn.Module):
         a different dropout stream per rank.  ``None`` restores single-GPU behaviour."""
         self._dist = ctx
         self._seed = None
+        self._seed_common = None
         return self
 
     # ---- static analysis ----------------------------------------------------------------------
@@ -158,7 +159,18 @@ class HeteroModule(nn.Module):
         return fusion
 
     # ---- execution ----------------------------------------------------------------------------
-    def _seed_state(self, device):
+    def _seed_state(self, device, common: bool = False):
+        """Philox (key, counter) on the device: one stream per rank, and -- ``common`` -- one that is
+        the same on every rank (same torch seed everywhere) for the replicated node types."""
+        if common:
+            if getattr(self, '_seed_common', None) is None or self._seed_common.device != device:
+                s = (torch.initial_seed() ^ 0x5DEECE66D) & 0x7fffffffffffffff
+                st = torch.tensor([s, 0], dtype=torch.int64, device=device)
+                if self._dist is not None:       # the ranks' torch seeds may differ: rank 0's
+                    from .dist import broadcast_
+                    broadcast_(st, self._dist.group)
+                self._seed_common = st
+            return self._seed_common
         if self._seed is None or self._seed.device != device:
             s = torch.initial_seed()
             if self._dist is not None:
@@ -181,14 +193,24 @@ class HeteroModule(nn.Module):
         views; every row is a multiple of 4 elements apart, so 128-bit accesses stay aligned)."""
         if self.dropout_masks is not None:
             return [self.dropout_masks[t] for t in types]
-        st = self._seed_state(device)
-        sizes = [((int(sh[0]) * int(sh[1]) + 3) // 4) * 4 for sh in shapes]
-        flat = ops.dropout_mask((sum(sizes),), p, st)
-        st[1] += sum(sizes) // 4     # advance the Philox counter (device side: graph-capturable)
-        out, off = [], 0
-        for sh, sz in zip(shapes, sizes):
-            out.append(flat[off:off + int(sh[0]) * int(sh[1])].view(int(sh[0]), int(sh[1])))
-            off += sz
+        rep = self._dist.replicated if self._dist is not None else frozenset()
+        out = [None] * len(types)
+        # replicated node types must see the SAME mask on every rank (their rows are computed by
+        # all ranks and have to stay identical): a second stream whose seed does not depend on the
+        # rank; the partitioned types draw from the per-rank stream
+        for common in (False, True):
+            sub = [i for i, t in enumerate(types) if (t in rep) == common]
+            if not sub:
+                continue
+            st = self._seed_state(device, common=common)
+            sizes = [((int(shapes[i][0]) * int(shapes[i][1]) + 3) // 4) * 4 for i in sub]
+            flat = ops.dropout_mask((sum(sizes),), p, st)
+            st[1] += sum(sizes) // 4     # advance the Philox counter (device side: graph-capturable)
+            off = 0
+            for i, sz in zip(sub, sizes):
+                r, c = int(shapes[i][0]), int(shapes[i][1])
+                out[i] = flat[off:off + r * c].view(r, c)
+                off += sz
         return out
 
     def _bump_batches_tracked(self, target, bns, types):
@@ -277,9 +299,16 @@ class HeteroModule(nn.Module):
             rel_specs.append((et, conv.aggr == 'mean', i_wl, i_bl, i_wr))
         spec = self._conv_specs.get(key)
         if spec is None:
+            partial = (self._dist.partial or {}) if self._dist is not None else {}
+            for et, cnt in partial.items():
+                # a partial relation's local rows hold SOME of a destination's edges: the divisor of
+                # scatter-mean (and of its transpose) is the in-degree over the edges of all ranks
+                plan[et].csr.cnt = cnt
             spec = ConvSpec(node_types=types,
-                            rels=[RelSpec(plan[et], mean, a, b, c) for et, mean, a, b, c in rel_specs],
-                            out_channels=params[0].shape[0])
+                            rels=[RelSpec(plan[et], mean, a, b, c, partial=et in partial)
+                                  for et, mean, a, b, c in rel_specs],
+                            out_channels=params[0].shape[0],
+                            group=self._dist.group if partial else None)
             if len(self._conv_specs) > 64:
                 self._conv_specs.clear()
             self._conv_specs[key] = spec
@@ -301,18 +330,42 @@ class HeteroModule(nn.Module):
                 dmasks = self._masks([x_dict[t].shape for t in types], p,
                                      x_dict[types[0]].device, types)
         self._bump_batches_tracked(node.target, bns, types)
-        spec = BNSpec(n=len(types), F=first.num_features, training=first.training or
-                      not first.track_running_stats, momentum=first.momentum, eps=first.eps,
-                      running=[(bns[t].running_mean, bns[t].running_var) for t in types],
-                      with_act=relu is not None, dmasks=dmasks,
-                      param_refs=([bns[t].weight for t in types], [bns[t].bias for t in types]))
-        if self._dist is not None:
-            spec.group = self._dist.group
-            ctx, dev = self._dist, x_dict[types[0]].device
-            spec.counts = ctx.counts(types, dev)
-            spec.counts_of = lambda idx: ctx.counts([types[i] for i in idx], dev)
-        res = AF.batch_norm_act(spec, [x_dict[t].contiguous() for t in types],
-                                [bns[t].weight for t in types], [bns[t].bias for t in types])
+
+        def run(sub: List[int], grouped: bool):
+            """BatchNorm of the node types ``sub`` (indices into ``types``) in one batched call;
+            ``grouped``: statistics over the rows of all ranks."""
+            tt = [types[i] for i in sub]
+            spec = BNSpec(n=len(tt), F=first.num_features, training=first.training or
+                          not first.track_running_stats, momentum=first.momentum, eps=first.eps,
+                          running=[(bns[t].running_mean, bns[t].running_var) for t in tt],
+                          with_act=relu is not None,
+                          dmasks=None if dmasks is None else [dmasks[i] for i in sub],
+                          param_refs=([bns[t].weight for t in tt], [bns[t].bias for t in tt]))
+            if grouped:
+                spec.group = self._dist.group
+                ctx, dev = self._dist, x_dict[tt[0]].device
+                spec.counts = ctx.counts(tt, dev)
+                spec.counts_of = lambda idx: ctx.counts([tt[i] for i in idx], dev)
+            return AF.batch_norm_act(spec, [x_dict[t].contiguous() for t in tt],
+                                     [bns[t].weight for t in tt], [bns[t].bias for t in tt])
+
+        n = len(types)
+        rep = self._dist.replicated if self._dist is not None else frozenset()
+        if self._dist is None or not rep:
+            res = run(list(range(n)), self._dist is not None)
+        else:
+            # replicated node types hold all their rows on every rank: their batch statistics are
+            # local (and identical everywhere); the partitioned types' run over all ranks
+            res = [None] * (2 * n if relu is not None else n)
+            for sub, grouped in (([i for i in range(n) if types[i] not in rep], True),
+                                 ([i for i in range(n) if types[i] in rep], False)):
+                if not sub:
+                    continue
+                out = run(sub, grouped)
+                for j, i in enumerate(sub):
+                    res[i] = out[j]
+                    if relu is not None:
+                        res[n + i] = out[len(sub) + j]
         n = len(types)
         y = OrderedDict(zip(types, res[:n]))
         act = OrderedDict(zip(types, res[n:])) if relu is not None else None

@@ -167,6 +167,13 @@ def _is_identity(x):
     return torch.tensor(int(x.shape[0] == x.shape[1] and bool(torch.equal(x, torch.eye(n)))))
 
 
+def _dropout_mask(shape, p, seed_state):
+    """Stand-in for the Philox kernel: a mask that is a deterministic function of the (key,
+    counter) state, so that equal states give equal masks (not the kernel's bit stream)."""
+    gen = torch.Generator().manual_seed(int((int(seed_state[0]) * 31 + int(seed_state[1])) % (2 ** 62)))
+    return (torch.rand(shape, generator=gen) >= p).float() / (1.0 - p)
+
+
 def _scale_mask(x, mask):
     return x * mask
 
@@ -410,7 +417,7 @@ _PATCHES = {
     'aggregate_chunks': _aggregate_chunks, 'GemmBatch': _GemmBatch,
     'gat_edge_softmax': _gat_edge_softmax, 'sddmm': _sddmm, 'sum_arrays': _sum_arrays,
     'colsum': _colsum, 'transpose_many': _transpose_many, 'is_identity': _is_identity,
-    'fill_': _fill_, 'scale_mask': _scale_mask, 'zeros': _zeros,
+    'fill_': _fill_, 'scale_mask': _scale_mask, 'zeros': _zeros, 'dropout_mask': _dropout_mask,
 }
 
 

@@ -193,7 +193,7 @@ def test_balanced_bounds_equalise_edges():
 # the PRODUCT's multi-GPU path itself (hetero module + dist.HaloExchange + cross-rank BatchNorm /
 # loss) on two gloo ranks, every agx entry point restated in torch (tests/cpu_shim.py)
 # ------------------------------------------------------------------------------------------------
-def _product_worker(rank, world, port, opname, errq):
+def _product_worker(rank, world, port, opname, replicate, errq):
     try:
         os.environ['MASTER_ADDR'] = '127.0.0.1'
         os.environ['MASTER_PORT'] = str(port)
@@ -210,23 +210,28 @@ def _product_worker(rank, world, port, opname, errq):
         md = (g.node_types, list(ei.keys()))
         n = g.num_nodes_dict
         y = g['artwork'].y_style
-        orc = go.HeteroSGNNOracle(getattr(go, opname), torch.nn.ReLU(), 'sum', 128, 32, md, 2, 0.0,
+        orc = go.HeteroSGNNOracle(getattr(go, opname), torch.nn.ReLU(), 'sum', 128, 32, md, 2, 0.4,
                                   True, False)
         with torch.no_grad():
             orc(g.x_dict, ei)
         util.fill_params_deterministic(orc)
         util.reset_bn(orc)
-        prod = agx.HeteroSGNN(getattr(agx, opname), torch.nn.ReLU(), 'sum', 128, 32, md, 2, 0.0,
+        prod = agx.HeteroSGNN(getattr(agx, opname), torch.nn.ReLU(), 'sum', 128, 32, md, 2, 0.4,
                               True, False)
         util.copy_state(orc, prod)
+        gen = torch.Generator().manual_seed(77)
+        masks = {t: (torch.rand(k, 128, generator=gen) >= 0.4).float() / 0.6 for t, k in n.items()}
         o64 = orc.double().train()
+        o64.gnn.dropout_masks = {t: m.double() for t, m in masks.items()}
         e_o, o_o = o64({k: v.double() for k, v in g.x_dict.items()}, ei)
         l_o = go.nll_loss_artwork(o_o[0], y)
         l_o.backward()
 
-        part = GraphPartition(ei, n, world, rank)
-        assert part.has_halo
+        rep = [t for t in n if t != 'artwork'] if replicate else []
+        part = GraphPartition(ei, n, world, rank, replicated=rep)
+        assert part.has_halo != replicate and (len(part.partial) > 0) == replicate
         ctx = partition_context(part, dist.group.WORLD, 'cpu')
+        prod.gnn.dropout_masks = {t: part.owned(t, m).contiguous() for t, m in masks.items()}
         for m in prod.modules():
             if isinstance(m, HeteroModule):
                 m.set_distributed(ctx)
@@ -239,7 +244,8 @@ def _product_worker(rank, world, port, opname, errq):
             l_p.backward()
         assert rel_err(l_p, l_o) <= 1e-5                      # the GLOBAL loss on every rank
         for t in e_o:
-            lo, hi = part.bounds[t][rank], part.bounds[t][rank + 1]
+            lo, hi = (0, n[t]) if t in part.replicated else \
+                (part.bounds[t][rank], part.bounds[t][rank + 1])
             if hi > lo:
                 assert rel_err(e_p[t], e_o[t][lo:hi]) <= 2e-5, ('emb', t)
                 assert rel_err(o_p[0][t], o_o[0][t][lo:hi]) <= 2e-5, ('logp', t)
@@ -261,6 +267,24 @@ def _product_worker(rank, world, port, opname, errq):
             assert err <= max(1e-4 * scale, 2e-6 * gmax), (k, err, scale)
         for (k, b_o), (_, b_p) in zip(o64.named_buffers(), prod.named_buffers()):
             assert rel_err(b_p, b_o) <= 1e-5, k                # running statistics of ALL rows
+        # dropout streams: per rank for the partitioned types, ONE stream for the replicated ones
+        hm = prod.gnn
+        hm.dropout_masks = None
+        with cpu_ops():
+            types = list(n.keys())
+            ms = hm._masks([(x_own[t].shape[0], 8) for t in types], 0.4, 'cpu', types)
+        for t, m in zip(types, ms):
+            if m.shape[0] == 0:
+                continue
+            both = [torch.empty_like(m) for _ in range(world)] if t in part.replicated else None
+            if both is not None:
+                dist.all_gather(both, m)
+                assert torch.equal(both[0], both[1]), t
+        if not replicate:
+            a = ms[0][:8].contiguous()
+            both = [torch.empty_like(a) for _ in range(world)]
+            dist.all_gather(both, a)
+            assert not torch.equal(both[0], both[1])
         dist.barrier()
         dist.destroy_process_group()
     except Exception:
@@ -268,16 +292,18 @@ def _product_worker(rank, world, port, opname, errq):
         raise
 
 
+@pytest.mark.parametrize('replicate', [False, True])
 @pytest.mark.parametrize('opname', ['SAGEConv', 'GraphConv'])
-def test_product_cut_partition_world2_gloo(opname):
+def test_product_cut_partition_world2_gloo(opname, replicate):
     """Two ranks, one graph cut by destination node: embeddings / log-probabilities of the owned
     rows, the global loss, the all-reduced weight gradients and the BatchNorm running statistics
-    equal the single-process oracle on the whole graph."""
+    equal the single-process oracle on the whole graph.  ``replicate``: every node type but
+    ``artwork`` lives on both ranks (no boundary rows; partial neighbour sums all-reduced)."""
     world = 2
     ctx = mp.get_context('spawn')
     errq = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_product_worker, args=(r, world, port, opname, errq))
+    procs = [ctx.Process(target=_product_worker, args=(r, world, port, opname, replicate, errq))
              for r in range(world)]
     for p in procs:
         p.start()

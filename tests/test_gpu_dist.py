@@ -76,8 +76,12 @@ def _gnn_case(rank, world, dev, kind, opname):
         assert rel_err(out_r[0]['artwork'], out_o[0]['artwork']) <= RTOL
 
     # --- this rank of the partitioned job ----------------------------------------------------------
-    part = GraphPartition(eg, n, world, rank)
-    assert part.has_halo == (kind != 'blocks')
+    # 'replicated': every node type but artwork lives on both ranks -- no boundary
+    # rows; the partial neighbour sums of the artwork -> X relations are all-reduced in the layer
+    part = GraphPartition(eg, n, world, rank,
+                          replicated=[t for t in n if t != 'artwork'] if kind == 'replicated' else ())
+    assert part.has_halo == (kind == 'cut')
+    assert (len(part.partial) > 0) == (kind == 'replicated')
     ctx = partition_context(part, dist.group.WORLD, dev)
     mod = make()
     mod.gnn.set_distributed(ctx)
@@ -166,7 +170,7 @@ def _heads_case(rank, world, dev):
         assert rel_err(gsum, pr.grad) <= GRAD_RTOL, (k, rel_err(gsum, pr.grad))
 
 
-def _worker(rank, world, port, errq):
+def _worker(rank, world, port, errq, cases=None):
     try:
         import torch.distributed as dist
         os.environ['MASTER_ADDR'] = '127.0.0.1'
@@ -174,9 +178,10 @@ def _worker(rank, world, port, errq):
         torch.cuda.set_device(rank)
         dev = torch.device('cuda', rank)
         dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
-        for kind, op in (('cut', 'SAGEConv'), ('blocks', 'SAGEConv'), ('cut', 'GraphConv')):
+        for kind, op in (cases or (('cut', 'SAGEConv'), ('blocks', 'SAGEConv'), ('cut', 'GraphConv'))):
             _gnn_case(rank, world, dev, kind, op)
-        _heads_case(rank, world, dev)
+        if cases is None:
+            _heads_case(rank, world, dev)
         dist.barrier()
         dist.destroy_process_group()
     except Exception:
@@ -185,13 +190,24 @@ def _worker(rank, world, port, errq):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_two_ranks_replicated_types_match_single_gpu():
+    """Partition with replicated small node types (CPU-verified on gloo in
+    tests/test_cpu_dist.py; this is its NCCL / CUDA-graph run)."""
+    _run_two_ranks((('replicated', 'SAGEConv'), ('replicated', 'GraphConv')))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
 def test_two_ranks_match_single_gpu():
+    _run_two_ranks(None)
+
+
+def _run_two_ranks(cases):
     import torch.multiprocessing as mp
     world = 2
     ctx = mp.get_context('spawn')
     errq = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, errq)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, errq, cases)) for r in range(world)]
     import time
     for p in procs:
         p.start()
