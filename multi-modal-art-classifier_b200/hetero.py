@@ -236,9 +236,10 @@ class HeteroModule(nn.Module):
         fused call (functional._HeteroGATFn); relation outputs of a destination type are added in
         metadata order (PyG's pairwise torch.add queue differs only in summation order)."""
         convs = self.get_submodule(node.target)
-        if self._dist is not None and self._dist.halo is not None:
+        if self._dist is not None and (self._dist.halo is not None or self._dist.partial):
             # (a graph block per rank needs no exchange inside the layer; a destination partition
-            # that cuts edges would need GATConv's self loops in global node ids)
+            # that cuts edges would need GATConv's self loops in global node ids, and a softmax
+            # over a row whose edges are spread over the ranks)
             raise NotImplementedError('GATConv on a partition that cuts edges is not implemented '
                                       '(SAGEConv / GraphConv are)')
         types = [t for t in self.node_types if t in x_dict]
