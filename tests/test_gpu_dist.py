@@ -190,6 +190,9 @@ def _worker(rank, world, port, errq, cases=None):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+@pytest.mark.skipif(os.environ.get('AGX_TEST_REPLICATED', '0') != '1',
+                    reason='first NCCL run of the replicated-types partition is pending (written '
+                           'after the GPU budget of round 1 was spent): AGX_TEST_REPLICATED=1')
 def test_two_ranks_replicated_types_match_single_gpu():
     """Partition with replicated small node types (CPU-verified on gloo in
     tests/test_cpu_dist.py; this is its NCCL / CUDA-graph run)."""
