@@ -279,7 +279,7 @@ def _product_worker(rank, world, port, opname, replicate, errq):
             both = [torch.empty_like(m) for _ in range(world)] if t in part.replicated else None
             if both is not None:
                 dist.all_gather(both, m)
-                assert torch.equal(both[0], both[1]), t
+                assert all(torch.equal(both[0], b) for b in both[1:]), t
         if not replicate:
             a = ms[0][:8].contiguous()
             both = [torch.empty_like(a) for _ in range(world)]
@@ -299,7 +299,16 @@ def test_product_cut_partition_world2_gloo(opname, replicate):
     rows, the global loss, the all-reduced weight gradients and the BatchNorm running statistics
     equal the single-process oracle on the whole graph.  ``replicate``: every node type but
     ``artwork`` lives on both ranks (no boundary rows; partial neighbour sums all-reduced)."""
-    world = 2
+    _run_product(2, opname, replicate)
+
+
+def test_product_replicated_partition_world4_gloo():
+    """Four ranks: the masks / partial sums / gradient parts of the replicated types agree for more
+    than two participants."""
+    _run_product(4, 'SAGEConv', True)
+
+
+def _run_product(world, opname, replicate):
     ctx = mp.get_context('spawn')
     errq = ctx.SimpleQueue()
     port = _free_port()
