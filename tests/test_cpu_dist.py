@@ -285,6 +285,31 @@ def _product_worker(rank, world, port, opname, replicate, errq):
             both = [torch.empty_like(a) for _ in range(world)]
             dist.all_gather(both, a)
             assert not torch.equal(both[0], both[1])
+        # three optimisation steps (gradients now ACCUMULATE into existing .grad buffers, the path
+        # the fused layers use with FlatAdam's arena): loss trajectory of the whole-graph oracle
+        hm.dropout_masks = {t: part.owned(t, m).contiguous() for t, m in masks.items()}
+        o32 = o64.float()
+        o32.gnn.dropout_masks = masks
+        opt_o = torch.optim.Adam(o32.parameters(), lr=0.01)
+        opt_p = torch.optim.Adam(prod.parameters(), lr=0.01)
+        for step in range(3):
+            opt_o.zero_grad(set_to_none=False)
+            _, oo = o32(g.x_dict, ei)
+            lo_ = go.nll_loss_artwork(oo[0], y)
+            lo_.backward()
+            opt_o.step()
+            opt_p.zero_grad(set_to_none=False)
+            with cpu_ops():
+                _, op_ = prod(x_own, part.edge_index)
+                lp_ = agx.functional.nll_loss(op_[0]['artwork'], part.owned('artwork', y),
+                                              dist.group.WORLD)
+                lp_.backward()
+            for p_ in prod.parameters():
+                if p_.grad is not None:
+                    dist.all_reduce(p_.grad)
+            opt_p.step()
+            # (Adam's first steps are sign-like on noise-level gradients: 2e-3, as on the GPU)
+            assert abs(float(lp_) - float(lo_)) <= 2e-3 * abs(float(lo_)), (step, float(lp_), float(lo_))
         dist.barrier()
         dist.destroy_process_group()
     except Exception:
