@@ -1093,13 +1093,15 @@ def _chain_sum(out: torch.Tensor, ins: list, bias: Optional[torch.Tensor] = None
 class _HeteroGATFn(torch.autograd.Function):
     """All GATConv relations of one hetero layer (PyG 2.0.2 GATConv inside to_hetero, aggr='sum'):
 
-        x_l = x_src W_l^T;  a_l = x_l att_l;  a_r = x_dst (W_r^T att_r)
+        x_l = x_src W_l^T;  a_l = x_src (W_l^T att_l);  a_r = x_dst (W_r^T att_r)
         alpha_ij = softmax_i(leaky_relu(a_l[j] + a_r[i]));  out[t] = sum_{r: dst(r)=t} (sum_j alpha_ij x_l[j] + b_r)
 
-    The dense parts run as two grouped-GEMM waves (``lin_r`` only ever meets ``att_r``, so
-    x_dst W_r^T [N_dst, C] is never formed: a_r is a matrix-vector product with v = W_r^T att_r);
-    the attention softmax of every relation is ONE scalar launch, the weighted neighbour sums of
-    every relation run on the edge-balanced aggregation kernels with per-edge weights."""
+    The dense parts run as two grouped-GEMM waves: the logits are matrix-vector products with the
+    projected attention vectors (PyG forms x_l att_l and (x_dst W_r^T) att_r; same value, and
+    x_dst W_r^T [N_dst, C] is never needed), stacked per node type so that every feature table is
+    read once.  The attention softmax of every relation is ONE scalar launch, the weighted
+    neighbour sums of every relation run on the edge-balanced aggregation kernels with per-edge
+    weights."""
 
     @staticmethod
     def forward(ctx, spec: GATSpec, *tensors):
@@ -1113,7 +1115,6 @@ class _HeteroGATFn(torch.autograd.Function):
                 raise TypeError(f'x[{t}] must be contiguous float32')
         C_ = spec.out_channels
         dev = tensors[0].device
-        R = len(spec.rels)
         f32 = dict(dtype=torch.float32, device=dev)
 
         # f1: x_l = x_src W_l^T (one-hot sources: W_l^T) and, per node type, the stacked logit
