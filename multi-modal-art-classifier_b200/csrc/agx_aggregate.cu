@@ -492,16 +492,22 @@ __device__ __forceinline__ Vec<T, VEC> load_smem_vec(const uint8_t* p) {
     return r;
 }
 
-constexpr int kCtaEdges = kAggWarps * AGX_CHUNK_EDGES;      // 1024 edges per CTA
+constexpr int kCtaEdges = kAggWarps * AGX_CHUNK_EDGES;      // 1024 edges per CTA (smallest unit)
 constexpr int kMaxChunkF = 256;                              // columns per launch (host loops)
+constexpr int kChunkCtasPerSm = 4;                           // residency of the register path
 
-template <typename T, int VEC, int LPR, bool TMA>
-__global__ void __launch_bounds__(kAggThreads, TMA ? 2 : 4)
+// CE = edges per warp (128, 192 or 256): the host picks the unit that fills whole waves of
+// resident CTAs (876 CTAs of 1024 edges on 592 slots ran as 1.48 waves: mean SM-active time 45 us
+// of a 77 us launch; 584 CTAs of 1536 edges are one wave).
+template <typename T, int VEC, int LPR, bool TMA, int CE>
+__global__ void __launch_bounds__(kAggThreads, TMA ? 2 : kChunkCtasPerSm)
 agg_chunks(const __grid_constant__ ChunkSegs P) {
     constexpr int SUB = 32 / LPR;
     constexpr int U = kGatherDepth;
-    __shared__ int s_col[TMA ? kAggWarps : 1][AGX_CHUNK_EDGES];
-    __shared__ float s_scl[TMA ? kAggWarps : 1][AGX_CHUNK_EDGES];
+    constexpr int CTA_EDGES = kAggWarps * CE;
+    static_assert(CE % 32 == 0 && (!TMA || CE == AGX_CHUNK_EDGES), "chunk size");
+    __shared__ int s_col[TMA ? kAggWarps : 1][CE];
+    __shared__ float s_scl[TMA ? kAggWarps : 1][CE];
     __shared__ uint64_t s_bar[kAggWarps][kRingGroups];
     // row pieces a warp could not finish alone: [warp][0] = head (its first row began in an earlier
     // warp's edges), [warp][1] = tail (its last row goes on); stitched by warp 0 after the barrier
@@ -519,8 +525,8 @@ agg_chunks(const __grid_constant__ ChunkSegs P) {
     const int F = P.F;
     const int cta = (int)blockIdx.x - P.chunk_start[si];          // block index inside the relation
     const int nctas = P.chunk_start[si + 1] - P.chunk_start[si];
-    const int start = cta * kCtaEdges + w * AGX_CHUNK_EDGES;
-    const int end = min(S.n_edges, start + AGX_CHUNK_EDGES);
+    const int start = cta * CTA_EDGES + w * CE;
+    const int end = min(S.n_edges, start + CE);
     const int n_rows = S.n_rows;
     float* lead = S.frag;                                         // [nctas][F]
     float* trail = S.frag + (size_t)nctas * F;
@@ -535,15 +541,15 @@ agg_chunks(const __grid_constant__ ChunkSegs P) {
     // ---- stage neighbour ids / scales ----------------------------------------------------------
     // lane i of register k holds edge k*32 + i of the chunk (register path: read by shuffles);
     // the TMA path issues its copies from the shared-memory copy
-    int cr[AGX_CHUNK_EDGES / 32];
-    float sr[AGX_CHUNK_EDGES / 32];
+    int cr[CE / 32];
+    float sr[CE / 32];
 #pragma unroll
-    for (int k = 0; k < AGX_CHUNK_EDGES / 32; ++k) {
+    for (int k = 0; k < CE / 32; ++k) {
         const int i = k * 32 + lane;
         cr[k] = start + i < end ? __ldg(R.col + start + i) : 0;
     }
 #pragma unroll
-    for (int k = 0; k < AGX_CHUNK_EDGES / 32; ++k) {
+    for (int k = 0; k < CE / 32; ++k) {
         const int i = k * 32 + lane;
         sr[k] = start + i < end ? edge_scale(R, start + i, cr[k]) : 1.0f;
         if constexpr (TMA) {
@@ -654,8 +660,14 @@ agg_chunks(const __grid_constant__ ChunkSegs P) {
                 constexpr int BATCH = SUB * U;
                 for (int base = (i0 / BATCH) * BATCH; base < i1; base += BATCH) {
                     const int kreg = base >> 5;                  // warp-uniform
-                    const int ck = kreg == 0 ? cr[0] : kreg == 1 ? cr[1] : kreg == 2 ? cr[2] : cr[3];
-                    const float sk = kreg == 0 ? sr[0] : kreg == 1 ? sr[1] : kreg == 2 ? sr[2] : sr[3];
+                    int ck = cr[0];
+                    float sk = sr[0];
+#pragma unroll
+                    for (int q = 1; q < CE / 32; ++q)
+                        if (kreg == q) {
+                            ck = cr[q];
+                            sk = sr[q];
+                        }
                     const int j0 = (base & 31) + sub;
                     int ci[U];
                     float sc[U];
@@ -774,7 +786,7 @@ agg_chunks(const __grid_constant__ ChunkSegs P) {
             for (int k = 0; k < 4; ++k)
                 if (c0 + k < F) f[c0 + k] = carry[j].v[k];
         }
-        const int c_first = carry_beg / kCtaEdges, c_last = (carry_end - 1) / kCtaEdges;
+        const int c_first = carry_beg / CTA_EDGES, c_last = (carry_end - 1) / CTA_EDGES;
         __threadfence();
         __syncwarp();
         int old = 0;
@@ -938,32 +950,69 @@ extern "C" size_t agx_chunk_counters(int64_t n_edges) {
     return (size_t)ceil_div(n_edges > 0 ? n_edges : 1, kCtaEdges);
 }
 
-template <typename T, int VEC, int LPR>
-static int launch_chunks_lpr(const ChunkSegs& P, unsigned grid, bool tma, cudaStream_t st) {
-    if (tma) {
-        const size_t smem = (size_t)kAggWarps * kRingGroups * kRingRows * (size_t)P.F * sizeof(T);
-        static bool attr_set = false;
-        if (!attr_set) {
-            AGX_CUDA(cudaFuncSetAttribute(agg_chunks<T, VEC, LPR, true>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          kAggWarps * kRingGroups * kRingRows * kRingMaxRowBytes));
-            attr_set = true;
+template <typename T, int VEC, int LPR, int CE>
+static int launch_chunks_ce(const ChunkSegs& P, unsigned grid, bool tma, cudaStream_t st) {
+    if constexpr (CE == AGX_CHUNK_EDGES) {
+        if (tma) {
+            const size_t smem = (size_t)kAggWarps * kRingGroups * kRingRows * (size_t)P.F * sizeof(T);
+            static bool attr_set = false;
+            if (!attr_set) {
+                AGX_CUDA(cudaFuncSetAttribute(agg_chunks<T, VEC, LPR, true, CE>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              kAggWarps * kRingGroups * kRingRows * kRingMaxRowBytes));
+                attr_set = true;
+            }
+            agg_chunks<T, VEC, LPR, true, CE><<<grid, kAggThreads, smem, st>>>(P);
+            AGX_LAUNCH_CHECK("agg_chunks");
+            return AGX_OK;
         }
-        agg_chunks<T, VEC, LPR, true><<<grid, kAggThreads, smem, st>>>(P);
-    } else {
-        agg_chunks<T, VEC, LPR, false><<<grid, kAggThreads, 0, st>>>(P);
     }
+    agg_chunks<T, VEC, LPR, false, CE><<<grid, kAggThreads, 0, st>>>(P);
     AGX_LAUNCH_CHECK("agg_chunks");
     return AGX_OK;
 }
 
-template <typename T, int VEC>
-static int launch_chunks(const ChunkSegs& P, int lpr, unsigned grid, bool tma, cudaStream_t st) {
-    switch (lpr) {
-        case 32: return launch_chunks_lpr<T, VEC, 32>(P, grid, tma, st);
-        case 16: return launch_chunks_lpr<T, VEC, 16>(P, grid, tma, st);
-        default: return launch_chunks_lpr<T, VEC, 8>(P, grid, tma, st);
+template <typename T, int VEC, int LPR>
+static int launch_chunks_lpr(const ChunkSegs& P, unsigned grid, bool tma, int ce, cudaStream_t st) {
+    switch (ce) {
+        case 256: return launch_chunks_ce<T, VEC, LPR, 256>(P, grid, false, st);
+        case 192: return launch_chunks_ce<T, VEC, LPR, 192>(P, grid, false, st);
+        default: return launch_chunks_ce<T, VEC, LPR, AGX_CHUNK_EDGES>(P, grid, tma, st);
     }
+}
+
+template <typename T, int VEC>
+static int launch_chunks(const ChunkSegs& P, int lpr, unsigned grid, bool tma, int ce,
+                         cudaStream_t st) {
+    switch (lpr) {
+        case 32: return launch_chunks_lpr<T, VEC, 32>(P, grid, tma, ce, st);
+        case 16: return launch_chunks_lpr<T, VEC, 16>(P, grid, tma, ce, st);
+        default: return launch_chunks_lpr<T, VEC, 8>(P, grid, tma, ce, st);
+    }
+}
+
+// Edges per warp for this launch: the unit whose CTA count comes closest to whole waves of the
+// 148 x 4 resident CTAs (time ~ waves x unit size); ties go to the smaller unit.
+static int pick_chunk_edges(const agx_chunk_seg_t* segs, int n_segs, bool tma) {
+    static const char* env = getenv("AGX_CHUNK_CE");
+    if (tma) return AGX_CHUNK_EDGES;
+    if (env) {
+        const int v = atoi(env);
+        if (v == 128 || v == 192 || v == 256) return v;
+    }
+    const int64_t slots = (int64_t)kNumSMs * kChunkCtasPerSm;
+    int best = AGX_CHUNK_EDGES;
+    int64_t best_cost = -1;
+    for (int ce : {AGX_CHUNK_EDGES, 192, 256}) {
+        int64_t ctas = 0;
+        for (int s = 0; s < n_segs; ++s) ctas += ceil_div(segs[s].n_edges, (int64_t)kAggWarps * ce);
+        const int64_t cost = ceil_div(ctas > 0 ? ctas : 1, slots) * ce;
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best = ce;
+        }
+    }
+    return best;
 }
 
 extern "C" int agx_aggregate_chunks(const agx_chunk_seg_t* h_segs, int n_segs, int F, int dtype,
@@ -1010,20 +1059,23 @@ extern "C" int agx_aggregate_chunks(const agx_chunk_seg_t* h_segs, int n_segs, i
                      aligned_to(S.rel.x, 16) && (S.rel.ldx * esz) % 16 == 0 &&
                      (S.n_edges == 0 || aligned_to(S.frag, 16));
             P.s[s] = S;
-            P.chunk_start[s + 1] = P.chunk_start[s] + (int32_t)ceil_div(S.n_edges, kCtaEdges);
         }
+        const bool tma = vec_ok && want_tma && (size_t)Fb * esz <= (size_t)kRingMaxRowBytes;
+        const int ce = pick_chunk_edges(h_segs, n_segs, tma);     // edges per warp of this launch
+        for (int s = 0; s < n_segs; ++s)
+            P.chunk_start[s + 1] =
+                P.chunk_start[s] + (int32_t)ceil_div(P.s[s].n_edges, (int64_t)kAggWarps * ce);
         const unsigned grid = (unsigned)P.chunk_start[n_segs];
         if (grid == 0) return AGX_OK;
-        const bool tma = vec_ok && want_tma && (size_t)Fb * esz <= (size_t)kRingMaxRowBytes;
         int rc;
         if (dtype == AGX_F32) {
-            rc = vec_ok ? launch_chunks<float, 4>(P, max(8, min(32, pow2_ceil(Fb / 4))), grid, tma, st)
-                        : launch_chunks<float, 1>(P, max(8, min(32, pow2_ceil(Fb))), grid, false, st);
+            rc = vec_ok ? launch_chunks<float, 4>(P, max(8, min(32, pow2_ceil(Fb / 4))), grid, tma, ce, st)
+                        : launch_chunks<float, 1>(P, max(8, min(32, pow2_ceil(Fb))), grid, false, ce, st);
         } else {
             rc = vec_ok ? launch_chunks<__nv_bfloat16, 8>(P, max(8, min(32, pow2_ceil(Fb / 8))), grid,
-                                                          tma, st)
+                                                          tma, ce, st)
                         : launch_chunks<__nv_bfloat16, 1>(P, max(8, min(32, pow2_ceil(Fb))), grid,
-                                                          false, st);
+                                                          false, ce, st);
         }
         if (rc) return rc;
     }
