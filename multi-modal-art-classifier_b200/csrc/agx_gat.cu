@@ -33,8 +33,8 @@ constexpr int kSddmmWarps = kSddmmThreads / 32;
 
 struct GatRels {
     agx_gat_rel_t r[AGX_MAX_GAT_RELS];
-    int32_t blk_start[AGX_MAX_GAT_RELS + 1];       // CTA -> relation (128 rows per CTA) ...
-    int32_t hub_start[AGX_MAX_GAT_RELS + 1];       // ... then one CTA per long row, per relation
+    int32_t hub_start[AGX_MAX_GAT_RELS + 1];       // first one CTA per long row, per relation ...
+    int32_t blk_start[AGX_MAX_GAT_RELS + 1];       // ... then CTA -> relation (128 rows per CTA)
     int32_t n;
     float slope;
 };
@@ -149,7 +149,7 @@ __device__ __forceinline__ void softmax_small(const agx_gat_rel_t& R, int row, i
 constexpr int kGatGroup = 8;                              // lanes per short row
 constexpr int kGatRowsPerWarp = 32 / kGatGroup;           // 4
 
-// The first blk_start[n] CTAs own 128 consecutive destination rows of one relation each, a warp 4:
+// The CTAs behind the hub CTAs own 128 consecutive destination rows of one relation each, a warp 4:
 //   deg <= 8             8 lanes per row, four rows of the warp at once (registers)
 //   8 < deg <= 32        the whole warp, one edge per lane (registers)
 //   32 < deg <= LONG     the whole warp, strided three-pass walk
@@ -158,7 +158,10 @@ constexpr int kGatRowsPerWarp = 32 / kGatGroup;           // 4
 template <bool BWD>
 __global__ void __launch_bounds__(kGatThreads) gat_edge_softmax(const __grid_constant__ GatRels P) {
     __shared__ float s_red[kGatWarps];
-    if ((int)blockIdx.x >= P.blk_start[P.n]) {                   // hub CTA (CTA-uniform branch)
+    // hub CTAs are the FIRST blocks of the grid: the longest rows start at once and finish behind
+    // the short rows instead of after them (they were the tail: 56 us of SM-active time in an 87 us
+    // launch)
+    if ((int)blockIdx.x < P.hub_start[P.n]) {                    // hub CTA (CTA-uniform branch)
         int ri = 0;
         while ((int)blockIdx.x >= P.hub_start[ri + 1]) ++ri;
         const agx_gat_rel_t& R = P.r[ri];
@@ -273,7 +276,9 @@ static int launch_edge_softmax(const agx_gat_rel_t* h_rels, int n_rels, float sl
     GatRels P;
     P.n = n_rels;
     P.slope = slope;
-    P.blk_start[0] = 0;
+    P.hub_start[0] = 0;
+    for (int i = 0; i < n_rels; ++i) P.hub_start[i + 1] = P.hub_start[i] + h_rels[i].n_long;
+    P.blk_start[0] = P.hub_start[n_rels];
     for (int i = 0; i < n_rels; ++i) {
         const agx_gat_rel_t& R = h_rels[i];
         AGX_CHECK_ARG(R.n_rows >= 0 && R.n_long >= 0 && R.n_long <= R.n_rows,
@@ -287,10 +292,8 @@ static int launch_edge_softmax(const agx_gat_rel_t* h_rels, int n_rels, float sl
         P.blk_start[i + 1] =
             P.blk_start[i] + (int32_t)ceil_div(R.n_rows, kGatWarps * kGatRowsPerWarp);
     }
-    P.hub_start[0] = P.blk_start[n_rels];
-    for (int i = 0; i < n_rels; ++i) P.hub_start[i + 1] = P.hub_start[i] + h_rels[i].n_long;
-    if (P.hub_start[n_rels] == 0) return AGX_OK;
-    gat_edge_softmax<BWD><<<(unsigned)P.hub_start[n_rels], kGatThreads, 0, (cudaStream_t)stream>>>(P);
+    if (P.blk_start[n_rels] == 0) return AGX_OK;
+    gat_edge_softmax<BWD><<<(unsigned)P.blk_start[n_rels], kGatThreads, 0, (cudaStream_t)stream>>>(P);
     AGX_LAUNCH_CHECK(what);
     return AGX_OK;
 }
