@@ -42,7 +42,12 @@ class _HeadBase(nn.Module):
             return None
         device = parts[0].device
         if self._seed is None or self._seed.device != device:
-            s = torch.initial_seed() & 0x7fffffffffffffff
+            s = torch.initial_seed()
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                # batch-sharded heads: every rank draws its own masks (as HeteroModule._seed_state)
+                s += 0x9E3779B97F4A7C15 * (dist.get_rank() + 1)
+            s &= 0x7fffffffffffffff
             self._seed = torch.tensor([s, 0], dtype=torch.int64, device=device)
         out = []
         for p in parts:

@@ -107,8 +107,18 @@ class HeteroModule(nn.Module):
         self._warned = set()
         self.dropout_masks: Optional[Dict[str, torch.Tensor]] = None   # test hook (injected masks)
         self._seed = None
+        self._seed_common = None
         self._dist = None            # dist.DistContext: this module runs one rank of a multi-GPU job
         self._nbt_flat: dict = {}
+
+    def __getstate__(self):
+        # copy.deepcopy(model) (the reference's save_embeddings, train_gnn_embeddings.py:84-85) and
+        # pickling: the cached layer plans hold process groups (not copyable) and every CSR / CSC
+        # tensor of the graph; they are rebuilt on the next forward
+        state = self.__dict__.copy()
+        state['_conv_specs'] = {}
+        state['_nbt_flat'] = {}
+        return state
 
     def set_distributed(self, ctx):
         """Run as one rank of a destination-partitioned multi-GPU job (dist.DistContext):

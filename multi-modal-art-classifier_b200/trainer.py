@@ -34,10 +34,13 @@ class _StateSnapshot:
         self.model, self.opt = model, opt
         self.opt_state = [t.clone() for t in (opt.flat, opt.exp_avg, opt.exp_avg_sq, opt.step_t)]
         self.buffers = {k: v.clone() for k, v in model.named_buffers()}
+        # Philox streams: the per-rank one and the one shared by the replicated node types
         self.seeds = {}
         for name, m in model.named_modules():
-            if hasattr(m, '_seed'):
-                self.seeds[name] = None if m._seed is None else m._seed.clone()
+            for attr in ('_seed', '_seed_common'):
+                if hasattr(m, attr):
+                    v = getattr(m, attr)
+                    self.seeds[(name, attr)] = None if v is None else v.clone()
 
     @torch.no_grad()
     def restore(self):
@@ -48,11 +51,13 @@ class _StateSnapshot:
             if k in self.buffers:
                 v.copy_(self.buffers[k])
         for name, m in self.model.named_modules():
-            if name in self.seeds and getattr(m, '_seed', None) is not None:
-                if self.seeds[name] is None:
-                    m._seed[1] = 0                      # the stream had not been started
-                else:
-                    m._seed.copy_(self.seeds[name])
+            for attr in ('_seed', '_seed_common'):
+                cur = getattr(m, attr, None)
+                if (name, attr) in self.seeds and cur is not None:
+                    if self.seeds[(name, attr)] is None:
+                        cur[1] = 0                      # the stream had not been started
+                    else:
+                        cur.copy_(self.seeds[(name, attr)])
 
 
 def _accuracy(logp: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
@@ -242,20 +247,39 @@ class GNNTrainer:
     def evaluate(self, x_dict=None, edge_index_dict=None, labels=None):
         """``hetero_test()`` on one graph: (loss, accuracy); BatchNorm in eval mode, dropout as
         traced."""
+        self._check_foreign_graph(x_dict, edge_index_dict)
         self.model.eval()
         x = self.x if x_dict is None else x_dict
         ei = self.ei if edge_index_dict is None else edge_index_dict
         y = self.y if labels is None else labels.to(torch.int64)
         _, out = self.model(x, ei)
         logp = out[0][self.node_type]
-        loss = AF.nll_loss(logp, y, self.group if x_dict is None else None)
+        loss = AF.nll_loss(logp, y, self.group)        # mean over the rows of all ranks
         self.model.train()
-        return loss, _accuracy(logp, y)
+        if self.group is None:
+            return loss, _accuracy(logp, y)
+        from .dist import all_reduce_
+        hits = torch.stack([logp.argmax(dim=1).eq(y).sum(), torch.tensor(y.numel(), device=y.device)])
+        hits = all_reduce_(hits.to(torch.float64), self.group)
+        return loss, (hits[0] / hits[1]).to(torch.float32)
+
+    def _check_foreign_graph(self, x_dict, edge_index_dict):
+        """Multi-GPU: the boundary-row exchange and the partial-sum relations are those of the
+        TRAINING partition; another graph (the reference's validation / test graphs,
+        train_gnn_embeddings.py:57-58) needs its own partition.  On the block partition every rank
+        evaluates its own block of the other graph, which is what this accepts."""
+        if (x_dict is not None or edge_index_dict is not None) and self.ctx is not None and \
+                (self.ctx.halo is not None or self.ctx.partial):
+            raise NotImplementedError(
+                'evaluate() / embeddings() on a graph other than the training partition: build a '
+                'GraphPartition + partition_context for that graph and a GNNTrainer on it (the '
+                "training partition's boundary lists and global in-degrees do not apply)")
 
     @torch.no_grad()
     def embeddings(self, x_dict=None, edge_index_dict=None) -> Dict[str, torch.Tensor]:
         """``save_embeddings()``: deep copy, eval mode, forward; returns the embedding dict (the
         reference saves ``emb['artwork']``; ``emb['style']`` / ``emb['genre']`` feed the heads)."""
+        self._check_foreign_graph(x_dict, edge_index_dict)
         clone = copy.deepcopy(self.model)
         clone.eval()
         emb, _ = clone(self.x if x_dict is None else x_dict,

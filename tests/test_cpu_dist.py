@@ -310,6 +310,22 @@ def _product_worker(rank, world, port, opname, replicate, errq):
             opt_p.step()
             # (Adam's first steps are sign-like on noise-level gradients: 2e-3, as on the GPU)
             assert abs(float(lp_) - float(lo_)) <= 2e-3 * abs(float(lo_)), (step, float(lp_), float(lo_))
+        # save_embeddings() (train_gnn_embeddings.py:82-93) = deepcopy + eval forward: the cached
+        # layer plans hold the process group, which must not be copied (GNNTrainer.embeddings())
+        import copy
+        clone = copy.deepcopy(prod).eval()
+        assert clone.gnn._dist is ctx and not clone.gnn._conv_specs
+        with cpu_ops(), torch.no_grad():
+            e_c, _ = clone(x_own, part.edge_index)
+        prod.eval()
+        o32.eval()
+        with cpu_ops(), torch.no_grad():
+            e_s, _ = prod(x_own, part.edge_index)
+            e_r, _ = o32(g.x_dict, ei)
+        assert torch.equal(e_c['artwork'], e_s['artwork'])
+        lo, hi = part.bounds['artwork'][rank], part.bounds['artwork'][rank + 1]
+        # three sign-like Adam steps apart from the oracle's trajectory: a sanity bound only
+        assert rel_err(e_c['artwork'], e_r['artwork'][lo:hi]) <= 5e-2
         dist.barrier()
         dist.destroy_process_group()
     except Exception:
