@@ -18,10 +18,12 @@ from oracle import heads_oracle as ho
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 
-# gradients are compared against the largest gradient entry of the SAME tensor; tensors whose
-# true gradient is rounding noise (biases in front of a training-mode BatchNorm) are compared on
-# the scale of the whole model's gradient instead
-GRAD_RTOL = 2e-5
+# gradients are compared against the largest gradient entry of the SAME tensor (util.rel_err:
+# max|a-b| / max|b|); tensors whose true gradient is rounding noise (biases in front of a
+# training-mode BatchNorm) are compared on the scale of the whole model's gradient instead.
+# north_star's bound; every tensor that needs the float64 argument of _compare_grads instead is
+# printed and recorded (util.parity_log, gpurun_out/parity_fallbacks.jsonl).
+GRAD_RTOL = 1e-5
 
 
 def _to_dev(d):
@@ -70,6 +72,7 @@ def _assert_close(p, r32, r64, what, rtol=RTOL_F32):
     scale = float(torch.as_tensor(r64).abs().max())
     ref_err = float((torch.as_tensor(r32).double() - r64).abs().max())
     prod_err = float((torch.as_tensor(p).detach().double().cpu() - r64).abs().max())
+    util.parity_log('fallback', what, e, prod_vs_f64=prod_err / scale, ref_vs_f64=ref_err / scale)
     assert prod_err <= max(4 * ref_err + 1e-6 * scale, 5e-5 * scale), (what, e, prod_err, ref_err)
 
 
@@ -93,12 +96,15 @@ def _compare_grads(orc, prod, g64=None):
         if scale <= 1e-4 * gmax:                        # noise-level gradient
             assert err <= GRAD_RTOL * gmax, (n, err, gmax)
             continue
+        util.parity_log('grad', n, err / scale)
         if err / scale <= GRAD_RTOL:
             worst = max(worst, err / scale)
             continue
         assert g64 is not None, (n, err / scale)
         ref_err = float((g.double() - g64[n]).abs().max())
         prod_err = float((p - g64[n]).abs().max())
+        util.parity_log('fallback', 'grad ' + n, err / scale, prod_vs_f64=prod_err / scale,
+                        ref_vs_f64=ref_err / scale, rows=int(g.shape[0]) if g.dim() else 1)
         # two float32 evaluations with different (equally valid) summation orders scatter around
         # the exact value independently: allow a small multiple of the reference's own distance
         # (observed: BatchNorm over the 18 / 30 rows of the genre / media types amplifies rounding
@@ -347,6 +353,39 @@ def test_heads_dropout_mask_vs_oracle():
     assert not torch.equal(a, b)
     m.eval()
     assert torch.equal(m(f_p, emb_s.to(DEV), emb_g.to(DEV))[0], m(f_p, emb_s.to(DEV), emb_g.to(DEV))[0])
+
+
+@pytest.mark.parametrize('opname', ['SAGEConv', 'GraphConv'])
+def test_full_config_training_step_vs_oracle(opname):
+    """BASELINE configs[1] itself -- the benchmarked 'full' graph (116,475 artworks, 1.79 M directed
+    edges), one-hot features, dropout masks injected: one training step (forward, nll_loss over
+    all artwork rows, backward) against the oracle.  This is the size at which agg_chunks sees
+    42 k-edge rows spanning ~41 CTAs, every tall transform runs on gemm_tf32x3_tc and every weight
+    gradient on gemm_tf32x3_tc_longk with K = 116,475
+    (/root/reference/src/train_gnn_embeddings.py:39-52)."""
+    g, ei, orc, prod = _build_pair(opname, 32, 'full', features='one-hot', dropout=0.4)
+    gen = torch.Generator().manual_seed(78)
+    masks = {t: (torch.rand(n, 128, generator=gen) >= 0.4).float() / 0.6
+             for t, n in g.num_nodes_dict.items()}
+    orc.gnn.dropout_masks = masks
+    prod.gnn.dropout_masks = {t: m.to(DEV) for t, m in masks.items()}
+    orc.train(); prod.train()
+    y = g['artwork'].y_style
+    e_o, o_o = orc(g.x_dict, ei)
+    l_o = go.nll_loss_artwork(o_o[0], y)
+    l_o.backward()
+    e_p, o_p = prod(_to_dev(g.x_dict), _to_dev(ei))
+    l_p = agx.functional.nll_loss(o_p[0]['artwork'], y.to(DEV))
+    l_p.backward()
+    torch.cuda.synchronize()
+    g64 = _oracle_grads_fp64(orc, g, ei, y, masks)
+    for t in e_o:
+        _assert_close(e_p[t], e_o[t].detach(), g64['__emb__'][t], ('emb', t))
+        _assert_close(o_p[0][t], o_o[0][t].detach(), g64['__logp__'][t], ('logp', t))
+    assert rel_err(l_p, l_o) <= RTOL_F32
+    _compare_grads(orc, prod, g64)
+    for (n, b_o), (_, b_p) in zip(orc.named_buffers(), prod.named_buffers()):
+        assert rel_err(b_p, b_o) <= RTOL_F32, n
 
 
 def test_full_size_properties():
