@@ -212,3 +212,11 @@ def stream_ptr() -> int:
 def require_cuda(t: torch.Tensor, name: str):
     if not t.is_cuda:
         raise AgxError(f'{name} must be a CUDA tensor: this package has no CPU execution path')
+
+
+def compute_device() -> torch.device:
+    """Where host inputs are staged for computation: the current CUDA device.  There is no CPU
+    execution path, so this raises without one."""
+    if not torch.cuda.is_available():
+        raise AgxError('no CUDA device: the kernels of libagx.so are the only execution path')
+    return torch.device('cuda', torch.cuda.current_device())

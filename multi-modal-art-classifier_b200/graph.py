@@ -145,7 +145,7 @@ def to_undirected_dict(edge_index_dict, num_nodes: Dict[str, int]):
             rev[(d, 'rev_' + r, s)] = torch.stack([ei[1], ei[0]], dim=0)
         else:
             was_cpu = not ei.is_cuda
-            e = ei.cuda() if was_cpu else ei
+            e = ei.to(L.compute_device()) if was_cpu else ei
             n = int(num_nodes[s])
             res = ops.coalesce_undirected(e[0], e[1], n)
             out[(s, r, d)] = res.cpu() if was_cpu else res

@@ -28,6 +28,7 @@ import torch.nn.functional as F
 
 from . import functional as AF
 from . import ops
+from . import _lib as L
 from .functional import BNSpec, ConvSpec, RelSpec
 from .graph import get_plan, key2str
 from .nn import Linear, MessagePassing
@@ -65,9 +66,53 @@ def _is_identity_input(x: torch.Tensor) -> bool:
     return hit
 
 
+class HostDict(dict):
+    """Result dict of a ``host_io`` module: values are computed on the device and copied to the
+    host (through autograd, so ``backward`` carries the gradient back) the first time they are
+    READ -- the reference reads ``out['artwork']`` only (train_gnn_embeddings.py:35), so the
+    log-probabilities of the eight dead node types never cross PCIe."""
+
+    def __init__(self, dev_dict):
+        super().__init__((k, None) for k in dev_dict)
+        self._dev = dev_dict
+        self._host = {}
+
+    def device_value(self, key):
+        return self._dev[key]
+
+    def __getitem__(self, key):
+        if key not in self._host:
+            self._host[key] = self._dev[key].cpu()
+        return self._host[key]
+
+    def get(self, key, default=None):
+        return self[key] if key in self._dev else default
+
+    def values(self):
+        return [self[k] for k in self._dev]
+
+    def items(self):
+        return [(k, self[k]) for k in self._dev]
+
+
+def _to_host(res):
+    if isinstance(res, dict):
+        return HostDict(res)
+    if isinstance(res, (tuple, list)):
+        return type(res)(_to_host(v) for v in res)
+    return res.cpu() if torch.is_tensor(res) else res
+
+
 class HeteroModule(nn.Module):
-    def __init__(self, module: nn.Module, metadata, aggr: str = 'sum', detect_identity: bool = True):
+    def __init__(self, module: nn.Module, metadata, aggr: str = 'sum', detect_identity: bool = True,
+                 host_io: bool = False):
         super().__init__()
+        # host_io: accept the HOST tensors the reference's CPU-only script passes
+        # (train_gnn_embeddings.py:42 -- it never calls .to(device)): inputs are staged on the
+        # device once per tensor version, the module moves itself there on its first call, and
+        # the result dicts hand values back to the host lazily (HostDict)
+        self.host_io = bool(host_io)
+        self._host_cache: Dict[tuple, torch.Tensor] = {}
         if aggr != 'sum':
             raise NotImplementedError("to_hetero: only aggr='sum' (the reference's setting, "
                                       "src/train_gnn_embeddings.py:130) is implemented")
@@ -118,7 +163,21 @@ class HeteroModule(nn.Module):
         state = self.__dict__.copy()
         state['_conv_specs'] = {}
         state['_nbt_flat'] = {}
+        state['_host_cache'] = {}
         return state
+
+    def _stage(self, t: torch.Tensor, dev: torch.device) -> torch.Tensor:
+        """Device copy of a host input tensor, made once per (storage, version)."""
+        if t.device == dev:
+            return t
+        key = (t.data_ptr(), tuple(t.shape), t.dtype)
+        hit = self._host_cache.get(key)
+        if hit is None or hit[0] != t._version or hit[2] is not t:
+            if len(self._host_cache) > 256:
+                self._host_cache.clear()
+            hit = (t._version, t.to(dev), t)       # (keeps t alive: data_ptr stays unique)
+            self._host_cache[key] = hit
+        return hit[1]
 
     def set_distributed(self, ctx):
         """Run as one rank of a destination-partitioned multi-GPU job (dist.DistContext):
@@ -390,6 +449,16 @@ class HeteroModule(nn.Module):
 
     def forward(self, x, edge_index):
         x_dict, ei_dict = x, edge_index
+        to_host = False
+        if self.host_io and any(not v.is_cuda for v in x_dict.values()):
+            dev = L.compute_device()
+            if any(p.device != dev for p in self.parameters()
+                   if not isinstance(p, nn.parameter.UninitializedParameter)) or \
+                    any(b.device != dev for b in self.buffers()):
+                self.to(dev)        # in place: optimizers created earlier keep their references
+            x_dict = OrderedDict((k, self._stage(v, dev)) for k, v in x_dict.items())
+            ei_dict = OrderedDict((k, self._stage(v, dev)) for k, v in ei_dict.items())
+            to_host = True
         num_nodes = {t: v.shape[0] for t, v in x_dict.items()}
         ei_dict = OrderedDict((tuple(k), v) for k, v in ei_dict.items())
         num_dst = None
@@ -476,7 +545,8 @@ class HeteroModule(nn.Module):
                     return getattr(a[0], node.target)(*a[1:], **kw)
                 env[node.name] = run(None) if keys is None else OrderedDict((k, run(k)) for k in keys)
             elif node.op == 'output':
-                return load(node.args[0])
+                res = load(node.args[0])
+                return _to_host(res) if to_host else res
         raise RuntimeError('fx graph without output node')
 
 

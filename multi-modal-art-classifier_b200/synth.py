@@ -52,80 +52,9 @@ SIZES = {
 }
 
 
-class NodeStore(dict):
-    """Attribute bag for one node type (``data['artwork'].x``)."""
-    __getattr__ = dict.__getitem__
-    __setattr__ = dict.__setitem__
+from .data import EdgeStore, HeteroData, NodeStore  # noqa: E402,F401
 
-
-class EdgeStore(dict):
-    __getattr__ = dict.__getitem__
-    __setattr__ = dict.__setitem__
-
-
-class HeteroGraph:
-    """Minimal stand-in for PyG ``HeteroData`` (absent in this image): insertion-ordered node and
-    edge stores, ``x_dict`` / ``edge_index_dict`` / ``metadata()`` as used at
-    /root/reference/src/train_gnn_embeddings.py:42,57-58,133."""
-
-    def __init__(self):
-        self._nodes: "OrderedDict[str, NodeStore]" = OrderedDict()
-        self._edges: "OrderedDict[Tuple[str, str, str], EdgeStore]" = OrderedDict()
-
-    def __getitem__(self, key):
-        if isinstance(key, tuple):
-            if key not in self._edges:
-                self._edges[key] = EdgeStore()
-            return self._edges[key]
-        if key not in self._nodes:
-            self._nodes[key] = NodeStore()
-        return self._nodes[key]
-
-    def __delitem__(self, key):
-        if isinstance(key, tuple):
-            del self._edges[key]
-        else:
-            del self._nodes[key]
-
-    @property
-    def node_types(self):
-        return list(self._nodes.keys())
-
-    @property
-    def edge_types(self):
-        return list(self._edges.keys())
-
-    def metadata(self):
-        return self.node_types, self.edge_types
-
-    @property
-    def x_dict(self) -> Dict[str, torch.Tensor]:
-        return OrderedDict((k, v['x']) for k, v in self._nodes.items() if 'x' in v)
-
-    @property
-    def edge_index_dict(self):
-        return OrderedDict((k, v['edge_index']) for k, v in self._edges.items()
-                           if 'edge_index' in v)
-
-    @property
-    def num_nodes_dict(self):
-        out = OrderedDict()
-        for k, v in self._nodes.items():
-            out[k] = int(v['x'].shape[0]) if 'x' in v else int(v['num_nodes'])
-        return out
-
-    def num_edges(self) -> int:
-        return sum(int(v['edge_index'].shape[1]) for v in self._edges.values())
-
-    def to(self, device, non_blocking=False):
-        g = HeteroGraph()
-        for k, v in self._nodes.items():
-            for a, t in v.items():
-                g[k][a] = t.to(device, non_blocking=non_blocking) if torch.is_tensor(t) else t
-        for k, v in self._edges.items():
-            for a, t in v.items():
-                g[k][a] = t.to(device, non_blocking=non_blocking) if torch.is_tensor(t) else t
-        return g
+HeteroGraph = HeteroData        # the name this module used before the container moved to data.py
 
 
 def _zipf_probs(n: int, s: float) -> torch.Tensor:
@@ -210,6 +139,37 @@ def make_artgraph(size: str = 'small', features: str = 'one-hot', seed: int | No
     return g
 
 
+def write_artgraph_raw(root: str, g: HeteroGraph) -> str:
+    """Write ``g`` (a directed graph from ``make_artgraph``) as the raw CSV tree the reference's
+    ``ArtGraph.process`` reads (/root/reference/src/data/artgraph.py:63-112), under ``root/raw``:
+
+        node-feat/artwork/node-feat.csv          A x 128 floats, no header           (:66-68)
+        node-label/artwork/node-label-{style,genre}.csv   one label per line         (:75-81)
+        num-node-dict.csv                        header = node types, one row        (:84-95)
+        relations/<h>___<r>___<t>/edge.csv       E x 2 ints (head, tail), no header  (:97-112)
+
+    so that the unmodified dataset class builds the same ``HeteroData`` from disk."""
+    import os
+    import numpy as np
+    raw = os.path.join(root, 'raw')
+    for sub in ('node-feat/artwork', 'node-label/artwork', 'relations'):
+        os.makedirs(os.path.join(raw, sub), exist_ok=True)
+    np.savetxt(os.path.join(raw, 'node-feat', 'artwork', 'node-feat.csv'),
+               g['artwork'].x.numpy(), delimiter=',', fmt='%.9g')
+    for lab in ('style', 'genre'):
+        np.savetxt(os.path.join(raw, 'node-label', 'artwork', f'node-label-{lab}.csv'),
+                   g['artwork'][f'y_{lab}'].numpy().astype(np.int64), fmt='%d')
+    n = g.num_nodes_dict
+    with open(os.path.join(raw, 'num-node-dict.csv'), 'w') as fh:
+        fh.write(','.join(NODE_TYPES) + '\n' + ','.join(str(n[t]) for t in NODE_TYPES) + '\n')
+    for (h, r, t) in EDGE_TYPES:
+        d = os.path.join(raw, 'relations', '___'.join((h, r[:-len('_rel')], t)))
+        os.makedirs(d, exist_ok=True)
+        np.savetxt(os.path.join(d, 'edge.csv'), g[(h, r, t)].edge_index.t().numpy(),
+                   delimiter=',', fmt='%d')
+    return raw
+
+
 def replicate(g: HeteroGraph, copies: int) -> HeteroGraph:
     """Block-diagonal ``copies``-fold replication (config 5): node ids of copy c are offset by
     ``c * N_t``; features are tiled so input widths stay unchanged."""
@@ -222,7 +182,7 @@ def replicate(g: HeteroGraph, copies: int) -> HeteroGraph:
         ei = g[(s, r, d)].edge_index
         parts = []
         for c in range(copies):
-            off = torch.tensor([[c * n[s]], [c * n[d]]], dtype=torch.int64)
+            off = torch.tensor([[c * n[s]], [c * n[d]]], dtype=torch.int64, device=ei.device)
             parts.append(ei + off)
         out[(s, r, d)].edge_index = torch.cat(parts, dim=1).contiguous()
     return out

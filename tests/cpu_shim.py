@@ -421,6 +421,17 @@ _PATCHES = {
 }
 
 
+def _coalesce_undirected(row, col, n_nodes):
+    """agx_coalesce_undirected contract: unique (row, col) pairs of the symmetrised list, ascending
+    by row * n_nodes + col."""
+    key = torch.cat([row * n_nodes + col, col * n_nodes + row])
+    key = torch.unique(key, sorted=True)
+    return torch.stack([key // n_nodes, key % n_nodes], dim=0)
+
+
+_PATCHES['coalesce_undirected'] = _coalesce_undirected
+
+
 @contextlib.contextmanager
 def cpu_ops():
     """Inside the block ``mmac_b200.ops`` computes with torch on CPU (see the module docstring)."""
@@ -428,12 +439,14 @@ def cpu_ops():
     from mmac_b200 import functional as AF
     saved = {k: getattr(ops, k) for k in _PATCHES}
     saved_req = L.require_cuda
+    saved_dev = L.compute_device
     saved_mod = [(m, m.lib, m.stream_ptr) for m in (AF, AD)]
     fake = _FakeLib()
     try:
         for k, v in _PATCHES.items():
             setattr(ops, k, v)
         L.require_cuda = lambda t, name: None
+        L.compute_device = lambda: torch.device('cpu')
         for m, _, _ in saved_mod:
             m.lib = lambda: fake
             m.stream_ptr = lambda: 0
@@ -442,5 +455,6 @@ def cpu_ops():
         for k, v in saved.items():
             setattr(ops, k, v)
         L.require_cuda = saved_req
+        L.compute_device = saved_dev
         for m, lib_, sp_ in saved_mod:
             m.lib, m.stream_ptr = lib_, sp_

@@ -388,6 +388,63 @@ def test_full_config_training_step_vs_oracle(opname):
         assert rel_err(b_p, b_o) <= RTOL_F32, n
 
 
+def test_host_io_reference_calling_convention():
+    """The reference script's calling convention on the real kernels (its own files run unchanged
+    in tests/test_cpu_reference_scripts.py, where the reference tree exists): HOST tensors in
+    (train_gnn_embeddings.py:42 never moves anything to a device), ``torch.optim.Adam`` created
+    before the lazy weights exist (:144-147), ``F.nll_loss`` against host labels (:30), results
+    read from the returned dicts on the host."""
+    import torch.nn.functional as F
+    g, ei, md = util.undirected_graph('tiny')
+    orc = go.HeteroSGNNOracle(go.SAGEConv, torch.nn.ReLU(), 'sum', 128, 32, md, 2, 0.0, True, False)
+    with torch.no_grad():
+        orc(g.x_dict, ei)
+    util.fill_params_deterministic(orc)
+    util.reset_bn(orc)
+    tmpl = agx.HeteroGNN(agx.SAGEConv, torch.nn.ReLU(), 128, 32, 2, 0.0, True, False)
+    model = torch.nn.Module()
+    model.gnn = agx.to_hetero(tmpl, md, aggr='sum', host_io=True)
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)        # lazy parameters inside
+    with torch.no_grad():
+        model.gnn(g.x_dict, ei)                                 # host tensors; module moves itself
+    assert all(p.is_cuda for p in model.parameters()
+               if not isinstance(p, torch.nn.parameter.UninitializedParameter))
+    util.copy_state(orc, model)
+    util.reset_bn(model)
+    y = g['artwork'].y_style
+    opt_o = torch.optim.Adam([p for p in orc.parameters()
+                              if not isinstance(p, torch.nn.parameter.UninitializedParameter)],
+                             lr=0.01)
+    orc.train(); model.train()
+    for step in range(3):
+        opt.zero_grad(); opt_o.zero_grad()
+        emb, out = model.gnn(g.x_dict, ei)
+        assert isinstance(out, agx.hetero.HostDict) and not out['artwork'].is_cuda
+        loss = F.nll_loss(out['artwork'], y.type(torch.LongTensor))
+        loss.backward()
+        opt.step()
+        e_o, o_o = orc(g.x_dict, ei)
+        l_o = go.nll_loss_artwork(o_o[0], y)
+        l_o.backward()
+        opt_o.step()
+        if step == 0:
+            assert rel_err(emb['artwork'], e_o['artwork']) <= RTOL_F32
+            assert rel_err(out['artwork'], o_o[0]['artwork']) <= RTOL_F32
+            assert rel_err(loss, l_o) <= RTOL_F32
+        else:
+            assert abs(float(loss) - float(l_o)) <= 2e-3 * abs(float(l_o))
+    # inputs were staged once: a second call with the same host tensors re-uses the device copies
+    n_staged = len(model.gnn._host_cache)
+    model.gnn(g.x_dict, ei)
+    assert len(model.gnn._host_cache) == n_staged
+    # deepcopy + eval forward (save_embeddings, :82-93) hands back a host tensor
+    import copy as _copy
+    clone = _copy.deepcopy(model).eval()
+    with torch.no_grad():
+        emb_c, _ = clone.gnn(g.x_dict, ei)
+    assert not emb_c['artwork'].is_cuda and emb_c['artwork'].shape == (300, 128)
+
+
 def test_full_size_properties():
     """BASELINE config 2 sizes: size-independent properties instead of an oracle run."""
     g = synth.make_artgraph('full', features='dense')
