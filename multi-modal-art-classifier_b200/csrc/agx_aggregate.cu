@@ -941,13 +941,15 @@ extern "C" int agx_aggregate_rows(const agx_row_group_t* h_groups, int n_groups,
     return launch_rows<__nv_bfloat16, 1>(P, max(4, min(32, pow2_ceil(F))), slots, st);
 }
 
+constexpr int kMinCtaEdges = kAggWarps * 32;                 // smallest unit a launch may pick
+
 extern "C" size_t agx_chunk_frag_floats(int64_t n_edges, int F) {
     const int fb = F < kMaxChunkF ? F : kMaxChunkF;             // one column block at a time
-    return (size_t)2 * (size_t)ceil_div(n_edges > 0 ? n_edges : 1, kCtaEdges) * (size_t)fb;
+    return (size_t)2 * (size_t)ceil_div(n_edges > 0 ? n_edges : 1, kMinCtaEdges) * (size_t)fb;
 }
 
 extern "C" size_t agx_chunk_counters(int64_t n_edges) {
-    return (size_t)ceil_div(n_edges > 0 ? n_edges : 1, kCtaEdges);
+    return (size_t)ceil_div(n_edges > 0 ? n_edges : 1, kMinCtaEdges);
 }
 
 template <typename T, int VEC, int LPR, int CE>
@@ -977,6 +979,8 @@ static int launch_chunks_lpr(const ChunkSegs& P, unsigned grid, bool tma, int ce
     switch (ce) {
         case 256: return launch_chunks_ce<T, VEC, LPR, 256>(P, grid, false, st);
         case 192: return launch_chunks_ce<T, VEC, LPR, 192>(P, grid, false, st);
+        case 64: return launch_chunks_ce<T, VEC, LPR, 64>(P, grid, false, st);
+        case 32: return launch_chunks_ce<T, VEC, LPR, 32>(P, grid, false, st);
         default: return launch_chunks_ce<T, VEC, LPR, AGX_CHUNK_EDGES>(P, grid, tma, st);
     }
 }
@@ -991,28 +995,26 @@ static int launch_chunks(const ChunkSegs& P, int lpr, unsigned grid, bool tma, i
     }
 }
 
-// Edges per warp for this launch: the unit whose CTA count comes closest to whole waves of the
-// 148 x 4 resident CTAs (time ~ waves x unit size); ties go to the smaller unit.
+// Edges per warp for this launch.  Measured on B200 (round 2, full graph, 7 launches per step):
+//     edges per warp    64      128      192      256
+//     us per step       436     553      649      783
+// Filling exactly one wave of resident CTAs with bigger units (the round-1 hypothesis) is SLOWER,
+// smaller units are faster: a warp walks its edges in serial batches of kGatherDepth gathers (one
+// L2 / DRAM round trip per batch), so a CTA lasts as long as its unit and the launch ends with the
+// slowest CTA, while the gathers themselves are far from the L2 ceiling at any residency
+// (profiles/probes/gather_probe2.cu: 12.5 TB/s with 2 CTAs per SM).  Default 64;
+// AGX_CHUNK_CE=32|64|128|192|256 overrides it.
+constexpr int kDefaultChunkEdges = 64;
 static int pick_chunk_edges(const agx_chunk_seg_t* segs, int n_segs, bool tma) {
     static const char* env = getenv("AGX_CHUNK_CE");
+    (void)segs;
+    (void)n_segs;
     if (tma) return AGX_CHUNK_EDGES;
     if (env) {
         const int v = atoi(env);
-        if (v == 128 || v == 192 || v == 256) return v;
+        if (v == 32 || v == 64 || v == 128 || v == 192 || v == 256) return v;
     }
-    const int64_t slots = (int64_t)kNumSMs * kChunkCtasPerSm;
-    int best = AGX_CHUNK_EDGES;
-    int64_t best_cost = -1;
-    for (int ce : {AGX_CHUNK_EDGES, 192, 256}) {
-        int64_t ctas = 0;
-        for (int s = 0; s < n_segs; ++s) ctas += ceil_div(segs[s].n_edges, (int64_t)kAggWarps * ce);
-        const int64_t cost = ceil_div(ctas > 0 ? ctas : 1, slots) * ce;
-        if (best_cost < 0 || cost < best_cost) {
-            best_cost = cost;
-            best = ce;
-        }
-    }
-    return best;
+    return kDefaultChunkEdges;
 }
 
 extern "C" int agx_aggregate_chunks(const agx_chunk_seg_t* h_segs, int n_segs, int F, int dtype,

@@ -116,7 +116,12 @@ def _gnn_case(rank, world, dev, kind, opname):
         dist.all_reduce(pmax, op=dist.ReduceOp.MAX)
         d = float((gsum - grads_r[k]).abs().max())
         scale = max(float(grads_r[k].abs().max()), float(pmax))
-        assert d <= GRAD_RTOL * scale or d <= 1e-5 * gmax, \
+        # weights of relations that touch a node type of a few dozen rows sit behind a BatchNorm
+        # over those rows (rounding amplified ~100x, see above): 1e-4 there, as for the embeddings
+        small = any(n[t] < 512 for t in n if f'{t}__' in k or f'__{t}.' in k or f'.{t}.' in k)
+        tol = 1e-4 if small else GRAD_RTOL
+        util.parity_log('dist-grad', f'{kind} {opname} {k}', d / max(scale, 1e-30), tol=tol)
+        assert d <= tol * scale or d <= 1e-5 * gmax, \
             (kind, 'grad', k, d, scale, gmax)
     # BatchNorm running statistics are those of the whole graph
     for (k, b), (_, br) in zip(mod.named_buffers(), ref.named_buffers()):
