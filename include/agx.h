@@ -360,6 +360,64 @@ typedef struct {
 int agx_sddmm(const agx_sddmm_seg_t* h_segs, int n_segs, int32_t F, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K5/K6 fused head step on the tensor cores (tcgen05, bf16 operands, float32 accumulation)
+ *   replaces, per mini-batch, the whole of
+ *     comb = cat(feat, emb); out = Linear(Dropout(comb)); loss = coef * CE(out, y; w); backward
+ *       src/models/models_kg.py:237-243 (multitask), :158-162 / :208-215 (single task)
+ *       src/train_new_multimodal_multitask.py:76-83 (run there under fp16 autocast)
+ *     out = encoder(feat); loss = SmoothL1(out, emb); backward
+ *       src/models/models_kg.py:261,278; src/train_projector.py:49-54 (fp16 autocast)
+ *   One "head" = one Linear with <= 64 output columns over the virtual concatenation of up to two
+ *   input parts; wider outputs (the projector's 128) are given as several heads over column slices.
+ *   Per 128-row tile ONE CTA: parts staged by TMA, dropout applied while converting to bf16 (Philox
+ *   from (seed, step) in-kernel, or an explicit mask), logits on tcgen05.mma into TMEM, softmax-CE /
+ *   SmoothL1 + the logit gradient in the TMEM epilogue, d_weight^T accumulated in TMEM by a second
+ *   tcgen05.mma pass over the same (L2-hot) tile; partials of the CTAs are combined in fixed order.
+ *   Requirements: width[0] % 64 == 0, (width[0] + width[1]) % 128 == 0, C <= 64, rows 16-byte
+ *   aligned.  Input gradients are NOT produced (precomputed backbone features, BASELINE config 4).
+ * ------------------------------------------------------------------------------------------ */
+#define AGX_HEAD_CE 0
+#define AGX_HEAD_SMOOTH_L1 1
+#define AGX_MAX_HEADS 4
+typedef struct agx_head_t {
+    const float* part[2];    /* [B, width[i]] float32 row-major; part[1] NULL when width[1] == 0 */
+    int64_t ld[2];
+    int32_t width[2];
+    int32_t C;               /* output columns, 1..64 */
+    int32_t loss;            /* AGX_HEAD_CE | AGX_HEAD_SMOOTH_L1 */
+    const float* weight;     /* [C, K] float32 row-major, K = width[0] + width[1] */
+    int64_t ldw;
+    const float* bias;       /* [C] or NULL */
+    const float* mask;       /* optional explicit multiplicative dropout mask [B, K]; overrides p_drop */
+    int64_t ld_mask;
+    const int64_t* labels;   /* CE: [B] */
+    const float* class_w;    /* CE: [C] or NULL */
+    float coef;              /* CE: weight of this head's loss term (0.5 in the multitask script) */
+    float inv_count;         /* SMOOTH_L1: 1 / (global rows * total output columns) */
+    const float* target;     /* SMOOTH_L1: [B, C] (column slice of the embedding) */
+    int64_t ld_target;
+    float* logits;           /* optional output [B, C] float32 */
+    int64_t ld_logits;
+    float* d_weight;         /* [C, K] gradient */
+    int64_t ld_dw;
+    float* d_bias;           /* [C] or NULL */
+} agx_head_t;
+
+/* bytes of caller-owned workspace for agx_head_step_prepare / agx_head_step (same n_heads, B) */
+size_t agx_head_step_workspace_bytes(const agx_head_t* h_heads, int n_heads, int32_t B);
+/* phase 1: bf16 copies of the weights into the workspace and norm[h] = sum_rows class_w[labels]
+ * (= B without class weights; untouched for SMOOTH_L1 heads).  The caller may all-reduce norm
+ * (batch-sharded heads) before phase 2. */
+int agx_head_step_prepare(const agx_head_t* h_heads, int n_heads, int32_t B, float* norm,
+                          void* workspace, size_t workspace_bytes, void* stream);
+/* phase 2: forward + loss + backward.  loss[0] (+)= sum_h coef_h * sum_rows w nll / norm[h]
+ * (resp. inv_count * sum huber); d_weight / d_bias are written, or added to when accumulate != 0.
+ * seed_state: device int64 [2] (Philox key, step counter), NULL or p_drop == 0: no dropout. */
+int agx_head_step(const agx_head_t* h_heads, int n_heads, int32_t B, float p_drop,
+                  const int64_t* seed_state, const float* norm, float* loss, int accumulate,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * ContextNet / Castellano encoder heads
  *   replaces: nn.Tanh of the encoder (src/models/models_kg.py:80-85,120-125), MSELoss and
  *   SGD(momentum=0.9) of src/train_baseline_context.py:47-54.

@@ -100,6 +100,18 @@ class ColsumDesc(C.Structure):
                 ('accumulate', c_i32), ('pad_', c_i32)]
 
 
+MAX_HEADS = 4
+HEAD_CE, HEAD_SMOOTH_L1 = 0, 1
+
+
+class Head(C.Structure):
+    _fields_ = [('part', vp * 2), ('ld', c_i64 * 2), ('width', c_i32 * 2), ('C', c_i32),
+                ('loss', c_i32), ('weight', vp), ('ldw', c_i64), ('bias', vp), ('mask', vp),
+                ('ld_mask', c_i64), ('labels', vp), ('class_w', vp), ('coef', c_f32),
+                ('inv_count', c_f32), ('target', vp), ('ld_target', c_i64), ('logits', vp),
+                ('ld_logits', c_i64), ('d_weight', vp), ('ld_dw', c_i64), ('d_bias', vp)]
+
+
 _SIGS = {
     'agx_version': (C.c_int, []),
     'agx_last_error': (C.c_char_p, []),
@@ -141,6 +153,10 @@ _SIGS = {
     'agx_gat_edge_softmax': (C.c_int, [C.POINTER(GatRel), C.c_int, c_f32, vp]),
     'agx_gat_edge_softmax_bwd': (C.c_int, [C.POINTER(GatRel), C.c_int, c_f32, vp]),
     'agx_sddmm': (C.c_int, [C.POINTER(SddmmSeg), C.c_int, c_i32, vp]),
+    'agx_head_step_workspace_bytes': (C.c_size_t, [C.POINTER(Head), C.c_int, c_i32]),
+    'agx_head_step_prepare': (C.c_int, [C.POINTER(Head), C.c_int, c_i32, vp, vp, C.c_size_t, vp]),
+    'agx_head_step': (C.c_int, [C.POINTER(Head), C.c_int, c_i32, c_f32, vp, vp, vp, C.c_int, vp,
+                                C.c_size_t, vp]),
     'agx_mse': (C.c_int, [vp, vp, c_i64, vp, vp, vp, vp]),
     'agx_tanh': (C.c_int, [vp, vp, c_i64, vp]),
     'agx_tanh_bwd': (C.c_int, [vp, vp, vp, c_i64, vp]),

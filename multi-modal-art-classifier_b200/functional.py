@@ -205,6 +205,10 @@ class _HeteroConvFn(torch.autograd.Function):
             for k, sz in zip(part_k, sizes):
                 G[k] = part_flat[off:off + sz].view(spec.rels[k].rel.n_dst, -1)
                 off += sz
+        # aggregations of the partial relations run first: their all-reduce is started as soon as
+        # they are done and overlaps everything of the layer that does not read the full sums
+        part_rows: Dict[int, list] = {}
+        part_chunks: Dict[int, list] = {}
         for k, rs in enumerate(spec.rels):
             if rs.transform_first:
                 continue
@@ -214,9 +218,22 @@ class _HeteroConvFn(torch.autograd.Function):
             G[k] = g
             arg = ops.RelArg(r.csr, xs[r.src], mean_rows=rs.mean)
             if r.csr.long_rows:
-                chunks_by_F.setdefault(fs, []).append((g, arg))
+                (part_chunks if rs.partial else chunks_by_F).setdefault(fs, []).append((g, arg))
+            elif rs.partial:
+                part_rows.setdefault(fs, []).append((g, [arg], False))
             else:
                 rows_by_F.setdefault((0, fs), []).append((g, [arg], False))
+        work = None
+        if part_flat is not None:
+            for F, grp in part_rows.items():
+                ops.aggregate_rows(grp, F)
+            for F, segs in part_chunks.items():
+                ops.aggregate_chunks(segs, F)
+            # partial neighbour sums of all ranks -> the full sums, on every rank (one all-reduce
+            # per layer, on the communicator's stream; the mean relations were divided by the
+            # GLOBAL in-degree above)
+            import torch.distributed as dist
+            work = dist.all_reduce(part_flat, group=spec.group, async_op=True)
         if tr:
             ops.transpose_many(tr)
         if gb.problems:
@@ -225,11 +242,6 @@ class _HeteroConvFn(torch.autograd.Function):
             ops.aggregate_rows(rows_by_F[(wave, F)], F)
         for F, segs in chunks_by_F.items():
             ops.aggregate_chunks(segs, F)
-        if part_flat is not None:
-            # partial neighbour sums of all ranks -> the full sums, on every rank (one all-reduce
-            # per layer; the mean relations were divided by the GLOBAL in-degree above)
-            import torch.distributed as dist
-            dist.all_reduce(part_flat, group=spec.group)
         if tf_long:
             items = []
             for t, temps in tf_long.items():
@@ -242,25 +254,32 @@ class _HeteroConvFn(torch.autograd.Function):
                 items.append((outs[t], ins))
             ops.sum_arrays(items)
 
-        # s3: one multi-segment GEMM per destination type
-        gb = ops.GemmBatch()
-        for t, lst in by_dst.items():
-            segs = []
-            for k, rs in enumerate(spec.rels):
-                if rs.rel.dst == t and not rs.transform_first:
-                    segs.append((G[k], _t(params[rs.i_wl])))
-            if wroot[t] is not None and not id_root[t]:
-                segs.append((xd[t], _t(wroot[t])))
-            if not segs and bsum[t] is not None:
-                # bias only (no dense segment left): rank-1 product ones[N,1] @ bias[1,O]
-                ones = ops.fill_(torch.empty(outs[t].shape[0], 1, dtype=torch.float32, device=dev), 1.0)
-                gb.add(outs[t], [(ones, bsum[t].view(1, -1))], accumulate=has_tf[t])
-            elif segs:
-                gb.add(outs[t], segs, bias=bsum[t], accumulate=has_tf[t])
-            elif not has_tf[t]:
-                ops.fill_(outs[t], 0.0)
-        if gb.problems:
-            gb.run()
+        # s3: one multi-segment GEMM per destination type; the types that read all-reduced sums
+        # wait for the collective, the others (artwork: most of the rows) are launched before
+        part_types = {spec.rels[k].rel.dst for k in part_k}
+        for dependent in (False, True):
+            if dependent and work is not None:
+                work.wait()
+            gb = ops.GemmBatch()
+            for t, lst in by_dst.items():
+                if (t in part_types) != dependent:
+                    continue
+                segs = []
+                for k, rs in enumerate(spec.rels):
+                    if rs.rel.dst == t and not rs.transform_first:
+                        segs.append((G[k], _t(params[rs.i_wl])))
+                if wroot[t] is not None and not id_root[t]:
+                    segs.append((xd[t], _t(wroot[t])))
+                if not segs and bsum[t] is not None:
+                    # bias only (no dense segment left): rank-1 product ones[N,1] @ bias[1,O]
+                    ones = ops.fill_(torch.empty(outs[t].shape[0], 1, dtype=torch.float32, device=dev), 1.0)
+                    gb.add(outs[t], [(ones, bsum[t].view(1, -1))], accumulate=has_tf[t])
+                elif segs:
+                    gb.add(outs[t], segs, bias=bsum[t], accumulate=has_tf[t])
+                elif not has_tf[t]:
+                    ops.fill_(outs[t], 0.0)
+            if gb.problems:
+                gb.run()
 
         ctx.spec = spec
         ctx.nt = nt
@@ -292,6 +311,28 @@ class _HeteroConvFn(torch.autograd.Function):
         pidx = lambda i: nt + i                                            # noqa: E731
 
         live = [(k, rs) for k, rs in enumerate(spec.rels) if dout[rs.rel.dst] is not None]
+
+        # b0: d(full neighbour sum) of the partial relations: every rank holds a PART of that gradient
+        # (its own consumers of the replicated rows); the transpose over a rank's edges needs the
+        # sum over the ranks -> one flat buffer, one all-reduce, started first so that it overlaps
+        # the rest of the layer's backward (it is only read by b5)
+        dG: Dict[int, torch.Tensor] = {}
+        part_k = [k for k, rs in live if rs.partial and need_x[rs.rel.src]]
+        dpart_flat = None
+        work = None
+        if part_k:
+            sizes = [spec.rels[k].rel.n_dst * xs[spec.rels[k].rel.src].shape[1] for k in part_k]
+            dpart_flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+            off = 0
+            gb0 = ops.GemmBatch()
+            for k, sz in zip(part_k, sizes):
+                rs = spec.rels[k]
+                dG[k] = dpart_flat[off:off + sz].view(rs.rel.n_dst, -1)
+                off += sz
+                gb0.add(dG[k], [(dout[rs.rel.dst], params[rs.i_wl])])
+            gb0.run()
+            import torch.distributed as dist
+            work = dist.all_reduce(dpart_flat, group=spec.group, async_op=True)
 
         # b1: bias gradients = column sums of dout, shared by the relations of a type
         cs_items = []
@@ -337,19 +378,6 @@ class _HeteroConvFn(torch.autograd.Function):
                 trb.append((dw, dout[t]))                        # dout^T I
             else:
                 gb.add(dw, [(_t(dout[t]), x)], split_k=ops.split_k_for(x.shape[0]))
-        dG: Dict[int, torch.Tensor] = {}
-        # d(full neighbour sum) of the partial relations: every rank holds a PART of that gradient
-        # (its own consumers of the replicated rows); the transpose over a rank's edges needs the
-        # sum over the ranks -> one flat buffer, one all-reduce
-        part_k = [k for k, rs in live if rs.partial and need_x[rs.rel.src]]
-        dpart_flat = None
-        if part_k:
-            sizes = [spec.rels[k].rel.n_dst * xs[spec.rels[k].rel.src].shape[1] for k in part_k]
-            dpart_flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
-            off = 0
-            for k, sz in zip(part_k, sizes):
-                dG[k] = dpart_flat[off:off + sz].view(spec.rels[k].rel.n_dst, -1)
-                off += sz
         for k, rs in live:
             r = rs.rel
             x = xs[r.src]
@@ -361,18 +389,16 @@ class _HeteroConvFn(torch.autograd.Function):
                 gb.add(dw, [(_t(dY[k]), x)], split_k=ops.split_k_for(r.n_src))
             else:
                 gb.add(dw, [(_t(dout[r.dst]), G[k])], split_k=ops.split_k_for(r.n_dst))
-                if need_x[r.src]:
-                    dg = dG[k] if k in dG else \
-                        torch.empty(r.n_dst, x.shape[1], dtype=torch.float32, device=dev)
+                if need_x[r.src] and k not in dG:
+                    dg = torch.empty(r.n_dst, x.shape[1], dtype=torch.float32, device=dev)
                     dG[k] = dg
                     gb.add(dg, [(dout[r.dst], params[rs.i_wl])])
         if trb:
             ops.transpose_many(trb)
         if gb.problems:
             gb.run()
-        if dpart_flat is not None:
-            import torch.distributed as dist
-            dist.all_reduce(dpart_flat, group=spec.group)
+        if work is not None:
+            work.wait()
         for k, rs in live:
             if rs.i_wr >= 0:
                 grads[pidx(rs.i_wr)] = dwroot[rs.rel.dst]

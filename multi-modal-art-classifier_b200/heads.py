@@ -60,6 +60,46 @@ class _HeadBase(nn.Module):
         parts = [feat.contiguous(), emb.contiguous()]
         return AF.fused_linear(parts, lin.weight, lin.bias, self._masks(name, seq, parts))
 
+    # ---- fused training step on the tensor cores (agx_head_step) ---------------------------------
+    def _tc_seed(self, device):
+        if self._seed is None or self._seed.device != device:
+            s = torch.initial_seed()
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                s += 0x9E3779B97F4A7C15 * (dist.get_rank() + 1)
+            self._seed = torch.tensor([s & 0x7fffffffffffffff, 0], dtype=torch.int64, device=device)
+        return self._seed
+
+    def _tc_head_arg(self, name, seq, feat, emb, labels, class_w, coef, logits):
+        lin = seq[1]
+        mask = None
+        if self.dropout_masks is not None:
+            mask = self.dropout_masks.get(name)
+        return ops.HeadArg(parts=[feat, emb], weight=lin.weight, bias=lin.bias,
+                           d_weight=_grad_of(lin.weight), d_bias=_grad_of(lin.bias), loss='ce',
+                           labels=labels, class_w=class_w, coef=coef, mask=mask, logits=logits)
+
+    def _tc_run(self, args, seq, group, accumulate):
+        """Launch the fused step; dropout = the module's p in training mode (Philox stream of this
+        module, one step counter per call), or the injected masks."""
+        if getattr(self, '_tc_step', None) is None:
+            self._tc_step = ops.HeadStep()
+        p = float(seq[0].p) if (self.training and self.dropout_masks is None) else 0.0
+        seed = self._tc_seed(args[0].weight.device) if p > 0 else None
+        loss = self._tc_step.run(args, p, seed, group=group, accumulate=accumulate)
+        if seed is not None:
+            seed[1] += 1            # device-side counter: graph-capturable
+        return loss.reshape(())
+
+
+def _grad_of(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """The parameter's gradient buffer (FlatAdam's arena view), created zeroed when absent."""
+    if p is None:
+        return None
+    if p.grad is None:
+        p.grad = torch.zeros_like(p)
+    return p.grad
+
 
 class NewMultiModalMultiTaskHead(_HeadBase):
     """models_kg.py:164-193 (ResNet, feat_size=2048) / :217-243 (ViT, feat_size=768)."""
@@ -77,6 +117,26 @@ class NewMultiModalMultiTaskHead(_HeadBase):
         out_genre = self._head('genre', self.class_genre, visual_features, embedding_genre)
         return [out_style, out_genre]
 
+    def tc_supported(self, visual_features, embedding_style) -> bool:
+        return ops.head_step_supported([visual_features, embedding_style], 1) and \
+            max(self.class_style[1].out_features, self.class_genre[1].out_features) <= 64
+
+    def train_step_tc(self, visual_features, embedding_style, embedding_genre, style_labels,
+                      genre_labels, w_style=None, w_genre=None, group=None, accumulate=True,
+                      logits=None) -> torch.Tensor:
+        """forward + ``0.5*CE_style + 0.5*CE_genre`` + backward of one mini-batch
+        (models_kg.py:237-243, train_new_multimodal_multitask.py:76-83) as ONE tensor-core kernel in
+        bf16 with float32 accumulation -- the precision class of the reference's fp16 autocast.
+        Adds the gradients to the parameters' ``.grad`` (``accumulate``) and returns the loss (this
+        rank's term of the global loss when ``group`` is given).  ``logits``: optional pair of
+        ``[B, C]`` float32 output buffers."""
+        lg = logits or (None, None)
+        args = [self._tc_head_arg('style', self.class_style, visual_features, embedding_style,
+                                  style_labels, w_style, 0.5, lg[0]),
+                self._tc_head_arg('genre', self.class_genre, visual_features, embedding_genre,
+                                  genre_labels, w_genre, 0.5, lg[1])]
+        return self._tc_run(args, self.class_style, group, accumulate)
+
 
 class NewMultiModalSingleTaskHead(_HeadBase):
     """models_kg.py:139-162 / :195-215."""
@@ -89,6 +149,17 @@ class NewMultiModalSingleTaskHead(_HeadBase):
     def forward(self, visual_features, embedding):
         return self._head('classifier', self.classifier, visual_features, embedding)
 
+    def tc_supported(self, visual_features, embedding) -> bool:
+        return ops.head_step_supported([visual_features, embedding], 1) and \
+            self.classifier[1].out_features <= 64
+
+    def train_step_tc(self, visual_features, embedding, labels, weight=None, group=None,
+                      accumulate=True, logits=None) -> torch.Tensor:
+        """Single-task variant (models_kg.py:158-162, train_new_multimodal.py:39-44): one CE."""
+        args = [self._tc_head_arg('classifier', self.classifier, visual_features, embedding, labels,
+                                  weight, 1.0, logits)]
+        return self._tc_run(args, self.classifier, group, accumulate)
+
 
 class LabelProjectorHead(nn.Module):
     """models_kg.py:245-280: ``encoder = Linear(feat_size, emb_size)``."""
@@ -99,6 +170,32 @@ class LabelProjectorHead(nn.Module):
 
     def forward(self, visual_features):
         return AF.fused_linear([visual_features], self.encoder.weight, self.encoder.bias)
+
+    def tc_supported(self, visual_features) -> bool:
+        return ops.head_step_supported([visual_features], 1) and \
+            self.encoder.out_features <= 64 * ops.L.MAX_HEADS
+
+    def train_step_tc(self, visual_features, embedding, global_rows=None, accumulate=True,
+                      out=None) -> torch.Tensor:
+        """forward + ``SmoothL1Loss()(encoder(feat), embedding)`` + backward of one mini-batch
+        (models_kg.py:261,278, train_projector.py:49-54) on the tensor cores; the 128 outputs run as
+        column slices of <= 64.  ``global_rows``: batch rows over all ranks (this rank's term of the
+        global mean)."""
+        if getattr(self, '_tc_step', None) is None:
+            self._tc_step = ops.HeadStep()
+        w, b = self.encoder.weight, self.encoder.bias
+        dw, db = _grad_of(w), _grad_of(b)
+        E = w.shape[0]
+        rows = visual_features.shape[0] if global_rows is None else int(global_rows)
+        args = []
+        for c0 in range(0, E, 64):
+            c1 = min(E, c0 + 64)
+            args.append(ops.HeadArg(parts=[visual_features], weight=w[c0:c1],
+                                    bias=None if b is None else b[c0:c1], d_weight=dw[c0:c1],
+                                    d_bias=None if db is None else db[c0:c1], loss='smooth_l1',
+                                    target=embedding[:, c0:c1], inv_count=1.0 / (rows * E),
+                                    logits=None if out is None else out[:, c0:c1]))
+        return self._tc_step.run(args, 0.0, None, accumulate=accumulate).reshape(())
 
 
 class ContextNetSingleTaskHead(nn.Module):

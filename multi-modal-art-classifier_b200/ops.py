@@ -533,6 +533,103 @@ def split_k_for(k_rows: int, slab: int = 384, max_split: int = 512) -> int:
 
 
 # ------------------------------------------------------------------------------------------------
+# K5/K6: fused head step on the tensor cores (agx_head_step)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class HeadArg:
+    """One Linear head with <= 64 outputs over the virtual concatenation of ``parts``."""
+    parts: Sequence[torch.Tensor]            # [feat] or [feat, emb], float32 [B, width]
+    weight: torch.Tensor                     # [C, K] float32 (a row slice of nn.Linear.weight)
+    bias: Optional[torch.Tensor]
+    d_weight: torch.Tensor                   # gradient destinations (same shapes)
+    d_bias: Optional[torch.Tensor]
+    loss: str = 'ce'                         # 'ce' | 'smooth_l1'
+    labels: Optional[torch.Tensor] = None    # int64 [B]
+    class_w: Optional[torch.Tensor] = None   # float32 [C]
+    coef: float = 1.0
+    target: Optional[torch.Tensor] = None    # float32 [B, C] view (row stride = target.stride(0))
+    inv_count: float = 0.0
+    mask: Optional[torch.Tensor] = None      # explicit multiplicative dropout mask [B, K]
+    logits: Optional[torch.Tensor] = None    # optional output [B, C]
+
+
+def head_step_supported(parts: Sequence[torch.Tensor], n_out: int) -> bool:
+    """Shapes agx_head_step takes (see include/agx.h): first part a multiple of 64 wide, total
+    width a multiple of 128, float32 rows 16-byte aligned."""
+    if not parts or len(parts) > 2:
+        return False
+    k = sum(p.shape[1] for p in parts)
+    ok = parts[0].shape[1] % 64 == 0 and k % 128 == 0 and n_out >= 1
+    return ok and all(p.is_cuda and p.dtype == torch.float32 and p.stride(1) == 1 and
+                      p.stride(0) % 4 == 0 and p.data_ptr() % 16 == 0 for p in parts)
+
+
+class HeadStep:
+    """Caller-owned buffers of one fused head step (workspace, label normaliser, loss) -- allocated
+    once per batch shape so that the step is CUDA-graph capturable."""
+
+    def __init__(self):
+        self.ws = None
+        self.norm = None
+        self.loss = None
+        self._key = None
+
+    def run(self, heads: Sequence[HeadArg], p_drop: float = 0.0,
+            seed_state: Optional[torch.Tensor] = None, group=None, accumulate: bool = False):
+        n = len(heads)
+        if n < 1 or n > L.MAX_HEADS:
+            raise ValueError(f'1..{L.MAX_HEADS} heads per step')
+        B = heads[0].parts[0].shape[0]
+        dev = heads[0].weight.device
+        arr = (L.Head * n)()
+        keep = []
+        for i, h in enumerate(heads):
+            a = arr[i]
+            for k, p_ in enumerate(h.parts):
+                L.require_cuda(p_, 'head input')
+                if p_.dtype != torch.float32 or p_.stride(1) != 1 or p_.shape[0] != B:
+                    raise TypeError('head inputs must be float32 [B, width] with contiguous rows')
+                a.part[k], a.ld[k], a.width[k] = ptr(p_), p_.stride(0), p_.shape[1]
+            a.C = h.weight.shape[0]
+            a.loss = L.HEAD_CE if h.loss == 'ce' else L.HEAD_SMOOTH_L1
+            if h.weight.stride(1) != 1 or h.d_weight.stride(1) != 1:
+                raise ValueError('head weight / gradient rows must be contiguous')
+            a.weight, a.ldw, a.bias = ptr(h.weight), h.weight.stride(0), ptr(h.bias)
+            if h.mask is not None:
+                a.mask, a.ld_mask = ptr(h.mask), h.mask.stride(0)
+            if h.loss == 'ce':
+                lab = h.labels.to(device=dev, dtype=torch.int64).contiguous()
+                keep.append(lab)
+                a.labels, a.class_w, a.coef = ptr(lab), ptr(h.class_w), float(h.coef)
+            else:
+                if h.target.stride(1) != 1:
+                    raise ValueError('projector target rows must be contiguous')
+                a.target, a.ld_target, a.inv_count = ptr(h.target), h.target.stride(0), float(h.inv_count)
+            if h.logits is not None:
+                a.logits, a.ld_logits = ptr(h.logits), h.logits.stride(0)
+            a.d_weight, a.ld_dw, a.d_bias = ptr(h.d_weight), h.d_weight.stride(0), ptr(h.d_bias)
+        nbytes = lib().agx_head_step_workspace_bytes(arr, n, B)
+        if nbytes == 0:
+            check(-1, 'agx_head_step_workspace_bytes')
+        key = (n, B, nbytes, str(dev))
+        if self._key != key:
+            self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self.norm = torch.ones(L.MAX_HEADS, dtype=torch.float32, device=dev)
+            self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+            self._key = key
+        check(lib().agx_head_step_prepare(arr, n, B, ptr(self.norm), ptr(self.ws), nbytes,
+                                          stream_ptr()), 'agx_head_step_prepare')
+        if group is not None and any(h.loss == 'ce' for h in heads):
+            import torch.distributed as dist       # weighted mean over the batch shards of all ranks
+            dist.all_reduce(self.norm, group=group)
+        check(lib().agx_head_step(arr, n, B, float(p_drop),
+                                  ptr(seed_state) if p_drop > 0 else None, ptr(self.norm),
+                                  ptr(self.loss), int(accumulate), ptr(self.ws), nbytes,
+                                  stream_ptr()), 'agx_head_step')
+        return self.loss
+
+
+# ------------------------------------------------------------------------------------------------
 # small batched ops
 # ------------------------------------------------------------------------------------------------
 def sum_arrays(items: Sequence[tuple]):

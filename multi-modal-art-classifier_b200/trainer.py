@@ -291,12 +291,18 @@ class HeadTrainer:
     """One fused step per mini-batch on device-resident (or freshly copied) features."""
 
     def __init__(self, head: torch.nn.Module, kind: str = 'multitask', lr: float = 3e-4,
-                 w_style=None, w_genre=None, group=None, use_cuda_graph: bool = False):
+                 w_style=None, w_genre=None, group=None, use_cuda_graph: bool = False,
+                 precision: str = 'fp32'):
         """``group``: batch-sharded data parallel -- ``step`` gets this rank's shard of the batch;
-        weights are replicated (rank 0's), gradients all-reduced (one NCCL call on the arena)."""
+        weights are replicated (rank 0's), gradients all-reduced (one NCCL call on the arena).
+        ``precision``: 'fp32' = exact float32 arithmetic (parity rel 1e-5); 'bf16' = the fused
+        tensor-core step (``train_step_tc``: bf16 operands, float32 accumulation, rel 2e-2 -- the
+        precision class of the reference's fp16 autocast, train_new_multimodal_multitask.py:76)."""
         assert kind in ('multitask', 'projector')
+        assert precision in ('fp32', 'bf16')
         self.head = head
         self.kind = kind
+        self.precision = precision
         self.opt = FlatAdam(head.parameters(), lr=lr).flatten()
         self.w_style, self.w_genre = w_style, w_genre
         self.group = group
@@ -344,8 +350,33 @@ class HeadTrainer:
         self._graph.replay()
         return self._loss
 
+    def _step_tc(self, feat, *rest) -> torch.Tensor:
+        """One fused kernel for forward + loss + backward, then (all-reduce,) Adam: every parameter
+        of the head receives its gradient from the step, so the arena is written, not cleared."""
+        if self.kind == 'multitask':
+            emb_s, emb_g, y_s, y_g = rest
+            loss = self.head.train_step_tc(feat, emb_s, emb_g, y_s, y_g, self.w_style, self.w_genre,
+                                           group=self.group, accumulate=False)
+        else:
+            (target,) = rest
+            loss = self.head.train_step_tc(feat, target, feat.shape[0] * self.world,
+                                           accumulate=False)
+        if self.group is not None:
+            from .dist import all_reduce_
+            all_reduce_(self.opt.grad, self.group)
+            loss = all_reduce_(loss.detach().clone(), self.group)
+        self.opt.step()
+        return loss
+
     def _step_eager(self, feat, *rest) -> torch.Tensor:
         self.head.train()
+        if self.precision == 'bf16':
+            ok = self.head.tc_supported(feat, rest[0]) if self.kind == 'multitask' else \
+                self.head.tc_supported(feat)
+            if not ok:
+                raise ValueError("precision='bf16': these shapes are not supported by agx_head_step "
+                                 "(feature width a multiple of 64, total width of 128, <= 64 classes)")
+            return self._step_tc(feat, *rest)
         self.opt.zero_grad()
         if self.kind == 'multitask':
             emb_s, emb_g, y_s, y_g = rest

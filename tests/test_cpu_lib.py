@@ -46,11 +46,11 @@ def test_ctypes_structs_match_c_layout():
              'agx_gemm_problem_t': L.GemmProblem, 'agx_sum_desc_t': L.SumDesc,
              'agx_bn_desc_t': L.BnDesc, 'agx_bn_bwd_desc_t': L.BnBwdDesc,
              'agx_colsum_desc_t': L.ColsumDesc, 'agx_gat_rel_t': L.GatRel,
-             'agx_sddmm_seg_t': L.SddmmSeg}
+             'agx_sddmm_seg_t': L.SddmmSeg, 'agx_head_t': L.Head}
     body = '\n'.join(f'printf("{n} %zu\\n", sizeof({n}));' for n in names)
     consts = ['AGX_MAX_CSR_RELS', 'AGX_MAX_REL_PER_GROUP', 'AGX_MAX_GROUPS', 'AGX_MAX_CHUNK_SEGS',
               'AGX_CHUNK_EDGES', 'AGX_MAX_GEMM_PROBLEMS', 'AGX_MAX_GEMM_SEGS', 'AGX_MAX_TENSORS',
-              'AGX_MAX_GAT_RELS', 'AGX_MAX_SDDMM_SEGS', 'AGX_GAT_LONG_ROW']
+              'AGX_MAX_GAT_RELS', 'AGX_MAX_SDDMM_SEGS', 'AGX_GAT_LONG_ROW', 'AGX_MAX_HEADS']
     body += '\n' + '\n'.join(f'printf("{c} %d\\n", (int){c});' for c in consts)
     with tempfile.TemporaryDirectory() as d:
         src = os.path.join(d, 't.c')
@@ -72,6 +72,7 @@ def test_ctypes_structs_match_c_layout():
     assert int(out['AGX_MAX_GAT_RELS']) == L.MAX_GAT_RELS
     assert int(out['AGX_MAX_SDDMM_SEGS']) == L.MAX_SDDMM_SEGS
     assert int(out['AGX_GAT_LONG_ROW']) == L.GAT_LONG_ROW
+    assert int(out['AGX_MAX_HEADS']) == L.MAX_HEADS
 
 
 def test_invalid_arguments_return_error_codes_not_crashes():
