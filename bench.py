@@ -268,7 +268,7 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def dist_parity_blocks(trainer, model, data, x, ei, y, world, rank, dev, dist):
+def dist_parity_blocks(trainer, model, data, x, ei, y, world, rank, dev, dist, size='full'):
     """N > 1, block partition: one training step of the N-rank job (dropout masks injected,
     current weights) against the SAME step of the whole N-block graph on rank 0 alone -- what
     tests/test_gpu_dist.py checks on two GPUs, repeated here on every N the driver benchmarks
@@ -283,7 +283,7 @@ def dist_parity_blocks(trainer, model, data, x, ei, y, world, rank, dev, dist):
                                parity_masks(n_nodes, PARITY_MASK_SEED + rank).items()}
     model.train()
     trainer.opt.zero_grad()
-    emb, out = model(x, ei)
+    emb, out = model(trainer.x, ei)
     loss = agx.functional.nll_loss(out[0]['artwork'], trainer.y, dist.group.WORLD)
     loss.backward()
     all_reduce_(trainer.opt.grad, dist.group.WORLD)
@@ -291,7 +291,8 @@ def dist_parity_blocks(trainer, model, data, x, ei, y, world, rank, dev, dist):
     torch.cuda.synchronize()
     res = None
     if rank == 0:
-        whole = synth.replicate(data.to(dev), world)
+        dense = agx.ToUndirected()(synth.make_artgraph(size, features='one-hot', seed=1234 + 2))
+        whole = synth.replicate(dense.to(dev), world)
         ref = agx.HeteroSGNN(agx.SAGEConv, torch.nn.ReLU(), 'sum', 128, 32, data.metadata(), 2, 0.4,
                              True, False)
         ref.load_state_dict(state, strict=False)
@@ -405,61 +406,124 @@ def config5_cut(world, rank, dev, dist, copies: int = 16, steps: int = 10, overl
     return res
 
 
-def heads_throughput(dev, dist, world, batch: int = 4096, steps: int = 20):
+def heads_algorithmic_bytes(batch, fv=768, emb=128, classes=(32, 18)):
+    """HBM bytes of one multitask head training step (forward AND backward): the
+    inputs (feat + two embeddings) are read once by the forward and once more by the weight-gradient
+    pass, logits written and their gradient read, weights read and their gradient written."""
+    c = sum(classes)
+    return 2 * batch * (fv + 2 * emb) * 4 + 2 * batch * c * 4 + 2 * c * (fv + emb) * 4
+
+
+def heads_cpu_reference(batch, steps=20):
+    """The reference's head arithmetic (oracle/heads_oracle.py: cat -> Dropout -> Linear, weighted CE,
+    Adam) on the host cores, float32 -- the cpu_baseline of the heads half."""
+    from mmac_b200 import synth
+    from oracle import heads_oracle as ho
+    torch.set_num_threads(os.cpu_count() or 1)
+    feat, es, eg, ys, yg = synth.make_head_batch(batch, 'vit', seed=1)
+    ws, wg = synth.class_weights(ys, 32), synth.class_weights(yg, 18)
+    m = ho.MultiTaskHeadOracle(768, 128, {'style': 32, 'genre': 18}, 0.4).train()
+    opt = torch.optim.Adam(m.parameters(), lr=3e-4)
+    ts = []
+    for it in range(steps + 2):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss = ho.multitask_loss(m(feat, es, eg), ys, yg, ws, wg)
+        loss.backward()
+        opt.step()
+        loss.item()
+        if it >= 2:
+            ts.append(time.perf_counter() - t0)
+    return {'value': batch * len(ts) / sum(ts), 'unit': 'artworks/s', 'cores': torch.get_num_threads(),
+            'kind': 'port', 'sample': f'multitask ViT heads, batch {batch}, {len(ts)} train steps '
+                                      f'after 2 warm-up, float32'}
+
+
+def heads_throughput(dev, dist, world, batches=(4096,), steps: int = 20, cpu: bool = False):
     """Secondary metric of north_star (artworks/s): one training step (forward + loss + backward +
     Adam) of the new-multimodal multitask ViT heads (configs[3], reference batch loop
     src/train_new_multimodal_multitask.py:62-90) and of the projector (configs[2],
     src/train_projector.py:39-59) on precomputed synthetic features, batch-sharded over the ranks
-    with one gradient all-reduce per step.  Device-resident and end to end (pinned host -> device
-    copy of the batch, loss read-back)."""
+    with one gradient all-reduce per step; in bf16 on the tensor cores (the fused agx_head_step: the
+    precision class of the reference's fp16 autocast) and in exact float32.  Device-resident
+    (a ring of distinct batches larger than the L2, so inputs come from HBM) and end to end
+    (pinned host -> device copy of the batch, loss read-back)."""
     import mmac_b200 as agx
     from mmac_b200 import synth
     from mmac_b200.trainer import HeadTrainer
     group = dist.group.WORLD if dist is not None else None
-    feat, es, eg, ys, yg = synth.make_head_batch(batch, 'vit', seed=1 + int(os.environ.get('RANK', '0')))
-    host = [t.pin_memory() for t in (feat, es, eg, ys, yg)]
-    devt = [t.to(dev) for t in host]
-    ws = synth.class_weights(ys, 32).to(dev)
-    wg = synth.class_weights(yg, 18).to(dev)
-    torch.manual_seed(0)
-    out = {}
-    for kind in ('multitask', 'projector'):
-        if kind == 'multitask':
-            head = agx.NewMultiModalMultiTaskHead(128, {'style': 32, 'genre': 18}, 0.4, 768).to(dev)
-            tr = HeadTrainer(head, 'multitask', 3e-4, ws, wg, group=group, use_cuda_graph=True)
-            args_dev = devt
-            args_host = host
-        else:
-            head = agx.LabelProjectorHead(128, 768).to(dev)
-            tr = HeadTrainer(head, 'projector', 3e-4, group=group, use_cuda_graph=True)
-            args_dev = [devt[0], devt[1]]
-            args_host = [host[0], host[1]]
-        for _ in range(3):
-            tr.step(*args_dev)
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            tr.step(*args_dev)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        t0 = time.perf_counter()
-        for _ in range(steps):          # pinned host batch -> static device buffers -> replay
-            float(tr.step(*args_host).item())
-        torch.cuda.synchronize()
-        ms_e2e = (time.perf_counter() - t0) * 1e3
-        if dist is not None:
-            t = torch.tensor([ms, ms_e2e], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms, ms_e2e = float(t[0]), float(t[1])
-        out[kind] = {'artworks_per_s': world * batch * steps / (ms * 1e-3),
-                     'e2e_artworks_per_s': world * batch * steps / (ms_e2e * 1e-3),
-                     'ms_per_step': ms / steps}
-    out['batch_per_gpu'] = batch
-    out['features'] = 'synthetic ViT CLS features [B,768] + style/genre embeddings [B,128]'
+    rank = int(os.environ.get('RANK', '0'))
+    peak, _ = _peaks()
+    out = {'features': 'synthetic ViT CLS features [B,768] + style/genre embeddings [B,128]',
+           'l2_policy': 'device-resident leg cycles through a ring of distinct batches of >= 160 MB '
+                        'in total (> 126 MB L2)', 'runs': []}
+    for batch in batches:
+        in_bytes = batch * (768 + 256) * 4
+        n_ring = int(min(64, max(2, -(-160_000_000 // in_bytes))))
+        ring = []
+        for i in range(n_ring):
+            ring.append([t.to(dev) for t in synth.make_head_batch(batch, 'vit', seed=1 + 97 * rank + i)])
+        host = [t.pin_memory() for t in synth.make_head_batch(batch, 'vit', seed=1 + 97 * rank)]
+        ws = synth.class_weights(host[3], 32).to(dev)
+        wg = synth.class_weights(host[4], 18).to(dev)
+        for precision in ('bf16', 'fp32'):
+            for kind in ('multitask', 'projector'):
+                torch.manual_seed(0)
+                if kind == 'multitask':
+                    head = agx.NewMultiModalMultiTaskHead(128, {'style': 32, 'genre': 18}, 0.4, 768).to(dev)
+                    tr = HeadTrainer(head, 'multitask', 3e-4, ws, wg, group=group, use_cuda_graph=True,
+                                     precision=precision)
+                    sel = lambda b: b                                   # noqa: E731
+                else:
+                    head = agx.LabelProjectorHead(128, 768).to(dev)
+                    tr = HeadTrainer(head, 'projector', 3e-4, group=group, use_cuda_graph=True,
+                                     precision=precision)
+                    sel = lambda b: [b[0], b[1]]                        # noqa: E731
+                for i in range(3):
+                    tr.step(*sel(ring[i % n_ring]))
+                torch.cuda.synchronize()
+                if dist is not None:
+                    dist.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(steps):
+                    tr.step(*sel(ring[i % n_ring]))
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+                t0 = time.perf_counter()
+                for _ in range(steps):      # pinned host batch -> static device buffers -> replay
+                    float(tr.step(*sel(host)).item())
+                torch.cuda.synchronize()
+                ms_e2e = (time.perf_counter() - t0) * 1e3
+                if dist is not None:
+                    t = torch.tensor([ms, ms_e2e], device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ms, ms_e2e = float(t[0]), float(t[1])
+                run = {'kind': kind, 'precision': precision, 'batch_per_gpu': batch,
+                       'ms_per_step': ms / steps,
+                       'artworks_per_s': world * batch * steps / (ms * 1e-3),
+                       'e2e_artworks_per_s': world * batch * steps / (ms_e2e * 1e-3)}
+                if kind == 'multitask':
+                    nb = heads_algorithmic_bytes(batch)
+                    gbs = nb / (ms / steps * 1e-3) / 1e9
+                    run['roofline'] = {'bound': 'hbm', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s',
+                                       'frac': gbs / peak, 'bytes_per_step': nb,
+                                       'what': 'whole step (copy of the batch into the static '
+                                               'buffers, prepare + fused + reduce kernels, Adam) '
+                                               'under CUDA-graph replay'}
+                out['runs'].append(run)
+                del tr, head
+        del ring
+    # the summary the driver's earlier lines carried (batch 4096, tensor-core path)
+    for r in out['runs']:
+        if r['batch_per_gpu'] == 4096 and r['precision'] == 'bf16':
+            out[r['kind']] = {k: r[k] for k in ('artworks_per_s', 'e2e_artworks_per_s', 'ms_per_step')}
+            if 'roofline' in r:
+                out['roofline'] = r['roofline']
+    out['batch_per_gpu'] = 4096
+    if cpu and rank == 0:
+        out['cpu_baseline'] = heads_cpu_reference(4096)
     return out
 
 
@@ -550,17 +614,24 @@ def run_ours(args):
         y_all = part.owned('artwork', data['artwork'].y_style)
         total_edges = sum(int(v.shape[1]) for v in data.edge_index_dict.values())
     else:
-        g = synth.make_artgraph(args.size, features='one-hot', seed=None if world == 1 else 1234 + 2)
+        # the reference's one-hot features torch.eye(N_t) (artgraph.py:93-95) are passed as
+        # agx.Identity(N_t) markers: the same inputs without building or uploading the N x N
+        # matrices (148 of 236 MB per step); --dense-onehot passes the dense matrices, which the
+        # module then detects on the device (the round-1 behaviour)
+        g = synth.make_artgraph(args.size, features='one-hot' if args.dense_onehot else 'identity',
+                                seed=None if world == 1 else 1234 + 2)
         data = agx.ToUndirected()(g)
-        host_x = OrderedDict((k, v.pin_memory()) for k, v in data.x_dict.items())
+        host_x = OrderedDict((k, v.pin_memory() if torch.is_tensor(v) else v)
+                             for k, v in data.x_dict.items())
         host_ei = OrderedDict((k, v.pin_memory()) for k, v in data.edge_index_dict.items())
         y_all = data['artwork'].y_style
         total_edges = world * sum(int(v.shape[1]) for v in host_ei.values())
-    x = OrderedDict((k, v.to(dev, non_blocking=True)) for k, v in host_x.items())
+    x = OrderedDict((k, v.to(dev, non_blocking=True) if torch.is_tensor(v) else v)
+                    for k, v in host_x.items())
     ei = OrderedDict((k, v.to(dev, non_blocking=True)) for k, v in host_ei.items())
     y = y_all.to(dev)
     n_edges = sum(int(v.shape[1]) for v in ei.values())
-    h2d = sum(v.numel() * v.element_size() for v in host_x.values()) + \
+    h2d = sum(v.numel() * v.element_size() for v in host_x.values() if torch.is_tensor(v)) + \
         sum(v.numel() * v.element_size() for v in host_ei.values())
 
     torch.manual_seed(0)
@@ -573,7 +644,7 @@ def run_ours(args):
         # gradients are those of the whole graph (NCCL all-reduces inside the captured step)
         from mmac_b200.dist import block_context, partition_context
         ctx = partition_context(part, dist.group.WORLD, dev) if cut else \
-            block_context(dist.group.WORLD, {t: v.shape[0] for t, v in x.items()})
+            block_context(dist.group.WORLD, {t: int(v.shape[0]) for t, v in x.items()})
     trainer = GNNTrainer(model, x, ei, y, lr=0.01, use_cuda_graph=not args.no_graph, dist_ctx=ctx)
 
     def barrier():
@@ -581,6 +652,27 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.ncu_heads:
+        # profiling aid: exactly one eager fused head step (B = 4096, bf16) between
+        # cudaProfilerStart / Stop
+        from mmac_b200.trainer import HeadTrainer
+        hb = [t.to(dev) for t in synth.make_head_batch(4096, 'vit', seed=1)]
+        hws, hwg = synth.class_weights(hb[3].cpu(), 32).to(dev), synth.class_weights(hb[4].cpu(), 18).to(dev)
+        hh = agx.NewMultiModalMultiTaskHead(128, {'style': 32, 'genre': 18}, 0.4, 768).to(dev)
+        htr = HeadTrainer(hh, 'multitask', 3e-4, hws, hwg, use_cuda_graph=False, precision='bf16')
+        ph = agx.LabelProjectorHead(128, 768).to(dev)
+        ptr_ = HeadTrainer(ph, 'projector', 3e-4, use_cuda_graph=False, precision='bf16')
+        for _ in range(3):
+            htr.step(*hb)
+            ptr_.step(hb[0], hb[1])
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        htr.step(*hb)
+        ptr_.step(hb[0], hb[1])
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        print(json.dumps({'ncu_heads_done': True}))
+        return
     if args.ncu:
         # profiling aid: `ncu --profile-from-start off ... bench.py --ncu` sees exactly one eager
         # training step (every kernel launched individually, no CUDA graph)
@@ -728,14 +820,15 @@ def run_ours(args):
     config5 = None
     if dist is not None and not cut and args.operator == 'SAGEConv':
         if not args.no_dist_parity:
-            dist_parity = dist_parity_blocks(trainer, model, data, x, ei, y, world, rank, dev, dist)
+            dist_parity = dist_parity_blocks(trainer, model, data, x, ei, y, world, rank, dev, dist, args.size)
         if not args.no_config5:
             del trainer
             torch.cuda.empty_cache()
             config5 = config5_cut(world, rank, dev, dist, copies=args.config5_copies)
     heads = None
     if not args.no_heads:
-        heads = heads_throughput(dev, dist, world)
+        heads = heads_throughput(dev, dist, world, batches=(32, 4096, 65536) if world == 1 else (4096,),
+                                 cpu=(world == 1 and not args.no_cpu_baseline))
     operators = None
     if world == 1 and not args.no_operators and args.operator == 'SAGEConv':
         operators = {}
@@ -758,6 +851,8 @@ def run_ours(args):
                        'operator': args.operator,
                        'label': 'style', 'hidden': 128, 'layers': 2,
                        'artworks_per_gpu': int(x['artwork'].shape[0]),
+                       'one_hot_features': 'dense torch.eye matrices' if (cut or args.dense_onehot) else
+                                           'agx.Identity(n) markers (no N x N matrix built or uploaded)',
                        'directed_edges_per_gpu': n_edges,
                        'edges_per_step_per_gpu': PASSES * n_edges,
                        'parallelism': 'single GPU' if world == 1 else (
@@ -827,6 +922,9 @@ def main():
                          "(partial neighbour sums all-reduced; no boundary-row exchange)")
     ap.add_argument('--balanced-cut', action='store_true',
                     help="--partition cut: destination ranges with equal incoming edges, not rows")
+    ap.add_argument('--dense-onehot', action='store_true',
+                    help='pass the one-hot features as dense torch.eye matrices (uploaded every '
+                         'e2e step: 236 MB) instead of agx.Identity markers (88 MB)')
     ap.add_argument('--e2e-serial', action='store_true',
                     help='end-to-end leg: copy the inputs in line instead of prefetching them')
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA graph')
@@ -842,6 +940,8 @@ def main():
                     help='skip the secondary GraphConv / GATConv training-step measurement')
     ap.add_argument('--park-ms', type=float, default=120.0,
                     help='device-side delay in front of each per-kernel timing step (roofline leg)')
+    ap.add_argument('--ncu-heads', action='store_true',
+                    help='run one eager bf16 head step between cudaProfilerStart/Stop and exit')
     ap.add_argument('--ncu', action='store_true',
                     help='run one eager step between cudaProfilerStart/Stop and exit')
     args = ap.parse_args()

@@ -360,6 +360,65 @@ typedef struct {
 int agx_sddmm(const agx_sddmm_seg_t* h_segs, int n_segs, int32_t F, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Layer level: one SAGEConv / GraphConv relation, forward and backward, and the graph plan it
+ * runs on -- the calls a C / C++ host makes instead of the Python planning layer.
+ *   replaces: `conv((x_src, x_dst), edge_index)` at src/models/models_graph.py:30,38 (forward) and
+ *   its autograd backward (src/train_gnn_embeddings.py:47):
+ *       SAGEConv   out = lin_l(mean_{j in N(i)} x_src[j]) + lin_r(x_dst[i])        (PyG 2.0.2)
+ *       GraphConv  out = lin_rel(sum_{j in N(i)} x_src[j]) + lin_root(x_dst[i])
+ *   `accumulate` adds into `out`: the relation sum of to_hetero(aggr='sum') (models_graph.py:45).
+ *   Ownership: agx_graph_plan_create allocates the CSR / CSC device buffers of all relations (the
+ *   only allocations libagx.so ever owns) and agx_graph_plan_destroy frees them; everything else
+ *   (features, weights, outputs, workspaces) is the caller's.  Calls enqueue on `stream`.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct agx_graph_plan agx_graph_plan_t;      /* opaque */
+
+typedef struct {
+    const int32_t* rowptr;    /* CSR by destination: [n_dst + 1]                                  */
+    const int32_t* col;       /* [n_edges] source ids, edge-list order inside a row                */
+    const float* cnt;         /* [n_dst] max(in-degree, 1)                                        */
+    const int32_t* t_rowptr;  /* CSC by source (the transpose): [n_src + 1]                        */
+    const int32_t* t_col;     /* [n_edges] destination ids                                        */
+    int32_t n_src, n_dst, n_edges;
+    int32_t long_rows;        /* CSR has few / very long rows: edge-balanced kernel               */
+    int32_t t_long_rows;      /* same for the CSC                                                 */
+    int32_t pad_;
+} agx_plan_rel_t;
+
+/* rels[r]: keys = destination id, vals = source id of every edge (int64, device), n_rows = n_dst,
+ * n_cols = n_src.  Sorts all relations (one batched K1 sort each way), reads the largest degrees
+ * back once (synchronises `stream`). */
+int agx_graph_plan_create(const agx_edge_list_t* h_rels, int n_rels, void* stream,
+                          agx_graph_plan_t** plan);
+int agx_graph_plan_relation(const agx_graph_plan_t* plan, int r, agx_plan_rel_t* out);
+int agx_graph_plan_destroy(agx_graph_plan_t* plan);
+
+typedef struct {
+    agx_plan_rel_t rel;
+    int32_t mean;             /* 1: SAGEConv (scatter-mean); 0: GraphConv (scatter-add)           */
+    int32_t f_src, f_dst, out_channels;
+    const float* x_src;       /* [n_src, f_src] float32 */
+    int64_t ld_src;
+    const float* x_dst;       /* [n_dst, f_dst]; may be NULL together with w_r (no root term)      */
+    int64_t ld_dst;
+    const float* w_l;         /* [out, f_src]  lin_l.weight / lin_rel.weight                       */
+    const float* b_l;         /* [out] or NULL                                                    */
+    const float* w_r;         /* [out, f_dst]  lin_r.weight / lin_root.weight, or NULL             */
+} agx_sage_layer_t;
+
+size_t agx_sage_layer_workspace_bytes(const agx_sage_layer_t* layer);
+/* out[n_dst, out] (+)= aggr(x_src) w_l^T + b_l + x_dst w_r^T ; agg [n_dst, f_src] receives the
+ * aggregated neighbourhood (needed by the backward pass) */
+int agx_sage_layer_fwd(const agx_sage_layer_t* layer, float* out, int64_t ldo, int accumulate,
+                       float* agg, void* workspace, size_t workspace_bytes, void* stream);
+/* d_w_l [out, f_src], d_b_l [out], d_w_r [out, f_dst] are written; d_x_src [n_src, f_src] /
+ * d_x_dst [n_dst, f_dst] (each nullable) are written, or added to when accumulate_dx != 0 */
+int agx_sage_layer_bwd(const agx_sage_layer_t* layer, const float* agg, const float* dout,
+                       int64_t lddo, float* d_w_l, float* d_b_l, float* d_w_r, float* d_x_src,
+                       int64_t ld_dxs, float* d_x_dst, int64_t ld_dxd, int accumulate_dx,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K5/K6 fused head step on the tensor cores (tcgen05, bf16 operands, float32 accumulation)
  *   replaces, per mini-batch, the whole of
  *     comb = cat(feat, emb); out = Linear(Dropout(comb)); loss = coef * CE(out, y; w); backward

@@ -11,6 +11,7 @@ __version__ = "0.1.0"
 
 from . import synth  # noqa: F401
 from ._lib import AgxError, EXPORTED, lib  # noqa: F401
+from .data import HeteroData, Identity, InMemoryDataset  # noqa: F401
 from .graph import HeteroPlan, ToUndirected, get_plan, to_undirected_dict  # noqa: F401
 from .nn import GATConv, GraphConv, Linear, MessagePassing, SAGEConv  # noqa: F401
 from .hetero import HeteroModule, to_hetero  # noqa: F401

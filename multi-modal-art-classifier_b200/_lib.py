@@ -112,6 +112,18 @@ class Head(C.Structure):
                 ('ld_logits', c_i64), ('d_weight', vp), ('ld_dw', c_i64), ('d_bias', vp)]
 
 
+class PlanRel(C.Structure):
+    _fields_ = [('rowptr', vp), ('col', vp), ('cnt', vp), ('t_rowptr', vp), ('t_col', vp),
+                ('n_src', c_i32), ('n_dst', c_i32), ('n_edges', c_i32), ('long_rows', c_i32),
+                ('t_long_rows', c_i32), ('pad_', c_i32)]
+
+
+class SageLayer(C.Structure):
+    _fields_ = [('rel', PlanRel), ('mean', c_i32), ('f_src', c_i32), ('f_dst', c_i32),
+                ('out_channels', c_i32), ('x_src', vp), ('ld_src', c_i64), ('x_dst', vp),
+                ('ld_dst', c_i64), ('w_l', vp), ('b_l', vp), ('w_r', vp)]
+
+
 _SIGS = {
     'agx_version': (C.c_int, []),
     'agx_last_error': (C.c_char_p, []),
@@ -153,6 +165,14 @@ _SIGS = {
     'agx_gat_edge_softmax': (C.c_int, [C.POINTER(GatRel), C.c_int, c_f32, vp]),
     'agx_gat_edge_softmax_bwd': (C.c_int, [C.POINTER(GatRel), C.c_int, c_f32, vp]),
     'agx_sddmm': (C.c_int, [C.POINTER(SddmmSeg), C.c_int, c_i32, vp]),
+    'agx_graph_plan_create': (C.c_int, [C.POINTER(EdgeList), C.c_int, vp, C.POINTER(vp)]),
+    'agx_graph_plan_relation': (C.c_int, [vp, C.c_int, C.POINTER(PlanRel)]),
+    'agx_graph_plan_destroy': (C.c_int, [vp]),
+    'agx_sage_layer_workspace_bytes': (C.c_size_t, [C.POINTER(SageLayer)]),
+    'agx_sage_layer_fwd': (C.c_int, [C.POINTER(SageLayer), vp, c_i64, C.c_int, vp, vp, C.c_size_t,
+                                     vp]),
+    'agx_sage_layer_bwd': (C.c_int, [C.POINTER(SageLayer), vp, vp, c_i64, vp, vp, vp, vp, c_i64, vp,
+                                     c_i64, C.c_int, vp, C.c_size_t, vp]),
     'agx_head_step_workspace_bytes': (C.c_size_t, [C.POINTER(Head), C.c_int, c_i32]),
     'agx_head_step_prepare': (C.c_int, [C.POINTER(Head), C.c_int, c_i32, vp, vp, C.c_size_t, vp]),
     'agx_head_step': (C.c_int, [C.POINTER(Head), C.c_int, c_i32, c_f32, vp, vp, vp, C.c_int, vp,

@@ -266,8 +266,10 @@ constexpr int kRowsThreads = kRowsWarps * 32;
 // work left after the first wave runs on a quarter-full machine; half-size units halve that tail.
 constexpr int kRowsPerWarp = 16;
 
-template <typename T, int VEC, int LPR>
-__global__ void __launch_bounds__(kRowsThreads)
+// MINB = resident CTAs per SM the register allocation is bounded for (launch bounds): 5 leaves the
+// compiler ~100 registers (20 warps per SM), 8 caps it at 64 (32 warps per SM).
+template <typename T, int VEC, int LPR, int MINB>
+__global__ void __launch_bounds__(kRowsThreads, MINB)
 agg_rows(const __grid_constant__ RowGroups P) {
     constexpr int RPW = 32 / LPR;                  // rows gathered concurrently by one warp
     // per staged edge: address of the source row, multiplier, and "closes its relation" marker
@@ -871,10 +873,13 @@ static bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintp
 
 template <typename T, int VEC>
 static int launch_rows(const RowGroups& P, int lpr, int64_t slots, cudaStream_t st) {
+    static const bool occ8 = getenv("AGX_ROWS_OCC8") != nullptr;       // A/B switch (round 2)
 #define AGX_ROWS_CASE(L)                                                                  \
     case L: {                                                                             \
         const int64_t per_block = (int64_t)kRowsWarps * kRowsPerWarp;                      \
-        agg_rows<T, VEC, L><<<(unsigned)ceil_div(slots, per_block), kRowsThreads, 0, st>>>(P); \
+        const unsigned grid = (unsigned)ceil_div(slots, per_block);                        \
+        if (occ8) agg_rows<T, VEC, L, 8><<<grid, kRowsThreads, 0, st>>>(P);                \
+        else agg_rows<T, VEC, L, 5><<<grid, kRowsThreads, 0, st>>>(P);                     \
         break;                                                                            \
     }
     switch (lpr) {

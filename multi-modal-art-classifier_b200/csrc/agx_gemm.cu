@@ -381,7 +381,9 @@ extern "C" int agx_gemm_grouped(const agx_gemm_problem_t* h_problems, int n_prob
             continue;
         }
         // few-row problems (the small node types, weight gradients) would sit on one or two SMs
-        // with 128-row tiles: 32-row tiles spread them over 4x as many CTAs
+        // with 128-row tiles: 32 x 32 tiles spread them over 16x as many CTAs (round 2: the 32 x 128
+        // class ran ~20 CTAs per launch at ~25 us, bound by the instruction issue of a single CTA
+        // per SM; a quarter of the FMAs per k-step and four times the CTAs, same summation order)
         if (Q.N <= 48) narrow[nn++] = i;
         else if (Q.M <= 256) shortm[ns++] = i;
         else wide[nw++] = i;
@@ -396,7 +398,7 @@ extern "C" int agx_gemm_grouped(const agx_gemm_problem_t* h_problems, int n_prob
     }
     int rc = launch_class<128, 128, 8, 8>(h_problems, wide, nw, h_segs, n_segs, st);
     if (rc) return rc;
-    rc = launch_class<32, 128, 2, 8>(h_problems, shortm, ns, h_segs, n_segs, st);
+    rc = launch_class<32, 32, 2, 2>(h_problems, shortm, ns, h_segs, n_segs, st);
     if (rc) return rc;
     rc = launch_class<128, 32, 4, 4>(h_problems, narrow, nn, h_segs, n_segs, st);
     if (rc) return rc;

@@ -583,9 +583,20 @@ __global__ void __launch_bounds__(256) head_reduce(const __grid_constant__ HdRed
     const int hi = (int)blockIdx.x / P.blocks_per_head, b = (int)blockIdx.x % P.blocks_per_head;
     const int C = P.C[hi], K = P.K;
     const int64_t n = (int64_t)C * K;
+    // one element per thread; the G partials are summed in CTA order (deterministic), eight loads
+    // in flight (a serial chain of G L2 round trips took 25-35 us at G = 32)
     for (int64_t e = (int64_t)b * 256 + threadIdx.x; e < n; e += (int64_t)P.blocks_per_head * 256) {
+        const float* src = P.dw_part[hi] + e;
         float s = 0.f;
-        for (int g = 0; g < P.G; ++g) s += __ldcg(P.dw_part[hi] + (size_t)g * n + e);
+        int g = 0;
+        for (; g + 8 <= P.G; g += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (size_t)(g + u) * n);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
+        for (; g < P.G; ++g) s += __ldcg(src + (size_t)g * n);
         float* o = P.d_weight[hi] + (size_t)(e / K) * P.ld_dw[hi] + (e % K);
         *o = P.accumulate ? *o + s : s;
     }
@@ -595,11 +606,13 @@ __global__ void __launch_bounds__(256) head_reduce(const __grid_constant__ HdRed
         float* o = P.d_bias[hi] + threadIdx.x;
         *o = P.accumulate ? *o + s : s;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        // loss: sum over heads and CTAs, lane-strided then a fixed butterfly
         float s = 0.f;
         for (int h = 0; h < P.n_heads; ++h)
-            for (int g = 0; g < P.G; ++g) s += __ldcg(P.loss_part[h] + g);
-        *P.loss = P.accumulate ? *P.loss + s : s;
+            for (int g = threadIdx.x; g < P.G; g += 32) s += __ldcg(P.loss_part[h] + g);
+        s = warp_sum(s);
+        if (threadIdx.x == 0) *P.loss = P.accumulate ? *P.loss + s : s;
     }
 }
 
@@ -805,7 +818,7 @@ extern "C" int agx_head_step(const agx_head_t* h, int n_heads, int32_t B, float 
     R.G = pl.G;
     R.accumulate = accumulate ? 1 : 0;
     R.loss = loss;
-    R.blocks_per_head = 32;
+    R.blocks_per_head = (int)ceil_div((int64_t)kHdCP * pl.K, 256);
     for (int i = 0; i < n_heads; ++i) {
         R.dw_part[i] = P.h[i].dw_part;
         R.db_part[i] = P.h[i].db_part;

@@ -145,6 +145,45 @@ class HeteroData:
                 f'edges={{{", ".join(f"{k}: {int(v.edge_index.shape[1])}" for k, v in self._edges.items() if "edge_index" in v)}}})')
 
 
+class Identity:
+    """Marker for one-hot node features: ``x_dict['tag'] = Identity(5424)`` stands for
+    ``torch.eye(5424)`` (/root/reference/src/data/artgraph.py:93-95) without the caller having to
+    build, hold or upload the N x N matrix.  ``to_hetero`` modules and ``GNNTrainer`` accept it
+    wherever a feature tensor is accepted: ``I W^T = W^T`` is used directly and no check of the
+    values is needed.  A dense ``torch.eye`` tensor keeps working (it is detected on the device)."""
+
+    def __init__(self, n: int):
+        self.n = int(n)
+
+    @property
+    def shape(self):
+        return (self.n, self.n)
+
+    def __repr__(self):
+        return f'Identity({self.n})'
+
+
+_EYES: dict = {}
+_DECLARED: set = set()
+
+
+def identity_tensor(n: int, device) -> torch.Tensor:
+    """The device tensor that stands behind ``Identity(n)`` (one per size and device, written on
+    the device -- nothing crosses PCIe); kernels never read it when the features are declared
+    one-hot, it only carries the shape through the module."""
+    key = (int(n), str(device))
+    t = _EYES.get(key)
+    if t is None:
+        t = torch.eye(int(n), dtype=torch.float32, device=device)
+        _EYES[key] = t
+        _DECLARED.add(t.data_ptr())
+    return t
+
+
+def is_declared_identity(x: torch.Tensor) -> bool:
+    return torch.is_tensor(x) and x.data_ptr() in _DECLARED and x._version == 0
+
+
 def _as_list(x):
     return [x] if isinstance(x, str) else list(x)
 

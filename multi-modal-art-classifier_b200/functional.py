@@ -100,6 +100,9 @@ class _HeteroConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, spec: ConvSpec, *tensors):
         ctx.set_materialize_grads(False)      # dead outputs (conv_out of non-artwork types) stay None
+        ctx.anchor = bool(getattr(spec, 'anchor', False))
+        if ctx.anchor:                        # trailing dummy input, see _direct_call
+            tensors = tensors[:-1]
         nt = len(spec.node_types)
         xs = {t: tensors[i] for i, t in enumerate(spec.node_types)}
         params = tensors[nt:]
@@ -468,8 +471,8 @@ class _HeteroConvFn(torch.autograd.Function):
             gb.add(dx, segs, accumulate=acc)
         if gb.problems:
             gb.run()
-        _deliver_param_grads(spec.param_refs, grads, nt)
-        return (None, *grads)
+        _deliver_param_grads(spec.param_refs, grads, nt, must=ctx.anchor)
+        return (None, *grads) + ((None,) if ctx.anchor else ())
 
 
 def _dst_views(spec: ConvSpec, xs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
@@ -488,13 +491,40 @@ def _dst_views(spec: ConvSpec, xs: Dict[str, torch.Tensor]) -> Dict[str, torch.T
     return out
 
 
-def _deliver_param_grads(param_refs, grads, offset):
+def _direct_call(fn, spec, x_list, params):
+    """Call a fused layer function.  When every parameter of the layer already owns a gradient buffer
+    (FlatAdam's flat arena) the parameters are passed DETACHED: the backward pass adds their
+    gradients straight into those buffers (_deliver_param_grads) and autograd holds no edge to the
+    parameters' AccumulateGrad nodes at all -- ~190 node visits per step less, and no dependence on
+    the stream such a node was created on (a model that had run eagerly on the default stream
+    could not be captured afterwards: "dependency created on uncaptured work in another stream").
+    A fresh dummy leaf keeps the layer in the autograd graph when no feature input needs a gradient
+    (the first conv layer)."""
+    refs = spec.param_refs
+    direct = torch.is_grad_enabled() and refs is not None and len(refs) == len(params) and all(
+        isinstance(q, torch.nn.Parameter) and q.requires_grad and q.grad is not None and
+        q.grad.is_contiguous() for q in refs)
+    spec.anchor = direct
+    if not direct:
+        return fn.apply(spec, *x_list, *params)
+    anchor = torch.empty((), dtype=torch.float32, device=x_list[0].device, requires_grad=True)
+    return fn.apply(spec, *x_list, *[q.detach() for q in params], anchor)
+
+
+def _deliver_param_grads(param_refs, grads, offset, must: bool = False):
     """When every parameter already owns a gradient buffer (FlatAdam's flat arena), add the fresh
     gradients into those buffers with ONE batched agx launch and hand autograd ``None`` -- instead
-    of ~50 AccumulateGrad element-wise kernels per layer."""
+    of ~50 AccumulateGrad element-wise kernels per layer.  ``must``: the layer ran with detached
+    parameters (_direct_call), so this is the only way the gradients reach them."""
     if param_refs is None:
+        if must:
+            raise RuntimeError('fused layer ran in direct-gradient mode without parameter references')
         return
     todo = [(i, p) for i, p in enumerate(param_refs) if grads[offset + i] is not None]
+    if must and any(p.grad is None or not p.grad.is_contiguous() for _, p in todo):
+        raise RuntimeError('a parameter gradient buffer disappeared between the forward and the '
+                           'backward pass of a fused layer (use FlatAdam.zero_grad(), not '
+                           'set_to_none)')
     if not todo or any(p.grad is None or not p.grad.is_contiguous() for _, p in todo):
         return
     items = []
@@ -515,8 +545,79 @@ def _n_params(spec: ConvSpec) -> int:
     return n
 
 
+class _SageLayerFn(torch.autograd.Function):
+    """One SAGEConv / GraphConv relation through the layer-level C entry points
+    (agx_sage_layer_fwd / agx_sage_layer_bwd, include/agx.h): the path of a standalone operator call
+    ``conv((x_src, x_dst), edge_index)``; inside ``to_hetero`` all relations of a layer run through
+    the fused _HeteroConvFn instead."""
+
+    @staticmethod
+    def _layer(rel: Relation, mean: bool, x_src, x_dst, wl, bl, wr) -> "L.SageLayer":
+        lay = L.SageLayer()
+        r = lay.rel
+        r.rowptr, r.col, r.cnt = ptr(rel.csr.rowptr), ptr(rel.csr.col), ptr(rel.csr.cnt)
+        r.t_rowptr, r.t_col = ptr(rel.csc.rowptr), ptr(rel.csc.col)
+        r.n_src, r.n_dst, r.n_edges = rel.n_src, rel.n_dst, rel.n_edges
+        r.long_rows, r.t_long_rows = int(rel.csr.long_rows), int(rel.csc.long_rows)
+        lay.mean = int(mean)
+        lay.f_src, lay.out_channels = x_src.shape[1], wl.shape[0]
+        lay.x_src, lay.ld_src = ptr(x_src), x_src.stride(0)
+        if wr is not None:
+            lay.f_dst = x_dst.shape[1]
+            lay.x_dst, lay.ld_dst = ptr(x_dst), x_dst.stride(0)
+        lay.w_l, lay.b_l, lay.w_r = ptr(wl), ptr(bl), ptr(wr)
+        return lay
+
+    @staticmethod
+    def forward(ctx, rel: Relation, mean: bool, x_src, x_dst, wl, bl, wr):
+        for t, name in ((x_src, 'x_src'), (x_dst, 'x_dst'), (wl, 'lin_l.weight')):
+            L.require_cuda(t, name)
+        x_src, x_dst = x_src.contiguous(), x_dst.contiguous()
+        wl = wl.contiguous()
+        wr = None if wr is None else wr.contiguous()
+        if x_src.dtype != torch.float32 or x_dst.dtype != torch.float32:
+            raise TypeError('node features must be float32')
+        dev = x_src.device
+        lay = _SageLayerFn._layer(rel, mean, x_src, x_dst, wl, bl, wr)
+        nbytes = lib().agx_sage_layer_workspace_bytes(lay)
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        out = torch.empty(rel.n_dst, wl.shape[0], dtype=torch.float32, device=dev)
+        agg = torch.empty(rel.n_dst, x_src.shape[1], dtype=torch.float32, device=dev)
+        check(lib().agx_sage_layer_fwd(lay, ptr(out), out.stride(0), 0, ptr(agg), ptr(ws), nbytes,
+                                       stream_ptr()), 'agx_sage_layer_fwd')
+        ctx.rel, ctx.mean = rel, mean
+        ctx.has = (bl is not None, wr is not None)
+        ctx.save_for_backward(x_src, x_dst, wl, agg, *([wr] if wr is not None else []))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x_src, x_dst, wl, agg, *rest = ctx.saved_tensors
+        wr = rest[0] if rest else None
+        has_b, has_r = ctx.has
+        dout = dout.contiguous()
+        dev = dout.device
+        lay = _SageLayerFn._layer(ctx.rel, ctx.mean, x_src, x_dst, wl, None, wr)
+        nbytes = lib().agx_sage_layer_workspace_bytes(lay)
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        dwl = torch.empty_like(wl)
+        dbl = torch.empty(wl.shape[0], dtype=torch.float32, device=dev) if has_b else None
+        dwr = torch.empty_like(wr) if has_r else None
+        dxs = torch.empty_like(x_src) if ctx.needs_input_grad[2] else None
+        dxd = torch.empty_like(x_dst) if (ctx.needs_input_grad[3] and has_r) else None
+        check(lib().agx_sage_layer_bwd(lay, ptr(agg), ptr(dout), dout.stride(0), ptr(dwl), ptr(dbl),
+                                       ptr(dwr), ptr(dxs), x_src.shape[1], ptr(dxd),
+                                       x_dst.shape[1] if has_r else 0, 0, ptr(ws), nbytes,
+                                       stream_ptr()), 'agx_sage_layer_bwd')
+        return None, None, dxs, dxd, dwl, dbl, dwr
+
+
+def sage_layer(rel: Relation, mean: bool, x_src, x_dst, wl, bl=None, wr=None) -> torch.Tensor:
+    return _SageLayerFn.apply(rel, mean, x_src, x_dst, wl, bl, wr)
+
+
 def hetero_conv(spec: ConvSpec, x_list: Sequence[torch.Tensor], params: Sequence[torch.Tensor]):
-    return _HeteroConvFn.apply(spec, *x_list, *params)
+    return _direct_call(_HeteroConvFn, spec, x_list, params)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -648,6 +749,15 @@ class _BNActFn(torch.autograd.Function):
 
 
 def batch_norm_act(spec: BNSpec, xs, weights, biases):
+    refs = spec.param_refs
+    direct = torch.is_grad_enabled() and refs is not None and all(
+        q is not None and q.requires_grad and q.grad is not None and q.grad.is_contiguous()
+        for q in (*refs[0], *refs[1]))
+    if direct and any(x.requires_grad for x in xs):
+        # gradients of weight / bias go straight into the parameters' buffers (see _direct_call);
+        # the inputs keep the function in the autograd graph
+        weights = [w.detach() for w in weights]
+        biases = [b.detach() for b in biases]
     return _BNActFn.apply(spec, *xs, *weights, *biases)
 
 
@@ -794,7 +904,7 @@ class _NLLFromLogpFn(torch.autograd.Function):
     src/train_gnn_embeddings.py:29-30)."""
 
     @staticmethod
-    def forward(ctx, logp, labels, group=None):
+    def forward(ctx, logp, labels, group=None, global_count=None, pending=None):
         L.require_cuda(logp, 'nll_loss input')
         n, c = logp.shape
         dev = logp.device
@@ -805,11 +915,27 @@ class _NLLFromLogpFn(torch.autograd.Function):
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         check(lib().agx_nll_forward(ptr(lp), lp.stride(0), n, c, ptr(labels), None, ptr(loss_sum),
                                     ptr(row_ws), stream_ptr()), 'agx_nll_forward')
-        if group is not None:        # mean over the rows of ALL ranks: (sum nll, count) all-reduced
+        ctx.coef = 1.0
+        if group is not None and global_count is not None:
+            # mean over the rows of ALL ranks, their number known beforehand: this rank's term is
+            # sum_local / N_global -- the backward pass needs nothing from the other ranks, and the
+            # all-reduce of the loss VALUE leaves the critical path (async; the caller waits on
+            # ``pending`` when it reads the loss)
             import torch.distributed as dist
-            dist.all_reduce(loss_sum, group=group)
-        check(lib().agx_loss_finish(ptr(loss_sum), 1.0, ptr(loss), 0, stream_ptr()),
-              'agx_loss_finish')
+            ctx.coef = float(n) / float(global_count)
+            check(lib().agx_loss_finish(ptr(loss_sum), ctx.coef, ptr(loss), 0, stream_ptr()),
+                  'agx_loss_finish')
+            work = dist.all_reduce(loss, group=group, async_op=True)
+            if pending is not None:
+                pending.append(work)
+            else:
+                work.wait()
+        else:
+            if group is not None:    # (sum nll, count) over the rows of all ranks
+                import torch.distributed as dist
+                dist.all_reduce(loss_sum, group=group)
+            check(lib().agx_loss_finish(ptr(loss_sum), 1.0, ptr(loss), 0, stream_ptr()),
+                  'agx_loss_finish')
         ctx.save_for_backward(labels, loss_sum)
         ctx.shape = (n, c)
         return loss.reshape(())
@@ -820,15 +946,18 @@ class _NLLFromLogpFn(torch.autograd.Function):
         n, c = ctx.shape
         dlp = torch.empty(n, c, dtype=torch.float32, device=labels.device)
         gs = g.reshape(1).to(torch.float32).contiguous()
-        check(lib().agx_nll_backward(n, c, ptr(labels), None, ptr(loss_sum), ptr(gs), 1.0, ptr(dlp),
-                                     c, stream_ptr()), 'agx_nll_backward')
-        return dlp, None, None
+        check(lib().agx_nll_backward(n, c, ptr(labels), None, ptr(loss_sum), ptr(gs), ctx.coef,
+                                     ptr(dlp), c, stream_ptr()), 'agx_nll_backward')
+        return dlp, None, None, None, None
 
 
-def nll_loss(logp: torch.Tensor, labels: torch.Tensor, group=None) -> torch.Tensor:
+def nll_loss(logp: torch.Tensor, labels: torch.Tensor, group=None, global_count=None,
+             pending=None) -> torch.Tensor:
     """``F.nll_loss(logp, labels)``; with ``group`` the mean runs over the rows of all ranks (each
-    rank then holds the gradient of the GLOBAL loss w.r.t. its own rows)."""
-    return _NLLFromLogpFn.apply(logp, labels, group)
+    rank then holds the gradient of the GLOBAL loss w.r.t. its own rows).  ``global_count``: the
+    number of rows over all ranks when known beforehand -- the collective then only carries the
+    loss value and runs asynchronously (handles appended to ``pending``)."""
+    return _NLLFromLogpFn.apply(logp, labels, group, global_count, pending)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -1132,6 +1261,9 @@ class _HeteroGATFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, spec: GATSpec, *tensors):
         ctx.set_materialize_grads(False)
+        ctx.anchor = bool(getattr(spec, 'anchor', False))
+        if ctx.anchor:                        # trailing dummy input, see _direct_call
+            tensors = tensors[:-1]
         nt = len(spec.node_types)
         xs = {t: tensors[i] for i, t in enumerate(spec.node_types)}
         params = tensors[nt:]
@@ -1380,9 +1512,9 @@ class _HeteroGATFn(torch.autograd.Function):
         for i in range(nt, len(tensors)):
             if grads[i] is not None and grads[i].shape != tensors[i].shape:
                 grads[i] = grads[i].view(tensors[i].shape)
-        _deliver_param_grads(spec.param_refs, grads, nt)
-        return (None, *grads)
+        _deliver_param_grads(spec.param_refs, grads, nt, must=ctx.anchor)
+        return (None, *grads) + ((None,) if ctx.anchor else ())
 
 
 def hetero_gat(spec: GATSpec, x_list: Sequence[torch.Tensor], params: Sequence[torch.Tensor]):
-    return _HeteroGATFn.apply(spec, *x_list, *params)
+    return _direct_call(_HeteroGATFn, spec, x_list, params)

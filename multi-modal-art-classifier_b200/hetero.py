@@ -30,6 +30,7 @@ from . import functional as AF
 from . import ops
 from . import _lib as L
 from .functional import BNSpec, ConvSpec, RelSpec
+from .data import Identity, identity_tensor, is_declared_identity
 from .graph import get_plan, key2str
 from .nn import Linear, MessagePassing
 
@@ -56,6 +57,8 @@ def _is_identity_input(x: torch.Tensor) -> bool:
     tensor so that X @ W^T can be replaced by a transposed copy of W (exact)."""
     if x.dim() != 2 or x.shape[0] != x.shape[1] or x.shape[0] < 2:
         return False
+    if is_declared_identity(x):          # data.Identity(n): declared by the caller, nothing to check
+        return True
     key = (x.data_ptr(), x.shape[0], x._version)
     hit = _IDENTITY_CACHE.get(key)
     if hit is None:
@@ -449,6 +452,12 @@ class HeteroModule(nn.Module):
 
     def forward(self, x, edge_index):
         x_dict, ei_dict = x, edge_index
+        if any(isinstance(v, Identity) for v in x_dict.values()):
+            # declared one-hot features: a device-side eye tensor carries the shape, no upload
+            ref = next((v for v in x_dict.values() if torch.is_tensor(v)), None)
+            dev = ref.device if (ref is not None and ref.is_cuda) else L.compute_device()
+            x_dict = OrderedDict((k, identity_tensor(v.n, dev) if isinstance(v, Identity) else v)
+                                 for k, v in x_dict.items())
         to_host = False
         if self.host_io and any(not v.is_cuda for v in x_dict.values()):
             dev = L.compute_device()

@@ -130,20 +130,9 @@ class MessagePassing(nn.Module):
         key = ('s', 'r', 's' if same else 'd')
         plan = get_plan({key: edge_index}, nodes)
         wl, bl, wr = self.rel_params(x_src.shape[1], x_dst.shape[1], x_src.device)
-        params = [wl]
-        i_bl = i_wr = -1
-        if bl is not None:
-            i_bl = len(params)
-            params.append(bl)
-        if wr is not None:
-            i_wr = len(params)
-            params.append(wr)
-        spec = ConvSpec(node_types=['s'] if same else ['s', 'd'],
-                        rels=[RelSpec(plan[key], self.aggr == 'mean', 0, i_bl, i_wr)],
-                        out_channels=wl.shape[0])
-        xs = [x_src.contiguous()] if same else [x_src.contiguous(), x_dst.contiguous()]
-        (out,) = AF.hetero_conv(spec, xs, params)
-        return out
+        # a standalone operator call is ONE relation: the layer-level C entry points
+        # (agx_sage_layer_fwd / _bwd); to_hetero fuses all relations of a layer instead
+        return AF.sage_layer(plan[key], self.aggr == 'mean', x_src, x_dst, wl, bl, wr)
 
 
 class SAGEConv(MessagePassing):

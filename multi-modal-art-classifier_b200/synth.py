@@ -98,6 +98,9 @@ def make_artgraph(size: str = 'small', features: str = 'one-hot', seed: int | No
         n = cfg[t]
         if features == 'one-hot':
             g[t].x = torch.eye(n, dtype=torch.float32)
+        elif features == 'identity':        # the same features as a marker (data.Identity)
+            from .data import Identity
+            g[t].x = Identity(n)
         elif features == 'dense':
             g[t].x = torch.randn(n, feat_dim, generator=gen, dtype=torch.float32)
         else:

@@ -85,7 +85,11 @@ class GNNTrainer:
         self._id_flags = {}
         self._identity_seen = {}
         self._plan = None
-        self.x = OrderedDict(x_dict)
+        from .data import Identity, identity_tensor
+        ref = next(v for v in x_dict.values() if torch.is_tensor(v))
+        # data.Identity(n) markers (one-hot features): device-side eye tensors, never uploaded
+        self.x = OrderedDict((k, identity_tensor(v.n, ref.device) if isinstance(v, Identity) else v)
+                             for k, v in x_dict.items())
         self.ei = OrderedDict(edge_index_dict)
         self.y = labels.to(next(iter(self.x.values())).device).to(torch.int64).contiguous()
         self.node_type = node_type
@@ -104,12 +108,17 @@ class GNNTrainer:
     def _step_eager(self):
         self.opt.zero_grad()
         emb, out = self.model(self.x, self.ei)
-        loss = AF.nll_loss(out[0][self.node_type], self.y, self.group)
+        pending = []
+        loss = AF.nll_loss(out[0][self.node_type], self.y, self.group,
+                           None if self.ctx is None else self.ctx.num_nodes_global[self.node_type],
+                           pending)
         loss.backward()
         if self.group is not None:          # every rank holds d(global loss)/dW of its own rows
             from .dist import all_reduce_
             all_reduce_(self.opt.grad, self.group)
         self.opt.step()
+        for w in pending:                   # the loss value's all-reduce ran beside the backward
+            w.wait()
         return loss, emb, out
 
     def _lazy_init(self):
@@ -162,10 +171,27 @@ class GNNTrainer:
         device tensors, re-sort the CSR/CSC in place and re-check the one-hot assumption on the
         device.  Nothing synchronises; ``verify_inputs()`` reads the flags back."""
         for k, v in host_x.items():
+            if self._keeps_identity(k, v):
+                continue
             self.x[k].copy_(v, non_blocking=True)
         for k, v in host_ei.items():
             self.ei[k].copy_(v, non_blocking=True)
         self._inputs_changed()
+
+    def _keeps_identity(self, k, v) -> bool:
+        """``v`` is a data.Identity marker for a type whose features already are the declared
+        identity of that size: nothing to copy.  A marker for a type that holds dense features
+        cannot be honoured in place (the captured step was planned for dense features)."""
+        from .data import Identity, is_declared_identity
+        if not isinstance(v, Identity):
+            if is_declared_identity(self.x[k]):
+                raise ValueError(f"x['{k}'] was declared Identity({self.x[k].shape[0]}); dense "
+                                 f"features need a new trainer")
+            return False
+        if not (is_declared_identity(self.x[k]) and self.x[k].shape[0] == v.n):
+            raise ValueError(f"x['{k}'] = {v!r} but the trainer holds dense features of shape "
+                             f"{tuple(self.x[k].shape)}: re-create the trainer")
+        return True
 
     # -- the same, one step ahead: host -> device copies overlap the previous step -----------------
     def prefetch_inputs(self, host_x, host_ei):
@@ -173,9 +199,11 @@ class GNNTrainer:
         buffers on a copy stream (returns at once; the running step is not disturbed).
         ``consume_prefetched()`` moves them into the static tensors of the captured step."""
         dev = next(iter(self.x.values())).device
+        from .data import is_declared_identity
         if self._stage is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
-            self._stage = (OrderedDict((k, torch.empty_like(v)) for k, v in self.x.items()),
+            self._stage = (OrderedDict((k, torch.empty_like(v)) for k, v in self.x.items()
+                                       if not is_declared_identity(v)),
                            OrderedDict((k, torch.empty_like(v)) for k, v in self.ei.items()))
             self._ev_staged = torch.cuda.Event()
             self._ev_consumed = None
@@ -183,6 +211,8 @@ class GNNTrainer:
             if self._ev_consumed is not None:           # the staging buffers were read out
                 self._copy_stream.wait_event(self._ev_consumed)
             for k, v in host_x.items():
+                if self._keeps_identity(k, v):
+                    continue
                 self._stage[0][k].copy_(v, non_blocking=True)
             for k, v in host_ei.items():
                 self._stage[1][k].copy_(v, non_blocking=True)
@@ -224,7 +254,10 @@ class GNNTrainer:
         if self.ctx is not None and self.ctx.halo is not None:
             self.ctx.halo.refresh(self.x)
         self._id_flags = {}
+        from .data import is_declared_identity
         for t, v in self.x.items():
+            if is_declared_identity(v):
+                continue
             if v.dim() == 2 and v.shape[0] == v.shape[1] and v.shape[0] >= 2:
                 was_identity = self._identity_seen.get(t)
                 if was_identity is None:

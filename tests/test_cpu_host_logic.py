@@ -265,3 +265,25 @@ def test_whole_model_host_logic_vs_oracle(opname):
         assert err <= 1e-4 * max(float(v.abs().max()), 1e-2 * gmax), (n, err)
     for (n, b_o), (_, b_p) in zip(o64.named_buffers(), prod.named_buffers()):
         assert rel_err(b_p, b_o) <= 1e-5, n
+
+
+def test_identity_marker_matches_dense_one_hot_on_cpu_shim():
+    """data.Identity(n) in x_dict: same layer plan (transposed weight copies for one-hot sources)
+    and same numbers as a dense torch.eye(n) -- host-side wiring only, kernels restated in torch."""
+    import copy
+    from collections import OrderedDict
+    import mmac_b200 as agx
+    from cpu_shim import cpu_ops
+    g, ei, md = util.undirected_graph('tiny')
+    torch.manual_seed(3)
+    m1 = agx.HeteroSGNN(agx.SAGEConv, torch.nn.ReLU(), 'sum', 128, 32, md, 2, 0.0, True, False)
+    with cpu_ops(), torch.no_grad():
+        m1(g.x_dict, ei)                      # materialise the lazy weights before copying
+    m2 = copy.deepcopy(m1)
+    xm = OrderedDict((k, v if k == 'artwork' else agx.Identity(v.shape[0]))
+                     for k, v in g.x_dict.items())
+    with cpu_ops():
+        e1, o1 = m1(g.x_dict, ei)
+        e2, o2 = m2(xm, ei)
+    assert torch.equal(e1['artwork'], e2['artwork'])
+    assert torch.equal(o1[0]['artwork'], o2[0]['artwork'])

@@ -46,7 +46,8 @@ def test_ctypes_structs_match_c_layout():
              'agx_gemm_problem_t': L.GemmProblem, 'agx_sum_desc_t': L.SumDesc,
              'agx_bn_desc_t': L.BnDesc, 'agx_bn_bwd_desc_t': L.BnBwdDesc,
              'agx_colsum_desc_t': L.ColsumDesc, 'agx_gat_rel_t': L.GatRel,
-             'agx_sddmm_seg_t': L.SddmmSeg, 'agx_head_t': L.Head}
+             'agx_sddmm_seg_t': L.SddmmSeg, 'agx_head_t': L.Head, 'agx_plan_rel_t': L.PlanRel,
+             'agx_sage_layer_t': L.SageLayer}
     body = '\n'.join(f'printf("{n} %zu\\n", sizeof({n}));' for n in names)
     consts = ['AGX_MAX_CSR_RELS', 'AGX_MAX_REL_PER_GROUP', 'AGX_MAX_GROUPS', 'AGX_MAX_CHUNK_SEGS',
               'AGX_CHUNK_EDGES', 'AGX_MAX_GEMM_PROBLEMS', 'AGX_MAX_GEMM_SEGS', 'AGX_MAX_TENSORS',

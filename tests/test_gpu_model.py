@@ -147,7 +147,11 @@ def test_product_matches_reference_golden(opname, label, C):
             # tensors whose true gradient is rounding noise (GATConv's lin_r only shifts the
             # logits of a softmax row: ~1e-12) are compared on the scale of the model's gradients
             err = float(np.abs(named[name].grad.cpu().numpy() - v).max())
-            assert err <= GRAD_RTOL * float(np.abs(v).max()) or err <= 1e-7 * gmax, (k, err)
+            util.parity_log('golden-grad', k, err / max(float(np.abs(v).max()), 1e-30))
+            # the fixtures hold float32 values only (no float64 second opinion as in
+            # _compare_grads): 2e-5 -- two float32 summation orders of the 18 / 32-row BatchNorm
+            # backward differ by up to 1.3e-5 on the genre graph (gpurun_out parity log, round 2)
+            assert err <= 2e-5 * float(np.abs(v).max()) or err <= 1e-7 * gmax, (k, err)
 
 
 @pytest.mark.parametrize('opname', ['SAGEConv', 'GraphConv'])
@@ -443,6 +447,40 @@ def test_host_io_reference_calling_convention():
     with torch.no_grad():
         emb_c, _ = clone.gnn(g.x_dict, ei)
     assert not emb_c['artwork'].is_cuda and emb_c['artwork'].shape == (300, 128)
+
+
+def test_identity_marker_equals_dense_one_hot_features():
+    """``x_dict[t] = agx.Identity(n)`` (no N x N matrix built or uploaded) gives bit-identical
+    results to the reference's dense ``torch.eye(n)`` features (artgraph.py:93-95), in a plain
+    forward / backward and through the trainer's input update path."""
+    from mmac_b200.trainer import GNNTrainer
+    g, ei, orc, prod = _build_pair('SAGEConv', 32, 'tiny', dropout=0.0)
+    prod2 = copy.deepcopy(prod)
+    xd, ed = _to_dev(g.x_dict), _to_dev(ei)
+    xm = OrderedDict((k, v if k == 'artwork' else agx.Identity(v.shape[0])) for k, v in xd.items())
+    y = g['artwork'].y_style.to(DEV)
+    prod.train(); prod2.train()
+    e1, o1 = prod(xd, ed)
+    e2, o2 = prod2(xm, ed)
+    assert torch.equal(e1['artwork'], e2['artwork']) and torch.equal(o1[0]['tag'], o2[0]['tag'])
+    agx.functional.nll_loss(o1[0]['artwork'], y).backward()
+    agx.functional.nll_loss(o2[0]['artwork'], y).backward()
+    for (n1, p1), (_, p2) in zip(prod.named_parameters(), prod2.named_parameters()):
+        if p1.grad is not None:
+            assert torch.equal(p1.grad, p2.grad), n1
+    # trainer: markers are never staged or copied; a dense update of a declared type is refused
+    tr = GNNTrainer(prod2, xm, ed, y, lr=0.01, use_cuda_graph=True)
+    l0 = float(tr.train_step().item())
+    host_x = OrderedDict((k, v.cpu().pin_memory() if torch.is_tensor(v) else v) for k, v in xm.items())
+    host_ei = OrderedDict((k, v.cpu().pin_memory()) for k, v in ed.items())
+    tr.prefetch_inputs(host_x, host_ei)
+    assert 'tag' not in tr._stage[0] and 'artwork' in tr._stage[0]
+    tr.consume_prefetched()
+    l1 = float(tr.train_step().item())
+    tr.verify_inputs()
+    assert l1 < l0
+    with pytest.raises(ValueError):
+        tr.update_inputs({'tag': torch.eye(40).pin_memory()}, {})
 
 
 def test_full_size_properties():
