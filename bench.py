@@ -715,7 +715,13 @@ def run_ours(args):
     # ahead on a copy stream, so the PCIe transfer overlaps the previous step's kernels), are moved
     # into the captured step's static tensors, the CSR/CSC are re-sorted, the step runs, the loss
     # is read back.  `--e2e-serial` copies in line instead (no overlap).
-    def e2e_step(first):
+    # The loss of EVERY step is read back (4 bytes D2H into pinned memory) and the input checks of
+    # every step are evaluated on the host -- one step late: step i+1 is queued before the host
+    # waits for step i, so the GPU never idles while Python enqueues (--e2e-serial: wait in line).
+    loss_pin = [torch.empty(1, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+    loss_ev = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_enqueue(i, first):
         if args.e2e_serial:
             trainer.update_inputs(host_x, host_ei)      # H2D of x_dict + edge_index_dict, re-sort
         else:
@@ -723,18 +729,37 @@ def run_ours(args):
                 trainer.prefetch_inputs(host_x, host_ei)
             trainer.consume_prefetched()                # D2D into the static tensors, re-sort
             trainer.prefetch_inputs(host_x, host_ei)    # next step's H2D, overlaps this step
-        loss_host = float(trainer.train_step().item())  # D2H of the loss
-        trainer.verify_inputs()
-        return loss_host
+        loss_dev = trainer.train_step()
+        loss_pin[i & 1].copy_(loss_dev.reshape(1), non_blocking=True)      # D2H of the loss
+        loss_ev[i & 1].record()
+        return trainer.verify_inputs_async()
 
-    for i in range(2):
-        e2e_step(i == 0)
+    def e2e_finish(i, check):
+        loss_ev[i & 1].synchronize()
+        check()
+        return float(loss_pin[i & 1][0])
+
+    def e2e_run(n, first):
+        prev = None
+        last = None
+        for i in range(n):
+            chk = e2e_enqueue(i, first and i == 0)
+            if args.e2e_serial:
+                last = e2e_finish(i, chk)
+            else:
+                if prev is not None:
+                    last = e2e_finish(*prev)
+                prev = (i, chk)
+        if prev is not None:
+            last = e2e_finish(*prev)
+        return last
+
+    e2e_run(2, True)
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        l_host = e2e_step(False)
+    l_host = e2e_run(args.steps, False)
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -879,7 +904,9 @@ def run_ours(args):
                                 + ('(in line)' if args.e2e_serial else
                                    '(prefetched one step ahead on a copy stream, overlapping the '
                                    'previous step)') +
-                                ', CSR/CSC re-sort, train step, loss read-back',
+                                ', CSR/CSC re-sort, train step, loss read-back and input checks '
+                                'of every step (evaluated on the host one step late, so step i+1 '
+                                'is queued while step i runs)',
                     'last_loss': l_host},
             'gpu_launches': int(launches),
             'clocks': clk,
@@ -887,6 +914,8 @@ def run_ours(args):
             'cpu_baseline': cpu_base,
             'parity': parity,
             'dist_parity': dist_parity,
+            'small_allreduce': (__import__('mmac_b200.dist', fromlist=['PEER_STATUS']).PEER_STATUS
+                                if dist is not None else None),
             'config5': config5,
             'heads': heads,
             'operators': operators,

@@ -39,7 +39,7 @@ typedef enum {
     AGX_ERR_UNSUPPORTED = -4
 } agx_status;
 
-enum { AGX_F32 = 0, AGX_BF16 = 1 };
+enum { AGX_F32 = 0, AGX_BF16 = 1, AGX_F64 = 2 /* agx_peer_allreduce only */ };
 enum { AGX_SUM = 0, AGX_MEAN = 1 };
 
 int agx_version(void);
@@ -515,6 +515,24 @@ int agx_pack_rows(const float* x, int64_t ld, const int32_t* idx, int32_t n, int
                   void* stream);
 int agx_unpack_rows_add(float* x, int64_t ld, const int32_t* idx, int32_t n, int32_t F,
                         const float* in, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Small all-reduce (sum) over NVLink / NVSwitch peer memory: one kernel, no NCCL call, for the
+ * latency-bound reductions on the critical path of a multi-GPU step (BatchNorm statistics of the
+ * rows of all ranks, the loss, the heads' label normaliser and gradient arena).  Push protocol:
+ * every rank writes its elements, each 32-bit word tagged with the call's epoch, into its receive
+ * slot on every peer and then collects the same elements of all ranks from its own buffer.
+ * d_peer_bufs: DEVICE array of `world` base pointers to the ranks' symmetric buffers (each
+ * agx_peer_allreduce_buffer_bytes(max payload, world) bytes, zero-initialised, mapped by the
+ * caller -- torch.distributed._symmetric_memory in the Python binding); d_epoch: device int64[4],
+ * zero-initialised, private to this rank.  Every rank must make the same sequence of calls.  Ranks
+ * are added in rank order: bit-identical results on all ranks.  CUDA-graph capturable (the epoch
+ * is advanced on the device).
+ * ------------------------------------------------------------------------------------------ */
+size_t agx_peer_allreduce_buffer_bytes(size_t max_payload_bytes, int world);
+int agx_peer_allreduce(void* const* d_peer_bufs, int rank, int world, const void* in, void* out,
+                       int64_t numel, int dtype /* AGX_F32 | AGX_F64 */, int64_t* d_epoch,
+                       size_t max_payload_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(PKG_DIR, 'libagx.so')
 STAMP = os.path.join(PKG_DIR, 'libagx.so.stamp')
 
 SOURCES = ['agx_api.cu', 'agx_csr.cu', 'agx_aggregate.cu', 'agx_gemm.cu', 'agx_gemm_tc.cu',
-           'agx_nn.cu', 'agx_gat.cu', 'agx_heads_tc.cu', 'agx_layer.cu']
+           'agx_nn.cu', 'agx_gat.cu', 'agx_heads_tc.cu', 'agx_layer.cu', 'agx_comm.cu']
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-DAGX_BUILD']

@@ -27,7 +27,7 @@ MAX_TENSORS = 48
 MAX_GAT_RELS = 24
 MAX_SDDMM_SEGS = 24
 GAT_LONG_ROW = 1024
-F32, BF16 = 0, 1
+F32, BF16, F64 = 0, 1, 2
 
 
 class EdgeList(C.Structure):
@@ -173,6 +173,9 @@ _SIGS = {
                                      vp]),
     'agx_sage_layer_bwd': (C.c_int, [C.POINTER(SageLayer), vp, vp, c_i64, vp, vp, vp, vp, c_i64, vp,
                                      c_i64, C.c_int, vp, C.c_size_t, vp]),
+    'agx_peer_allreduce_buffer_bytes': (C.c_size_t, [C.c_size_t, C.c_int]),
+    'agx_peer_allreduce': (C.c_int, [vp, C.c_int, C.c_int, vp, vp, c_i64, C.c_int, vp, C.c_size_t,
+                                     vp]),
     'agx_head_step_workspace_bytes': (C.c_size_t, [C.POINTER(Head), C.c_int, c_i32]),
     'agx_head_step_prepare': (C.c_int, [C.POINTER(Head), C.c_int, c_i32, vp, vp, C.c_size_t, vp]),
     'agx_head_step': (C.c_int, [C.POINTER(Head), C.c_int, c_i32, c_f32, vp, vp, vp, C.c_int, vp,

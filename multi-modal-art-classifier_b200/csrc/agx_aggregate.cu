@@ -1007,9 +1007,9 @@ static int launch_chunks(const ChunkSegs& P, int lpr, unsigned grid, bool tma, i
 // smaller units are faster: a warp walks its edges in serial batches of kGatherDepth gathers (one
 // L2 / DRAM round trip per batch), so a CTA lasts as long as its unit and the launch ends with the
 // slowest CTA, while the gathers themselves are far from the L2 ceiling at any residency
-// (profiles/probes/gather_probe2.cu: 12.5 TB/s with 2 CTAs per SM).  Default 64;
-// AGX_CHUNK_CE=32|64|128|192|256 overrides it.
-constexpr int kDefaultChunkEdges = 64;
+// (profiles/probes/gather_probe2.cu: 12.5 TB/s with 2 CTAs per SM).  The same holds on launches
+// of many waves (16x replicated graph, 14 M edges per launch: 5.5 ms per step at 64, 6.2 at 128,
+// 6.5 at 256).  Default 64; AGX_CHUNK_CE=32|64|128|192|256 overrides.
 static int pick_chunk_edges(const agx_chunk_seg_t* segs, int n_segs, bool tma) {
     static const char* env = getenv("AGX_CHUNK_CE");
     (void)segs;
@@ -1019,7 +1019,7 @@ static int pick_chunk_edges(const agx_chunk_seg_t* segs, int n_segs, bool tma) {
         const int v = atoi(env);
         if (v == 32 || v == 64 || v == 128 || v == 192 || v == 256) return v;
     }
-    return kDefaultChunkEdges;
+    return 64;
 }
 
 extern "C" int agx_aggregate_chunks(const agx_chunk_seg_t* h_segs, int n_segs, int F, int dtype,

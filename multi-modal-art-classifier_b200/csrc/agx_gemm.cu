@@ -350,6 +350,7 @@ extern "C" int agx_gemm_grouped(const agx_gemm_problem_t* h_problems, int n_prob
     cudaStream_t st = (cudaStream_t)stream;
     int wide[AGX_MAX_GEMM_PROBLEMS], narrow[AGX_MAX_GEMM_PROBLEMS], nw = 0, nn = 0;
     int shortm[AGX_MAX_GEMM_PROBLEMS], ns = 0;
+    int64_t short_tiles = 0;
     int tc[AGX_MAX_GEMM_PROBLEMS], ntc = 0;
     int lk[AGX_MAX_GEMM_PROBLEMS], nlk = 0, lk_used[AGX_MAX_GEMM_PROBLEMS];
     static const bool use_tc = getenv("AGX_DISABLE_TC") == nullptr;   // A/B switch for tests
@@ -380,13 +381,19 @@ extern "C" int agx_gemm_grouped(const agx_gemm_problem_t* h_problems, int n_prob
             lk[nlk++] = i;
             continue;
         }
-        // few-row problems (the small node types, weight gradients) would sit on one or two SMs
-        // with 128-row tiles: 32 x 32 tiles spread them over 16x as many CTAs (round 2: the 32 x 128
-        // class ran ~20 CTAs per launch at ~25 us, bound by the instruction issue of a single CTA
-        // per SM; a quarter of the FMAs per k-step and four times the CTAs, same summation order)
+        // few-row problems (the small node types, their weight gradients) would sit on one or two
+        // SMs with 128-row tiles: 32-row tiles spread them over 4x as many CTAs.  When even that
+        // leaves the launch under two CTAs per SM (the full graph: 6..68 CTAs of 32 x 128 per
+        // launch at ~25 us, bound by the instruction issue of one CTA per SM) the launch takes
+        // 32 x 32 tiles -- a quarter of the FMAs per k-step on four times the CTAs, same
+        // summation order.  Launches that already fill the machine (split-K weight gradients of
+        // the 16x graph) keep 32 x 128: narrower tiles re-read the long operand four times
+        // (measured there: 17.5 ms of GEMM per step with 32 x 32 everywhere, 10.4 with this rule).
         if (Q.N <= 48) narrow[nn++] = i;
-        else if (Q.M <= 256) shortm[ns++] = i;
-        else wide[nw++] = i;
+        else if (Q.M <= 256) {
+            shortm[ns++] = i;
+            short_tiles += ceil_div(Q.M, 32) * ceil_div(Q.N, 128) * (Q.split_k > 1 ? Q.split_k : 1);
+        } else wide[nw++] = i;
     }
     if (ntc > 0) {
         const int rc_tc = gemm_tc_launch(h_problems, tc, ntc, h_segs, st);
@@ -398,7 +405,10 @@ extern "C" int agx_gemm_grouped(const agx_gemm_problem_t* h_problems, int n_prob
     }
     int rc = launch_class<128, 128, 8, 8>(h_problems, wide, nw, h_segs, n_segs, st);
     if (rc) return rc;
-    rc = launch_class<32, 32, 2, 2>(h_problems, shortm, ns, h_segs, n_segs, st);
+    if (short_tiles < 2 * kNumSMs)
+        rc = launch_class<32, 32, 2, 2>(h_problems, shortm, ns, h_segs, n_segs, st);
+    else
+        rc = launch_class<32, 128, 2, 8>(h_problems, shortm, ns, h_segs, n_segs, st);
     if (rc) return rc;
     rc = launch_class<128, 32, 4, 4>(h_problems, narrow, nn, h_segs, n_segs, st);
     if (rc) return rc;

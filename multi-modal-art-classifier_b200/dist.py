@@ -33,6 +33,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import ops
+from . import _lib as L
 from ._lib import check, lib, ptr, stream_ptr
 
 
@@ -326,6 +327,87 @@ def partition_context(part: GraphPartition, group, device) -> DistContext:
     return DistContext(group, part.rank, part.world, dict(part.num_nodes), halo,
                        replicated=frozenset(part.replicated),
                        partial={k: v.to(device) for k, v in part.partial.items()})
+
+
+class PeerAllReduce:
+    """In-place sum all-reduce of SMALL float32 / float64 tensors by one agx kernel over NVLink peer
+    memory (agx_peer_allreduce, csrc/agx_comm.cu) instead of an NCCL call: the BatchNorm-statistic,
+    loss and label-normaliser reductions of a multi-GPU step (4 B .. 18 KB) and the heads' gradient
+    arena (180 KB) are purely latency-bound.  The symmetric buffers are allocated and exchanged by
+    ``torch.distributed._symmetric_memory`` (plumbing); larger tensors keep using NCCL."""
+
+    MAX_BYTES = 256 * 1024
+
+    def __init__(self, group, device):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        nbytes = int(lib().agx_peer_allreduce_buffer_bytes(self.MAX_BYTES, self.world))
+        self.buf = symm.empty(nbytes, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, group)
+        self.ptrs = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64,
+                                 device=device)
+        self.epoch = torch.zeros(4, dtype=torch.int64, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                 # every rank has zeroed its flags before the first call
+        self.calls = 0
+
+    def fits(self, t: torch.Tensor) -> bool:
+        return t.is_cuda and t.is_contiguous() and t.dtype in (torch.float32, torch.float64) and \
+            0 < t.numel() * t.element_size() <= self.MAX_BYTES
+
+    def __call__(self, t: torch.Tensor) -> torch.Tensor:
+        dt = L.F64 if t.dtype == torch.float64 else L.F32
+        check(lib().agx_peer_allreduce(ptr(self.ptrs), self.rank, self.world, ptr(t), ptr(t),
+                                       t.numel(), dt, ptr(self.epoch), self.MAX_BYTES, stream_ptr()),
+              'agx_peer_allreduce')
+        self.calls += 1
+        return t
+
+
+_PEER: Dict[int, object] = {}          # id(group) -> PeerAllReduce | False (set-up failed)
+PEER_STATUS: Dict[str, str] = {}
+
+
+def enable_peer_allreduce(group, device) -> bool:
+    """Set up the peer-memory all-reduce for ``group`` (collective call: every rank of the group).
+    Returns False -- and the small reductions stay on NCCL -- when symmetric memory cannot be
+    established on this machine (the reason is kept in ``dist.PEER_STATUS``)."""
+    import os
+    import torch.distributed as dist
+    key = id(group)
+    if key in _PEER:
+        return bool(_PEER[key])
+    ok = torch.ones(1, dtype=torch.int32, device=device)
+    par = None
+    if os.environ.get('AGX_PEER_ALLREDUCE', '1') == '0':
+        ok.zero_()
+        PEER_STATUS['reason'] = 'disabled by AGX_PEER_ALLREDUCE=0'
+    else:
+        try:
+            par = PeerAllReduce(group, device)
+        except Exception as e:  # noqa: BLE001  (no P2P / fabric handles: NCCL keeps doing the job)
+            ok.zero_()
+            PEER_STATUS['reason'] = f'{type(e).__name__}: {e}'[:300]
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)     # all ranks or none
+    if int(ok.item()) != 1:
+        par = None
+    _PEER[key] = par if par is not None else False
+    PEER_STATUS['mode'] = 'peer-memory kernel (agx_peer_allreduce)' if par is not None else 'nccl'
+    return par is not None
+
+
+def small_all_reduce_(t: torch.Tensor, group) -> torch.Tensor:
+    """Sum all-reduce in place: the peer-memory kernel when it is set up for ``group`` and the
+    tensor is small, NCCL otherwise."""
+    par = _PEER.get(id(group))
+    if par and par.fits(t):
+        return par(t)
+    import torch.distributed as dist
+    dist.all_reduce(t, group=group)
+    return t
 
 
 def all_reduce_(t: torch.Tensor, group) -> torch.Tensor:

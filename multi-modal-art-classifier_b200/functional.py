@@ -679,7 +679,8 @@ class _BNActFn(torch.autograd.Function):
                                                  n_ws, phase, ptr(sums), ptr(spec.counts),
                                                  stream_ptr()), 'agx_bn_forward_phase')
                 if phase == 1:
-                    dist.all_reduce(sums, group=spec.group)
+                    from .dist import small_all_reduce_    # 18 KB: one peer-memory kernel, or NCCL
+                    small_all_reduce_(sums, spec.group)
         else:
             check(lib().agx_bn_forward(arr, n, F, int(spec.training), spec.momentum, spec.eps,
                                        ptr(wsb), n_ws, stream_ptr()), 'agx_bn_forward')
@@ -736,7 +737,8 @@ class _BNActFn(torch.autograd.Function):
                 counts = spec.counts_of(tuple(idx)) if len(idx) != n else spec.counts
                 check(lib().agx_bn_backward_phase(arr, len(idx), F, 1, ptr(wsb), n_ws, 1, ptr(totals),
                                                   ptr(counts), stream_ptr()), 'agx_bn_backward_phase')
-                dist.all_reduce(totals, group=spec.group)
+                from .dist import small_all_reduce_
+                small_all_reduce_(totals, spec.group)
                 check(lib().agx_bn_backward_phase(arr, len(idx), F, 1, ptr(wsb), n_ws, 2, ptr(totals),
                                                   ptr(counts), stream_ptr()), 'agx_bn_backward_phase')
             else:
@@ -866,7 +868,8 @@ class _SoftmaxNLLFn(torch.autograd.Function):
                                         ptr(row_ws), stream_ptr()), 'agx_log_softmax_nll')
         if group is not None:
             import torch.distributed as dist
-            dist.all_reduce(loss_sum, group=group)
+            from .dist import small_all_reduce_
+            small_all_reduce_(loss_sum, group)
         check(lib().agx_loss_finish(ptr(loss_sum), coef, ptr(loss), 0, stream_ptr()),
               'agx_loss_finish')
         ctx.save_for_backward(logp, labels, loss_sum, class_w if class_w is not None else logp)
@@ -925,15 +928,20 @@ class _NLLFromLogpFn(torch.autograd.Function):
             ctx.coef = float(n) / float(global_count)
             check(lib().agx_loss_finish(ptr(loss_sum), ctx.coef, ptr(loss), 0, stream_ptr()),
                   'agx_loss_finish')
-            work = dist.all_reduce(loss, group=group, async_op=True)
-            if pending is not None:
-                pending.append(work)
+            from .dist import _PEER, small_all_reduce_
+            import os
+            if _PEER.get(id(group)) and os.environ.get('AGX_PEER_LOSS', '1') != '0':
+                small_all_reduce_(loss, group)          # one small kernel on this stream
             else:
-                work.wait()
+                work = dist.all_reduce(loss, group=group, async_op=True)
+                if pending is not None:
+                    pending.append(work)
+                else:
+                    work.wait()
         else:
             if group is not None:    # (sum nll, count) over the rows of all ranks
-                import torch.distributed as dist
-                dist.all_reduce(loss_sum, group=group)
+                from .dist import small_all_reduce_
+                small_all_reduce_(loss_sum, group)
             check(lib().agx_loss_finish(ptr(loss_sum), 1.0, ptr(loss), 0, stream_ptr()),
                   'agx_loss_finish')
         ctx.save_for_backward(labels, loss_sum)

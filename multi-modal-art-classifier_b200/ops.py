@@ -620,8 +620,8 @@ class HeadStep:
         check(lib().agx_head_step_prepare(arr, n, B, ptr(self.norm), ptr(self.ws), nbytes,
                                           stream_ptr()), 'agx_head_step_prepare')
         if group is not None and any(h.loss == 'ce' for h in heads):
-            import torch.distributed as dist       # weighted mean over the batch shards of all ranks
-            dist.all_reduce(self.norm, group=group)
+            from .dist import small_all_reduce_    # weighted mean over the batch shards of all ranks
+            small_all_reduce_(self.norm, group)
         check(lib().agx_head_step(arr, n, B, float(p_drop),
                                   ptr(seed_state) if p_drop > 0 else None, ptr(self.norm),
                                   ptr(self.loss), int(accumulate), ptr(self.ws), nbytes,

@@ -77,6 +77,10 @@ class GNNTrainer:
         self.model = model
         self.ctx = dist_ctx
         self.group = dist_ctx.group if dist_ctx is not None else None
+        dev0 = next(v for v in x_dict.values() if torch.is_tensor(v)).device
+        if self.group is not None and dev0.type == 'cuda':
+            from .dist import enable_peer_allreduce          # small reductions: one NVLink kernel
+            enable_peer_allreduce(self.group, dev0)
         if dist_ctx is not None:
             from .hetero import HeteroModule
             for m in model.modules():
@@ -275,6 +279,35 @@ class GNNTrainer:
                 raise RuntimeError(f"x['{t}'] is no longer an identity matrix: re-create the "
                                    f"trainer (the captured step assumed one-hot features)")
 
+    def verify_inputs_async(self):
+        """The checks of ``verify_inputs`` without stalling the stream: the flags are copied to
+        pinned host memory behind the work already queued; the returned callable waits for that
+        copy only and raises like ``verify_inputs``.  Lets a caller queue the next step before it
+        looks at the previous one."""
+        flags = []
+        if getattr(self, '_plan', None) is not None:
+            flags += [b[4].reshape(1).to(torch.int32) for b in self._plan._buffers]
+        n_err = len(flags)
+        names = list(self._id_flags.keys())
+        flags += [self._id_flags[t].reshape(1).to(torch.int32) for t in names]
+        if not flags:
+            return lambda: None
+        dev_flags = torch.cat(flags)
+        host = torch.empty(dev_flags.shape, dtype=torch.int32, pin_memory=True)
+        host.copy_(dev_flags, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+
+        def check():
+            ev.synchronize()
+            if any(int(v) != 0 for v in host[:n_err]):
+                raise IndexError('edge_index contains node ids outside [0, num_nodes)')
+            for t, v in zip(names, host[n_err:]):
+                if int(v) != 1:
+                    raise RuntimeError(f"x['{t}'] is no longer an identity matrix: re-create the "
+                                       f"trainer (the captured step assumed one-hot features)")
+        return check
+
     # -- evaluation --------------------------------------------------------------------------------
     @torch.no_grad()
     def evaluate(self, x_dict=None, edge_index_dict=None, labels=None):
@@ -342,9 +375,11 @@ class HeadTrainer:
         self.world = 1
         if group is not None:
             import torch.distributed as dist
-            from .dist import broadcast_
+            from .dist import broadcast_, enable_peer_allreduce
             self.world = dist.get_world_size(group)
             broadcast_(self.opt.flat, group)
+            if self.opt.flat.is_cuda:
+                enable_peer_allreduce(group, self.opt.flat.device)
         # CUDA graph: a head step is ~20 small launches, i.e. launch-bound from Python; the batch is
         # copied into static buffers and the captured step replayed (one batch shape per trainer)
         self.use_cuda_graph = use_cuda_graph
@@ -395,9 +430,9 @@ class HeadTrainer:
             loss = self.head.train_step_tc(feat, target, feat.shape[0] * self.world,
                                            accumulate=False)
         if self.group is not None:
-            from .dist import all_reduce_
-            all_reduce_(self.opt.grad, self.group)
-            loss = all_reduce_(loss.detach().clone(), self.group)
+            from .dist import small_all_reduce_      # 180 KB of head gradients: peer-memory kernel
+            small_all_reduce_(self.opt.grad, self.group)
+            loss = small_all_reduce_(loss.detach().clone(), self.group)
         self.opt.step()
         return loss
 
@@ -420,9 +455,9 @@ class HeadTrainer:
             loss = projector_loss(self.head(feat), target, feat.shape[0] * self.world)
         loss.backward()
         if self.group is not None:
-            from .dist import all_reduce_
-            all_reduce_(self.opt.grad, self.group)
+            from .dist import small_all_reduce_
+            small_all_reduce_(self.opt.grad, self.group)
             if self.kind == 'projector':
-                loss = all_reduce_(loss.detach().clone(), self.group)
+                loss = small_all_reduce_(loss.detach().clone(), self.group)
         self.opt.step()
         return loss

@@ -175,6 +175,52 @@ def _heads_case(rank, world, dev):
         assert rel_err(gsum, pr.grad) <= GRAD_RTOL, (k, rel_err(gsum, pr.grad))
 
 
+def _peer_allreduce_case(rank, world, dev):
+    """agx_peer_allreduce (one kernel over NVLink peer memory) against NCCL: same sums, bit-identical
+    on all ranks, correct over many calls (epoch / slot reuse) and inside a replayed CUDA graph."""
+    import torch.distributed as dist
+    from mmac_b200 import dist as AD
+    ok = AD.enable_peer_allreduce(dist.group.WORLD, dev)
+    assert ok, AD.PEER_STATUS
+    par = AD._PEER[id(dist.group.WORLD)]
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)
+    for it, (n, dt) in enumerate([(1, torch.float32), (2, torch.float32), (4608, torch.float64),
+                                  (45050, torch.float32), (131072, torch.float32), (7, torch.float64)] * 3):
+        x = torch.randn(n, generator=gen, device=dev, dtype=dt)
+        ref = x.clone()
+        dist.all_reduce(ref)
+        got = AD.small_all_reduce_(x.clone(), dist.group.WORLD)
+        assert torch.allclose(got, ref, rtol=1e-6 if dt == torch.float32 else 1e-13, atol=1e-6), (it, n, dt)
+        both = [torch.empty_like(got) for _ in range(world)]
+        dist.all_gather(both, got)
+        assert all(torch.equal(both[0], b) for b in both[1:]), 'ranks disagree bitwise'
+    assert par.calls >= 18
+    big = torch.ones(1 << 20, device=dev)            # too large for the slot: NCCL path
+    assert float(AD.small_all_reduce_(big, dist.group.WORLD)[0]) == world
+    # captured: 20 replays of two back-to-back reductions
+    a = torch.full((1000,), float(rank + 1), device=dev)
+    b = torch.zeros(3, device=dev, dtype=torch.float64)
+    out_a, out_b = torch.empty_like(a), torch.empty_like(b)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            out_a.copy_(a); AD.small_all_reduce_(out_a, dist.group.WORLD)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr, capture_error_mode='thread_local'):
+        out_a.copy_(a); AD.small_all_reduce_(out_a, dist.group.WORLD)
+        out_b.copy_(b); AD.small_all_reduce_(out_b, dist.group.WORLD)
+    for k in range(20):
+        b.fill_(k + rank)
+        gr.replay()
+        torch.cuda.synchronize()
+        assert float(out_a[0]) == world * (world + 1) / 2
+        assert float(out_b[0]) == sum(k + r for r in range(world)), (k, out_b)
+    dist.barrier()
+
+
 def _worker(rank, world, port, errq, cases=None):
     try:
         import torch.distributed as dist
@@ -187,6 +233,7 @@ def _worker(rank, world, port, errq, cases=None):
             _gnn_case(rank, world, dev, kind, op)
         if cases is None:
             _heads_case(rank, world, dev)
+            _peer_allreduce_case(rank, world, dev)
         dist.barrier()
         dist.destroy_process_group()
     except Exception:
