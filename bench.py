@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader',
-                                       '-i', str(self.idx), '-lms', '100'], stdout=self.f,
+                                       '-i', str(self.idx), '-lms', '20'], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -688,11 +688,16 @@ def run_ours(args):
         return
 
     # ---- device-resident timing --------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        trainer.train_step()
-    barrier()
+    # the clock sampler (nvidia-smi, one sample per 20 ms) needs ~0.1 s to come up and the timed
+    # region is 20 x 2 ms: it is started before the warm-up steps and the GPU is kept under the same
+    # load (untimed steps) until it has delivered samples; it stops right after the timed region
     clocks = ClockSampler(local)
     clocks.start()
+    for _ in range(max(args.warmup, 3)):
+        trainer.train_step()
+    for _ in range(150):                # untimed steps under the sampler (a FIXED count: every
+        trainer.train_step()            # step holds collectives, all ranks must run the same steps)
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = launch_count()
     ev0.record()

@@ -22,10 +22,12 @@ from .graph import HeteroPlan, get_plan
 class Linear(nn.Module):
     """PyG-style ``Linear`` with lazy (-1) input size (src/models/models_graph.py:18)."""
 
-    def __init__(self, in_channels: int, out_channels: int, bias: bool = True):
+    def __init__(self, in_channels: int, out_channels: int, bias: bool = True,
+                 weight_initializer: Optional[str] = None):
         super().__init__()
         self.in_channels = in_channels
         self.out_channels = out_channels
+        self.weight_initializer = weight_initializer     # 'glorot': PyG's GATConv projections
         if in_channels > 0:
             self.weight = nn.Parameter(torch.empty(out_channels, in_channels))
         else:
@@ -44,7 +46,11 @@ class Linear(nn.Module):
         if self.in_channels > 0 and not self.is_lazy:
             bound = 1.0 / math.sqrt(self.in_channels)
             with torch.no_grad():
-                self.weight.uniform_(-bound, bound)
+                if self.weight_initializer == 'glorot':
+                    g = math.sqrt(6.0 / (self.in_channels + self.out_channels))
+                    self.weight.uniform_(-g, g)
+                else:
+                    self.weight.uniform_(-bound, bound)
                 if self.bias is not None:
                     self.bias.uniform_(-bound, bound)
 
@@ -207,8 +213,8 @@ class GATConv(MessagePassing):
             in_channels = (in_channels, in_channels)
         self.in_channels, self.out_channels = in_channels, out_channels
         self.heads, self.negative_slope, self.add_self_loops = 1, negative_slope, add_self_loops
-        self.lin_l = Linear(in_channels[0], out_channels, bias=False)
-        self.lin_r = Linear(in_channels[1], out_channels, bias=False)
+        self.lin_l = Linear(in_channels[0], out_channels, bias=False, weight_initializer='glorot')
+        self.lin_r = Linear(in_channels[1], out_channels, bias=False, weight_initializer='glorot')
         self.att_l = nn.Parameter(torch.empty(1, 1, out_channels))
         self.att_r = nn.Parameter(torch.empty(1, 1, out_channels))
         if bias:

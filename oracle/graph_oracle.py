@@ -84,10 +84,12 @@ def propagate(x_src: torch.Tensor, edge_index: torch.Tensor, n_dst: int, reduce:
 # PyG ``Linear`` with lazy (-1) input size -- used at src/models/models_graph.py:18 and inside convs
 # --------------------------------------------------------------------------------------------
 class Linear(nn.Module):
-    def __init__(self, in_channels: int, out_channels: int, bias: bool = True):
+    def __init__(self, in_channels: int, out_channels: int, bias: bool = True,
+                 weight_initializer: Optional[str] = None):
         super().__init__()
         self.in_channels = in_channels
         self.out_channels = out_channels
+        self.weight_initializer = weight_initializer
         if in_channels > 0:
             self.weight = nn.Parameter(torch.empty(out_channels, in_channels))
         else:
@@ -102,7 +104,11 @@ class Linear(nn.Module):
         if self.in_channels > 0:
             bound = 1.0 / math.sqrt(self.in_channels)
             with torch.no_grad():
-                self.weight.uniform_(-bound, bound)      # kaiming_uniform(a=sqrt(5))
+                if self.weight_initializer == 'glorot':  # PyG inits.glorot: U(+-sqrt(6/(in+out)))
+                    g = math.sqrt(6.0 / (self.in_channels + self.out_channels))
+                    self.weight.uniform_(-g, g)
+                else:
+                    self.weight.uniform_(-bound, bound)      # kaiming_uniform(a=sqrt(5))
                 if self.bias is not None:
                     self.bias.uniform_(-bound, bound)
 
@@ -232,8 +238,8 @@ class GATConv(MessagePassing):
             in_channels = (in_channels, in_channels)
         self.negative_slope, self.add_self_loops = negative_slope, add_self_loops
         self.out_channels = out_channels
-        self.lin_l = Linear(in_channels[0], out_channels, bias=False)
-        self.lin_r = Linear(in_channels[1], out_channels, bias=False)
+        self.lin_l = Linear(in_channels[0], out_channels, bias=False, weight_initializer='glorot')
+        self.lin_r = Linear(in_channels[1], out_channels, bias=False, weight_initializer='glorot')
         self.att_l = nn.Parameter(torch.empty(1, 1, out_channels))
         self.att_r = nn.Parameter(torch.empty(1, 1, out_channels))
         self.bias = nn.Parameter(torch.empty(out_channels)) if bias else None
