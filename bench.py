@@ -319,11 +319,14 @@ def dist_parity_blocks(trainer, model, data, x, ei, y, world, rank, dev, dist, s
     return res
 
 
-def config5_cut(world, rank, dev, dist, copies: int = 16, steps: int = 10, overlap: bool = True):
+def config5_cut(world, rank, dev, dist, copies: int = 16, steps: int = 10, overlap: bool = True,
+                scattered=('tag', 'artist')):
     """BASELINE configs[4]: ONE graph -- the 16x replicated synthetic ArtGraph with the artwork ids
     permuted, so that a contiguous cut crosses the copies -- partitioned by destination node over
-    the N ranks (artwork rows cut, every other node type replicated; the partial neighbour sums
-    of the artwork -> X relations are all-reduced inside every conv layer), against
+    the N ranks (artwork rows cut; ``scattered`` types -- tag, artist -- cut into equal chunks, with a
+    reduce-scatter of the artwork -> tag / artist partial sums to the owners and an all-gather of
+    their rows for the reverse relations; every other node type replicated, the partial neighbour
+    sums of the relations into them all-reduced inside every conv layer), against
     the same training step of the whole graph on one GPU (rank 0 alone).  Strong scaling:
     efficiency = t(1 GPU) / (N * t(N GPUs))."""
     import mmac_b200 as agx
@@ -347,7 +350,9 @@ def config5_cut(world, rank, dev, dist, copies: int = 16, steps: int = 10, overl
         ei[(s, r, d)] = torch.stack([perm[e[0]] if s == 'artwork' else e[0],
                                      perm[e[1]] if d == 'artwork' else e[1]]).contiguous()
     total_edges = sum(int(v.shape[1]) for v in ei.values())
-    part = GraphPartition(ei, n, world, rank, replicated=[t for t in n if t != 'artwork'])
+    scattered = [t for t in scattered if t in n and n[t] >= world]
+    part = GraphPartition(ei, n, world, rank, scattered=scattered,
+                          replicated=[t for t in n if t != 'artwork' and t not in scattered])
     ctx = partition_context(part, dist.group.WORLD, dev)
     torch.manual_seed(0)
     model = agx.HeteroSGNN(agx.SAGEConv, torch.nn.ReLU(), 'sum', 128, 32, data.metadata(), 2, 0.4,
@@ -379,6 +384,7 @@ def config5_cut(world, rank, dev, dist, copies: int = 16, steps: int = 10, overl
     part_bytes = []
     for width in (128, 128, 128):            # conv0 (dense 128-d inputs), conv1, conv_out inputs
         part_bytes.append(sum(n[d] * width * 4 for (s, r, d) in part.partial))
+    scat_bytes = sum(int(c.shape[0]) * 128 * 4 for c in part.scatter.values())
     res = None
     del tr
     if rank == 0:
@@ -390,9 +396,14 @@ def config5_cut(world, rank, dev, dist, copies: int = 16, steps: int = 10, overl
         res = {'workload': f"{copies}x replicated synthetic ArtGraph 'full' (128-d features for every "
                            f"node type), artwork ids permuted: {A} artworks, {total_edges} directed "
                            f"edges; SAGEConv training step",
-               'partition': f'artwork rows cut into {world} contiguous ranges, the other node types '
-                            f'replicated; per conv layer ONE all-reduce of the partial neighbour '
-                            f'sums of the artwork -> X relations',
+               'partition': f'artwork rows cut into {world} contiguous ranges' +
+                            (f'; {", ".join(scattered)} cut into {world} equal chunks (partial sums '
+                             f'into them reduce-scattered to the owners, their rows all-gathered '
+                             f'for the reverse relations)' if scattered else '') +
+                            '; the other node types replicated, per conv layer ONE all-reduce of '
+                            'the partial neighbour sums of the relations into them',
+               'scattered_types': list(scattered),
+               'reduce_scatter_bytes_per_layer_fwd': scat_bytes,
                'n_gpus': world, 'ms_per_step': ms_n, 'ms_per_step_1gpu': ms_1,
                'edges_per_s': PASSES * total_edges / (ms_n * 1e-3),
                'edges_per_s_1gpu': PASSES * total_edges / (ms_1 * 1e-3),
@@ -558,6 +569,27 @@ def _workload_name(size, operator='SAGEConv'):
 
 # ------------------------------------------------------------------------------------------------
 # this repo's CUDA path
+def _pin_to_gpu_cpus(local: int):
+    """One process per GPU on a two-socket host: run this rank (and allocate its pinned staging
+    buffers, first-touch) on the cores NVML lists as local to its GPU -- what ``numactl
+    --cpunodebind`` would do in a launcher script.  Returns the number of cores, or None when NVML
+    gives nothing usable (nothing is changed then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if len(cpus) < 2:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
     import mmac_b200 as agx
@@ -573,6 +605,7 @@ def run_ours(args):
                          '(use --impl reference for the host baseline)')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa = _pin_to_gpu_cpus(local) if (world > 1 and not args.no_numa_pin) else None
     dist = None
     if world > 1:
         # the image exports NCCL_DEBUG=VERSION, which makes NCCL print a banner on stdout next to
@@ -854,7 +887,8 @@ def run_ours(args):
         if not args.no_config5:
             del trainer
             torch.cuda.empty_cache()
-            config5 = config5_cut(world, rank, dev, dist, copies=args.config5_copies)
+            config5 = config5_cut(world, rank, dev, dist, copies=args.config5_copies,
+                                  scattered=[t for t in args.config5_scattered.split(',') if t])
     heads = None
     if not args.no_heads:
         heads = heads_throughput(dev, dist, world, batches=(32, 4096, 65536) if world == 1 else (4096,),
@@ -921,6 +955,7 @@ def run_ours(args):
             'dist_parity': dist_parity,
             'small_allreduce': (__import__('mmac_b200.dist', fromlist=['PEER_STATUS']).PEER_STATUS
                                 if dist is not None else None),
+            'host_cores_bound': numa,       # N > 1: cores local to the rank's GPU (NVML), or None
             'config5': config5,
             'heads': heads,
             'operators': operators,
@@ -969,7 +1004,12 @@ def main():
                     help='N > 1: skip the N-rank step vs whole-graph-on-one-GPU comparison')
     ap.add_argument('--no-config5', action='store_true',
                     help='N > 1: skip the strong-scaling measurement of the cut 16x graph')
+    ap.add_argument('--no-numa-pin', action='store_true',
+                    help='N > 1: do not bind the rank to the cores local to its GPU')
     ap.add_argument('--config5-copies', type=int, default=16)
+    ap.add_argument('--config5-scattered', default='tag,artist',
+                    help="node types cut into equal chunks in the config-5 partition ('' = replicate "
+                         "everything but artwork)")
     ap.add_argument('--no-operators', action='store_true',
                     help='skip the secondary GraphConv / GATConv training-step measurement')
     ap.add_argument('--park-ms', type=float, default=120.0,

@@ -391,7 +391,8 @@ agg_rows(const __grid_constant__ RowGroups P) {
 //     the LAST warp to deliver a fragment of that row (one counter per row, self-resetting) adds
 //     them up in chunk order: trail[c0] + lead[c0+1] + ... -- a fixed order whoever does it, so
 //     results are reproducible; no float atomics, no second kernel;
-//   * rows without edges are zero-filled by the chunk that holds the preceding edge (no memset).
+//   * rows without edges are zero-filled by the kernel too (no memset), dealt out evenly over the
+//     relation's warps.
 // ------------------------------------------------------------------------------------------------
 constexpr int kGatherDepth = 4;                    // feature-row loads in flight per lane
 
@@ -539,6 +540,25 @@ agg_chunks(const __grid_constant__ ChunkSegs P) {
         s_tail_row[w] = -1;
     }
 
+    // ---- rows without edges: zeros.  The relation's rows are dealt out evenly over ALL its warps
+    // (not to the chunk that holds the preceding edge: a source table that carries other ranks'
+    // boundary rows has runs of tens of thousands of empty rows, which one warp would clear alone)
+    {
+        const int64_t gw = (int64_t)cta * kAggWarps + w, GW = (int64_t)nctas * kAggWarps;
+        const int z0 = (int)((int64_t)n_rows * gw / GW), z1 = (int)((int64_t)n_rows * (gw + 1) / GW);
+        for (int r = z0; r < z1; r += 32) {
+            const int rr = r + lane;
+            bool empty = false;
+            if (rr < z1) empty = __ldg(R.rowptr + rr) == __ldg(R.rowptr + rr + 1);
+            unsigned m = __ballot_sync(0xffffffffu, empty);
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                zero_rows<T, VEC>(S, F, r + b, r + b + 1, lane);
+            }
+        }
+    }
+
     if (has_work) {
     // ---- stage neighbour ids / scales ----------------------------------------------------------
     // lane i of register k holds edge k*32 + i of the chunk (register path: read by shuffles);
@@ -598,7 +618,6 @@ agg_chunks(const __grid_constant__ ChunkSegs P) {
         __syncwarp();
         for (int g = 0; g < kRingGroups && g < ngroups; ++g) issue_group(g);
     }
-    if (start == 0) zero_rows<T, VEC>(S, F, 0, row, lane);
 
     int wrow = row;                                // row-extent window: lane i holds rowptr[wrow+1+i]
     int rp = wrow + 1 + lane <= n_rows ? __ldg(R.rowptr + wrow + 1 + lane) : INT_MAX;
@@ -730,7 +749,7 @@ agg_chunks(const __grid_constant__ ChunkSegs P) {
         }
         e = e1;
         if (rend > end) break;                     // the row continues in the next chunk
-        // ---- next row with edges; the empty rows in between are this chunk's to clear -------------
+        // ---- next row with edges (the empty rows in between were cleared above) ------------------
         int nr = row + 1;
         while (nr < n_rows) {
             if (nr - wrow >= 32) {
@@ -739,9 +758,7 @@ agg_chunks(const __grid_constant__ ChunkSegs P) {
             }
             const unsigned m = __ballot_sync(0xffffffffu, rp > rend) & (0xffffffffu << (nr - wrow));
             const int stop = m ? wrow + (__ffs(m) - 1) : wrow + 32;
-            const int upto = min(stop, n_rows);
-            zero_rows<T, VEC>(S, F, nr, upto, lane);
-            nr = upto;
+            nr = min(stop, n_rows);
             if (m) break;
         }
         if (e >= end || nr >= n_rows) break;

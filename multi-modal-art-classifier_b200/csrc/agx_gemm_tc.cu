@@ -768,8 +768,11 @@ bool gemm_tc_longk_eligible(const agx_gemm_problem_t& Q, const agx_gemm_seg_t* s
     if ((reinterpret_cast<uintptr_t>(S.A) % 16) != 0 || (reinterpret_cast<uintptr_t>(S.B) % 16) != 0)
         return false;
     // the caller sized the partial buffer for split_k slabs: enough for the splits used here?
+    // (the launch gives a CTA at least total_kb / 140 + 1 k-blocks -- one wave -- so a problem
+    // never takes more than ~140 slabs however long K is: 1.9 M rows on the 16x graph)
     const int total_kb = (S.K + 31) / 32;
-    const int items = (total_kb + kLkBlocksPerCta - 1) / kLkBlocksPerCta;
+    const int per = total_kb / 140 + 1 > kLkBlocksPerCta ? total_kb / 140 + 1 : kLkBlocksPerCta;
+    const int items = (total_kb + per - 1) / per;
     return items <= Q.split_k && (reinterpret_cast<uintptr_t>(Q.partial) % 16) == 0;
 }
 

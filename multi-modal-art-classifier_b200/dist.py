@@ -87,7 +87,7 @@ class GraphPartition:
     """
 
     def __init__(self, edge_index_dict, num_nodes: Dict[str, int], world: int, rank: int,
-                 bounds: Optional[Dict[str, List[int]]] = None, replicated=()):
+                 bounds: Optional[Dict[str, List[int]]] = None, replicated=(), scattered=()):
         self.world, self.rank = int(world), int(rank)
         self.num_nodes = OrderedDict((t, int(n)) for t, n in num_nodes.items())
         # ``replicated`` node types (the tiny ones -- style, genre, field, media,
@@ -101,8 +101,23 @@ class GraphPartition:
         for t in self.replicated:
             if t not in self.num_nodes:
                 raise ValueError(f'replicated type {t} is not a node type')
+        # ``scattered`` node types (the mid-sized ones: tag, artist) are cut into ``world`` equal
+        # chunks of ceil(N / world) rows like any partitioned type -- their dense work (products,
+        # BatchNorm, dropout) is done once, by the owner -- but a relation INTO them from a plain
+        # partitioned type (artwork -> tag) keeps its edges with their SOURCE: every rank produces
+        # partial neighbour sums for all N rows and one **reduce-scatter** hands each owner the full
+        # sums of its chunk (half the volume of the replicated types' all-reduce, no redundant
+        # dense work).  Their rows reach the ranks that need them as sources (tag -> artwork) through
+        # the boundary-row all-gather like those of every partitioned type.
+        self.scattered = set(scattered)
+        for t in self.scattered:
+            if t not in self.num_nodes or t in self.replicated:
+                raise ValueError(f'scattered type {t} must be a non-replicated node type')
+        self.chunk = {t: -(-self.num_nodes[t] // world) for t in self.scattered}
         self.bounds = {t: list(bounds[t]) if bounds and t in bounds else split_bounds(n, world)
                        for t, n in self.num_nodes.items()}
+        for t in self.scattered:
+            self.bounds[t] = [min(q * self.chunk[t], self.num_nodes[t]) for q in range(world + 1)]
         for t, b in self.bounds.items():
             if len(b) != world + 1 or b[0] != 0 or b[-1] != self.num_nodes[t] or \
                     any(b[i] > b[i + 1] for i in range(world)):
@@ -118,6 +133,8 @@ class GraphPartition:
         own_dst = {}
         rep = self.replicated
         self.partial: "OrderedDict[tuple, torch.Tensor]" = OrderedDict()
+        self.scatter: "OrderedDict[tuple, torch.Tensor]" = OrderedDict()
+        sc = self.scattered
         for (s, r, d), ei in edge_index_dict.items():
             if ei.numel() and (int(ei[0].max()) >= self.num_nodes[s] or int(ei[0].min()) < 0 or
                                int(ei[1].max()) >= self.num_nodes[d] or int(ei[1].min()) < 0):
@@ -130,6 +147,13 @@ class GraphPartition:
                     # max(in-degree over ALL ranks' edges, 1): the divisor of scatter-mean
                     self.partial[(s, r, d)] = torch.bincount(
                         ei[1], minlength=self.num_nodes[d]).clamp(min=1).to(torch.float32)
+                continue
+            if d in sc and s not in rep and s not in sc:
+                # edges follow their SOURCE; destination ids stay global, in a table of
+                # world * chunk rows (the reduce-scatter's equal pieces; the tail rows are empty)
+                own_dst[(s, r, d)] = owner(s, ei[0])
+                self.scatter[(s, r, d)] = torch.bincount(
+                    ei[1], minlength=world * self.chunk[d]).clamp(min=1).to(torch.float32)
                 continue
             od = owner(d, ei[1])
             own_dst[(s, r, d)] = od
@@ -179,7 +203,7 @@ class GraphPartition:
         self.edge_index = OrderedDict()
         for (s, r, d), ei in edge_index_dict.items():
             m = own_dst[(s, r, d)] == rank
-            dst0 = 0 if d in rep else self.bounds[d][rank]
+            dst0 = 0 if (d in rep or (s, r, d) in self.scatter) else self.bounds[d][rank]
             self.edge_index[(s, r, d)] = torch.stack(
                 [ext_of_global[s][ei[0][m]], ei[1][m] - dst0], dim=0).contiguous()
 
@@ -297,9 +321,24 @@ class DistContext:
     _counts: Optional[dict] = None
     replicated: frozenset = frozenset()         # node types every rank holds completely
     partial: Optional[dict] = None              # edge type -> global max(in-degree, 1) [N_dst]
+    scatter: Optional[dict] = None              # edge type -> the same over world * chunk rows
+    n_owned: Optional[dict] = None              # node type -> rows this rank owns
 
     def __deepcopy__(self, memo):           # process groups are not copyable; share the context
         return self
+
+    def plan_rows(self, num_nodes: Dict[str, int]):
+        """(rows of every type's table as a SOURCE, rows as a DESTINATION or None) for graph.get_plan
+        given the rows this rank holds: source tables carry the boundary rows behind the owned
+        ones; a scatter relation produces sums for the destination rows of ALL ranks."""
+        num_dst = None
+        if self.halo is not None:
+            num_dst, num_nodes = num_nodes, {t: self.halo.n_ext.get(t, n)
+                                             for t, n in num_nodes.items()}
+        if self.scatter:
+            num_dst = dict(num_dst if num_dst is not None else num_nodes)
+            num_dst.update({et: int(c.shape[0]) for et, c in self.scatter.items()})
+        return num_nodes, num_dst
 
     def counts(self, types, device) -> torch.Tensor:
         """float64 [len(types)] global row counts (BatchNorm over the rows of all ranks)."""
@@ -326,7 +365,9 @@ def partition_context(part: GraphPartition, group, device) -> DistContext:
     halo = HaloExchange(part, group, device) if part.has_halo else None
     return DistContext(group, part.rank, part.world, dict(part.num_nodes), halo,
                        replicated=frozenset(part.replicated),
-                       partial={k: v.to(device) for k, v in part.partial.items()})
+                       partial={k: v.to(device) for k, v in part.partial.items()},
+                       scatter={k: v.to(device) for k, v in part.scatter.items()},
+                       n_owned=dict(part.n_owned))
 
 
 class PeerAllReduce:
@@ -408,6 +449,20 @@ def small_all_reduce_(t: torch.Tensor, group) -> torch.Tensor:
     import torch.distributed as dist
     dist.all_reduce(t, group=group)
     return t
+
+
+def reduce_scatter_rows(own: torch.Tensor, full: torch.Tensor, group):
+    """own [chunk, F] <- this rank's piece of the sum over the ranks of full [world * chunk, F];
+    returns the async work handle (NCCL ``ncclReduceScatter`` on the communicator's stream).  The
+    ``gloo`` backend of the CPU test-suite has no reduce-scatter: all-reduce + slice there."""
+    import torch.distributed as dist
+    if dist.get_backend(group) == 'gloo':
+        tmp = full.clone()
+        dist.all_reduce(tmp, group=group)
+        r = dist.get_rank(group)
+        own.copy_(tmp[r * own.shape[0]:(r + 1) * own.shape[0]])
+        return None
+    return dist.reduce_scatter_tensor(own, full, group=group, async_op=True)
 
 
 def all_reduce_(t: torch.Tensor, group) -> torch.Tensor:

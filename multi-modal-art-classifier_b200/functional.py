@@ -38,6 +38,15 @@ class RelSpec:
     partial: bool = False         # multi-GPU: this rank holds SOME of each destination's edges
                                   # (partitioned source -> replicated destination type); the
                                   # neighbour sums of all ranks are all-reduced inside the layer
+    own_rows: int = -1            # multi-GPU scatter relation (dist.GraphPartition(scattered=)): the
+                                  # rank's edges give partial sums for the rel.n_dst = world * chunk
+                                  # destination rows of ALL ranks; a reduce-scatter leaves the full
+                                  # sums of the own_rows rows this rank owns (backward: all-gather)
+
+    @property
+    def rows(self) -> int:
+        """Destination rows this rank computes the layer's output for."""
+        return self.own_rows if self.own_rows >= 0 else self.rel.n_dst
 
 
 @dataclass
@@ -73,7 +82,7 @@ class ConvSpec:
             tf += r.n_edges * O * 4.0 / _BYTE_RATE
             af = r.n_edges * fs * 4.0 / _BYTE_RATE + gemm_cost(r.n_dst)
             rs.transform_first = tf < af or (tf <= af * 1.05 and r.n_src <= r.n_dst)
-            if rs.partial:
+            if rs.partial or rs.own_rows >= 0:
                 # aggregate first: the [N_dst, F_src] partial sums are what is all-reduced, before
                 # any term that every rank computes in full (root weight, bias) is added
                 rs.transform_first = False
@@ -170,12 +179,12 @@ class _HeteroConvFn(torch.autograd.Function):
         tf_long: Dict[str, list] = {}
         # all destination types' outputs are row blocks of ONE buffer (consumers that run the same
         # row-wise op on every type -- log_softmax -- then need a single launch)
-        out_rows = [lst[0].rel.n_dst for lst in by_dst.values()]
+        out_rows = [lst[0].rows for lst in by_dst.values()]
         out_all = torch.empty(sum(out_rows), O, dtype=torch.float32, device=dev)
         row0 = 0
         for t, lst in by_dst.items():
-            outs[t] = out_all[row0:row0 + lst[0].rel.n_dst]
-            row0 += lst[0].rel.n_dst
+            outs[t] = out_all[row0:row0 + lst[0].rows]
+            row0 += lst[0].rows
             # root product against one-hot features: x[t] W^T = W^T, written first, rest accumulates
             id_root[t] = bool(spec.identity.get(t, False)) and wroot[t] is not None and \
                 xd[t] is xs[t]
@@ -212,6 +221,7 @@ class _HeteroConvFn(torch.autograd.Function):
         # they are done and overlaps everything of the layer that does not read the full sums
         part_rows: Dict[int, list] = {}
         part_chunks: Dict[int, list] = {}
+        scat_full: Dict[int, torch.Tensor] = {}
         for k, rs in enumerate(spec.rels):
             if rs.transform_first:
                 continue
@@ -219,24 +229,36 @@ class _HeteroConvFn(torch.autograd.Function):
             fs = xs[r.src].shape[1]
             g = G[k] if rs.partial else torch.empty(r.n_dst, fs, dtype=torch.float32, device=dev)
             G[k] = g
+            early = rs.partial or rs.own_rows >= 0
+            if rs.own_rows >= 0:
+                scat_full[k] = g
             arg = ops.RelArg(r.csr, xs[r.src], mean_rows=rs.mean)
             if r.csr.long_rows:
-                (part_chunks if rs.partial else chunks_by_F).setdefault(fs, []).append((g, arg))
-            elif rs.partial:
+                (part_chunks if early else chunks_by_F).setdefault(fs, []).append((g, arg))
+            elif early:
                 part_rows.setdefault(fs, []).append((g, [arg], False))
             else:
                 rows_by_F.setdefault((0, fs), []).append((g, [arg], False))
-        work = None
-        if part_flat is not None:
+        works = []
+        if part_flat is not None or scat_full:
             for F, grp in part_rows.items():
                 ops.aggregate_rows(grp, F)
             for F, segs in part_chunks.items():
                 ops.aggregate_chunks(segs, F)
+            import torch.distributed as dist
+            # scatter relations: every owner receives the full sums of its chunk of rows
+            for k, full in scat_full.items():
+                world = dist.get_world_size(spec.group)
+                own = torch.empty(full.shape[0] // world, full.shape[1], dtype=torch.float32,
+                                  device=dev)
+                from .dist import reduce_scatter_rows
+                works.append(reduce_scatter_rows(own, full, spec.group))
+                G[k] = own[:spec.rels[k].own_rows]
             # partial neighbour sums of all ranks -> the full sums, on every rank (one all-reduce
             # per layer, on the communicator's stream; the mean relations were divided by the
             # GLOBAL in-degree above)
-            import torch.distributed as dist
-            work = dist.all_reduce(part_flat, group=spec.group, async_op=True)
+            if part_flat is not None:
+                works.append(dist.all_reduce(part_flat, group=spec.group, async_op=True))
         if tr:
             ops.transpose_many(tr)
         if gb.problems:
@@ -259,10 +281,14 @@ class _HeteroConvFn(torch.autograd.Function):
 
         # s3: one multi-segment GEMM per destination type; the types that read all-reduced sums
         # wait for the collective, the others (artwork: most of the rows) are launched before
-        part_types = {spec.rels[k].rel.dst for k in part_k}
+        part_types = {spec.rels[k].rel.dst for k in part_k} | \
+            {spec.rels[k].rel.dst for k in scat_full}
         for dependent in (False, True):
-            if dependent and work is not None:
-                work.wait()
+            if dependent:
+                for w in works:
+                    if w is not None:
+                        w.wait()
+                scat_full.clear()
             gb = ops.GemmBatch()
             for t, lst in by_dst.items():
                 if (t in part_types) != dependent:
@@ -321,21 +347,39 @@ class _HeteroConvFn(torch.autograd.Function):
         # the rest of the layer's backward (it is only read by b5)
         dG: Dict[int, torch.Tensor] = {}
         part_k = [k for k, rs in live if rs.partial and need_x[rs.rel.src]]
+        scat_k = [k for k, rs in live if rs.own_rows >= 0 and need_x[rs.rel.src]]
         dpart_flat = None
-        work = None
-        if part_k:
-            sizes = [spec.rels[k].rel.n_dst * xs[spec.rels[k].rel.src].shape[1] for k in part_k]
-            dpart_flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
-            off = 0
+        works = []
+        if part_k or scat_k:
+            import torch.distributed as dist
             gb0 = ops.GemmBatch()
+            # scatter relations: the owner computes d(full sum) of its rows; every rank needs all
+            # rows for the transpose over its own edges -> all-gather
+            d_own = {}
+            for k in scat_k:
+                rs = spec.rels[k]
+                world = dist.get_world_size(spec.group)
+                chunk, fs = rs.rel.n_dst // world, xs[rs.rel.src].shape[1]
+                d_own[k] = torch.empty(chunk, fs, dtype=torch.float32, device=dev) \
+                    if chunk == rs.own_rows else ops.zeros((chunk, fs), dev)
+                gb0.add(d_own[k][:rs.own_rows], [(dout[rs.rel.dst], params[rs.i_wl])])
+            sizes = [spec.rels[k].rel.n_dst * xs[spec.rels[k].rel.src].shape[1] for k in part_k]
+            if part_k:
+                dpart_flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+            off = 0
             for k, sz in zip(part_k, sizes):
                 rs = spec.rels[k]
                 dG[k] = dpart_flat[off:off + sz].view(rs.rel.n_dst, -1)
                 off += sz
                 gb0.add(dG[k], [(dout[rs.rel.dst], params[rs.i_wl])])
             gb0.run()
-            import torch.distributed as dist
-            work = dist.all_reduce(dpart_flat, group=spec.group, async_op=True)
+            for k in scat_k:
+                rs = spec.rels[k]
+                dG[k] = torch.empty(rs.rel.n_dst, d_own[k].shape[1], dtype=torch.float32, device=dev)
+                works.append(dist.all_gather_into_tensor(dG[k], d_own[k], group=spec.group,
+                                                         async_op=True))
+            if part_k:
+                works.append(dist.all_reduce(dpart_flat, group=spec.group, async_op=True))
 
         # b1: bias gradients = column sums of dout, shared by the relations of a type
         cs_items = []
@@ -391,7 +435,7 @@ class _HeteroConvFn(torch.autograd.Function):
             elif rs.transform_first:
                 gb.add(dw, [(_t(dY[k]), x)], split_k=ops.split_k_for(r.n_src))
             else:
-                gb.add(dw, [(_t(dout[r.dst]), G[k])], split_k=ops.split_k_for(r.n_dst))
+                gb.add(dw, [(_t(dout[r.dst]), G[k])], split_k=ops.split_k_for(rs.rows))
                 if need_x[r.src] and k not in dG:
                     dg = torch.empty(r.n_dst, x.shape[1], dtype=torch.float32, device=dev)
                     dG[k] = dg
@@ -400,8 +444,8 @@ class _HeteroConvFn(torch.autograd.Function):
             ops.transpose_many(trb)
         if gb.problems:
             gb.run()
-        if work is not None:
-            work.wait()
+        for w in works:
+            w.wait()
         for k, rs in live:
             if rs.i_wr >= 0:
                 grads[pidx(rs.i_wr)] = dwroot[rs.rel.dst]
@@ -485,9 +529,9 @@ def _dst_views(spec: ConvSpec, xs: Dict[str, torch.Tensor]) -> Dict[str, torch.T
         if t in out or t not in xs:
             continue
         x = xs[t]
-        if x.shape[0] < rs.rel.n_dst:
-            raise ValueError(f"x['{t}'] has {x.shape[0]} rows, the graph has {rs.rel.n_dst}")
-        out[t] = x if x.shape[0] == rs.rel.n_dst else x[:rs.rel.n_dst]
+        if x.shape[0] < rs.rows:
+            raise ValueError(f"x['{t}'] has {x.shape[0]} rows, the graph has {rs.rows}")
+        out[t] = x if x.shape[0] == rs.rows else x[:rs.rows]
     return out
 
 

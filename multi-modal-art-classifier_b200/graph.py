@@ -50,10 +50,10 @@ class HeteroPlan:
             L.require_cuda(ei, 'edge_index')
             if ei.dim() != 2 or ei.shape[0] != 2 or ei.dtype != torch.int64:
                 raise ValueError(f'edge_index of {(s, r, d)} must be int64 [2, E]')
-            lists.append((ei[1], ei[0], num_dst[d], num_nodes[s]))       # CSR: key = dst
+            lists.append((ei[1], ei[0], num_dst.get((s, r, d), num_dst[d]), num_nodes[s]))  # CSR: key = dst
         for (s, r, d) in keys:
             ei = edge_index_dict[(s, r, d)]
-            lists.append((ei[0], ei[1], num_nodes[s], num_dst[d]))       # CSC: key = src
+            lists.append((ei[0], ei[1], num_nodes[s], num_dst.get((s, r, d), num_dst[d])))  # CSC: key = src
         return keys, lists
 
     def rebuild_(self, edge_index_dict):
@@ -75,7 +75,9 @@ class HeteroPlan:
                  num_dst: Optional[Dict[str, int]] = None):
         # num_nodes: rows of every type's feature table as a SOURCE; num_dst: rows it has as a
         # DESTINATION (fewer on a rank of a partitioned graph, whose source tables carry the
-        # boundary rows of the other ranks behind the owned rows -- dist.GraphPartition)
+        # boundary rows of the other ranks behind the owned rows -- dist.GraphPartition); an EDGE
+        # TYPE key in num_dst overrides the destination rows of that one relation (a scatter
+        # relation's partial sums cover the rows of all ranks)
         self.num_nodes = dict(num_nodes)
         self.num_dst = dict(num_dst) if num_dst is not None else self.num_nodes
         keys, lists = self._edge_lists(edge_index_dict)
@@ -91,7 +93,8 @@ class HeteroPlan:
         R = len(keys)
         self.rels: "OrderedDict[EdgeType, Relation]" = OrderedDict()
         for i, (s, r, d) in enumerate(keys):
-            self.rels[(s, r, d)] = Relation(s, r, d, self.num_nodes[s], self.num_dst[d],
+            self.rels[(s, r, d)] = Relation(s, r, d, self.num_nodes[s],
+                                            self.num_dst.get((s, r, d), self.num_dst[d]),
                                             built[i].n_edges, built[i], built[R + i])
         self.n_edges = sum(r.n_edges for r in self.rels.values())
 
@@ -111,7 +114,7 @@ def get_plan(edge_index_dict, num_nodes: Dict[str, int], cache: bool = True,
         return HeteroPlan(edge_index_dict, num_nodes, num_dst)
     sig = tuple((k, v.data_ptr(), tuple(v.shape)) for k, v in edge_index_dict.items())
     sig = (sig, tuple(sorted(num_nodes.items())),
-           None if num_dst is None else tuple(sorted(num_dst.items())))
+           None if num_dst is None else tuple(sorted(num_dst.items(), key=str)))
     versions = tuple(v._version for v in edge_index_dict.values())
     plan = _PLAN_CACHE.get(sig)
     if plan is None:

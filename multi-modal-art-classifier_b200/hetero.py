@@ -308,7 +308,8 @@ class HeteroModule(nn.Module):
         fused call (functional._HeteroGATFn); relation outputs of a destination type are added in
         metadata order (PyG's pairwise torch.add queue differs only in summation order)."""
         convs = self.get_submodule(node.target)
-        if self._dist is not None and (self._dist.halo is not None or self._dist.partial):
+        if self._dist is not None and (self._dist.halo is not None or self._dist.partial or
+                                       self._dist.scatter):
             # (a graph block per rank needs no exchange inside the layer; a destination partition
             # that cuts edges would need GATConv's self loops in global node ids, and a softmax
             # over a row whose edges are spread over the ranks)
@@ -373,15 +374,17 @@ class HeteroModule(nn.Module):
         spec = self._conv_specs.get(key)
         if spec is None:
             partial = (self._dist.partial or {}) if self._dist is not None else {}
-            for et, cnt in partial.items():
+            scatter = (self._dist.scatter or {}) if self._dist is not None else {}
+            for et, cnt in list(partial.items()) + list(scatter.items()):
                 # a partial relation's local rows hold SOME of a destination's edges: the divisor of
                 # scatter-mean (and of its transpose) is the in-degree over the edges of all ranks
                 plan[et].csr.cnt = cnt
             spec = ConvSpec(node_types=types,
-                            rels=[RelSpec(plan[et], mean, a, b, c, partial=et in partial)
+                            rels=[RelSpec(plan[et], mean, a, b, c, partial=et in partial,
+                                          own_rows=self._dist.n_owned[et[2]] if et in scatter else -1)
                                   for et, mean, a, b, c in rel_specs],
                             out_channels=params[0].shape[0],
-                            group=self._dist.group if partial else None)
+                            group=self._dist.group if (partial or scatter) else None)
             if len(self._conv_specs) > 64:
                 self._conv_specs.clear()
             self._conv_specs[key] = spec
@@ -471,9 +474,8 @@ class HeteroModule(nn.Module):
         num_nodes = {t: v.shape[0] for t, v in x_dict.items()}
         ei_dict = OrderedDict((tuple(k), v) for k, v in ei_dict.items())
         num_dst = None
-        if self._dist is not None and self._dist.halo is not None:
-            num_dst, num_nodes = num_nodes, {t: self._dist.halo.n_ext.get(t, n)
-                                             for t, n in num_nodes.items()}
+        if self._dist is not None:
+            num_nodes, num_dst = self._dist.plan_rows(num_nodes)
         plan_box: list = []
 
         def plan():

@@ -243,9 +243,8 @@ class GNNTrainer:
         from .hetero import _is_identity_input
         num_nodes = {t: v.shape[0] for t, v in self.x.items()}
         num_dst = None
-        if self.ctx is not None and self.ctx.halo is not None:
-            num_dst, num_nodes = num_nodes, {t: self.ctx.halo.n_ext.get(t, n)
-                                             for t, n in num_nodes.items()}
+        if self.ctx is not None:
+            num_nodes, num_dst = self.ctx.plan_rows(num_nodes)
         if any(type(m).__name__ == 'GATConv' for m in self.model.modules()):
             # GATConv sorts self-loop augmented edge lists whose LENGTH depends on the data
             # (functional.GATPlan): no in-place re-sort under a captured step; steps that follow an
@@ -335,7 +334,7 @@ class GNNTrainer:
         train_gnn_embeddings.py:57-58) needs its own partition.  On the block partition every rank
         evaluates its own block of the other graph, which is what this accepts."""
         if (x_dict is not None or edge_index_dict is not None) and self.ctx is not None and \
-                (self.ctx.halo is not None or self.ctx.partial):
+                (self.ctx.halo is not None or self.ctx.partial or self.ctx.scatter):
             raise NotImplementedError(
                 'evaluate() / embeddings() on a graph other than the training partition: build a '
                 'GraphPartition + partition_context for that graph and a GNNTrainer on it (the '

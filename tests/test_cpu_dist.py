@@ -227,9 +227,16 @@ def _product_worker(rank, world, port, opname, replicate, errq):
         l_o = go.nll_loss_artwork(o_o[0], y)
         l_o.backward()
 
-        rep = [t for t in n if t != 'artwork'] if replicate else []
-        part = GraphPartition(ei, n, world, rank, replicated=rep)
-        assert part.has_halo != replicate and (len(part.partial) > 0) == replicate
+        scat = ['tag', 'artist'] if replicate == 'scatter' else []
+        rep = [t for t in n if t != 'artwork' and t not in scat] if replicate else []
+        part = GraphPartition(ei, n, world, rank, replicated=rep, scattered=scat)
+        if replicate == 'scatter':
+            # tag / artist rows are owned in equal chunks; artwork -> tag / artist edges stay with
+            # their source rank (reduce-scatter), tag -> artwork reads gathered boundary rows
+            assert part.has_halo and part.partial and len(part.scatter) == 2
+            assert part.max_boundary['artwork'] == 0
+        else:
+            assert part.has_halo != replicate and (len(part.partial) > 0) == replicate
         ctx = partition_context(part, dist.group.WORLD, 'cpu')
         prod.gnn.dropout_masks = {t: part.owned(t, m).contiguous() for t, m in masks.items()}
         for m in prod.modules():
@@ -341,6 +348,14 @@ def test_product_cut_partition_world2_gloo(opname, replicate):
     equal the single-process oracle on the whole graph.  ``replicate``: every node type but
     ``artwork`` lives on both ranks (no boundary rows; partial neighbour sums all-reduced)."""
     _run_product(2, opname, replicate)
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_product_scattered_partition_gloo(world):
+    """tag and artist cut into equal chunks (their dense work done once, by the owner): relations
+    from artwork into them keep their edges with the source rank and reduce-scatter the partial
+    sums; with three ranks the last chunk is shorter than the others (padding rows)."""
+    _run_product(world, 'SAGEConv', 'scatter')
 
 
 def test_product_replicated_partition_world4_gloo():

@@ -78,10 +78,16 @@ def _gnn_case(rank, world, dev, kind, opname):
     # --- this rank of the partitioned job ----------------------------------------------------------
     # 'replicated': every node type but artwork lives on both ranks -- no boundary
     # rows; the partial neighbour sums of the artwork -> X relations are all-reduced in the layer
-    part = GraphPartition(eg, n, world, rank,
-                          replicated=[t for t in n if t != 'artwork'] if kind == 'replicated' else ())
-    assert part.has_halo == (kind == 'cut')
-    assert (len(part.partial) > 0) == (kind == 'replicated')
+    # 'scattered': as 'replicated', but tag and artist are cut into equal chunks -- artwork -> tag /
+    # artist partial sums are reduce-scattered to the owners, tag / artist rows all-gathered for the
+    # reverse relations
+    scat = ['tag', 'artist'] if kind == 'scattered' else []
+    part = GraphPartition(eg, n, world, rank, scattered=scat,
+                          replicated=[t for t in n if t != 'artwork' and t not in scat]
+                          if kind in ('replicated', 'scattered') else ())
+    assert part.has_halo == (kind in ('cut', 'scattered'))
+    assert (len(part.partial) > 0) == (kind in ('replicated', 'scattered'))
+    assert len(part.scatter) == (2 if kind == 'scattered' else 0)
     ctx = partition_context(part, dist.group.WORLD, dev)
     mod = make()
     mod.gnn.set_distributed(ctx)
@@ -246,6 +252,14 @@ def test_two_ranks_replicated_types_match_single_gpu():
     """Partition with replicated small node types (CPU-verified on gloo in
     tests/test_cpu_dist.py; this is its NCCL / CUDA-graph run)."""
     _run_two_ranks((('replicated', 'SAGEConv'), ('replicated', 'GraphConv')))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_two_ranks_scattered_types_match_single_gpu():
+    """Partition with tag / artist cut into chunks (reduce-scatter of the partial sums into them,
+    all-gather of their rows out of them) and the tiny types replicated: the config-5 partition
+    of bench.py."""
+    _run_two_ranks((('scattered', 'SAGEConv'), ('scattered', 'GraphConv')))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')

@@ -270,7 +270,8 @@ def test_gemm_nt_nn_tn(M, K, N):
 
 
 @pytest.mark.parametrize('M,N,K', [(128, 128, 20000), (32, 128, 116475), (128, 32, 5000),
-                                   (100, 72, 3001), (128, 128, 2048), (8, 8, 4100)])
+                                   (100, 72, 3001), (128, 128, 2048), (8, 8, 4100),
+                                   (64, 128, 1000003)])      # the 16x graph: > 140 * 768 rows
 def test_gemm_tensor_core_long_k_weight_gradient(M, N, K):
     """dW = dOut^T X over a very long row dimension takes the split-K tcgen05 path (MN-major
     operands, accumulators drained every 256 rows): float32 accuracy (rel 1e-5 against float64),
