@@ -1,5 +1,6 @@
 // Library-level entry points: version, thread-local error string, kernel inventory.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -20,6 +21,53 @@ void set_error(const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
     return AGX_ERR_CUDA;
+}
+
+// ---- side streams (agx_common.cuh) ------------------------------------------------------------------
+namespace {
+constexpr int kMaxDev = 16, kSidePerDev = 2;
+struct SideRes {
+    cudaStream_t s[kSidePerDev];
+    cudaEvent_t ev_fork[kSidePerDev], ev_join[kSidePerDev];
+    bool ready;
+};
+SideRes g_side[kMaxDev];
+}  // namespace
+
+int SideStream::fork(cudaStream_t main_stream, int which) {
+    static const bool off = getenv("AGX_NO_SIDE_STREAMS") != nullptr;
+    main = side = main_stream;
+    forked = false;
+    int dev = 0;
+    if (off || which < 0 || which >= kSidePerDev) return AGX_OK;
+    AGX_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDev) return AGX_OK;
+    SideRes& R = g_side[dev];
+    if (!R.ready) {
+        for (int i = 0; i < kSidePerDev; ++i) {
+            AGX_CUDA(cudaStreamCreateWithFlags(&R.s[i], cudaStreamNonBlocking));
+            AGX_CUDA(cudaEventCreateWithFlags(&R.ev_fork[i], cudaEventDisableTiming));
+            AGX_CUDA(cudaEventCreateWithFlags(&R.ev_join[i], cudaEventDisableTiming));
+        }
+        R.ready = true;
+    }
+    AGX_CUDA(cudaEventRecord(R.ev_fork[which], main_stream));
+    AGX_CUDA(cudaStreamWaitEvent(R.s[which], R.ev_fork[which], 0));
+    side = R.s[which];
+    forked = true;
+    which_ = which;
+    return AGX_OK;
+}
+
+int SideStream::join() {
+    if (!forked) return AGX_OK;
+    int dev = 0;
+    AGX_CUDA(cudaGetDevice(&dev));
+    SideRes& R = g_side[dev];
+    AGX_CUDA(cudaEventRecord(R.ev_join[which_], side));
+    AGX_CUDA(cudaStreamWaitEvent(main, R.ev_join[which_], 0));
+    forked = false;
+    return AGX_OK;
 }
 
 static std::atomic<uint64_t> g_launches{0};

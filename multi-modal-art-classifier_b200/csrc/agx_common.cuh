@@ -18,6 +18,19 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 
+// Side streams for INDEPENDENT launches of one entry point (the latency-bound few-CTA GEMM classes
+// next to the tensor-core launch).  fork(): the side stream waits for everything queued on `main`
+// so far; join(): `main` waits for the side stream.  Works under stream capture (the branch becomes
+// a parallel path of the captured graph).  One pair per device, created on first use; env
+// AGX_NO_SIDE_STREAMS=1 makes fork() hand back `main` itself (serial launches, A/B switch).
+struct SideStream {
+    cudaStream_t main, side;
+    bool forked;
+    int which_;
+    int fork(cudaStream_t main_stream, int which = 0);
+    int join();
+};
+
 }  // namespace agx
 
 #define AGX_CHECK_ARG(cond, ...)                       \

@@ -395,6 +395,26 @@ extern "C" int agx_gemm_grouped(const agx_gemm_problem_t* h_problems, int n_prob
             short_tiles += ceil_div(Q.M, 32) * ceil_div(Q.N, 128) * (Q.split_k > 1 ? Q.split_k : 1);
         } else wide[nw++] = i;
     }
+    // The problems of a call are independent (distinct outputs).  The few-row and narrow classes run
+    // on a handful of CTAs each, bound by the serial k-loop of one CTA (~20-30 us per launch on the
+    // full graph, nine such launches per step): they go to a side stream NEXT TO the tensor-core
+    // launches instead of behind them; the split-K reduction joins both.
+    SideStream fk;
+    const bool big = ntc > 0 || nlk > 0 || nw > 0, small = ns > 0 || nn > 0;
+    int rc = fk.fork(st, 0);
+    if (rc) return rc;
+    if (!(big && small)) {               // nothing to overlap: stay on the caller's stream
+        rc = fk.join();
+        if (rc) return rc;
+        fk.side = st;
+    }
+    if (short_tiles < 2 * kNumSMs)
+        rc = launch_class<32, 32, 2, 2>(h_problems, shortm, ns, h_segs, n_segs, fk.side);
+    else
+        rc = launch_class<32, 128, 2, 8>(h_problems, shortm, ns, h_segs, n_segs, fk.side);
+    if (rc) return rc;
+    rc = launch_class<128, 32, 4, 4>(h_problems, narrow, nn, h_segs, n_segs, fk.side);
+    if (rc) return rc;
     if (ntc > 0) {
         const int rc_tc = gemm_tc_launch(h_problems, tc, ntc, h_segs, st);
         if (rc_tc) return rc_tc;
@@ -403,14 +423,9 @@ extern "C" int agx_gemm_grouped(const agx_gemm_problem_t* h_problems, int n_prob
         const int rc_lk = gemm_tc_longk_launch(h_problems, lk, nlk, h_segs, lk_used, st);
         if (rc_lk) return rc_lk;
     }
-    int rc = launch_class<128, 128, 8, 8>(h_problems, wide, nw, h_segs, n_segs, st);
+    rc = launch_class<128, 128, 8, 8>(h_problems, wide, nw, h_segs, n_segs, st);
     if (rc) return rc;
-    if (short_tiles < 2 * kNumSMs)
-        rc = launch_class<32, 32, 2, 2>(h_problems, shortm, ns, h_segs, n_segs, st);
-    else
-        rc = launch_class<32, 128, 2, 8>(h_problems, shortm, ns, h_segs, n_segs, st);
-    if (rc) return rc;
-    rc = launch_class<128, 32, 4, 4>(h_problems, narrow, nn, h_segs, n_segs, st);
+    rc = fk.join();
     if (rc) return rc;
     if (any_split) {
         ReduceParams R;

@@ -595,17 +595,36 @@ log_softmax_nll(const float* __restrict__ logits, int64_t ld, int n_rows, int C,
     }
 }
 
-// ordered float64 reduction of interleaved pairs: out[0] = sum in[2i], out[1] = sum in[2i+1]
-__global__ void __launch_bounds__(1024)
+// ordered float64 reduction of interleaved pairs: out[0] = sum in[2i], out[1] = sum in[2i+1].
+// One thread-block CLUSTER of 8 CTAs (8 SMs pull the row workspace instead of one): CTA r reduces
+// the r-th eighth of the pairs (thread t: elements t, t + 1024, ... of its range, four loads in
+// flight; then a shared-memory tree), CTA 0 adds the eight CTA totals in rank order out of their
+// shared memory (DSMEM).  The order is fixed by (n, 8, 1024) alone: reproducible.
+constexpr int kPairCtas = 8;
+__global__ void __cluster_dims__(kPairCtas, 1, 1) __launch_bounds__(1024)
 reduce_pairs(const float* __restrict__ in, int64_t n, float* __restrict__ out, int accumulate) {
     __shared__ double s0[1024], s1[1024];
-    double a0 = 0.0, a1 = 0.0;
-    for (int64_t i = threadIdx.x; i < n; i += 1024) {
-        a0 += (double)in[2 * i];
-        a1 += (double)in[2 * i + 1];
+    __shared__ double tot[2];
+    const unsigned rank = blockIdx.x;                      // grid = one cluster
+    const int64_t per = (n + kPairCtas - 1) / kPairCtas;
+    const int64_t lo = per * rank, hi = lo + per < n ? lo + per : n;
+    const float2* in2 = reinterpret_cast<const float2*>(in);
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0, c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+    int64_t i = lo + threadIdx.x;
+    for (; i + 3 * 1024 < hi; i += 4 * 1024) {
+        const float2 v0 = in2[i], v1 = in2[i + 1024], v2 = in2[i + 2048], v3 = in2[i + 3072];
+        a0 += (double)v0.x; a1 += (double)v0.y;
+        b0 += (double)v1.x; b1 += (double)v1.y;
+        c0 += (double)v2.x; c1 += (double)v2.y;
+        d0 += (double)v3.x; d1 += (double)v3.y;
     }
-    s0[threadIdx.x] = a0;
-    s1[threadIdx.x] = a1;
+    for (; i < hi; i += 1024) {
+        const float2 v = in2[i];
+        a0 += (double)v.x;
+        a1 += (double)v.y;
+    }
+    s0[threadIdx.x] = (a0 + b0) + (c0 + d0);
+    s1[threadIdx.x] = (a1 + b1) + (c1 + d1);
     __syncthreads();
     for (int o = 512; o > 0; o >>= 1) {
         if (threadIdx.x < o) {
@@ -615,9 +634,30 @@ reduce_pairs(const float* __restrict__ in, int64_t n, float* __restrict__ out, i
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        out[0] = (accumulate ? out[0] : 0.f) + (float)s0[0];
-        out[1] = (accumulate ? out[1] : 0.f) + (float)s1[0];
+        tot[0] = s0[0];
+        tot[1] = s1[0];
     }
+    // cluster barrier (release / acquire): every CTA's total is visible through DSMEM
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    if (rank == 0 && threadIdx.x == 0) {
+        double t0 = 0.0, t1 = 0.0;
+        const uint32_t local = (uint32_t)__cvta_generic_to_shared(tot);
+        for (unsigned r = 0; r < kPairCtas; ++r) {
+            uint32_t remote;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+            double v0, v1;
+            asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v0) : "r"(remote));
+            asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v1) : "r"(remote + 8));
+            t0 += v0;
+            t1 += v1;
+        }
+        out[0] = (accumulate ? out[0] : 0.f) + (float)t0;
+        out[1] = (accumulate ? out[1] : 0.f) + (float)t1;
+    }
+    // nobody leaves while CTA 0 may still read its shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
 
 __global__ void __launch_bounds__(256)
@@ -1098,6 +1138,8 @@ extern "C" int agx_log_softmax_nll(const float* logits, int64_t ld, int32_t n_ro
     AGX_CHECK_ARG(logits && n_rows >= 0 && C >= 1, "agx_log_softmax_nll: bad arguments");
     AGX_CHECK_ARG(!labels || (loss_sum && row_ws),
                   "agx_log_softmax_nll: labels need loss_sum and row_ws");
+    AGX_CHECK_ARG((reinterpret_cast<uintptr_t>(row_ws) % 8) == 0,
+                  "agx_log_softmax_nll: row_ws must be 8-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     if (n_rows > 0) {
         log_softmax_nll<<<(unsigned)ceil_div(n_rows, 8), 256, 0, st>>>(logits, ld, n_rows, C, labels,
@@ -1105,7 +1147,7 @@ extern "C" int agx_log_softmax_nll(const float* logits, int64_t ld, int32_t n_ro
         AGX_LAUNCH_CHECK("log_softmax_nll");
     }
     if (labels) {
-        reduce_pairs<<<1, 1024, 0, st>>>(row_ws, n_rows, loss_sum, 0);
+        reduce_pairs<<<kPairCtas, 1024, 0, st>>>(row_ws, n_rows, loss_sum, 0);
         AGX_LAUNCH_CHECK("reduce_pairs");
     }
     return AGX_OK;
@@ -1114,15 +1156,16 @@ extern "C" int agx_log_softmax_nll(const float* logits, int64_t ld, int32_t n_ro
 extern "C" int agx_nll_forward(const float* logp, int64_t ld, int32_t n_rows, int32_t C,
                                const int64_t* labels, const float* class_w, float* loss_sum,
                                float* row_ws, void* stream) {
-    AGX_CHECK_ARG(logp && labels && loss_sum && row_ws && n_rows >= 0 && C >= 1,
-                  "agx_nll_forward: bad arguments");
+    AGX_CHECK_ARG(logp && labels && loss_sum && row_ws && n_rows >= 0 && C >= 1 &&
+                      (reinterpret_cast<uintptr_t>(row_ws) % 8) == 0,
+                  "agx_nll_forward: bad arguments (row_ws: 8-byte aligned)");
     cudaStream_t st = (cudaStream_t)stream;
     if (n_rows > 0) {
         nll_forward<<<grid_for(n_rows, 256), 256, 0, st>>>(logp, ld, n_rows, C, labels, class_w,
                                                            row_ws);
         AGX_LAUNCH_CHECK("nll_forward");
     }
-    reduce_pairs<<<1, 1024, 0, st>>>(row_ws, n_rows, loss_sum, 0);
+    reduce_pairs<<<kPairCtas, 1024, 0, st>>>(row_ws, n_rows, loss_sum, 0);
     AGX_LAUNCH_CHECK("reduce_pairs");
     return AGX_OK;
 }

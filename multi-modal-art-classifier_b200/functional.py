@@ -263,10 +263,13 @@ class _HeteroConvFn(torch.autograd.Function):
             ops.transpose_many(tr)
         if gb.problems:
             gb.run()
+        fk = ops.fork(dev)                  # distinct outputs: the two kernels run side by side
+        with fk:
+            for F, segs in chunks_by_F.items():
+                ops.aggregate_chunks(segs, F)
         for (wave, F) in sorted(rows_by_F.keys()):
             ops.aggregate_rows(rows_by_F[(wave, F)], F)
-        for F, segs in chunks_by_F.items():
-            ops.aggregate_chunks(segs, F)
+        fk.join()
         if tf_long:
             items = []
             for t, temps in tf_long.items():
@@ -408,8 +411,10 @@ class _HeteroConvFn(torch.autograd.Function):
                 chunks.append((dy, arg))
             else:
                 rows.append((dy, [arg], False))
+        fk = ops.fork(dev)
+        with fk:
+            ops.aggregate_chunks(chunks, O)
         ops.aggregate_rows(rows, O)
-        ops.aggregate_chunks(chunks, O)
 
         # b2/b3: weight gradients and the aggregate-first input gradients dG = dout W_l
         gb = ops.GemmBatch()
@@ -440,6 +445,7 @@ class _HeteroConvFn(torch.autograd.Function):
                     dg = torch.empty(r.n_dst, x.shape[1], dtype=torch.float32, device=dev)
                     dG[k] = dg
                     gb.add(dg, [(dout[r.dst], params[rs.i_wl])])
+        fk.join()
         if trb:
             ops.transpose_many(trb)
         if gb.problems:
@@ -494,10 +500,13 @@ class _HeteroConvFn(torch.autograd.Function):
                 late_root.append((dx[:xd[t].shape[0]], [(dout[t], wroot[t])], True))
             groups.setdefault(('gemm',), []).append((dx, segs, bool(af)))
         gb = ops.GemmBatch()
+        fk = ops.fork(dev)
+        with fk:
+            for F_, segs_ in long_chunks.items():
+                ops.aggregate_chunks(segs_, F_)
         for key in sorted(k for k in groups.keys() if k != ('gemm',)):
             ops.aggregate_rows(groups[key], key[1])
-        for F_, segs_ in long_chunks.items():
-            ops.aggregate_chunks(segs_, F_)
+        fk.join()
         last = []
         for dx_, ins in long_sums:
             while len(ins) > 8:

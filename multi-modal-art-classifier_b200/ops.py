@@ -68,6 +68,53 @@ TIMER: Optional[KernelTimer] = None
 _DEBUG = bool(int(__import__('os').environ.get('AGX_DEBUG', '0')))
 
 
+# ------------------------------------------------------------------------------------------------
+# side stream for INDEPENDENT launches of one fused layer (the edge-balanced aggregation of the
+# long-row relations next to the row-parallel one of the others: both leave part of the machine
+# idle in their tails).  Under stream capture the branch becomes a parallel path of the graph.
+# ------------------------------------------------------------------------------------------------
+_NO_SIDE = __import__('os').environ.get('AGX_NO_SIDE_STREAMS') is not None
+_SIDE: dict = {}
+
+
+class Fork:
+    """``fk = fork(device)``; ``with fk: <launches for the side stream>``; launches for the main
+    stream; ``fk.join()``.  A no-op (everything stays on the current stream) on CPU tensors (the
+    test-suite's restated kernels), while per-kernel timing is on, and with AGX_NO_SIDE_STREAMS."""
+
+    def __init__(self, device):
+        self.main = self.side = None
+        if _NO_SIDE or TIMER is not None or device.type != 'cuda':
+            return
+        self.main = torch.cuda.current_stream(device)
+        side = _SIDE.get(device.index)
+        if side is None:
+            side = _SIDE[device.index] = torch.cuda.Stream(device)
+        self.side = side
+        side.wait_stream(self.main)
+        self._ctx = None
+
+    def __enter__(self):
+        if self.side is not None:
+            self._ctx = torch.cuda.stream(self.side)
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.side is not None:
+            self._ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        if self.side is not None:
+            self.main.wait_stream(self.side)
+            self.side = None
+
+
+def fork(device) -> Fork:
+    return Fork(device)
+
+
 def aggregation_bytes(n_edges: int, n_rows: int, F: int, elem: int = 4) -> int:
     """Algorithmic HBM bytes of one relation's aggregation pass:
     E*(F*s + 4) gathered rows + column ids, (N+1)*4 row pointers, N*F*s output rows."""
