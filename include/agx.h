@@ -205,14 +205,20 @@ int agx_sum_arrays(const agx_sum_desc_t* h_descs, int n, void* stream);
  * Training statistics: two passes (mean, then centred second moment), per-slab float32 partials
  * combined in float64 (the reference's CPU kernel accumulates in double). */
 typedef struct {
-    const float* x; float* y;            /* [n_rows, F] contiguous                               */
-    float* y_act;                         /* nullable: relu(y) * dmask                            */
+    const float* x; float* y;            /* [n_rows, F] contiguous; y nullable if y_act is given   */
+    float* y_act;                         /* nullable: relu(y) * dropout mask                     */
     const float* dmask;                   /* nullable: [n_rows, F] multiplicative dropout mask    */
     const float* weight; const float* bias;   /* [F] affine                                       */
     float* running_mean; float* running_var;  /* [F]; updated in training mode, read in eval mode */
     float* save_mean; float* save_invstd;     /* [F] saved for backward                           */
     int32_t n_rows;
-    int32_t pad_;
+    /* dropout WITHOUT a materialised mask (dmask == NULL, drop_seed != NULL, drop_p > 0): element e
+     * is kept iff agx_dropout_mask(mask, numel, drop_p, drop_seed) would have kept element
+     * drop_offset + e of its buffer -- the same Philox4x32-10 stream, generated in the normalising
+     * pass (kept values are scaled by 1 / (1 - drop_p)) */
+    float drop_p;
+    const uint64_t* drop_seed;            /* device: {key, counter}                               */
+    int64_t drop_offset;                  /* multiple of 4                                        */
 } agx_bn_desc_t;
 size_t agx_bn_workspace_floats(int64_t total_rows, int n_descs, int F);
 int agx_bn_forward(const agx_bn_desc_t* h_descs, int n, int F, int training, float momentum,
@@ -220,7 +226,9 @@ int agx_bn_forward(const agx_bn_desc_t* h_descs, int n, int F, int training, flo
 
 typedef struct {
     const float* x;                       /* BN input saved from forward                          */
-    const float* y;                       /* BN output (relu mask); required if dy_act            */
+    const float* y;                       /* BN output OR y_act (only "> 0" is read: the relu
+                                           * gate; dropped elements get no gradient either way);
+                                           * required if dy_act                                    */
     const float* dy;                      /* grad wrt y (nullable -> 0)                           */
     const float* dy_act;                  /* grad wrt y_act (nullable -> 0)                       */
     const float* dmask;                   /* nullable                                             */
@@ -229,7 +237,9 @@ typedef struct {
     float* dx;                            /* nullable                                             */
     float* dweight; float* dbias;         /* nullable; accumulated (+=)                           */
     int32_t n_rows;
-    int32_t pad_;
+    float act_scale;                      /* dmask == NULL: dy_act is multiplied by act_scale
+                                           * (dropout without a mask tensor: y = y_act, scale
+                                           * 1 / (1 - p) in float32); 0 = no scaling               */
 } agx_bn_bwd_desc_t;
 int agx_bn_backward(const agx_bn_bwd_desc_t* h_descs, int n, int F, int training, float* workspace,
                     size_t workspace_floats, void* stream);

@@ -86,13 +86,13 @@ class SddmmSeg(C.Structure):
 class BnDesc(C.Structure):
     _fields_ = [('x', vp), ('y', vp), ('y_act', vp), ('dmask', vp), ('weight', vp), ('bias', vp),
                 ('running_mean', vp), ('running_var', vp), ('save_mean', vp), ('save_invstd', vp),
-                ('n_rows', c_i32), ('pad_', c_i32)]
+                ('n_rows', c_i32), ('drop_p', c_f32), ('drop_seed', vp), ('drop_offset', c_i64)]
 
 
 class BnBwdDesc(C.Structure):
     _fields_ = [('x', vp), ('y', vp), ('dy', vp), ('dy_act', vp), ('dmask', vp), ('weight', vp),
                 ('save_mean', vp), ('save_invstd', vp), ('dx', vp), ('dweight', vp), ('dbias', vp),
-                ('n_rows', c_i32), ('pad_', c_i32)]
+                ('n_rows', c_i32), ('act_scale', c_f32)]
 
 
 class ColsumDesc(C.Structure):

@@ -226,6 +226,29 @@ __global__ void __launch_bounds__(1024) bn_finalize(const __grid_constant__ BnPa
     }
 }
 
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+
+// keep / drop decision of agx_dropout_mask for the four elements of Philox block `ctr`
+__device__ __forceinline__ void drop_keep4(uint64_t key, uint64_t ctr, float p, float keep, float k[4]) {
+    uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
+    philox4x32_10(c, (uint32_t)key, (uint32_t)(key >> 32));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float u = (float)(c[i] >> 8) * (1.0f / 16777216.0f);   // [0, 1)
+        k[i] = u >= p ? keep : 0.f;
+    }
+}
+
 __global__ void __launch_bounds__(256) bn_apply(const __grid_constant__ BnParams P) {
     int di = 0;
     while ((int)blockIdx.x >= P.slab_start[di + 1]) ++di;
@@ -234,6 +257,9 @@ __global__ void __launch_bounds__(256) bn_apply(const __grid_constant__ BnParams
     const int F = P.F;
     const int64_t e0 = (int64_t)slab * kBnSlab * F;
     const int64_t e1 = min((int64_t)D.n_rows * F, e0 + (int64_t)kBnSlab * F);
+    const bool philox = D.y_act && !D.dmask && D.drop_seed && D.drop_p > 0.f;
+    const uint64_t key = philox ? D.drop_seed[0] : 0, base = philox ? D.drop_seed[1] : 0;
+    const float keep = 1.0f / (1.0f - D.drop_p);
     if ((F & 3) == 0) {      // 128-bit path (rows are 16-byte aligned: torch allocations, F % 4 == 0)
         for (int64_t e = e0 + 4 * (int64_t)threadIdx.x; e < e1; e += 4 * (int64_t)blockDim.x) {
             const int c = (int)(e % F);
@@ -247,13 +273,17 @@ __global__ void __launch_bounds__(256) bn_apply(const __grid_constant__ BnParams
             y.y = (x.y - m.y) * is.y * wv.y + bv.y;
             y.z = (x.z - m.z) * is.z * wv.z + bv.z;
             y.w = (x.w - m.w) * is.w * wv.w + bv.w;
-            *reinterpret_cast<float4*>(D.y + e) = y;
+            if (D.y) *reinterpret_cast<float4*>(D.y + e) = y;
             if (D.y_act) {
                 float4 a = make_float4(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f), fmaxf(y.z, 0.f),
                                        fmaxf(y.w, 0.f));
                 if (D.dmask) {
                     const float4 k = *reinterpret_cast<const float4*>(D.dmask + e);
                     a.x *= k.x; a.y *= k.y; a.z *= k.z; a.w *= k.w;
+                } else if (philox) {
+                    float k[4];
+                    drop_keep4(key, base + (uint64_t)((D.drop_offset + e) >> 2), D.drop_p, keep, k);
+                    a.x *= k[0]; a.y *= k[1]; a.z *= k[2]; a.w *= k[3];
                 }
                 *reinterpret_cast<float4*>(D.y_act + e) = a;
             }
@@ -264,10 +294,17 @@ __global__ void __launch_bounds__(256) bn_apply(const __grid_constant__ BnParams
         const int c = (int)(e % F);
         const float xh = (D.x[e] - D.save_mean[c]) * D.save_invstd[c];
         const float y = xh * D.weight[c] + D.bias[c];
-        D.y[e] = y;
+        if (D.y) D.y[e] = y;
         if (D.y_act) {
             float a = y > 0.f ? y : 0.f;
-            if (D.dmask) a *= D.dmask[e];
+            if (D.dmask) {
+                a *= D.dmask[e];
+            } else if (philox) {
+                float k[4];
+                const int64_t ge = D.drop_offset + e;
+                drop_keep4(key, base + (uint64_t)(ge >> 2), D.drop_p, keep, k);
+                a *= k[ge & 3];
+            }
             D.y_act[e] = a;
         }
     }
@@ -289,6 +326,7 @@ __device__ __forceinline__ float bn_dy_total(const agx_bn_bwd_desc_t& D, int64_t
     if (D.dy_act) {
         float a = D.dy_act[e];
         if (D.dmask) a *= D.dmask[e];
+        else if (D.act_scale != 0.f) a *= D.act_scale;
         if (!(D.y[e] > 0.f)) a = 0.f;
         g += a;
     }
@@ -302,6 +340,9 @@ __device__ __forceinline__ float4 bn_dy_total4(const agx_bn_bwd_desc_t& D, int64
         if (D.dmask) {
             const float4 k = *reinterpret_cast<const float4*>(D.dmask + e);
             a.x *= k.x; a.y *= k.y; a.z *= k.z; a.w *= k.w;
+        } else {
+            const float sc = D.act_scale != 0.f ? D.act_scale : 1.0f;
+            a.x *= sc; a.y *= sc; a.z *= sc; a.w *= sc;
         }
         const float4 y = *reinterpret_cast<const float4*>(D.y + e);
         g.x += y.x > 0.f ? a.x : 0.f;
@@ -757,17 +798,6 @@ adam_step(float* __restrict__ p, const float* __restrict__ g, float* __restrict_
 // ------------------------------------------------------------------------------------------------
 // dropout mask: Philox4x32-10, 4 uniforms per counter
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-        const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
-        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-}
 
 __global__ void __launch_bounds__(256)
 dropout_mask(float* __restrict__ mask, int64_t n, float p, const uint64_t* __restrict__ seed) {
@@ -977,9 +1007,12 @@ static int bn_forward_impl(const agx_bn_desc_t* h_descs, int n, int F, int train
     int64_t rows = 0;
     for (int i = 0; i < n; ++i) {
         const agx_bn_desc_t& D = h_descs[i];
-        AGX_CHECK_ARG(D.n_rows >= 0 && D.x && D.y && D.weight && D.bias && D.save_mean &&
-                          D.save_invstd,
+        AGX_CHECK_ARG(D.n_rows >= 0 && D.x && (D.y || D.y_act) && D.weight && D.bias &&
+                          D.save_mean && D.save_invstd,
                       "agx_bn_forward: desc %d has null pointers", i);
+        AGX_CHECK_ARG(!(D.drop_seed && !D.dmask && D.drop_p > 0.f) ||
+                          (D.drop_p < 1.f && (D.drop_offset & 3) == 0 && D.drop_offset >= 0),
+                      "agx_bn_forward: desc %d: drop_p in [0,1), drop_offset a multiple of 4", i);
         AGX_CHECK_ARG(training || (D.running_mean && D.running_var),
                       "agx_bn_forward: desc %d: eval mode needs running stats", i);
         AGX_CHECK_ARG(!training || D.n_rows > 1 || counts,

@@ -259,16 +259,32 @@ class _HeteroConvFn(torch.autograd.Function):
             # GLOBAL in-degree above)
             if part_flat is not None:
                 works.append(dist.all_reduce(part_flat, group=spec.group, async_op=True))
+        # distinct outputs: the edge-balanced launches run on the side stream next to the row-parallel
+        # ones; those that gather input features (not a transformed table Y) start before the
+        # transform-first products
+        y_ids = {id(y) for y in Y.values()}
+        early = {F: [sg for sg in segs if id(sg[1].x) not in y_ids] for F, segs in chunks_by_F.items()}
+        late = {F: [sg for sg in segs if id(sg[1].x) in y_ids] for F, segs in chunks_by_F.items()}
+        n_early = sum(sg[1].csr.n_edges for segs in early.values() for sg in segs)
+        n_late = sum(sg[1].csr.n_edges for segs in late.values() for sg in segs)
+        if min(n_early, n_late) < 0.25 * max(n_early, n_late, 1):
+            # a second launch for a few small relations costs more than starting the others early
+            early, late = {}, chunks_by_F
+        fk = ops.fork(dev)
+        with fk:
+            for F, segs in early.items():
+                ops.aggregate_chunks(segs, F)
         if tr:
             ops.transpose_many(tr)
         if gb.problems:
             gb.run()
-        fk = ops.fork(dev)                  # distinct outputs: the two kernels run side by side
-        with fk:
-            for F, segs in chunks_by_F.items():
+        fk2 = ops.fork(dev)
+        with fk2:
+            for F, segs in late.items():
                 ops.aggregate_chunks(segs, F)
         for (wave, F) in sorted(rows_by_F.keys()):
             ops.aggregate_rows(rows_by_F[(wave, F)], F)
+        fk2.join()
         fk.join()
         if tf_long:
             items = []
@@ -411,14 +427,19 @@ class _HeteroConvFn(torch.autograd.Function):
                 chunks.append((dy, arg))
             else:
                 rows.append((dy, [arg], False))
+        # ... on the side stream, next to the products below that do not read dY (gathers are
+        # latency / bandwidth bound, the products run on the tensor cores); the products that do
+        # read dY (gb_late, trb_late) go with the last launch of the layer
         fk = ops.fork(dev)
         with fk:
             ops.aggregate_chunks(chunks, O)
-        ops.aggregate_rows(rows, O)
+            ops.aggregate_rows(rows, O)
 
         # b2/b3: weight gradients and the aggregate-first input gradients dG = dout W_l
         gb = ops.GemmBatch()
+        gb_late = ops.GemmBatch()
         trb: list = []
+        trb_late: list = []
         dwroot: Dict[str, torch.Tensor] = {}
         for t in spec.dst_types:
             if dout[t] is None or t not in wroot:
@@ -436,16 +457,15 @@ class _HeteroConvFn(torch.autograd.Function):
             dw = torch.empty(O, x.shape[1], dtype=torch.float32, device=dev)
             grads[pidx(rs.i_wl)] = dw
             if rs.transform_first and spec.identity.get(r.src, False):
-                trb.append((dw, dY[k]))
+                trb_late.append((dw, dY[k]))
             elif rs.transform_first:
-                gb.add(dw, [(_t(dY[k]), x)], split_k=ops.split_k_for(r.n_src))
+                gb_late.add(dw, [(_t(dY[k]), x)], split_k=ops.split_k_for(r.n_src))
             else:
                 gb.add(dw, [(_t(dout[r.dst]), G[k])], split_k=ops.split_k_for(rs.rows))
                 if need_x[r.src] and k not in dG:
                     dg = torch.empty(r.n_dst, x.shape[1], dtype=torch.float32, device=dev)
                     dG[k] = dg
                     gb.add(dg, [(dout[r.dst], params[rs.i_wl])])
-        fk.join()
         if trb:
             ops.transpose_many(trb)
         if gb.problems:
@@ -499,14 +519,17 @@ class _HeteroConvFn(torch.autograd.Function):
                     ops.fill_(dx, 0.0)
                 late_root.append((dx[:xd[t].shape[0]], [(dout[t], wroot[t])], True))
             groups.setdefault(('gemm',), []).append((dx, segs, bool(af)))
-        gb = ops.GemmBatch()
-        fk = ops.fork(dev)
-        with fk:
+        fk5 = ops.fork(dev)
+        with fk5:
             for F_, segs_ in long_chunks.items():
                 ops.aggregate_chunks(segs_, F_)
         for key in sorted(k for k in groups.keys() if k != ('gemm',)):
             ops.aggregate_rows(groups[key], key[1])
-        fk.join()
+        fk5.join()
+        fk.join()                                   # dY is complete (b4a, same side stream)
+        if trb_late:
+            ops.transpose_many(trb_late)
+        gb = gb_late                                # + the input-gradient products below
         last = []
         for dx_, ins in long_sums:
             while len(ins) > 8:
@@ -686,10 +709,21 @@ class BNSpec:
     running: List[Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]]   # per type buffers
     with_act: bool                           # also produce relu(y) * dmask
     dmasks: Optional[List[Optional[torch.Tensor]]] = None
+    # dropout without mask tensors: per type (seed state [2] int64, element offset into the virtual
+    # flat mask agx_dropout_mask would have written) -- generated inside the normalising pass
+    drop: Optional[List[Optional[Tuple[torch.Tensor, int]]]] = None
+    drop_p: float = 0.0
+    need_y: bool = True                      # False (with_act only): y itself is never written
     param_refs: Optional[tuple] = None       # ([weight Parameters], [bias Parameters])
     group: object = None                     # torch.distributed process group -> SyncBN
     counts: Optional[torch.Tensor] = None    # float64 [n] global row counts (with group)
     counts_of: Optional[object] = None       # callable(indices) -> counts of a subset (cached)
+
+
+def _keep_scale(p: float) -> float:
+    """1 / (1 - p) as the kernels compute it (float32 arithmetic)."""
+    import numpy as np
+    return float(np.float32(1.0) / (np.float32(1.0) - np.float32(p)))
 
 
 class _BNActFn(torch.autograd.Function):
@@ -710,14 +744,19 @@ class _BNActFn(torch.autograd.Function):
             L.require_cuda(x, 'BatchNorm input')
             if x.dtype != torch.float32 or not x.is_contiguous() or x.shape[1] != F:
                 raise TypeError('BatchNorm input must be contiguous float32 [N, F]')
-            y = torch.empty_like(x)
+            need_y = spec.need_y or not spec.with_act
+            y = torch.empty_like(x) if need_y else None
             a = torch.empty_like(x) if spec.with_act else None
             m = torch.empty(F, dtype=torch.float32, device=dev)
             s = torch.empty(F, dtype=torch.float32, device=dev)
             dm = spec.dmasks[i] if (spec.with_act and spec.dmasks is not None) else None
+            dr = spec.drop[i] if (spec.with_act and spec.drop is not None and dm is None) else None
             rm, rv = spec.running[i]
             arr[i] = L.BnDesc(ptr(x), ptr(y), ptr(a), ptr(dm), ptr(ws[i]), ptr(bs[i]), ptr(rm),
-                              ptr(rv), ptr(m), ptr(s), x.shape[0], 0)
+                              ptr(rv), ptr(m), ptr(s), x.shape[0],
+                              float(spec.drop_p) if dr is not None else 0.0,
+                              ptr(dr[0]) if dr is not None else None,
+                              int(dr[1]) if dr is not None else 0)
             ys.append(y); acts.append(a); means.append(m); invstds.append(s)
             rows += x.shape[0]
         n_ws = lib().agx_bn_workspace_floats(rows, n, F)
@@ -738,7 +777,13 @@ class _BNActFn(torch.autograd.Function):
             check(lib().agx_bn_forward(arr, n, F, int(spec.training), spec.momentum, spec.eps,
                                        ptr(wsb), n_ws, stream_ptr()), 'agx_bn_forward')
         ctx.spec = spec
-        ctx.save_for_backward(*xs, *ws, *ys, *means, *invstds)
+        # the relu gate of the backward pass: y, or y_act when y was not written (y_act > 0 <=> y > 0
+        # and the element was kept; a dropped element gets no gradient either way)
+        gates = [y if y is not None else a for y, a in zip(ys, acts)]
+        ctx.save_for_backward(*xs, *ws, *gates, *means, *invstds)
+        ctx.has_y = spec.need_y or not spec.with_act
+        if not ctx.has_y:
+            return tuple(acts)
         if spec.with_act:
             return (*ys, *acts)
         return tuple(ys)
@@ -750,8 +795,11 @@ class _BNActFn(torch.autograd.Function):
         sv = ctx.saved_tensors
         xs, ws, ys, means, invstds = (sv[0:n], sv[n:2 * n], sv[2 * n:3 * n], sv[3 * n:4 * n],
                                       sv[4 * n:5 * n])
-        dys = grads[:n]
-        dacts = grads[n:2 * n] if spec.with_act else [None] * n
+        if ctx.has_y:
+            dys = grads[:n]
+            dacts = grads[n:2 * n] if spec.with_act else [None] * n
+        else:
+            dys, dacts = [None] * n, grads[:n]
         dev = xs[0].device
         idx = [i for i in range(n) if dys[i] is not None or dacts[i] is not None]
         dxs: List[Optional[torch.Tensor]] = [None] * n
@@ -778,9 +826,12 @@ class _BNActFn(torch.autograd.Function):
                     dws[i] = zbuf[2 * j * F:(2 * j + 1) * F]
                     dbs[i] = zbuf[(2 * j + 1) * F:(2 * j + 2) * F]
                 dm = spec.dmasks[i] if (spec.with_act and spec.dmasks is not None) else None
+                philox = spec.with_act and dm is None and spec.drop is not None and \
+                    spec.drop[i] is not None and spec.drop_p > 0
                 arr[j] = L.BnBwdDesc(ptr(xs[i]), ptr(ys[i]), ptr(dy), ptr(da), ptr(dm), ptr(ws[i]),
                                      ptr(means[i]), ptr(invstds[i]), ptr(dxs[i]), ptr(dws[i]),
-                                     ptr(dbs[i]), xs[i].shape[0], 0)
+                                     ptr(dbs[i]), xs[i].shape[0],
+                                     _keep_scale(spec.drop_p) if philox else 0.0)
                 rows += xs[i].shape[0]
             n_ws = lib().agx_bn_workspace_floats(rows, len(idx), F)
             wsb = torch.empty(n_ws, dtype=torch.float32, device=dev)
@@ -893,7 +944,11 @@ def log_softmax_many(xs: Sequence[torch.Tensor]) -> List[torch.Tensor]:
             p += x.numel() * 4
     if not ok:
         return [log_softmax(x, 1) for x in xs]
-    return list(_LogSoftmaxManyFn.apply(*xs))
+    res = list(_LogSoftmaxManyFn.apply(*xs))
+    for r, x in zip(res, xs):
+        # nll_loss on exactly this tensor differentiates log_softmax + nll in one kernel (below)
+        r._agx_logits = x
+    return res
 
 
 def log_softmax(x: torch.Tensor, dim: int = 1) -> torch.Tensor:
@@ -997,6 +1052,7 @@ class _NLLFromLogpFn(torch.autograd.Function):
                 small_all_reduce_(loss_sum, group)
             check(lib().agx_loss_finish(ptr(loss_sum), 1.0, ptr(loss), 0, stream_ptr()),
                   'agx_loss_finish')
+        ctx.to_save = (labels, loss_sum)
         ctx.save_for_backward(labels, loss_sum)
         ctx.shape = (n, c)
         return loss.reshape(())
@@ -1012,12 +1068,41 @@ class _NLLFromLogpFn(torch.autograd.Function):
         return dlp, None, None, None, None
 
 
+class _NLLOfLogSoftmaxFn(torch.autograd.Function):
+    """nll_loss(log_softmax(logits)) when the log-probabilities are the tensor log_softmax_many
+    returned: same forward arithmetic as _NLLFromLogpFn (on the log-probabilities), but the
+    gradient goes to the LOGITS in one kernel -- g * (softmax - onehot) -- instead of a dense
+    [N, C] d(logp) written by one kernel and folded through log_softmax's backward by another."""
+
+    @staticmethod
+    def forward(ctx, logits, logp, labels, group, global_count, pending):
+        loss = _NLLFromLogpFn.forward(ctx, logp, labels, group, global_count, pending)
+        labels_, loss_sum = ctx.to_save
+        ctx.save_for_backward(labels_, loss_sum, logp)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        labels, loss_sum, logp = ctx.saved_tensors
+        n, c = ctx.shape
+        gs = g.reshape(1).to(torch.float32).contiguous()
+        dx = torch.empty(n, c, dtype=torch.float32, device=logp.device)
+        check(lib().agx_log_softmax_nll_bwd(ptr(logp), logp.stride(0), n, c, ptr(labels), None,
+                                            ptr(loss_sum), ptr(gs), ctx.coef, None, 0, ptr(dx), c,
+                                            stream_ptr()), 'agx_log_softmax_nll_bwd')
+        return dx, None, None, None, None, None
+
+
 def nll_loss(logp: torch.Tensor, labels: torch.Tensor, group=None, global_count=None,
              pending=None) -> torch.Tensor:
     """``F.nll_loss(logp, labels)``; with ``group`` the mean runs over the rows of all ranks (each
     rank then holds the gradient of the GLOBAL loss w.r.t. its own rows).  ``global_count``: the
     number of rows over all ranks when known beforehand -- the collective then only carries the
     loss value and runs asynchronously (handles appended to ``pending``)."""
+    src = getattr(logp, '_agx_logits', None)
+    if src is not None and torch.is_grad_enabled() and src.requires_grad and \
+            src.shape == logp.shape and logp.is_contiguous():
+        return _NLLOfLogSoftmaxFn.apply(src, logp.detach(), labels, group, global_count, pending)
     return _NLLFromLogpFn.apply(logp, labels, group, global_count, pending)
 
 

@@ -227,7 +227,10 @@ class HeteroModule(nn.Module):
                 if training is True and d.args[0] is relu:
                     p = d.kwargs.get('p', d.args[1] if len(d.args) > 1 else 0.5)
                     drop = (d.name, float(p))
-            fusion[n.name] = (relu.name, drop)
+            # y itself is written only if something else reads it (the model returning the last
+            # hidden BatchNorm output as the embedding)
+            y_live = any(u.name in self._live and u is not relu for u in n.users)
+            fusion[n.name] = (relu.name, drop, y_live)
         return fusion
 
     # ---- execution ----------------------------------------------------------------------------
@@ -284,6 +287,26 @@ class HeteroModule(nn.Module):
                 out[i] = flat[off:off + r * c].view(r, c)
                 off += sz
         return out
+
+    def _virtual_masks(self, shapes, device, types):
+        """What ``_masks`` would draw, without drawing it: per type the Philox state and the element
+        offset of its mask inside the flat buffer agx_dropout_mask would have filled (the
+        normalising kernel generates the same keep / drop decisions in place); plus the counter
+        advances to apply once the kernels are queued."""
+        rep = self._dist.replicated if self._dist is not None else frozenset()
+        out = [None] * len(types)
+        advance = []
+        for common in (False, True):
+            sub = [i for i, t in enumerate(types) if (t in rep) == common]
+            if not sub:
+                continue
+            st = self._seed_state(device, common=common)
+            off = 0
+            for i in sub:
+                out[i] = (st, off)
+                off += ((int(shapes[i][0]) * int(shapes[i][1]) + 3) // 4) * 4
+            advance.append((st, off // 4))
+        return out, advance
 
     def _bump_batches_tracked(self, target, bns, types):
         """``num_batches_tracked += 1`` of every BatchNorm of a layer as one add: the per-module
@@ -396,15 +419,21 @@ class HeteroModule(nn.Module):
 
     def _bn(self, node, x_dict):
         bns = self.get_submodule(node.target)
-        relu, drop = self._fusion.get(node.name, (None, None))
+        relu, drop, y_live = self._fusion.get(node.name, (None, None, True))
         types = list(x_dict.keys())
         first = bns[types[0]]
         dmasks = None
+        virt = None            # dropout without mask tensors: (seed state, offset) per type
+        p_drop = 0.0
         if drop is not None:
             p = drop[1]
-            if p > 0 or self.dropout_masks is not None:
+            if self.dropout_masks is not None:
                 dmasks = self._masks([x_dict[t].shape for t in types], p,
                                      x_dict[types[0]].device, types)
+            elif p > 0:
+                p_drop = float(p)
+                virt, advance = self._virtual_masks([x_dict[t].shape for t in types],
+                                                    x_dict[types[0]].device, types)
         self._bump_batches_tracked(node.target, bns, types)
 
         def run(sub: List[int], grouped: bool):
@@ -416,6 +445,8 @@ class HeteroModule(nn.Module):
                           running=[(bns[t].running_mean, bns[t].running_var) for t in tt],
                           with_act=relu is not None,
                           dmasks=None if dmasks is None else [dmasks[i] for i in sub],
+                          drop=None if virt is None else [virt[i] for i in sub], drop_p=p_drop,
+                          need_y=relu is None or y_live,
                           param_refs=([bns[t].weight for t in tt], [bns[t].bias for t in tt]))
             if grouped:
                 spec.group = self._dist.group
@@ -432,7 +463,8 @@ class HeteroModule(nn.Module):
         else:
             # replicated node types hold all their rows on every rank: their batch statistics are
             # local (and identical everywhere); the partitioned types' run over all ranks
-            res = [None] * (2 * n if relu is not None else n)
+            both = relu is not None and y_live
+            res = [None] * (2 * n if both else n)
             for sub, grouped in (([i for i in range(n) if types[i] not in rep], True),
                                  ([i for i in range(n) if types[i] in rep], False)):
                 if not sub:
@@ -440,9 +472,14 @@ class HeteroModule(nn.Module):
                 out = run(sub, grouped)
                 for j, i in enumerate(sub):
                     res[i] = out[j]
-                    if relu is not None:
+                    if both:
                         res[n + i] = out[len(sub) + j]
         n = len(types)
+        if virt is not None:
+            for st, k in advance:      # the kernels above read the counters: advance them now
+                st[1] += k             # (device side: graph-capturable)
+        if relu is not None and not y_live:      # fused: only relu(y) [* dropout] is written
+            return None, OrderedDict(zip(types, res[:n])), relu, drop
         y = OrderedDict(zip(types, res[:n]))
         act = OrderedDict(zip(types, res[n:])) if relu is not None else None
         return y, act, relu, drop

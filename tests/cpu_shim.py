@@ -202,6 +202,23 @@ def _view(addr, rows, cols, ld=None, dtype=torch.float32):
     return torch.as_strided(flat, (rows, cols), (ld, 1))
 
 
+def _bn_outputs(d, y64, N, F):
+    """y (optional) and relu(y) * dropout of one agx_bn_desc_t: mask tensor, or the (key, counter,
+    offset) form -- here the stand-in stream of _dropout_mask at counter + offset / 4."""
+    y32 = y64.float()
+    if d.y:
+        _view(d.y, N, F).copy_(y32)
+    if d.y_act:
+        a = torch.relu(y32.double())
+        if d.dmask:
+            a = a * _view(d.dmask, N, F).double()
+        elif d.drop_seed and d.drop_p > 0:
+            st = _view(d.drop_seed, 1, 2, dtype=torch.int64).view(-1)
+            m = _dropout_mask((N, F), float(d.drop_p), [int(st[0]), int(st[1]) + int(d.drop_offset) // 4])
+            a = a * m.double()
+        _view(d.y_act, N, F).copy_(a.float())
+
+
 class _FakeLib:
     """The agx_* functions with device pointers replaced by host addresses (include/agx.h
     semantics, float64 arithmetic, results rounded to float32 once)."""
@@ -229,14 +246,9 @@ class _FakeLib:
                 mean, var = rm.double(), rv.double()
             invstd = 1.0 / torch.sqrt(var + eps)
             y = (x - mean) * invstd * w + b
-            _view(d.y, N, F).copy_(y.float())
             _view(d.save_mean, 1, F).copy_(mean.float())
             _view(d.save_invstd, 1, F).copy_(invstd.float())
-            if d.y_act:
-                a = torch.relu(_view(d.y, N, F).double())
-                if d.dmask:
-                    a = a * _view(d.dmask, N, F).double()
-                _view(d.y_act, N, F).copy_(a.float())
+            _bn_outputs(d, y, N, F)
         return 0
 
     def agx_bn_backward(self, arr, n, F, training, ws, n_ws, stream):
@@ -251,6 +263,8 @@ class _FakeLib:
                 ga = _view(d.dy_act, N, F).double() * (_view(d.y, N, F) > 0).double()
                 if d.dmask:
                     ga = ga * _view(d.dmask, N, F).double()
+                else:
+                    ga = ga * (float(d.act_scale) if d.act_scale else 1.0)
                 g = g + ga
             w = _view(d.weight, 1, F).double()
             mean, invstd = _view(d.save_mean, 1, F).double(), _view(d.save_invstd, 1, F).double()
@@ -292,14 +306,9 @@ class _FakeLib:
                     rv.copy_(((1 - momentum) * rv.double() + momentum * var * c / (c - 1)).float())
                 invstd = 1.0 / torch.sqrt(var + eps)
                 w, b = _view(d.weight, 1, F).double(), _view(d.bias, 1, F).double()
-                _view(d.y, N, F).copy_(((x - mean) * invstd * w + b).float())
                 _view(d.save_mean, 1, F).copy_(mean.float())
                 _view(d.save_invstd, 1, F).copy_(invstd.float())
-                if d.y_act:
-                    a = torch.relu(_view(d.y, N, F).double())
-                    if d.dmask:
-                        a = a * _view(d.dmask, N, F).double()
-                    _view(d.y_act, N, F).copy_(a.float())
+                _bn_outputs(d, (x - mean) * invstd * w + b, N, F)
         return 0
 
     def agx_bn_backward_phase(self, arr, n, F, training, ws, n_ws, phases, totals, counts, stream):
@@ -316,6 +325,8 @@ class _FakeLib:
                 ga = _view(d.dy_act, N, F).double() * (_view(d.y, N, F) > 0).double()
                 if d.dmask:
                     ga = ga * _view(d.dmask, N, F).double()
+                else:
+                    ga = ga * (float(d.act_scale) if d.act_scale else 1.0)
                 g = g + ga
             mean, invstd = _view(d.save_mean, 1, F).double(), _view(d.save_invstd, 1, F).double()
             xhat = (x - mean) * invstd

@@ -481,6 +481,50 @@ def test_batch_norm_act_batched(training):
         assert rel_err(bnd[i].running_var, r[6]) <= RTOL_F32, i
 
 
+@pytest.mark.parametrize('F', [128, 30])
+def test_batch_norm_dropout_without_mask_tensor(F):
+    """Dropout generated inside the normalising pass (agx_bn_desc_t.drop_seed / drop_offset) keeps
+    exactly the elements agx_dropout_mask keeps for the same Philox state, y itself is not written
+    (need_y=False), and the backward pass -- relu gate read from y_act, gradient scaled by
+    1 / (1 - p), no mask tensor -- equals the path with the materialised mask bit for bit."""
+    gen = torch.Generator().manual_seed(40 + F)
+    sizes = [515, 32, 1201]
+    p = 0.4
+    xs = [torch.randn(n, F, generator=gen) * (1 + i) + i for i, n in enumerate(sizes)]
+    gas = [torch.randn(n, F, generator=gen).to(DEV) for n in sizes]
+    seed = torch.tensor([0x1234567, 977], dtype=torch.int64, device=DEV)
+    padded = [((n * F + 3) // 4) * 4 for n in sizes]
+    flat = ops.dropout_mask((sum(padded),), p, seed)
+    offs = [sum(padded[:i]) for i in range(len(sizes))]
+    masks = [flat[o:o + n * F].view(n, F) for o, n in zip(offs, sizes)]
+    assert 0.5 < float(flat.count_nonzero()) / flat.numel() < 0.7
+
+    def run(virtual):
+        bns = [torch.nn.BatchNorm1d(F).to(DEV).train() for _ in sizes]
+        for i, bn in enumerate(bns):
+            with torch.no_grad():
+                bn.weight.fill_(0.5 + 0.25 * i)
+                bn.bias.fill_(0.1 * i - 0.1)
+        xd = [x.to(DEV).requires_grad_(True) for x in xs]
+        spec = AF.BNSpec(n=len(sizes), F=F, training=True, momentum=0.1, eps=1e-5,
+                         running=[(b.running_mean, b.running_var) for b in bns], with_act=True,
+                         dmasks=None if virtual else masks,
+                         drop=[(seed, o) for o in offs] if virtual else None, drop_p=p,
+                         need_y=not virtual)
+        res = AF.batch_norm_act(spec, xd, [b.weight for b in bns], [b.bias for b in bns])
+        acts = res[-len(sizes):]
+        assert len(res) == (len(sizes) if virtual else 2 * len(sizes))
+        sum((a * g).sum() for a, g in zip(acts, gas)).backward()
+        return acts, [x.grad for x in xd], [b.weight.grad for b in bns], [b.bias.grad for b in bns]
+
+    a0, dx0, dw0, db0 = run(False)
+    a1, dx1, dw1, db1 = run(True)
+    for i in range(len(sizes)):
+        assert torch.equal(a0[i], a1[i]), i
+        assert torch.equal(dx0[i], dx1[i]), i
+        assert torch.equal(dw0[i], dw1[i]) and torch.equal(db0[i], db1[i]), i
+
+
 def test_bn_training_rejects_single_row():
     x = torch.randn(1, 128, device=DEV)
     bn = torch.nn.BatchNorm1d(128).to(DEV)
