@@ -954,7 +954,9 @@ def log_softmax_many(xs: Sequence[torch.Tensor]) -> List[torch.Tensor]:
 def log_softmax(x: torch.Tensor, dim: int = 1) -> torch.Tensor:
     if x.dim() != 2 or dim not in (1, -1):
         raise NotImplementedError('log_softmax: only 2-D input, dim=1')
-    return _LogSoftmaxFn.apply(x)
+    r = _LogSoftmaxFn.apply(x)
+    r._agx_logits = x          # see log_softmax_many
+    return r
 
 
 class _SoftmaxNLLFn(torch.autograd.Function):
