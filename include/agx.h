@@ -516,7 +516,11 @@ int agx_is_identity(const float* x, int64_t ld, int32_t n, int32_t* flag, int32_
 int agx_transpose(const float* in, int64_t ld_in, int32_t rows, int32_t cols, float* out,
                   int64_t ld_out, const int32_t* only_if_flag, void* stream);
 /* up to AGX_MAX_TENSORS transposes in one launch (the W^T copies of a hetero layer) */
-typedef struct { const float* in; int64_t ld_in; float* out; int64_t ld_out; int32_t rows; int32_t cols; } agx_transpose_desc_t;
+typedef struct {
+    const float* in; int64_t ld_in; float* out; int64_t ld_out; int32_t rows; int32_t cols;
+    int32_t accumulate;       /* out += in^T (a weight gradient added into its optimizer buffer) */
+    int32_t pad_;
+} agx_transpose_desc_t;
 int agx_transpose_batched(const agx_transpose_desc_t* h_descs, int n, void* stream);
 
 /* halo exchange support (config 5): pack rows listed in idx into a contiguous send buffer, and

@@ -64,7 +64,7 @@ class GemmProblem(C.Structure):
 
 class TransposeDesc(C.Structure):
     _fields_ = [('inp', vp), ('ld_in', c_i64), ('out', vp), ('ld_out', c_i64), ('rows', c_i32),
-                ('cols', c_i32)]
+                ('cols', c_i32), ('accumulate', c_i32), ('pad_', c_i32)]
 
 
 class SumDesc(C.Structure):

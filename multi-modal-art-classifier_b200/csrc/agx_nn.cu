@@ -1422,7 +1422,10 @@ __global__ void __launch_bounds__(256) transpose_batched(const __grid_constant__
     __syncthreads();
     for (int j = ty; j < 32; j += 8) {
         const int c = bx + j, r = by + tx;          // out[c][r]
-        if (c < D.cols && r < D.rows) D.out[(int64_t)c * D.ld_out + r] = tile[tx][j];
+        if (c < D.cols && r < D.rows) {
+            float* o = D.out + (int64_t)c * D.ld_out + r;
+            *o = D.accumulate ? *o + tile[tx][j] : tile[tx][j];
+        }
     }
 }
 

@@ -441,27 +441,49 @@ class _HeteroConvFn(torch.autograd.Function):
         trb: list = []
         trb_late: list = []
         dwroot: Dict[str, torch.Tensor] = {}
+        # gradient buffers the optimizer already owns (FlatAdam's arena): a weight gradient with a
+        # single producer is ADDED into its buffer by the producing kernel itself (the accumulate
+        # forms of the GEMM epilogue / the transposed copy) instead of being written to a temporary
+        # and added by _deliver_param_grads afterwards (one read + one write of every weight less;
+        # the one-hot input layer holds most of the model's 5 M weights)
+        refs = spec.param_refs
+        in_place = refs is not None and all(
+            p.grad is not None and p.grad.is_contiguous() for p in refs)
+        placed: Dict[int, bool] = {}
+
+        def grad_buffer(i_param, shape):
+            """(tensor to produce the gradient in, accumulate?)"""
+            if in_place and tuple(refs[i_param].grad.shape) == tuple(shape):
+                placed[i_param] = True
+                return refs[i_param].grad, True
+            return torch.empty(shape, dtype=torch.float32, device=dev), False
+
         for t in spec.dst_types:
             if dout[t] is None or t not in wroot:
                 continue
             x = xd[t]
-            dw = torch.empty(O, x.shape[1], dtype=torch.float32, device=dev)
+            owners = [rs.i_wr for _, rs in live if rs.rel.dst == t and rs.i_wr >= 0]
+            if len(owners) == 1:                      # one relation's lin_r: straight into its buffer
+                dw, acc = grad_buffer(owners[0], (O, x.shape[1]))
+            else:
+                dw, acc = torch.empty(O, x.shape[1], dtype=torch.float32, device=dev), False
             dwroot[t] = dw
             if spec.identity.get(t, False) and x is xs[t]:
-                trb.append((dw, dout[t]))                        # dout^T I
+                trb.append((dw, dout[t], acc))                   # dout^T I
             else:
-                gb.add(dw, [(_t(dout[t]), x)], split_k=ops.split_k_for(x.shape[0]))
+                gb.add(dw, [(_t(dout[t]), x)], split_k=ops.split_k_for(x.shape[0]), accumulate=acc)
         for k, rs in live:
             r = rs.rel
             x = xs[r.src]
-            dw = torch.empty(O, x.shape[1], dtype=torch.float32, device=dev)
+            dw, acc = grad_buffer(rs.i_wl, (O, x.shape[1]))
             grads[pidx(rs.i_wl)] = dw
             if rs.transform_first and spec.identity.get(r.src, False):
-                trb_late.append((dw, dY[k]))
+                trb_late.append((dw, dY[k], acc))
             elif rs.transform_first:
-                gb_late.add(dw, [(_t(dY[k]), x)], split_k=ops.split_k_for(r.n_src))
+                gb_late.add(dw, [(_t(dY[k]), x)], split_k=ops.split_k_for(r.n_src), accumulate=acc)
             else:
-                gb.add(dw, [(_t(dout[r.dst]), G[k])], split_k=ops.split_k_for(rs.rows))
+                gb.add(dw, [(_t(dout[r.dst]), G[k])], split_k=ops.split_k_for(rs.rows),
+                       accumulate=acc)
                 if need_x[r.src] and k not in dG:
                     dg = torch.empty(r.n_dst, x.shape[1], dtype=torch.float32, device=dev)
                     dG[k] = dg
@@ -547,6 +569,8 @@ class _HeteroConvFn(torch.autograd.Function):
             gb.add(dx, segs, accumulate=acc)
         if gb.problems:
             gb.run()
+        for i_param in placed:                      # already added into the optimizer's buffers
+            grads[pidx(i_param)] = None
         _deliver_param_grads(spec.param_refs, grads, nt, must=ctx.anchor)
         return (None, *grads) + ((None,) if ctx.anchor else ())
 

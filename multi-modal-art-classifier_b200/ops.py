@@ -761,15 +761,18 @@ def is_identity(x: torch.Tensor) -> torch.Tensor:
 
 
 def transpose_many(pairs: Sequence[Tuple[torch.Tensor, torch.Tensor]]):
-    """``pairs``: (out [cols, rows], inp [rows, cols]) -- all transposes in one launch per 48."""
+    """``pairs``: (out [cols, rows], inp [rows, cols]) or (out, inp, accumulate) -- all transposes
+    in one launch per 48; ``accumulate``: out += inp^T."""
     for base in range(0, len(pairs), L.MAX_TENSORS):
         part = pairs[base:base + L.MAX_TENSORS]
         arr = (L.TransposeDesc * len(part))()
-        for i, (out, inp) in enumerate(part):
+        for i, item in enumerate(part):
+            out, inp = item[0], item[1]
+            acc = bool(item[2]) if len(item) > 2 else False
             if inp.stride(1) != 1 or out.stride(1) != 1 or out.shape != (inp.shape[1], inp.shape[0]):
                 raise ValueError('transpose_many: row-major [r, c] -> [c, r] expected')
             arr[i] = L.TransposeDesc(ptr(inp), inp.stride(0), ptr(out), out.stride(0), inp.shape[0],
-                                     inp.shape[1])
+                                     inp.shape[1], int(acc), 0)
         check(lib().agx_transpose_batched(arr, len(part), stream_ptr()), 'agx_transpose_batched')
 
 

@@ -154,8 +154,12 @@ def _colsum(items):
 
 
 def _transpose_many(pairs):
-    for out, inp in pairs:
-        out.copy_(inp.t())
+    for item in pairs:
+        out, inp = item[0], item[1]
+        if len(item) > 2 and item[2]:
+            out.add_(inp.t())
+        else:
+            out.copy_(inp.t())
 
 
 def _fill_(t, v):
