@@ -175,11 +175,53 @@ __device__ __forceinline__ double slab_total_32x32(const double* __restrict__ pa
     return t;
 }
 
+// The same for TWO column blocks `off` apart in every slab (sum x and sum x^2; sum dy and sum dy*xhat)
+// in ONE pass: both chains of loads are in flight together, one barrier pair instead of two.  Same
+// summation order per total as slab_total_32x32.
+__device__ __forceinline__ void slab_total2_32x32(const double* __restrict__ part, int slabs,
+                                                  size_t stride, size_t off, int col0, int ncols,
+                                                  double (*sm)[33], double (*sm2)[33], double& t1,
+                                                  double& t2) {
+    const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+    double a = 0.0, b = 0.0;
+    if (col0 + c < ncols) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+        int s = g;
+        for (; s + 96 < slabs; s += 128) {
+            const double* q = part + (size_t)s * stride + col0 + c;
+            a0 += q[0];
+            a1 += q[32 * stride];
+            a2 += q[64 * stride];
+            a3 += q[96 * stride];
+            b0 += q[off];
+            b1 += q[32 * stride + off];
+            b2 += q[64 * stride + off];
+            b3 += q[96 * stride + off];
+        }
+        for (; s < slabs; s += 32) {
+            a0 += part[(size_t)s * stride + col0 + c];
+            b0 += part[(size_t)s * stride + off + col0 + c];
+        }
+        a = (a0 + a1) + (a2 + a3);
+        b = (b0 + b1) + (b2 + b3);
+    }
+    sm[g][c] = a;
+    sm2[g][c] = b;
+    __syncthreads();
+    t1 = t2 = 0.0;
+    if (g == 0)
+        for (int k = 0; k < 32; ++k) {
+            t1 += sm[k][c];
+            t2 += sm2[k][c];
+        }
+    __syncthreads();
+}
+
 // grid (descriptor, 32-column block); float64 combination of slab partials.
 // P.mode: 0 = finalize from the local partials; 1 = only write the local column sums to
 // sums[n][2F] (multi-GPU: all-reduced by the caller); 2 = finalize from sums with the global counts
 __global__ void __launch_bounds__(1024) bn_finalize(const __grid_constant__ BnParams P) {
-    __shared__ double sm[32][33];
+    __shared__ double sm[32][33], sm2[32][33];
     const agx_bn_desc_t& D = P.d[blockIdx.x];
     const int s0 = P.slab_start[blockIdx.x], s1 = P.slab_start[blockIdx.x + 1];
     const int F = P.F;
@@ -200,8 +242,7 @@ __global__ void __launch_bounds__(1024) bn_finalize(const __grid_constant__ BnPa
         }
     } else {
         const double* part = P.ws + (size_t)s0 * 2 * F;
-        a1 = slab_total_32x32(part, s1 - s0, (size_t)2 * F, col0, F, sm);
-        a2 = slab_total_32x32(part + F, s1 - s0, (size_t)2 * F, col0, F, sm);
+        slab_total2_32x32(part, s1 - s0, (size_t)2 * F, (size_t)F, col0, F, sm, sm2, a1, a2);
     }
     if (P.mode == 1) {
         if (threadIdx.x < 32 && c < F) {
@@ -432,14 +473,14 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce(const __grid_constan
 }
 
 __global__ void __launch_bounds__(1024) bn_bwd_finalize(const __grid_constant__ BnBwdParams P) {
-    __shared__ double sm[32][33];
+    __shared__ double sm[32][33], sm2[32][33];
     const agx_bn_bwd_desc_t& D = P.d[blockIdx.x];
     const int s0 = P.slab_start[blockIdx.x], s1 = P.slab_start[blockIdx.x + 1];
     const int F = P.F;
     const int col0 = blockIdx.y * 32;
     const double* part = P.ws + (size_t)s0 * 2 * F;
-    const double a0 = slab_total_32x32(part, s1 - s0, (size_t)2 * F, col0, F, sm);
-    const double a1 = slab_total_32x32(part + F, s1 - s0, (size_t)2 * F, col0, F, sm);
+    double a0, a1;
+    slab_total2_32x32(part, s1 - s0, (size_t)2 * F, (size_t)F, col0, F, sm, sm2, a0, a1);
     const int c = col0 + (int)threadIdx.x;
     if (threadIdx.x < 32 && c < F) {
         P.totals[(size_t)blockIdx.x * 2 * F + c] = a0;
@@ -634,6 +675,87 @@ log_softmax_nll(const float* __restrict__ logits, int64_t ld, int n_rows, int C,
         row_ws[2 * (int64_t)row] = ok ? -(x[y] - lse) * w : 0.f;
         row_ws[2 * (int64_t)row + 1] = w;
     }
+}
+
+// C <= 32, C % 4 == 0 (the 32 style classes of the GNN's output layer): 8 lanes x float4 per row, four
+// rows per warp -- a quarter of the warp instructions per row of the warp-per-row kernel above
+__global__ void __launch_bounds__(256)
+log_softmax_nll_v4(const float* __restrict__ logits, int64_t ld, int n_rows, int C,
+                   const int64_t* __restrict__ labels, const float* __restrict__ class_w,
+                   float* __restrict__ logp, int64_t ldp, float* __restrict__ row_ws) {
+    const int lane = threadIdx.x & 31, l = lane & 7;
+    const int row = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 4 + (lane >> 3);
+    const bool rv = row < n_rows;
+    const bool has = rv && l * 4 < C;
+    const float* x = logits + (int64_t)(rv ? row : 0) * ld;
+    float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (has) v = *reinterpret_cast<const float4*>(x + l * 4);
+    float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float s = has ? (expf(v.x - mx) + expf(v.y - mx)) + (expf(v.z - mx) + expf(v.w - mx)) : 0.f;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float lse = mx + logf(s);
+    if (logp && has)
+        *reinterpret_cast<float4*>(logp + (int64_t)row * ldp + l * 4) =
+            make_float4(v.x - lse, v.y - lse, v.z - lse, v.w - lse);
+    if (labels && rv && l == 0) {
+        const int64_t y = labels[row];
+        const bool ok = y >= 0 && y < C;
+        const float w = ok ? (class_w ? class_w[y] : 1.0f) : 0.f;
+        row_ws[2 * (int64_t)row] = ok ? -(x[y] - lse) * w : 0.f;
+        row_ws[2 * (int64_t)row + 1] = w;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+log_softmax_nll_bwd_v4(const float* __restrict__ logp, int64_t ldp, int n_rows, int C,
+                       const int64_t* __restrict__ labels, const float* __restrict__ class_w,
+                       const float* __restrict__ loss_sum, const float* __restrict__ gscale,
+                       float coef, const float* __restrict__ dlogp, int64_t lddp,
+                       float* __restrict__ dlogits, int64_t ld) {
+    const int lane = threadIdx.x & 31, l = lane & 7;
+    const int row = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 4 + (lane >> 3);
+    const bool rv = row < n_rows;
+    const bool has = rv && l * 4 < C;
+    float g = 0.f;
+    int y = -1;
+    if (labels && rv) {
+        const int64_t yy = labels[row];
+        const bool ok = yy >= 0 && yy < C;
+        const float w = ok ? (class_w ? class_w[yy] : 1.0f) : 0.f;
+        g = w * coef * (gscale ? gscale[0] : 1.0f) / loss_sum[1];
+        y = ok ? (int)yy : -1;
+    }
+    float4 dl = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sd = 0.f;
+    if (dlogp) {
+        if (has) dl = *reinterpret_cast<const float4*>(dlogp + (int64_t)row * lddp + l * 4);
+        sd = (dl.x + dl.y) + (dl.z + dl.w);
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
+    }
+    if (!has) return;
+    const float4 lp = *reinterpret_cast<const float4*>(logp + (int64_t)row * ldp + l * 4);
+    const float pv[4] = {expf(lp.x), expf(lp.y), expf(lp.z), expf(lp.w)};
+    const float dv[4] = {dl.x, dl.y, dl.z, dl.w};
+    float o4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float d = g * (pv[i] - (l * 4 + i == y ? 1.0f : 0.f));
+        if (dlogp) d += dv[i] - pv[i] * sd;
+        o4[i] = d;
+    }
+    *reinterpret_cast<float4*>(dlogits + (int64_t)row * ld + l * 4) =
+        make_float4(o4[0], o4[1], o4[2], o4[3]);
+}
+
+static bool lsm_v4_ok(int C, int64_t a, int64_t b, int64_t c, const void* p0, const void* p1,
+                      const void* p2) {
+    auto al = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % 16) == 0; };
+    return C <= 32 && (C & 3) == 0 && (a & 3) == 0 && (b & 3) == 0 && (c & 3) == 0 && al(p0) &&
+           al(p1) && al(p2);
 }
 
 // ordered float64 reduction of interleaved pairs: out[0] = sum in[2i], out[1] = sum in[2i+1].
@@ -1175,8 +1297,12 @@ extern "C" int agx_log_softmax_nll(const float* logits, int64_t ld, int32_t n_ro
                   "agx_log_softmax_nll: row_ws must be 8-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     if (n_rows > 0) {
-        log_softmax_nll<<<(unsigned)ceil_div(n_rows, 8), 256, 0, st>>>(logits, ld, n_rows, C, labels,
-                                                                       class_w, logp, ldp, row_ws);
+        if (lsm_v4_ok(C, ld, logp ? ldp : 0, 0, logits, logp, nullptr))
+            log_softmax_nll_v4<<<(unsigned)ceil_div(n_rows, 32), 256, 0, st>>>(
+                logits, ld, n_rows, C, labels, class_w, logp, ldp, row_ws);
+        else
+            log_softmax_nll<<<(unsigned)ceil_div(n_rows, 8), 256, 0, st>>>(
+                logits, ld, n_rows, C, labels, class_w, logp, ldp, row_ws);
         AGX_LAUNCH_CHECK("log_softmax_nll");
     }
     if (labels) {
@@ -1231,8 +1357,12 @@ extern "C" int agx_log_softmax_nll_bwd(const float* logp, int64_t ldp, int32_t n
     AGX_CHECK_ARG(logp && dlogits && n_rows >= 0 && C >= 1, "agx_log_softmax_nll_bwd: bad arguments");
     AGX_CHECK_ARG(!labels || loss_sum, "agx_log_softmax_nll_bwd: labels need loss_sum");
     if (n_rows == 0) return AGX_OK;
-    log_softmax_nll_bwd<<<(unsigned)ceil_div(n_rows, 8), 256, 0, (cudaStream_t)stream>>>(
-        logp, ldp, n_rows, C, labels, class_w, loss_sum, gscale, coef, dlogp, lddp, dlogits, ld);
+    if (lsm_v4_ok(C, ldp, ld, dlogp ? lddp : 0, logp, dlogits, dlogp))
+        log_softmax_nll_bwd_v4<<<(unsigned)ceil_div(n_rows, 32), 256, 0, (cudaStream_t)stream>>>(
+            logp, ldp, n_rows, C, labels, class_w, loss_sum, gscale, coef, dlogp, lddp, dlogits, ld);
+    else
+        log_softmax_nll_bwd<<<(unsigned)ceil_div(n_rows, 8), 256, 0, (cudaStream_t)stream>>>(
+            logp, ldp, n_rows, C, labels, class_w, loss_sum, gscale, coef, dlogp, lddp, dlogits, ld);
     AGX_LAUNCH_CHECK("log_softmax_nll_bwd");
     return AGX_OK;
 }

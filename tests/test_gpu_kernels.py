@@ -390,7 +390,7 @@ def test_adam_matches_torch():
 
 def test_log_softmax_nll_and_ce_weighted():
     gen = torch.Generator().manual_seed(6)
-    for n, c in ((500, 32), (333, 18), (64, 100)):
+    for n, c in ((500, 32), (333, 18), (64, 100), (501, 20), (77, 8)):   # c % 4 == 0, c <= 32: float4 kernels
         x = torch.randn(n, c, generator=gen) * 3
         y = torch.randint(0, c, (n,), generator=gen)
         w = torch.rand(c, generator=gen) + 0.5
@@ -413,6 +413,13 @@ def test_log_softmax_nll_and_ce_weighted():
         assert rel_err(lp, torch.log_softmax(x, 1)) <= RTOL_F32
         assert rel_err(l2d, l2) <= RTOL_F32
         assert rel_err(xd2.grad, xr2.grad) <= RTOL_F32
+        # an arbitrary upstream gradient on the log-probabilities (the un-fused backward)
+        r = torch.randn(n, c, generator=gen)
+        xr3 = x.clone().requires_grad_(True)
+        (torch.log_softmax(xr3, 1) * r).sum().backward()
+        xd3 = x.to(DEV).requires_grad_(True)
+        (AF.log_softmax(xd3, 1) * r.to(DEV)).sum().backward()
+        assert rel_err(xd3.grad, xr3.grad) <= RTOL_F32
 
 
 def test_smooth_l1():
