@@ -412,7 +412,24 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce(const __grid_constan
         if (g < groups) {
             const float4 m = *reinterpret_cast<const float4*>(D.save_mean + c);
             const float4 is = *reinterpret_cast<const float4*>(D.save_invstd + c);
-            for (int r = r0 + g; r < r1; r += groups) {
+            int r = r0 + g;
+            for (; r + 3 * groups < r1; r += 4 * groups) {       // four rows in flight, same order
+                float4 gy[4], x[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t e = (int64_t)(r + u * groups) * F + c;
+                    gy[u] = bn_dy_total4(D, e);
+                    x[u] = *reinterpret_cast<const float4*>(D.x + e);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    s0[0] += (double)gy[u].x; s1[0] += (double)gy[u].x * (double)((x[u].x - m.x) * is.x);
+                    s0[1] += (double)gy[u].y; s1[1] += (double)gy[u].y * (double)((x[u].y - m.y) * is.y);
+                    s0[2] += (double)gy[u].z; s1[2] += (double)gy[u].z * (double)((x[u].z - m.z) * is.z);
+                    s0[3] += (double)gy[u].w; s1[3] += (double)gy[u].w * (double)((x[u].w - m.w) * is.w);
+                }
+            }
+            for (; r < r1; r += groups) {
                 const int64_t e = (int64_t)r * F + c;
                 const float4 gy = bn_dy_total4(D, e);
                 const float4 x = *reinterpret_cast<const float4*>(D.x + e);

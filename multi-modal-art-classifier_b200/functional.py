@@ -267,7 +267,9 @@ class _HeteroConvFn(torch.autograd.Function):
         late = {F: [sg for sg in segs if id(sg[1].x) in y_ids] for F, segs in chunks_by_F.items()}
         n_early = sum(sg[1].csr.n_edges for segs in early.values() for sg in segs)
         n_late = sum(sg[1].csr.n_edges for segs in late.values() for sg in segs)
-        if min(n_early, n_late) < 0.25 * max(n_early, n_late, 1):
+        if n_late == 0:
+            early, late = chunks_by_F, {}           # nothing waits for the transform-first products
+        elif min(n_early, n_late) < 0.25 * max(n_early, n_late, 1):
             # a second launch for a few small relations costs more than starting the others early
             early, late = {}, chunks_by_F
         fk = ops.fork(dev)
