@@ -107,6 +107,7 @@ class GNNTrainer:
         self.launches_per_step = 0
         self._stage = None
         self._prefetched = False
+        self._refresh_graph = None
 
     # -- one optimisation step, eager ------------------------------------------------------------
     def _step_eager(self):
@@ -230,14 +231,42 @@ class GNNTrainer:
             raise RuntimeError('consume_prefetched() without prefetch_inputs()')
         cur = torch.cuda.current_stream()
         cur.wait_event(self._ev_staged)
-        for k, v in self._stage[0].items():
-            self.x[k].copy_(v, non_blocking=True)
-        for k, v in self._stage[1].items():
-            self.ei[k].copy_(v, non_blocking=True)
+        fast = getattr(self, '_plan', None) is not None and \
+            not getattr(self, '_eager_only', False) and \
+            (self.ctx is None or self.ctx.halo is None)
+        if not fast:
+            for k, v in self._stage[0].items():
+                self.x[k].copy_(v, non_blocking=True)
+            for k, v in self._stage[1].items():
+                self.ei[k].copy_(v, non_blocking=True)
+            self._inputs_changed()
+        elif self._refresh_graph is not None:
+            self._refresh_graph.replay()
+        else:
+            self._refresh_from_stage()
+            if self.use_cuda_graph:
+                # the ~40 launches of the refresh (feature copies, batched radix sort, one-hot
+                # checks) as ONE graph launch from now on
+                g = torch.cuda.CUDAGraph()
+                mode = 'thread_local' if self.group is not None else 'global'
+                with torch.cuda.graph(g, capture_error_mode=mode):
+                    self._refresh_from_stage()
+                g.replay()            # (the flag tensors of the captured run hold values now)
+                self._refresh_graph = g
         self._ev_consumed = torch.cuda.Event()
         self._ev_consumed.record(cur)
         self._prefetched = False
-        self._inputs_changed()
+
+    def _refresh_from_stage(self):
+        """Prefetched inputs -> the state the captured step reads: features are copied into the
+        static tensors; the CSR / CSC are re-sorted STRAIGHT from the staged edge lists (the step
+        never reads ``self.ei`` itself -- 22 device-to-device copies less per step); the one-hot
+        checks re-run.  No allocation that outlives the call, no host synchronisation:
+        capturable."""
+        for k, v in self._stage[0].items():
+            self.x[k].copy_(v, non_blocking=True)
+        self._plan.rebuild_(self._stage[1])
+        self._refresh_identity_flags()
 
     def _inputs_changed(self):
         from .hetero import _is_identity_input
@@ -256,6 +285,10 @@ class GNNTrainer:
             self._plan = get_plan(self.ei, num_nodes, num_dst=num_dst)   # version bump -> re-sort
         if self.ctx is not None and self.ctx.halo is not None:
             self.ctx.halo.refresh(self.x)
+        self._refresh_identity_flags()
+
+    def _refresh_identity_flags(self):
+        from .hetero import _is_identity_input
         self._id_flags = {}
         from .data import is_declared_identity
         for t, v in self.x.items():

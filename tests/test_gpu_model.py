@@ -600,6 +600,11 @@ def test_prefetched_inputs_equal_inline_update():
         b.verify_inputs()
     assert la == lb, (la, lb)
     assert len(set(la)) == 3
+    # the prefetch path sorts straight from the staged edge lists (the static ``ei`` tensors keep
+    # the first epoch's lists): whatever runs the model afterwards sees the LAST epoch's graph
+    ea, eb = a.embeddings(), b.embeddings()
+    assert torch.equal(ea['artwork'], eb['artwork'])
+    assert b._refresh_graph is not None
 
 
 def test_hetero_mgnn_three_towers_vs_oracle():
