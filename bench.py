@@ -502,9 +502,30 @@ def heads_throughput(dev, dist, world, batches=(4096,), steps: int = 20, cpu: bo
                 e1.record()
                 torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1)
+                # end to end: every step's batch travels from pinned host memory (copy stream, one
+                # step ahead: HeadTrainer.prefetch / step_prefetched), the loss of EVERY step is
+                # read on the host one step late
+                pin = [torch.empty(1, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+                evs = [torch.cuda.Event() for _ in range(2)]
+
+                def e2e_loop(n):
+                    tr.prefetch(*sel(host))
+                    last = None
+                    for i in range(n):
+                        loss = tr.step_prefetched()
+                        if i + 1 < n:
+                            tr.prefetch(*sel(host))
+                        pin[i & 1].copy_(loss.detach().reshape(1), non_blocking=True)
+                        evs[i & 1].record()
+                        if i > 0:
+                            evs[(i - 1) & 1].synchronize()
+                            last = float(pin[(i - 1) & 1][0])
+                    evs[(n - 1) & 1].synchronize()
+                    return float(pin[(n - 1) & 1][0])
+                e2e_loop(2)
+                torch.cuda.synchronize()
                 t0 = time.perf_counter()
-                for _ in range(steps):      # pinned host batch -> static device buffers -> replay
-                    float(tr.step(*sel(host)).item())
+                e2e_loop(steps)
                 torch.cuda.synchronize()
                 ms_e2e = (time.perf_counter() - t0) * 1e3
                 if dist is not None:

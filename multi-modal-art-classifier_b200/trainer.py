@@ -450,6 +450,49 @@ class HeadTrainer:
         self._graph.replay()
         return self._loss
 
+    # -- the next batch one step ahead: its host -> device copy overlaps the running step -----------
+    def prefetch(self, feat, *rest):
+        """Start copying the NEXT mini-batch from (pinned) host memory into device staging buffers
+        on a copy stream; returns at once.  ``step_prefetched()`` runs the step on it.  (What a
+        ``DataLoader(pin_memory=True)`` + ``.to(device, non_blocking=True)`` loop does for the
+        reference, src/train_new_multimodal_multitask.py:62-90.)"""
+        batch = (feat, *rest)
+        dev = self.opt.flat.device
+        stage = getattr(self, '_stage', None)
+        if stage is None or any(a.shape != b.shape or a.dtype != b.dtype
+                                for a, b in zip(batch, stage)):
+            self._stage = [torch.empty_like(t, device=dev) for t in batch]
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._ev_staged = torch.cuda.Event()
+            self._ev_consumed = None
+        with torch.cuda.stream(self._copy_stream):
+            if self._ev_consumed is not None:           # the staging buffers were read out
+                self._copy_stream.wait_event(self._ev_consumed)
+            for st, t in zip(self._stage, batch):
+                st.copy_(t, non_blocking=True)
+            self._ev_staged.record(self._copy_stream)
+        self._staged = True
+
+    def step_prefetched(self) -> torch.Tensor:
+        if not getattr(self, '_staged', False):
+            raise RuntimeError('step_prefetched() without prefetch()')
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._ev_staged)
+        self._staged = False
+        ready = self.use_cuda_graph and self._graph is not None and all(
+            a.shape == b.shape and a.dtype == b.dtype for a, b in zip(self._stage, self._static))
+        if not ready:
+            loss = self.step(*self._stage)              # first batch / new shape / eager trainer
+            self._ev_consumed = torch.cuda.Event()
+            self._ev_consumed.record(cur)
+            return loss
+        for st, t in zip(self._static, self._stage):
+            st.copy_(t, non_blocking=True)
+        self._ev_consumed = torch.cuda.Event()
+        self._ev_consumed.record(cur)                   # the next prefetch may start under the step
+        self._graph.replay()
+        return self._loss
+
     def _step_tc(self, feat, *rest) -> torch.Tensor:
         """One fused kernel for forward + loss + backward, then (all-reduce,) Adam: every parameter
         of the head receives its gradient from the step, so the arena is written, not cleared."""

@@ -566,6 +566,33 @@ def test_trainers_cuda_graph_steps_equal_eager_steps():
             assert rel_err(q, p) <= 1e-5, (kind, k)
 
 
+def test_head_trainer_prefetch_equals_inline_batches():
+    """HeadTrainer.prefetch / step_prefetched (host batch copied on a copy stream one step ahead)
+    feeds the captured head step what step(batch) feeds it: same losses, same weights."""
+    from mmac_b200 import synth
+    from mmac_b200.trainer import HeadTrainer
+    batches = [[t.pin_memory() for t in synth.make_head_batch(256, 'vit', seed=40 + i)] for i in range(4)]
+    ws = synth.class_weights(batches[0][3], 32).to(DEV)
+    wg = synth.class_weights(batches[0][4], 18).to(DEV)
+    for precision in ('fp32', 'bf16'):
+        torch.manual_seed(3)
+        h1 = agx.NewMultiModalMultiTaskHead(128, {'style': 32, 'genre': 18}, 0.0, 768).to(DEV)
+        h2 = copy.deepcopy(h1)
+        a = HeadTrainer(h1, 'multitask', 3e-4, ws, wg, use_cuda_graph=True, precision=precision)
+        b = HeadTrainer(h2, 'multitask', 3e-4, ws, wg, use_cuda_graph=True, precision=precision)
+        la = [float(a.step(*batches[i % 4]).item()) for i in range(6)]
+        lb = []
+        b.prefetch(*batches[0])
+        for i in range(6):
+            loss = b.step_prefetched()
+            if i + 1 < 6:
+                b.prefetch(*batches[(i + 1) % 4])
+            lb.append(float(loss.item()))
+        assert la == lb, (precision, la, lb)
+        for (k, p), (_, q) in zip(h1.state_dict().items(), h2.state_dict().items()):
+            assert torch.equal(p, q), (precision, k)
+
+
 def test_prefetched_inputs_equal_inline_update():
     """The input pipeline (host -> staging on a copy stream, staging -> static tensors on the step's
     stream) feeds the captured step exactly what update_inputs() feeds it: different graphs per
