@@ -409,7 +409,8 @@ class _HeteroConvFn(torch.autograd.Function):
             if dout[t] is not None and any(rs.i_bl >= 0 for _, rs in live if rs.rel.dst == t):
                 dbias[t] = torch.empty(O, dtype=torch.float32, device=dev)
                 cs_items.append((dout[t], dbias[t], False))
-        ops.colsum(cs_items)
+        # (launched below, on the side stream in front of the dY aggregation: nothing in this layer
+        # reads the bias gradients)
         for k, rs in live:
             if rs.i_bl >= 0:
                 grads[pidx(rs.i_bl)] = dbias[rs.rel.dst]
@@ -434,6 +435,7 @@ class _HeteroConvFn(torch.autograd.Function):
         # read dY (gb_late, trb_late) go with the last launch of the layer
         fk = ops.fork(dev)
         with fk:
+            ops.colsum(cs_items)
             ops.aggregate_chunks(chunks, O)
             ops.aggregate_rows(rows, O)
 
