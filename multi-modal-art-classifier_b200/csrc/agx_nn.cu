@@ -394,7 +394,7 @@ __device__ __forceinline__ float4 bn_dy_total4(const agx_bn_bwd_desc_t& D, int64
     return g;
 }
 
-__global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce(const __grid_constant__ BnBwdParams P) {
+__global__ void __launch_bounds__(kBnThreads, 4) bn_bwd_reduce(const __grid_constant__ BnBwdParams P) {
     int di = 0;
     while ((int)blockIdx.x >= P.slab_start[di + 1]) ++di;
     const agx_bn_bwd_desc_t& D = P.d[di];
@@ -921,17 +921,39 @@ adam_step(float* __restrict__ p, const float* __restrict__ g, float* __restrict_
     const double bc2 = 1.0 - pow((double)b2, (double)t);
     const float step_size = (float)((double)lr / bc1);
     const float bc2_sqrt = (float)sqrt(bc2);
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        float grad = g[i];
-        if (wd != 0.f) grad += wd * p[i];
-        const float mi = m[i] + (grad - m[i]) * (1.0f - b1);           // lerp_
-        const float vi = v[i] * b2 + (1.0f - b2) * grad * grad;        // mul_ + addcmul_
-        m[i] = mi;
-        v[i] = vi;
+    auto upd = [&](float& pi, float gi, float& mi_, float& vi_) {
+        float grad = gi;
+        if (wd != 0.f) grad += wd * pi;
+        const float mi = mi_ + (grad - mi_) * (1.0f - b1);             // lerp_
+        const float vi = vi_ * b2 + (1.0f - b2) * grad * grad;         // mul_ + addcmul_
+        mi_ = mi;
+        vi_ = vi;
         const float denom = sqrtf(vi) / bc2_sqrt + eps;
-        p[i] = p[i] - step_size * (mi / denom);
+        pi = pi - step_size * (mi / denom);
+    };
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    int64_t done = 0;
+    if (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
+          reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0) {
+        // 128-bit accesses, several elements per thread (the two pow() above are per thread)
+        const int64_t n4 = n >> 2;
+        for (int64_t q = tid; q < n4; q += nthr) {
+            float4 P4 = reinterpret_cast<float4*>(p)[q];
+            const float4 G4 = reinterpret_cast<const float4*>(g)[q];
+            float4 M4 = reinterpret_cast<float4*>(m)[q];
+            float4 V4 = reinterpret_cast<float4*>(v)[q];
+            upd(P4.x, G4.x, M4.x, V4.x);
+            upd(P4.y, G4.y, M4.y, V4.y);
+            upd(P4.z, G4.z, M4.z, V4.z);
+            upd(P4.w, G4.w, M4.w, V4.w);
+            reinterpret_cast<float4*>(m)[q] = M4;
+            reinterpret_cast<float4*>(v)[q] = V4;
+            reinterpret_cast<float4*>(p)[q] = P4;
+        }
+        done = n4 << 2;
     }
+    for (int64_t i = done + tid; i < n; i += nthr) upd(p[i], g[i], m[i], v[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1390,7 +1412,9 @@ extern "C" int agx_adam_step(float* param, const float* grad, float* exp_avg, fl
     AGX_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && step && numel >= 0,
                   "agx_adam_step: null pointer");
     if (numel == 0) return AGX_OK;
-    adam_step<<<grid_for(numel, 256), 256, 0, (cudaStream_t)stream>>>(
+    int grid = grid_for((numel + 3) / 4, 256);
+    if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+    adam_step<<<grid, 256, 0, (cudaStream_t)stream>>>(
         param, grad, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps, weight_decay, step);
     AGX_LAUNCH_CHECK("adam_step");
     return AGX_OK;
