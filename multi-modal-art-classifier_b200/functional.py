@@ -440,8 +440,9 @@ class _HeteroConvFn(torch.autograd.Function):
             ops.aggregate_rows(rows, O)
 
         # b2/b3: weight gradients and the aggregate-first input gradients dG = dout W_l
-        gb = ops.GemmBatch()
-        gb_late = ops.GemmBatch()
+        gb = ops.GemmBatch()          # products the rest of this backward reads (dG)
+        gb_w = ops.GemmBatch()        # weight gradients from dout
+        gb_late = ops.GemmBatch()     # weight gradients from dY
         trb: list = []
         trb_late: list = []
         dwroot: Dict[str, torch.Tensor] = {}
@@ -475,7 +476,7 @@ class _HeteroConvFn(torch.autograd.Function):
             if spec.identity.get(t, False) and x is xs[t]:
                 trb.append((dw, dout[t], acc))                   # dout^T I
             else:
-                gb.add(dw, [(_t(dout[t]), x)], split_k=ops.split_k_for(x.shape[0]), accumulate=acc)
+                gb_w.add(dw, [(_t(dout[t]), x)], split_k=ops.split_k_for(x.shape[0]), accumulate=acc)
         for k, rs in live:
             r = rs.rel
             x = xs[r.src]
@@ -486,14 +487,23 @@ class _HeteroConvFn(torch.autograd.Function):
             elif rs.transform_first:
                 gb_late.add(dw, [(_t(dY[k]), x)], split_k=ops.split_k_for(r.n_src), accumulate=acc)
             else:
-                gb.add(dw, [(_t(dout[r.dst]), G[k])], split_k=ops.split_k_for(rs.rows),
-                       accumulate=acc)
+                gb_w.add(dw, [(_t(dout[r.dst]), G[k])], split_k=ops.split_k_for(rs.rows),
+                         accumulate=acc)
                 if need_x[r.src] and k not in dG:
                     dg = torch.empty(r.n_dst, x.shape[1], dtype=torch.float32, device=dev)
                     dG[k] = dg
                     gb.add(dg, [(dout[r.dst], params[rs.i_wl])])
-        if trb:
-            ops.transpose_many(trb)
+        # In direct-gradient mode nothing reads a weight gradient before the optimizer step: those
+        # products leave the critical path (ops.defer: a third stream, joined when the whole
+        # backward pass is over) and run under the BatchNorm backward / the next layer's backward.
+        deferred = in_place and ctx.anchor
+        hold = [t for t in dout.values() if t is not None] + list(xs.values()) + list(G.values()) + \
+            list(dwroot.values())
+        with (ops.defer(dev, hold) if deferred else ops.defer(torch.device('cpu'))) as dfr:
+            if trb:
+                ops.transpose_many(trb)
+            if gb_w.problems:
+                gb_w.run(dfr.keep)
         if gb.problems:
             gb.run()
         for w in works:
@@ -553,9 +563,12 @@ class _HeteroConvFn(torch.autograd.Function):
             ops.aggregate_rows(groups[key], key[1])
         fk5.join()
         fk.join()                                   # dY is complete (b4a, same side stream)
-        if trb_late:
-            ops.transpose_many(trb_late)
-        gb = gb_late                                # + the input-gradient products below
+        with (ops.defer(dev, list(dY.values())) if deferred
+              else ops.defer(torch.device('cpu'))) as dfr:
+            if trb_late:
+                ops.transpose_many(trb_late)
+            if gb_late.problems:
+                gb_late.run(dfr.keep)
         last = []
         for dx_, ins in long_sums:
             while len(ins) > 8:
@@ -575,7 +588,9 @@ class _HeteroConvFn(torch.autograd.Function):
             gb.run()
         for i_param in placed:                      # already added into the optimizer's buffers
             grads[pidx(i_param)] = None
-        _deliver_param_grads(spec.param_refs, grads, nt, must=ctx.anchor)
+        with (ops.defer(dev, [g for g in grads if g is not None]) if deferred
+              else ops.defer(torch.device('cpu'))):
+            _deliver_param_grads(spec.param_refs, grads, nt, must=ctx.anchor)
         return (None, *grads) + ((None,) if ctx.anchor else ())
 
 

@@ -115,6 +115,77 @@ def fork(device) -> Fork:
     return Fork(device)
 
 
+# Work nobody reads before the END of the backward pass (weight gradients that are added straight
+# into the optimizer's buffers) goes to a third stream and is NOT joined by the layer that issues
+# it: it runs under the BatchNorm backward and the next layer's backward.  ``Deferred.join`` is
+# queued as an autograd-engine callback (runs when the backward pass finishes, also inside a stream
+# capture), so that after ``loss.backward()`` the caller's stream has waited for everything.  The
+# tensors those launches read are kept alive until then (autograd frees a layer's saved tensors and
+# incoming gradients when its backward returns; the caching allocator would hand their memory to
+# the main stream while the deferred launch still reads it).
+_DEFER: dict = {}
+
+
+class Deferred:
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device)
+        self.main = None
+        self.keep: list = []
+        self.pending = False
+
+    def join(self):
+        if self.pending:
+            self.main.wait_stream(self.stream)
+            self.pending = False
+        self.keep.clear()
+
+
+class _DeferCtx:
+    def __init__(self, d, main):
+        self.d, self.main = d, main
+        self.keep = d.keep            # launches inside add what they must keep alive
+
+    def __enter__(self):
+        self.d.stream.wait_stream(self.main)
+        self._ctx = torch.cuda.stream(self.d.stream)
+        self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        self._ctx.__exit__(*exc)
+        return False
+
+
+class _NoDefer:
+    keep = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def defer(device, keep=()):
+    """Context manager: launches inside go to the deferred stream (after everything queued on the
+    current stream so far); ``keep``: tensors those launches read / write.  Only valid inside a
+    backward pass (the join is an engine callback).  No-op where ``fork`` is one."""
+    if _NO_SIDE or TIMER is not None or device.type != 'cuda':
+        return _NoDefer()
+    d = _DEFER.get(device.index)
+    if d is None:
+        d = _DEFER[device.index] = Deferred(device)
+    main = torch.cuda.current_stream(device)
+    if d.pending and d.main is not None and d.main != main:
+        d.join()                                  # (another stream took over: settle the old one)
+    if not d.pending:
+        d.main = main
+        d.pending = True
+        torch.autograd.Variable._execution_engine.queue_callback(d.join)
+    d.keep.extend(t for t in keep if t is not None)
+    return _DeferCtx(d, main)
+
+
 def aggregation_bytes(n_edges: int, n_rows: int, F: int, elem: int = 4) -> int:
     """Algorithmic HBM bytes of one relation's aggregation pass:
     E*(F*s + 4) gathered rows + column ids, (N+1)*4 row pointers, N*F*s output rows."""
@@ -522,7 +593,9 @@ class GemmBatch:
         self.problems.append(p)
         self._keep += [C_out, bias, row_scale, skip_flag]
 
-    def run(self):
+    def run(self, keep_into: Optional[list] = None):
+        """``keep_into``: receives the tensors the launches use (operands, split-K partials,
+        transposed weight copies) -- for launches on a stream that is joined later (ops.defer)."""
         if self._transposes:
             transpose_many(self._transposes)
             self._transposes = []
@@ -569,10 +642,12 @@ class GemmBatch:
                         nb += (src.M + src.N) * K * 4
                 TIMER.end('gemm', nb, fl, t0)
             i = j
+        if keep_into is not None:
+            keep_into.extend(t for t in self._keep if t is not None)
         self.problems, self.segs, self._keep = [], [], []
         later, self._later = self._later, []
         for gb in later:
-            gb.run()
+            gb.run(keep_into)
 
 
 def split_k_for(k_rows: int, slab: int = 384, max_split: int = 512) -> int:

@@ -87,7 +87,7 @@ class _GemmBatch:
             assert len(segs) == 1
         self.problems.append((C_out, list(segs), bias, accumulate))
 
-    def run(self):
+    def run(self, keep_into=None):
         for C_out, segs, bias, acc in self.problems:
             tot = torch.zeros(C_out.shape, dtype=torch.float64)
             for sg in segs:
