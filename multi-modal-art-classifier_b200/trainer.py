@@ -202,35 +202,51 @@ class GNNTrainer:
     def prefetch_inputs(self, host_x, host_ei):
         """Start copying the NEXT step's inputs from pinned host memory into device staging
         buffers on a copy stream (returns at once; the running step is not disturbed).
-        ``consume_prefetched()`` moves them into the static tensors of the captured step."""
+        ``consume_prefetched()`` moves them into the state of the captured step.  Two staging sets
+        alternate, so the copy for step i+2 may start as soon as the one for step i+1 is done
+        (it only waits until step i's set has been read out)."""
         dev = next(iter(self.x.values())).device
         from .data import is_declared_identity
         if self._stage is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
-            self._stage = (OrderedDict((k, torch.empty_like(v)) for k, v in self.x.items()
-                                       if not is_declared_identity(v)),
-                           OrderedDict((k, torch.empty_like(v)) for k, v in self.ei.items()))
-            self._ev_staged = torch.cuda.Event()
-            self._ev_consumed = None
+            self._stages = [(OrderedDict((k, torch.empty_like(v)) for k, v in self.x.items()
+                                         if not is_declared_identity(v)),
+                             OrderedDict((k, torch.empty_like(v)) for k, v in self.ei.items()))
+                            for _ in range(2)]
+            self._stage = self._stages[0]
+            self._ev_staged = [torch.cuda.Event(), torch.cuda.Event()]
+            self._ev_consumed = [None, None]
+            self._pf_issued = 0
+            self._pf_queue = []
+            self._refresh_graphs = [None, None]
+            self._slot_flags = [None, None]
+        if len(self._pf_queue) >= 2:
+            raise RuntimeError('prefetch_inputs(): two prefetched steps are already waiting')
+        slot = self._pf_issued % 2
+        self._pf_issued += 1
+        stage = self._stages[slot]
         with torch.cuda.stream(self._copy_stream):
-            if self._ev_consumed is not None:           # the staging buffers were read out
-                self._copy_stream.wait_event(self._ev_consumed)
+            if self._ev_consumed[slot] is not None:     # this set was read out
+                self._copy_stream.wait_event(self._ev_consumed[slot])
             for k, v in host_x.items():
                 if self._keeps_identity(k, v):
                     continue
-                self._stage[0][k].copy_(v, non_blocking=True)
+                stage[0][k].copy_(v, non_blocking=True)
             for k, v in host_ei.items():
-                self._stage[1][k].copy_(v, non_blocking=True)
-            self._ev_staged.record(self._copy_stream)
+                stage[1][k].copy_(v, non_blocking=True)
+            self._ev_staged[slot].record(self._copy_stream)
+        self._pf_queue.append(slot)
         self._prefetched = True
 
     def consume_prefetched(self):
-        """Device-to-device copy of the prefetched inputs into the static tensors (waits for the
-        host copy on the device, not on the host), then as ``update_inputs``."""
-        if not getattr(self, '_prefetched', False):
+        """The oldest prefetched inputs become the state of the captured step (waits for the host
+        copy on the device, not on the host)."""
+        if not getattr(self, '_prefetched', False) or not self._pf_queue:
             raise RuntimeError('consume_prefetched() without prefetch_inputs()')
+        slot = self._pf_queue.pop(0)
+        self._stage = self._stages[slot]
         cur = torch.cuda.current_stream()
-        cur.wait_event(self._ev_staged)
+        cur.wait_event(self._ev_staged[slot])
         fast = getattr(self, '_plan', None) is not None and \
             not getattr(self, '_eager_only', False) and \
             (self.ctx is None or self.ctx.halo is None)
@@ -240,22 +256,26 @@ class GNNTrainer:
             for k, v in self._stage[1].items():
                 self.ei[k].copy_(v, non_blocking=True)
             self._inputs_changed()
-        elif self._refresh_graph is not None:
-            self._refresh_graph.replay()
+        elif self._refresh_graphs[slot] is not None:
+            self._refresh_graphs[slot].replay()
+            self._id_flags = self._slot_flags[slot]
         else:
             self._refresh_from_stage()
             if self.use_cuda_graph:
                 # the ~40 launches of the refresh (feature copies, batched radix sort, one-hot
-                # checks) as ONE graph launch from now on
+                # checks) as ONE graph launch from now on (one graph per staging set)
                 g = torch.cuda.CUDAGraph()
                 mode = 'thread_local' if self.group is not None else 'global'
                 with torch.cuda.graph(g, capture_error_mode=mode):
                     self._refresh_from_stage()
                 g.replay()            # (the flag tensors of the captured run hold values now)
+                self._refresh_graphs[slot] = g
+                self._slot_flags[slot] = self._id_flags
                 self._refresh_graph = g
-        self._ev_consumed = torch.cuda.Event()
-        self._ev_consumed.record(cur)
-        self._prefetched = False
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self._ev_consumed[slot] = ev
+        self._prefetched = bool(self._pf_queue)
 
     def _refresh_from_stage(self):
         """Prefetched inputs -> the state the captured step reads: features are copied into the
