@@ -178,10 +178,11 @@ def defer(device, keep=()):
     main = torch.cuda.current_stream(device)
     if d.pending and d.main is not None and d.main != main:
         d.join()                                  # (another stream took over: settle the old one)
-    if not d.pending:
-        d.main = main
-        d.pending = True
-        torch.autograd.Variable._execution_engine.queue_callback(d.join)
+    d.main = main
+    d.pending = True
+    # one callback per use (join() is idempotent): a flag "already queued for this pass" would
+    # survive a backward pass that died with an exception and silence the join of the next one
+    torch.autograd.Variable._execution_engine.queue_callback(d.join)
     d.keep.extend(t for t in keep if t is not None)
     return _DeferCtx(d, main)
 
