@@ -364,7 +364,29 @@ class GNNTrainer:
     @torch.no_grad()
     def evaluate(self, x_dict=None, edge_index_dict=None, labels=None):
         """``hetero_test()`` on one graph: (loss, accuracy); BatchNorm in eval mode, dropout as
-        traced."""
+        traced.  On the trainer's own graph (no arguments) with ``use_cuda_graph``
+        the evaluation forward is captured once and replayed, like the training step (its ~60
+        launches are otherwise bound by the Python launch path: 3-4 ms instead of 0.5)."""
+        own = x_dict is None and edge_index_dict is None and labels is None
+        if own and self.use_cuda_graph and not getattr(self, '_eager_only', False):
+            self._lazy_init()
+            if getattr(self, '_eval_graph', None) is None:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    self._evaluate_eager(None, None, None)           # plans, workspaces
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                mode = 'thread_local' if self.group is not None else 'global'
+                with torch.cuda.graph(g, capture_error_mode=mode):
+                    self._eval_out = self._evaluate_eager(None, None, None)
+                self._eval_graph = g
+            self._eval_graph.replay()
+            return self._eval_out
+        return self._evaluate_eager(x_dict, edge_index_dict, labels)
+
+    def _evaluate_eager(self, x_dict, edge_index_dict, labels):
         self._check_foreign_graph(x_dict, edge_index_dict)
         self.model.eval()
         x = self.x if x_dict is None else x_dict

@@ -201,6 +201,25 @@ def test_eval_mode_uses_running_stats_and_keeps_dropout_semantics():
     assert torch.equal(e_c['artwork'], e_p['artwork'])
 
 
+def test_captured_evaluate_equals_eager_evaluate():
+    """GNNTrainer.evaluate() on the trainer's own graph replays a captured evaluation forward
+    (hetero_test(), train_gnn_embeddings.py:54-75): same loss / accuracy as the eager path, also after
+    further training steps changed the weights and the BatchNorm running statistics."""
+    from mmac_b200.trainer import GNNTrainer
+    g, ei, orc, prod = _build_pair('SAGEConv', 32, 'tiny', dropout=0.0)
+    y = g['artwork'].y_style
+    t = GNNTrainer(prod, _to_dev(g.x_dict), _to_dev(ei), y, lr=0.01, use_cuda_graph=True)
+    for _ in range(2):
+        t.train_step()
+    for _ in range(2):
+        l_g, a_g = t.evaluate()
+        l_g, a_g = float(l_g.item()), float(a_g.item())
+        l_e, a_e = t._evaluate_eager(None, None, None)
+        assert l_g == float(l_e.item()) and a_g == float(a_e.item())
+        t.train_step()
+    assert t._eval_graph is not None
+
+
 def test_dropout_is_active_and_embedding_is_dropout_free():
     g, ei, orc, prod = _build_pair('SAGEConv', 32, 'tiny', dropout=0.4)
     prod.eval()                                              # dropout baked in by tracing
