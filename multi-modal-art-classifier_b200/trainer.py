@@ -399,8 +399,10 @@ class GNNTrainer:
         if self.group is None:
             return loss, _accuracy(logp, y)
         from .dist import all_reduce_
-        hits = torch.stack([logp.argmax(dim=1).eq(y).sum(), torch.tensor(y.numel(), device=y.device)])
-        hits = all_reduce_(hits.to(torch.float64), self.group)
+        # (torch.full, not torch.tensor: no host -> device copy, so the call can be captured)
+        hits = torch.stack([logp.argmax(dim=1).eq(y).sum().to(torch.float64),
+                            torch.full((), float(y.numel()), dtype=torch.float64, device=y.device)])
+        hits = all_reduce_(hits, self.group)
         return loss, (hits[0] / hits[1]).to(torch.float32)
 
     def _check_foreign_graph(self, x_dict, edge_index_dict):
