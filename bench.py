@@ -268,6 +268,30 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def _reinit_for_parity(model, seed: int = 20261019):
+    """Deterministic re-initialisation IN PLACE (the parameters are views of the optimizer's flat
+    arena): U(+-1/sqrt(fan_in)) matrices, small biases, BatchNorm scale near 1, running statistics
+    reset.  Host generator with a fixed seed: identical on every rank."""
+    gen = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if isinstance(p, torch.nn.parameter.UninitializedParameter):
+                continue
+            u = torch.rand(p.shape, generator=gen) * 2 - 1
+            if p.dim() >= 2:
+                v = u / float(p.shape[1]) ** 0.5
+            elif '.bns.' in name and name.endswith('weight'):
+                v = 1.0 + 0.1 * u
+            else:
+                v = 0.1 * u
+            p.copy_(v.to(p.device))
+        for name, b in model.named_buffers():
+            if name.endswith('running_mean'):
+                b.zero_()
+            elif name.endswith('running_var'):
+                b.fill_(1.0)
+
+
 def dist_parity_blocks(trainer, model, data, x, ei, y, world, rank, dev, dist, size='full'):
     """N > 1, block partition: one training step of the N-rank job (dropout masks injected,
     current weights) against the SAME step of the whole N-block graph on rank 0 alone -- what
@@ -277,6 +301,15 @@ def dist_parity_blocks(trainer, model, data, x, ei, y, world, rank, dev, dist, s
     from mmac_b200 import synth
     from mmac_b200.dist import all_reduce_
     n_nodes = OrderedDict((t, int(v.shape[0])) for t, v in x.items())
+    # Fresh random weights (same on every rank), not the state the timed steps left behind: the
+    # check then does not depend on how long the timed loops trained (after a few hundred steps on
+    # this synthetic task the loss is ~1e-5).  Gradient tensors are compared relative to their OWN
+    # largest entry and, as a second figure, relative to the model's largest gradient: the small
+    # tensors are sums of cancelling terms whose float32 value depends on the summation order
+    # (N partial sums + NCCL here, one sum over N times the rows there) -- measured bit-identical
+    # with and without side streams / in-place gradient accumulation (AGX_NO_SIDE_STREAMS,
+    # AGX_NO_INPLACE_GRADS), i.e. arithmetic, not a race.
+    _reinit_for_parity(model)
     state = {k: v.detach().clone() for k, v in model.state_dict().items()
              if not isinstance(v, torch.nn.parameter.UninitializedParameter)}
     model.gnn.dropout_masks = {t: m.to(dev) for t, m in

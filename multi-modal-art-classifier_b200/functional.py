@@ -22,6 +22,7 @@ from ._lib import check, lib, ptr, stream_ptr
 from .graph import HeteroPlan, Relation
 
 # relative cost model for choosing transform-first vs aggregate-first per relation
+_NO_INPLACE = __import__('os').environ.get('AGX_NO_INPLACE_GRADS') is not None   # A/B switch
 _FLOP_RATE = 40e12      # sustained fp32 FFMA flop/s of the grouped GEMM (whole chip)
 _CTA_FLOP_RATE = 0.25e12  # one CTA's share: latency floor of a problem with a single row tile
 _BYTE_RATE = 5e12       # gather bandwidth
@@ -452,7 +453,7 @@ class _HeteroConvFn(torch.autograd.Function):
         # and added by _deliver_param_grads afterwards (one read + one write of every weight less;
         # the one-hot input layer holds most of the model's 5 M weights)
         refs = spec.param_refs
-        in_place = refs is not None and all(
+        in_place = refs is not None and not _NO_INPLACE and all(
             p.grad is not None and p.grad.is_contiguous() for p in refs)
         placed: Dict[int, bool] = {}
 
