@@ -168,6 +168,52 @@ def test_partition_single_rank_is_identity():
         assert torch.equal(part.edge_index[k], v)
 
 
+def test_scattered_partition_index_arithmetic():
+    """GraphPartition(scattered=): every edge lands on exactly one rank; relations from artwork into
+    a scattered type follow their SOURCE (global destination ids in a table of world * chunk rows,
+    divisor = global in-degree); the other relations of a scattered type follow the destination
+    and read gathered boundary rows; chunk bounds are equal-sized up to the last one."""
+    import mmac_b200  # noqa: F401
+    from mmac_b200 import synth
+    from mmac_b200.dist import GraphPartition
+    g = synth.make_artgraph('small', features='dense')
+    ei = go.to_undirected(g.edge_index_dict)
+    n = g.num_nodes_dict
+    scat = ['tag', 'artist']
+    rep = [t for t in n if t != 'artwork' and t not in scat]
+    for world in (2, 3, 5):
+        parts = [GraphPartition(ei, n, world, r, replicated=rep, scattered=scat) for r in range(world)]
+        for t in scat:
+            chunk = -(-n[t] // world)
+            assert parts[0].chunk[t] == chunk
+            assert parts[0].bounds[t] == [min(q * chunk, n[t]) for q in range(world + 1)]
+            assert sum(p.n_owned[t] for p in parts) == n[t]
+        for et, e in ei.items():
+            s_, _, d_ = et
+            per_rank = [p.edge_index[et] for p in parts]
+            both_rep = s_ in rep and d_ in rep
+            total = sum(x.shape[1] for x in per_rank)
+            assert total == (world if both_rep else 1) * e.shape[1], et
+            if et in parts[0].scatter:
+                assert d_ in scat and s_ == 'artwork'
+                cnt = torch.bincount(e[1], minlength=world * parts[0].chunk[d_]).clamp(min=1).float()
+                for r, p in enumerate(parts):
+                    assert torch.equal(p.scatter[et], cnt)
+                    lo = p.bounds[s_][r]
+                    # sources are owned rows (local index), destinations global ids, edge order kept
+                    m = (e[0] >= lo) & (e[0] < p.bounds[s_][r + 1])
+                    assert torch.equal(p.edge_index[et][0], e[0][m] - lo)
+                    assert torch.equal(p.edge_index[et][1], e[1][m])
+            elif d_ in scat:
+                for r, p in enumerate(parts):        # destination-owned, local destination ids
+                    lo, hi = p.bounds[d_][r], p.bounds[d_][r + 1]
+                    m = (e[1] >= lo) & (e[1] < hi)
+                    assert torch.equal(p.edge_index[et][1], e[1][m] - lo)
+        # tag / artist rows that artworks of another rank read are boundary rows, artwork has none
+        assert all(p.max_boundary['artwork'] == 0 for p in parts)
+        assert all(p.max_boundary['tag'] > 0 for p in parts)
+
+
 def test_balanced_bounds_equalise_edges():
     import mmac_b200  # noqa: F401
     from mmac_b200 import synth
