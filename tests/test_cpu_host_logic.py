@@ -287,3 +287,44 @@ def test_identity_marker_matches_dense_one_hot_on_cpu_shim():
         e2, o2 = m2(xm, ei)
     assert torch.equal(e1['artwork'], e2['artwork'])
     assert torch.equal(o1[0]['artwork'], o2[0]['artwork'])
+
+
+def test_batch_norm_without_mask_tensor_host_logic():
+    """BNSpec.drop (dropout decided inside the normalising pass, y not written, backward gate read
+    from the activation and scaled by 1 / (1 - p)) against the same layer with the materialised
+    mask: identical activations and gradients.  (Kernel layer restated on the CPU; the stand-in
+    dropout stream of tests/cpu_shim.py is a function of (key, counter) like the Philox one.)"""
+    import cpu_shim
+    import mmac_b200.functional as AF
+    gen = torch.Generator().manual_seed(5)
+    sizes, F, p = [40, 7], 16, 0.25
+    xs = [torch.randn(n, F, generator=gen) for n in sizes]
+    gas = [torch.randn(n, F, generator=gen) for n in sizes]
+    seed = torch.tensor([12345, 77], dtype=torch.int64)
+    offs = [0, ((sizes[0] * F + 3) // 4) * 4]
+    masks = [cpu_shim._dropout_mask((n, F), p, [int(seed[0]), int(seed[1]) + o // 4])
+             for n, o in zip(sizes, offs)]
+
+    def run(virtual):
+        bns = [torch.nn.BatchNorm1d(F).train() for _ in sizes]
+        xd = [x.clone().requires_grad_(True) for x in xs]
+        spec = AF.BNSpec(n=len(sizes), F=F, training=True, momentum=0.1, eps=1e-5,
+                         running=[(b.running_mean, b.running_var) for b in bns], with_act=True,
+                         dmasks=None if virtual else masks,
+                         drop=[(seed, o) for o in offs] if virtual else None, drop_p=p,
+                         need_y=not virtual)
+        with cpu_ops():
+            res = AF.batch_norm_act(spec, xd, [b.weight for b in bns], [b.bias for b in bns])
+            assert len(res) == (len(sizes) if virtual else 2 * len(sizes))
+            acts = res[-len(sizes):]
+            sum((a * g).sum() for a, g in zip(acts, gas)).backward()
+        return acts, [x.grad for x in xd], [b.weight.grad for b in bns], [b.bias.grad for b in bns]
+
+    a0, dx0, dw0, db0 = run(False)
+    a1, dx1, dw1, db1 = run(True)
+    for i in range(len(sizes)):
+        assert torch.equal(a0[i], a1[i])
+        assert 0 < int((a1[i] == 0).sum()) < a1[i].numel()
+        assert torch.allclose(dx0[i], dx1[i], rtol=1e-6, atol=1e-7)
+        assert torch.allclose(dw0[i], dw1[i], rtol=1e-6, atol=1e-7)
+        assert torch.allclose(db0[i], db1[i], rtol=1e-6, atol=1e-7)
