@@ -328,3 +328,27 @@ def test_batch_norm_without_mask_tensor_host_logic():
         assert torch.allclose(dx0[i], dx1[i], rtol=1e-6, atol=1e-7)
         assert torch.allclose(dw0[i], dw1[i], rtol=1e-6, atol=1e-7)
         assert torch.allclose(db0[i], db1[i], rtol=1e-6, atol=1e-7)
+
+
+def test_nll_of_log_softmax_fused_backward_host_logic():
+    """functional.nll_loss on the tensor functional.log_softmax returned differentiates both in one
+    call (g * (softmax - onehot) on the logits); on any other tensor (a slice, a clone) it takes the
+    general two-step path.  Both equal torch's F.nll_loss(F.log_softmax(x))."""
+    import mmac_b200.functional as AF
+    gen = torch.Generator().manual_seed(6)
+    x = torch.randn(37, 12, generator=gen)
+    y = torch.randint(0, 12, (37,), generator=gen)
+    xr = x.clone().requires_grad_(True)
+    ref = torch.nn.functional.nll_loss(torch.log_softmax(xr, 1), y)
+    ref.backward()
+    for fused in (True, False):
+        xd = x.clone().requires_grad_(True)
+        with cpu_ops():
+            lp = AF.log_softmax(xd, 1)
+            assert getattr(lp, '_agx_logits', None) is xd
+            arg = lp if fused else lp.clone()
+            loss = AF.nll_loss(arg, y)
+            assert (type(loss.grad_fn).__name__ == '_NLLOfLogSoftmaxFnBackward') == fused
+            loss.backward()
+        assert torch.allclose(loss, ref, rtol=1e-6)
+        assert torch.allclose(xd.grad, xr.grad, rtol=1e-5, atol=1e-8)
